@@ -1,0 +1,962 @@
+// C ABI of afft_b200 (see include/afft_b200.h): stateless operators + the model-level forward of
+// everything under BaseModel.future_predictor (reference models/base_model.py:59,
+// models/future_prediction.py:257-291).
+#include "../../include/afft_b200.h"
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "gemm_launch.cuh"
+#include "kernels.cuh"
+
+using namespace afft;
+typedef __nv_bfloat16 bf16;
+
+// ================================================================================================
+// errors
+// ================================================================================================
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+static int cuda_fail(const char* what, cudaError_t e) {
+  return fail(AFFT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+extern "C" int afft_abi_version(void) { return 1; }
+extern "C" const char* afft_last_error(void) { return g_err.c_str(); }
+
+static int device_sm_count(int* out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail("cudaGetDevice", e);
+  static int cached[64] = {0};
+  if (dev < 64 && cached[dev] > 0) {
+    *out = cached[dev];
+    return AFFT_OK;
+  }
+  int major = 0, sms = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return cuda_fail("cudaDeviceGetAttribute", e);
+  if (major != 10) return fail(AFFT_ERR_UNSUPPORTED, "afft_b200 kernels are sm_100a only (device is not compute capability 10.x)");
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return cuda_fail("cudaDeviceGetAttribute", e);
+  if (dev < 64) cached[dev] = sms;
+  *out = sms;
+  return AFFT_OK;
+}
+
+// ================================================================================================
+// stateless operators
+// ================================================================================================
+static int run_gemm(const afft_gemm_desc& d, int num_sms, cudaStream_t stream) {
+  GemmOperands g;
+  g.a = static_cast<const bf16*>(d.a_hi);
+  g.a_lo = static_cast<const bf16*>(d.a_lo);
+  g.lda = d.lda;
+  g.w = static_cast<const bf16*>(d.w_hi);
+  g.w_lo = static_cast<const bf16*>(d.w_lo);
+  g.ldw = d.ldw;
+  g.M = d.M;
+  g.N = d.N;
+  g.K = d.K;
+  GemmEpilogue ep;
+  ep.bias = d.bias;
+  ep.res = d.res;
+  ep.ld_res = d.ld_res;
+  ep.res_mod = d.res_mod;
+  ep.out_f32 = d.out_f32;
+  ep.ld_f32 = d.ld_f32;
+  ep.out_hi = static_cast<bf16*>(d.out_hi);
+  ep.out_lo = static_cast<bf16*>(d.out_lo);
+  ep.ld_bf16 = d.ld_bf16;
+  ep.act = d.act;
+  ep.row_group = d.row_group;
+  ep.row_stride = d.row_stride;
+  ep.row_off = d.row_off;
+  if (g.a == nullptr || g.w == nullptr) return fail(AFFT_ERR_INVALID, "gemm: null operand");
+  if (ep.out_f32 == nullptr && ep.out_hi == nullptr) return fail(AFFT_ERR_INVALID, "gemm: no output");
+  std::string err;
+  if (!launch_gemm(g, ep, d.strict != 0, d.force_block_n, num_sms, stream, &err)) return fail(AFFT_ERR_CUDA, err);
+  return AFFT_OK;
+}
+
+extern "C" int afft_gemm(const afft_gemm_desc* d, void* stream) {
+  if (d == nullptr) return fail(AFFT_ERR_INVALID, "gemm: null descriptor");
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc != AFFT_OK) return rc;
+  return run_gemm(*d, sms, static_cast<cudaStream_t>(stream));
+}
+
+static int run_convert(const float* src, long long lds, int rows, int cols, bf16* hi, bf16* lo, long long ldd,
+                       int transpose, cudaStream_t stream) {
+  if (src == nullptr || hi == nullptr || rows <= 0 || cols <= 0) return fail(AFFT_ERR_INVALID, "convert: bad argument");
+  if (transpose) {
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    convert_transpose_f32_bf16_kernel<<<grid, block, 0, stream>>>(src, lds, rows, cols, hi, lo, ldd);
+  } else {
+    const long long total = static_cast<long long>(rows) * cols;
+    int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    convert_f32_bf16_kernel<<<blocks, 256, 0, stream>>>(src, lds, rows, cols, hi, lo, ldd);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("convert launch", e);
+  return AFFT_OK;
+}
+
+extern "C" int afft_convert_bf16(const float* src, int64_t lds, int32_t rows, int32_t cols, void* hi, void* lo,
+                                 int64_t ldd, int32_t transpose, void* stream) {
+  return run_convert(src, lds, rows, cols, static_cast<bf16*>(hi), static_cast<bf16*>(lo), ldd, transpose,
+                     static_cast<cudaStream_t>(stream));
+}
+
+static int run_layernorm(const LayerNormArgs& a, cudaStream_t stream) {
+  if (a.x == nullptr || a.rows <= 0) return fail(AFFT_ERR_INVALID, "layernorm: bad argument");
+  if (a.dim % 128 != 0) return fail(AFFT_ERR_INVALID, "layernorm: dim must be a multiple of 128");
+  const int blocks = (a.rows + 7) / 8;  // 8 warps (rows) per 256-thread block
+  switch (a.dim / 128) {
+    case 2: layernorm_kernel<2><<<blocks, 256, 0, stream>>>(a); break;
+    case 4: layernorm_kernel<4><<<blocks, 256, 0, stream>>>(a); break;
+    case 6: layernorm_kernel<6><<<blocks, 256, 0, stream>>>(a); break;
+    case 8: layernorm_kernel<8><<<blocks, 256, 0, stream>>>(a); break;
+    case 12: layernorm_kernel<12><<<blocks, 256, 0, stream>>>(a); break;
+    case 16: layernorm_kernel<16><<<blocks, 256, 0, stream>>>(a); break;
+    default: return fail(AFFT_ERR_INVALID, "layernorm: unsupported dim (256, 512, 768, 1024, 1536, 2048)");
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("layernorm launch", e);
+  return AFFT_OK;
+}
+
+extern "C" int afft_layernorm(const afft_layernorm_desc* d, void* stream) {
+  if (d == nullptr) return fail(AFFT_ERR_INVALID, "layernorm: null descriptor");
+  LayerNormArgs a;
+  a.x = d->x;
+  a.ldx = d->ldx;
+  a.in_group = d->in_group;
+  a.in_stride = d->in_stride;
+  a.n_avg = d->n_avg;
+  a.avg_stride = d->avg_stride;
+  a.gamma = d->gamma;
+  a.beta = d->beta;
+  a.eps = d->eps;
+  a.rows = d->rows;
+  a.dim = d->dim;
+  a.y_f32 = d->y_f32;
+  a.y_hi = static_cast<bf16*>(d->y_hi);
+  a.y_lo = static_cast<bf16*>(d->y_lo);
+  a.ldy = d->ldy;
+  a.aux_mod = d->aux_mod;
+  a.aux_stride = d->aux_stride;
+  a.aux_f32 = d->aux_f32;
+  a.aux_hi = static_cast<bf16*>(d->aux_hi);
+  a.aux_lo = static_cast<bf16*>(d->aux_lo);
+  a.ld_aux = d->ld_aux;
+  return run_layernorm(a, static_cast<cudaStream_t>(stream));
+}
+
+template <typename TIn, int HD>
+static int launch_attention(const AttentionArgs& a, cudaStream_t stream) {
+  auto kern = attention_small_kernel<TIn, HD>;
+  const size_t smem = static_cast<size_t>(2) * a.L * HD * sizeof(TIn);
+  if (smem > 48 * 1024) {
+    static size_t configured[64] = {0};  // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (smem > configured[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return cuda_fail("attention smem attribute", e);
+      configured[dev] = smem;
+    }
+  }
+  int warps = a.L < 8 ? a.L : 8;
+  kern<<<a.n_seq * a.H, warps * 32, smem, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("attention launch", e);
+  return AFFT_OK;
+}
+
+static int run_attention(const AttentionArgs& a, int head_dim, bool in_f32, cudaStream_t stream) {
+  if (a.q == nullptr || a.k == nullptr || a.v == nullptr || a.out_hi == nullptr)
+    return fail(AFFT_ERR_INVALID, "attention: null pointer");
+  if (a.L < 1 || a.L > 64) return fail(AFFT_ERR_INVALID, "attention: sequence length must be in [1, 64]");
+  if (a.n_seq <= 0 || a.H <= 0) return fail(AFFT_ERR_INVALID, "attention: empty problem");
+  if (head_dim == 256) return in_f32 ? launch_attention<float, 256>(a, stream) : launch_attention<bf16, 256>(a, stream);
+  if (head_dim == 512) return in_f32 ? launch_attention<float, 512>(a, stream) : launch_attention<bf16, 512>(a, stream);
+  return fail(AFFT_ERR_INVALID, "attention: head_dim must be 256 or 512");
+}
+
+extern "C" int afft_attention(const afft_attention_desc* d, void* stream) {
+  if (d == nullptr) return fail(AFFT_ERR_INVALID, "attention: null descriptor");
+  AttentionArgs a;
+  a.q = d->q;
+  a.k = d->k;
+  a.v = d->v;
+  a.ldq = d->ldq;
+  a.ldk = d->ldk;
+  a.ldv = d->ldv;
+  a.n_seq = d->n_seq;
+  a.L = d->L;
+  a.H = d->H;
+  a.scale = d->scale;
+  a.mask = d->mask;
+  a.T = d->T > 0 ? d->T : 1;
+  a.out_hi = static_cast<bf16*>(d->out_hi);
+  a.out_lo = static_cast<bf16*>(d->out_lo);
+  a.ldo = d->ldo;
+  a.probs = d->probs;
+  a.p_outer = d->p_outer;
+  a.p_inner_stride = d->p_inner_stride;
+  a.p_inner = d->p_inner > 0 ? d->p_inner : 1;
+  return run_attention(a, d->head_dim, d->in_f32 != 0, static_cast<cudaStream_t>(stream));
+}
+
+// ================================================================================================
+// model-level
+// ================================================================================================
+namespace {
+
+struct Tensor {
+  // exactly one representation is populated
+  bf16* hi = nullptr;  // packed GEMM weight [N, K]
+  bf16* lo = nullptr;
+  float* f32 = nullptr;  // vectors / tables
+  long long rows = 0, cols = 0;  // packed: N, K.  f32: flattened [rows, cols]
+};
+
+enum class Pack { Gemm, GemmT, F32 };
+
+struct Expect {
+  Pack pack;
+  long long numel;
+  long long d0, d1;  // expected 2-D view (rows, cols) of the source tensor
+  long long min_rows = 0;  // > 0: embedding table, any row count >= min_rows is accepted
+};
+
+struct PairBuf {  // bf16 activation, hi (+ lo in strict mode)
+  bf16* hi = nullptr;
+  bf16* lo = nullptr;
+};
+
+}  // namespace
+
+struct afft_handle {
+  afft_config cfg;
+  int num_sms = 0;
+  std::string err;
+  std::map<std::string, Expect> expected;
+  std::map<std::string, Tensor> w;
+  size_t weight_bytes = 0;
+
+  // workspace
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+  int n_slots = 0;  // tokens per (b, t) in the fuser stream (CA: 1)
+  float* h = nullptr;
+  PairBuf y, att, f;
+  void* qkv = nullptr;  // bf16, or fp32 in strict mode
+  PairBuf xin[AFFT_MAX_MODS];
+  float* mem[AFFT_MAX_MODS] = {nullptr};  // CA-Fuser memories (+pos emb)
+  PairBuf ykv;
+  float* table = nullptr;  // [T, dim] additive embedding rows for projected modalities
+  PairBuf zb;
+  float* g = nullptr;
+  PairBuf y2, att2, f2, pfb;
+  void* qkv2 = nullptr;
+  int launches = 0;
+  int fuser_chunk = 0;
+};
+
+static int hfail(afft_handle* h, int code, const std::string& msg) {
+  h->err = msg;
+  g_err = msg;
+  return code;
+}
+
+static std::string blk_name(const char* prefix, int i, const char* suffix) {
+  return std::string(prefix) + std::to_string(i) + suffix;
+}
+
+static void build_expected(afft_handle* h) {
+  const afft_config& c = h->cfg;
+  auto& E = h->expected;
+  const long long D = c.dim, G = c.gpt_dim;
+  auto gemm = [&](const std::string& n, long long out, long long in) { E[n] = {Pack::Gemm, out * in, out, in, 0}; };
+  auto gemm_t = [&](const std::string& n, long long in, long long out) { E[n] = {Pack::GemmT, out * in, in, out, 0}; };
+  auto vec = [&](const std::string& n, long long rows, long long cols) { E[n] = {Pack::F32, rows * cols, rows, cols, 0}; };
+  auto table = [&](const std::string& n, long long cols) { E[n] = {Pack::F32, 0, 0, cols, c.T}; };
+  auto ln = [&](const std::string& n, long long d, bool affine) {
+    if (affine) {
+      vec(n + ".weight", 1, d);
+      vec(n + ".bias", 1, d);
+    }
+  };
+  for (int m = 0; m < c.n_mod; ++m)
+    if (c.mod_dim[m] != c.dim) gemm(std::string("mapping.") + c.mod_name[m] + ".mapping.0.weight", D, c.mod_dim[m]);
+
+  const int n_slots = h->n_slots;
+  const bool affine = (c.fuser_kind == AFFT_FUSER_SA) ? (c.norm_elementwise != 0) : true;
+  if (c.fuser_kind == AFFT_FUSER_SA) {
+    vec("fuser.modal_token", c.frame_level_token ? c.T : 1, D);
+    if (c.modal_encoding) vec("fuser.modality_embedding", n_slots, D);
+  } else if (c.fuser_kind == AFFT_FUSER_TSA) {
+    if (c.frame_level_token) vec("fuser.modal_token", c.T, D);
+    if (c.modal_encoding) vec("fuser.modality_embedding", n_slots, D);
+    table("fuser.position_embeddings.weight", D);
+  } else if (c.fuser_kind == AFFT_FUSER_CA) {
+    table("fuser.position_embeddings.weight", D);
+  }
+  for (int i = 0; i < c.fuser_depth; ++i) {
+    const std::string p = blk_name("fuser.blocks.", i, ".");
+    if (c.fuser_kind == AFFT_FUSER_CA) {
+      ln(p + "norm_self", D, true);
+      ln(p + "norm_q", D, true);
+      ln(p + "norm_kv", D, true);
+      ln(p + "norm_mlp", D, true);
+      gemm(p + "cross_attn.w_q.weight", D, D);
+      gemm(p + "cross_attn.w_k.weight", D, D);
+      gemm(p + "cross_attn.w_v.weight", D, D);
+      gemm(p + "cross_attn.proj.weight", D, D);
+      vec(p + "cross_attn.proj.bias", 1, D);
+    } else {
+      ln(p + "norm1", D, affine);
+      ln(p + "norm2", D, affine);
+    }
+    gemm(p + "attn.qkv.weight", 3 * D, D);
+    gemm(p + "attn.proj.weight", D, D);
+    vec(p + "attn.proj.bias", 1, D);
+    gemm(p + "mlp.mlp.0.weight", 4 * D, D);
+    vec(p + "mlp.mlp.0.bias", 1, 4 * D);
+    gemm(p + "mlp.mlp.2.weight", D, 4 * D);
+    vec(p + "mlp.mlp.2.bias", 1, D);
+  }
+  ln("fuser.norm", D, affine);
+  if (c.dim != c.gpt_dim) {
+    gemm("dim_encoder.weight", G, D);
+    gemm("dim_decoder.weight", D, G);
+  }
+  const std::string gp = "future_predictor.gpt_model.";
+  table(gp + "wpe.weight", G);
+  for (int i = 0; i < c.gpt_layers; ++i) {
+    const std::string p = gp + blk_name("h.", i, ".");
+    ln(p + "ln_1", G, true);
+    ln(p + "ln_2", G, true);
+    gemm_t(p + "attn.c_attn.weight", G, 3 * G);
+    vec(p + "attn.c_attn.bias", 1, 3 * G);
+    gemm_t(p + "attn.c_proj.weight", G, G);
+    vec(p + "attn.c_proj.bias", 1, G);
+    gemm_t(p + "mlp.c_fc.weight", G, 4 * G);
+    vec(p + "mlp.c_fc.bias", 1, 4 * G);
+    gemm_t(p + "mlp.c_proj.weight", 4 * G, G);
+    vec(p + "mlp.c_proj.bias", 1, G);
+  }
+  ln(gp + "ln_f", G, true);
+  for (int k = 0; k < c.n_cls; ++k) {
+    const std::string p = std::string("classifiers.") + c.cls_name[k] + ".all-fused.1.";
+    gemm(p + "weight", c.cls_dim[k], D);
+    vec(p + "bias", 1, c.cls_dim[k]);
+  }
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
+  if (cfg == nullptr || out == nullptr) return fail(AFFT_ERR_INVALID, "create: null argument");
+  *out = nullptr;
+  const afft_config& c = *cfg;
+  if (c.fuser_kind < 0 || c.fuser_kind > 3) return fail(AFFT_ERR_INVALID, "create: unknown fuser_kind");
+  if (c.n_mod < 1 || c.n_mod > AFFT_MAX_MODS - 1) return fail(AFFT_ERR_INVALID, "create: n_mod out of range");
+  if (c.n_cls < 1 || c.n_cls > AFFT_MAX_CLS) return fail(AFFT_ERR_INVALID, "create: n_cls out of range");
+  if (c.T < 1 || c.T > 64) return fail(AFFT_ERR_INVALID, "create: T must be in [1, 64]");
+  if (c.max_batch < 1) return fail(AFFT_ERR_INVALID, "create: max_batch must be >= 1");
+  if (c.dim % 128 != 0 || c.gpt_dim % 128 != 0) return fail(AFFT_ERR_INVALID, "create: dim and gpt_dim must be multiples of 128");
+  if (c.fuser_heads < 1 || c.gpt_heads < 1 || c.dim % c.fuser_heads != 0 || c.gpt_dim % c.gpt_heads != 0)
+    return fail(AFFT_ERR_INVALID, "create: heads must divide dims");
+  const int hd1 = c.dim / c.fuser_heads, hd2 = c.gpt_dim / c.gpt_heads;
+  if ((hd1 != 256 && hd1 != 512) || (hd2 != 256 && hd2 != 512))
+    return fail(AFFT_ERR_INVALID, "create: head_dim must be 256 or 512");
+  if (c.dim == c.gpt_dim) return fail(AFFT_ERR_INVALID, "create: common_dim == fp_inter_dim (Identity encoder) is not supported");
+  for (int m = 0; m < c.n_mod; ++m)
+    if (c.mod_dim[m] < 8 || c.mod_dim[m] % 8 != 0) return fail(AFFT_ERR_INVALID, "create: modality dims must be multiples of 8");
+  if (c.fuser_kind == AFFT_FUSER_CA && c.n_mod < 2) return fail(AFFT_ERR_INVALID, "create: CA-Fuser needs >= 2 modalities");
+
+  cudaError_t e = cudaSetDevice(c.device);
+  if (e != cudaSuccess) return cuda_fail("cudaSetDevice", e);
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc != AFFT_OK) return rc;
+
+  afft_handle* h = new afft_handle();
+  h->cfg = c;
+  h->num_sms = sms;
+  switch (c.fuser_kind) {
+    case AFFT_FUSER_SA: h->n_slots = c.n_mod + 1; break;
+    case AFFT_FUSER_SA_NOTOKEN: h->n_slots = c.n_mod; break;
+    case AFFT_FUSER_TSA: h->n_slots = c.n_mod + (c.frame_level_token ? 1 : 0); break;
+    default: h->n_slots = 1; break;
+  }
+  if (c.fuser_kind == AFFT_FUSER_TSA && h->n_slots * c.T > 64) {
+    delete h;
+    return fail(AFFT_ERR_INVALID, "create: T-SA-Fuser sequence (slots * T) must be <= 64");
+  }
+  if (c.fuser_kind == AFFT_FUSER_CA && c.fuser_depth != c.n_mod - 1) h->cfg.fuser_depth = c.n_mod - 1;
+  build_expected(h);
+  if (const char* env = getenv("AFFT_FUSER_CHUNK")) h->fuser_chunk = atoi(env);
+
+  // ---- workspace ----
+  const bool strict = c.strict != 0;
+  const size_t B = c.max_batch, T = c.T, D = c.dim, G = c.gpt_dim;
+  const size_t R2 = B * T, R1 = R2 * h->n_slots, RP = B * (T + 1);
+  struct Req {
+    void** dst;
+    size_t bytes;
+  };
+  std::vector<Req> reqs;
+  auto want = [&](void** p, size_t bytes) { reqs.push_back({p, align_up(bytes, 256)}); };
+  auto want_pair = [&](PairBuf& pb, size_t elems) {
+    want(reinterpret_cast<void**>(&pb.hi), elems * 2);
+    if (strict) want(reinterpret_cast<void**>(&pb.lo), elems * 2);
+  };
+  want(reinterpret_cast<void**>(&h->h), R1 * D * 4);
+  want_pair(h->y, R1 * D);
+  want_pair(h->att, R1 * D);
+  want_pair(h->f, R1 * 4 * D);
+  want(&h->qkv, R1 * 3 * D * (strict ? 4 : 2));
+  for (int m = 0; m < c.n_mod; ++m)
+    if (c.mod_dim[m] != c.dim) want_pair(h->xin[m], R2 * c.mod_dim[m]);
+  if (c.fuser_kind == AFFT_FUSER_CA) {
+    for (int m = 1; m < c.n_mod; ++m) want(reinterpret_cast<void**>(&h->mem[m]), R2 * D * 4);
+    want_pair(h->ykv, R2 * D);
+  }
+  want(reinterpret_cast<void**>(&h->table), T * D * 4);
+  want_pair(h->zb, R2 * D);
+  want(reinterpret_cast<void**>(&h->g), R2 * G * 4);
+  want_pair(h->y2, R2 * G);
+  want_pair(h->att2, R2 * G);
+  want_pair(h->f2, R2 * 4 * G);
+  want(&h->qkv2, R2 * 3 * G * (strict ? 4 : 2));
+  want_pair(h->pfb, RP * D);
+  size_t total = 0;
+  for (auto& r : reqs) total += r.bytes;
+  e = cudaMalloc(reinterpret_cast<void**>(&h->ws), total);
+  if (e != cudaSuccess) {
+    delete h;
+    return cuda_fail("cudaMalloc(workspace)", e);
+  }
+  h->ws_bytes = total;
+  size_t off = 0;
+  for (auto& r : reqs) {
+    *r.dst = h->ws + off;
+    off += r.bytes;
+  }
+  *out = h;
+  return AFFT_OK;
+}
+
+extern "C" void afft_destroy(afft_handle* h) {
+  if (h == nullptr) return;
+  cudaSetDevice(h->cfg.device);
+  for (auto& kv : h->w) {
+    if (kv.second.hi) cudaFree(kv.second.hi);
+    if (kv.second.lo) cudaFree(kv.second.lo);
+    if (kv.second.f32) cudaFree(kv.second.f32);
+  }
+  if (h->ws) cudaFree(h->ws);
+  delete h;
+}
+
+extern "C" const char* afft_handle_error(const afft_handle* h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" size_t afft_workspace_bytes(const afft_handle* h) { return h ? h->ws_bytes : 0; }
+extern "C" size_t afft_weight_bytes(const afft_handle* h) { return h ? h->weight_bytes : 0; }
+extern "C" int afft_last_launch_count(const afft_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int afft_set_weight(afft_handle* h, const char* name, const float* src, int32_t ndim, const int64_t* shape,
+                               void* stream_) {
+  if (h == nullptr) return fail(AFFT_ERR_INVALID, "set_weight: null handle");
+  if (name == nullptr || src == nullptr || shape == nullptr || ndim < 1 || ndim > 3)
+    return hfail(h, AFFT_ERR_INVALID, "set_weight: bad argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  auto it = h->expected.find(name);
+  if (it == h->expected.end()) return hfail(h, AFFT_ERR_INVALID, std::string("set_weight: unexpected tensor name '") + name + "'");
+  const Expect& ex = it->second;
+  long long numel = 1;
+  for (int i = 0; i < ndim; ++i) numel *= shape[i];
+  if (ex.min_rows > 0) {
+    if (numel % ex.d1 != 0 || numel / ex.d1 < ex.min_rows)
+      return hfail(h, AFFT_ERR_INVALID, std::string("set_weight: table '") + name + "' has fewer rows than T");
+  } else if (numel != ex.numel) {
+    return hfail(h, AFFT_ERR_INVALID, std::string("set_weight: size mismatch for '") + name + "'");
+  }
+  if (ex.pack != Pack::F32) {
+    if (ndim != 2 || shape[0] != ex.d0 || shape[1] != ex.d1)
+      return hfail(h, AFFT_ERR_INVALID, std::string("set_weight: shape mismatch for '") + name + "'");
+  }
+  cudaError_t e = cudaSetDevice(h->cfg.device);
+  if (e != cudaSuccess) return hfail(h, AFFT_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  Tensor& t = h->w[name];
+  const bool strict = h->cfg.strict != 0;
+  if (ex.pack == Pack::F32) {
+    if (t.f32 == nullptr) {
+      e = cudaMalloc(reinterpret_cast<void**>(&t.f32), align_up(numel * 4, 256));
+      if (e != cudaSuccess) return hfail(h, AFFT_ERR_CUDA, std::string("cudaMalloc(weight): ") + cudaGetErrorString(e));
+      h->weight_bytes += numel * 4;
+    }
+    t.rows = numel / ex.d1;
+    t.cols = ex.d1;
+    e = cudaMemcpyAsync(t.f32, src, numel * 4, cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) return hfail(h, AFFT_ERR_CUDA, std::string("cudaMemcpyAsync(weight): ") + cudaGetErrorString(e));
+    return AFFT_OK;
+  }
+  // GEMM weight -> bf16 [N, K], K contiguous
+  const long long N = (ex.pack == Pack::Gemm) ? ex.d0 : ex.d1;
+  const long long K = (ex.pack == Pack::Gemm) ? ex.d1 : ex.d0;
+  if (t.hi == nullptr) {
+    e = cudaMalloc(reinterpret_cast<void**>(&t.hi), align_up(N * K * 2, 256));
+    if (e != cudaSuccess) return hfail(h, AFFT_ERR_CUDA, std::string("cudaMalloc(weight): ") + cudaGetErrorString(e));
+    h->weight_bytes += N * K * 2;
+    if (strict) {
+      e = cudaMalloc(reinterpret_cast<void**>(&t.lo), align_up(N * K * 2, 256));
+      if (e != cudaSuccess) return hfail(h, AFFT_ERR_CUDA, std::string("cudaMalloc(weight): ") + cudaGetErrorString(e));
+      h->weight_bytes += N * K * 2;
+    }
+  }
+  t.rows = N;
+  t.cols = K;
+  int rc = (ex.pack == Pack::Gemm)
+               ? run_convert(src, K, static_cast<int>(N), static_cast<int>(K), t.hi, t.lo, K, 0, stream)
+               : run_convert(src, N, static_cast<int>(K), static_cast<int>(N), t.hi, t.lo, K, 1, stream);
+  if (rc != AFFT_OK) h->err = g_err;
+  return rc;
+}
+
+extern "C" int afft_missing_weights(const afft_handle* h, char* buf, size_t buf_len) {
+  if (h == nullptr) return -1;
+  int n = 0;
+  std::string names;
+  for (auto& kv : h->expected) {
+    if (h->w.find(kv.first) == h->w.end()) {
+      ++n;
+      names += kv.first;
+      names += '\n';
+    }
+  }
+  if (buf != nullptr && buf_len > 0) {
+    strncpy(buf, names.c_str(), buf_len - 1);
+    buf[buf_len - 1] = '\0';
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Fwd {
+  afft_handle* h;
+  cudaStream_t stream;
+  bool strict;
+  int rc = AFFT_OK;
+
+  const Tensor* W(const std::string& n) {
+    auto it = h->w.find(n);
+    return it == h->w.end() ? nullptr : &it->second;
+  }
+  const float* V(const std::string& n) {
+    const Tensor* t = W(n);
+    return t ? t->f32 : nullptr;
+  }
+  bool ok() const { return rc == AFFT_OK; }
+  void check(int r) {
+    if (rc == AFFT_OK && r != AFFT_OK) {
+      rc = r;
+      h->err = g_err;
+    }
+    if (r == AFFT_OK) ++h->launches;
+  }
+
+  // out = epilogue(A . W^T)
+  void gemm(const PairBuf& A, long long lda, int M, const std::string& wname, const float* bias, int act,
+            const float* res, long long ld_res, int res_mod, float* out_f32, long long ld_f32, const PairBuf* out_b,
+            long long ld_bf16, int row_group = 0, int row_stride = 0, int row_off = 0) {
+    if (!ok()) return;
+    const Tensor* w = W(wname);
+    afft_gemm_desc d;
+    memset(&d, 0, sizeof(d));
+    d.a_hi = A.hi;
+    d.a_lo = A.lo;
+    d.lda = lda;
+    d.w_hi = w->hi;
+    d.w_lo = w->lo;
+    d.ldw = w->cols;
+    d.M = M;
+    d.N = static_cast<int>(w->rows);
+    d.K = static_cast<int>(w->cols);
+    d.strict = strict ? 1 : 0;
+    d.bias = bias;
+    d.res = res;
+    d.ld_res = ld_res;
+    d.res_mod = res_mod;
+    d.act = act;
+    d.out_f32 = out_f32;
+    d.ld_f32 = ld_f32;
+    if (out_b != nullptr) {
+      d.out_hi = out_b->hi;
+      d.out_lo = out_b->lo;
+    }
+    d.ld_bf16 = ld_bf16;
+    d.row_group = row_group;
+    d.row_stride = row_stride;
+    d.row_off = row_off;
+    check(run_gemm(d, h->num_sms, stream));
+  }
+
+  void layernorm(const float* x, long long ldx, int rows, int dim, const std::string& name, float eps, const PairBuf* yb,
+                 float* y_f32, long long ldy, int in_group = 0, int in_stride = 0, int n_avg = 0, int avg_stride = 0,
+                 int aux_mod = 0, int aux_stride = 0, float* aux_f32 = nullptr, const PairBuf* aux_b = nullptr,
+                 long long ld_aux = 0) {
+    if (!ok()) return;
+    LayerNormArgs a;
+    a.x = x;
+    a.ldx = ldx;
+    a.in_group = in_group;
+    a.in_stride = in_stride;
+    a.n_avg = n_avg;
+    a.avg_stride = avg_stride;
+    a.gamma = V(name + ".weight");
+    a.beta = V(name + ".bias");
+    a.eps = eps;
+    a.rows = rows;
+    a.dim = dim;
+    a.y_f32 = y_f32;
+    a.y_hi = yb ? yb->hi : nullptr;
+    a.y_lo = yb ? yb->lo : nullptr;
+    a.ldy = ldy;
+    a.aux_mod = aux_mod;
+    a.aux_stride = aux_stride;
+    a.aux_f32 = aux_f32;
+    a.aux_hi = aux_b ? aux_b->hi : nullptr;
+    a.aux_lo = aux_b ? aux_b->lo : nullptr;
+    a.ld_aux = ld_aux;
+    check(run_layernorm(a, stream));
+  }
+
+  // q/k/v live in one buffer of row pitch ld (elements) at column offsets qo/ko/vo
+  void attention(const void* buf, long long ld, long long qo, long long ko, long long vo, int n_seq, int L, int H,
+                 int hd, int mask, int T, const PairBuf& out, long long ldo, float* probs, long long p_outer,
+                 long long p_inner_stride, int p_inner) {
+    if (!ok()) return;
+    const size_t es = strict ? 4 : 2;
+    AttentionArgs a;
+    a.q = static_cast<const char*>(buf) + qo * es;
+    a.k = static_cast<const char*>(buf) + ko * es;
+    a.v = static_cast<const char*>(buf) + vo * es;
+    a.ldq = a.ldk = a.ldv = ld;
+    a.n_seq = n_seq;
+    a.L = L;
+    a.H = H;
+    a.scale = 1.0f / sqrtf(static_cast<float>(hd));
+    a.mask = mask;
+    a.T = T > 0 ? T : 1;
+    a.out_hi = out.hi;
+    a.out_lo = out.lo;
+    a.ldo = ldo;
+    a.probs = probs;
+    a.p_outer = p_outer;
+    a.p_inner_stride = p_inner_stride;
+    a.p_inner = p_inner > 0 ? p_inner : 1;
+    check(run_attention(a, hd, strict, stream));
+  }
+
+  void convert(const float* src, long long lds, int rows, int cols, const PairBuf& dst, long long ldd) {
+    if (!ok()) return;
+    check(run_convert(src, lds, rows, cols, dst.hi, dst.lo, ldd, 0, stream));
+  }
+
+  void assemble(const AssembleArgs& a) {
+    if (!ok()) return;
+    const long long total = static_cast<long long>(a.B) * a.T * a.n_slots * (a.dim / 4);
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    assemble_tokens_kernel<<<blocks, 256, 0, stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    check(e == cudaSuccess ? AFFT_OK : cuda_fail("assemble launch", e));
+  }
+
+  void embed_table(float* table, const float* pos, const float* mod, int T, int dim) {
+    if (!ok()) return;
+    embed_table_kernel<<<(T * dim + 255) / 256, 256, 0, stream>>>(table, pos, mod, T, dim);
+    cudaError_t e = cudaGetLastError();
+    check(e == cudaSuccess ? AFFT_OK : cuda_fail("embed_table launch", e));
+  }
+};
+
+// qkv buffer views for the GEMM epilogue: bf16 output in fast mode, fp32 in strict mode.
+struct QkvOut {
+  float* f32;
+  PairBuf b;
+  const PairBuf* bp;
+};
+static QkvOut qkv_out(void* buf, bool strict, long long col_off) {
+  QkvOut o;
+  o.f32 = strict ? static_cast<float*>(buf) + col_off : nullptr;
+  o.b.hi = strict ? nullptr : static_cast<bf16*>(buf) + col_off;
+  o.b.lo = nullptr;
+  o.bp = strict ? nullptr : &o.b;
+  return o;
+}
+
+}  // namespace
+
+// Self-attention transformer block shared by SA / T-SA / CA fusers
+// (reference models/transformerblock.py:118-135).  rows x D stream in h->h.
+static void fuser_block(Fwd& F, const std::string& p, const char* n1, const char* n2, int rows, int n_seq, int L,
+                        int mask, int T, float* probs, long long p_outer, long long p_inner_stride, int p_inner) {
+  afft_handle* h = F.h;
+  const afft_config& c = h->cfg;
+  const int D = c.dim, H = c.fuser_heads, hd = D / H;
+  F.layernorm(h->h, D, rows, D, p + n1, 1e-6f, &h->y, nullptr, D);
+  QkvOut q = qkv_out(h->qkv, F.strict, 0);
+  F.gemm(h->y, D, rows, p + "attn.qkv.weight", nullptr, ACT_NONE, nullptr, 0, 0, q.f32, 3 * D, q.bp, 3 * D);
+  F.attention(h->qkv, 3 * D, 0, D, 2 * D, n_seq, L, H, hd, mask, T, h->att, D, probs, p_outer, p_inner_stride, p_inner);
+  F.gemm(h->att, D, rows, p + "attn.proj.weight", F.V(p + "attn.proj.bias"), ACT_NONE, h->h, D, 0, h->h, D, nullptr, 0);
+  (void)n2;
+}
+
+static void fuser_mlp(Fwd& F, const std::string& p, const char* norm, int rows) {
+  afft_handle* h = F.h;
+  const int D = h->cfg.dim;
+  F.layernorm(h->h, D, rows, D, p + norm, 1e-6f, &h->y, nullptr, D);
+  F.gemm(h->y, D, rows, p + "mlp.mlp.0.weight", F.V(p + "mlp.mlp.0.bias"), ACT_GELU_ERF, nullptr, 0, 0, nullptr, 0,
+         &h->f, 4 * D);
+  F.gemm(h->f, 4 * D, rows, p + "mlp.mlp.2.weight", F.V(p + "mlp.mlp.2.bias"), ACT_NONE, h->h, D, 0, h->h, D, nullptr,
+         0);
+}
+
+// Fuser over clips [b0, b0 + nb): writes z into orig_past / zb / slot 0 of past_futures & pfb.
+static void run_fuser(Fwd& F, const afft_io& io, int b0, int nb) {
+  afft_handle* h = F.h;
+  const afft_config& c = h->cfg;
+  const int T = c.T, D = c.dim, n = h->n_slots, H = c.fuser_heads, depth = c.fuser_depth;
+  const int R2 = nb * T;
+  const long long zoff = static_cast<long long>(b0) * T * D;          // into orig_past / zb
+  const long long poff = static_cast<long long>(b0) * (T + 1) * D;    // into past_futures / pfb
+  PairBuf zb = {h->zb.hi + zoff, h->zb.lo ? h->zb.lo + zoff : nullptr};
+  PairBuf pfb = {h->pfb.hi + poff, h->pfb.lo ? h->pfb.lo + poff : nullptr};
+  float* orig_past = io.orig_past + zoff;
+  float* pf = io.past_futures + poff;
+  const float* feat[AFFT_MAX_MODS];
+  for (int m = 0; m < c.n_mod; ++m) feat[m] = io.feat[m] + static_cast<long long>(b0) * T * c.mod_dim[m];
+
+  if (c.fuser_kind == AFFT_FUSER_CA) {
+    // x = rgb + pos; mems = others + pos  (fusion.py:262-264)
+    const float* pos = F.V("fuser.position_embeddings.weight");
+    F.embed_table(h->table, pos, nullptr, T, D);
+    for (int m = 0; m < c.n_mod; ++m) {
+      float* dst = (m == 0) ? h->h : h->mem[m];
+      if (c.mod_dim[m] != D) {
+        F.convert(feat[m], c.mod_dim[m], R2, c.mod_dim[m], h->xin[m], c.mod_dim[m]);
+        F.gemm(h->xin[m], c.mod_dim[m], R2, std::string("mapping.") + c.mod_name[m] + ".mapping.0.weight", nullptr,
+               ACT_NONE, h->table, D, T, dst, D, nullptr, 0);
+      } else {
+        AssembleArgs a;
+        memset(&a, 0, sizeof(a));
+        a.h = dst;
+        a.B = nb;
+        a.T = T;
+        a.dim = D;
+        a.n_slots = 1;
+        a.layout = 0;
+        a.src[0] = feat[m];
+        a.tok_mod = 1;
+        a.pos_emb = pos;
+        F.assemble(a);
+      }
+    }
+    const int hd = D / H;
+    for (int i = 0; i < depth; ++i) {
+      const std::string p = blk_name("fuser.blocks.", i, ".");
+      fuser_block(F, p, "norm_self", nullptr, R2, nb, T, /*causal*/ 1, T, nullptr, 0, 0, 1);
+      // cross attention: q from x, k/v from memory i  (transformerblock.py:60-76,160)
+      F.layernorm(h->h, D, R2, D, p + "norm_q", 1e-6f, &h->y, nullptr, D);
+      F.layernorm(h->mem[i + 1], D, R2, D, p + "norm_kv", 1e-6f, &h->ykv, nullptr, D);
+      QkvOut q = qkv_out(h->qkv, F.strict, 0), k = qkv_out(h->qkv, F.strict, D), v = qkv_out(h->qkv, F.strict, 2 * D);
+      F.gemm(h->y, D, R2, p + "cross_attn.w_q.weight", nullptr, ACT_NONE, nullptr, 0, 0, q.f32, 3 * D, q.bp, 3 * D);
+      F.gemm(h->ykv, D, R2, p + "cross_attn.w_k.weight", nullptr, ACT_NONE, nullptr, 0, 0, k.f32, 3 * D, k.bp, 3 * D);
+      F.gemm(h->ykv, D, R2, p + "cross_attn.w_v.weight", nullptr, ACT_NONE, nullptr, 0, 0, v.f32, 3 * D, v.bp, 3 * D);
+      F.attention(h->qkv, 3 * D, 0, D, 2 * D, nb, T, H, hd, 1, T, h->att, D, nullptr, 0, 0, 1);
+      F.gemm(h->att, D, R2, p + "cross_attn.proj.weight", F.V(p + "cross_attn.proj.bias"), ACT_NONE, h->h, D, 0, h->h,
+             D, nullptr, 0);
+      fuser_mlp(F, p, "norm_mlp", R2);
+    }
+    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, 0, 0, 0, 0, T, T + 1, pf, &pfb, D);
+    return;
+  }
+
+  const bool tsa = (c.fuser_kind == AFFT_FUSER_TSA);
+  const bool has_token = (c.fuser_kind == AFFT_FUSER_SA) || (tsa && c.frame_level_token);
+  const int R1 = R2 * n;
+  const float* pos = tsa ? F.V("fuser.position_embeddings.weight") : nullptr;
+  const float* modemb = c.modal_encoding ? F.V("fuser.modality_embedding") : nullptr;
+
+  // 1. token assembly + projections of modalities whose width differs from dim
+  AssembleArgs a;
+  memset(&a, 0, sizeof(a));
+  a.h = h->h;
+  a.B = nb;
+  a.T = T;
+  a.dim = D;
+  a.n_slots = n;
+  a.layout = tsa ? 1 : 0;
+  a.token = has_token ? F.V("fuser.modal_token") : nullptr;
+  a.tok_mod = (has_token && (tsa || c.frame_level_token)) ? T : 1;
+  a.pos_emb = pos;
+  a.mod_emb = modemb;
+  for (int m = 0; m < c.n_mod; ++m) {
+    const int s = m + (has_token ? 1 : 0);
+    if (c.mod_dim[m] == D) {
+      a.src[s] = feat[m];
+      continue;
+    }
+    a.src[s] = nullptr;
+    F.convert(feat[m], c.mod_dim[m], R2, c.mod_dim[m], h->xin[m], c.mod_dim[m]);
+    const std::string wn = std::string("mapping.") + c.mod_name[m] + ".mapping.0.weight";
+    const float* res = nullptr;
+    int res_mod = 0;
+    if (tsa) {
+      F.embed_table(h->table, pos, modemb ? modemb + static_cast<long long>(s) * D : nullptr, T, D);
+      res = h->table;
+      res_mod = T;
+    } else if (modemb != nullptr) {
+      res = modemb + static_cast<long long>(s) * D;
+      res_mod = 1;
+    }
+    if (tsa)
+      F.gemm(h->xin[m], c.mod_dim[m], R2, wn, nullptr, ACT_NONE, res, D, res_mod, h->h, D, nullptr, 0, T, n * T, s * T);
+    else
+      F.gemm(h->xin[m], c.mod_dim[m], R2, wn, nullptr, ACT_NONE, res, D, res_mod, h->h + static_cast<long long>(s) * D,
+             static_cast<long long>(n) * D, nullptr, 0);
+  }
+  if (has_token) a.is_token[0] = 1;
+  F.assemble(a);
+
+  // 2. blocks
+  const int L = tsa ? n * T : n;
+  const int n_seq = tsa ? nb : R2;
+  const int mask = tsa ? 2 : (c.cross_attn ? 3 : 0);
+  for (int i = 0; i < depth; ++i) {
+    const std::string p = blk_name("fuser.blocks.", i, ".");
+    float* probs = nullptr;
+    long long p_outer = 0, p_inner_stride = 0;
+    int p_inner = 1;
+    if (io.fuser_attn != nullptr) {
+      const long long per_seq = static_cast<long long>(H) * L * L;
+      if (tsa) {
+        p_outer = depth * per_seq;
+        probs = io.fuser_attn + b0 * p_outer + i * per_seq;
+      } else {
+        p_outer = static_cast<long long>(depth) * T * per_seq;
+        p_inner = T;
+        p_inner_stride = per_seq;
+        probs = io.fuser_attn + b0 * p_outer + static_cast<long long>(i) * T * per_seq;
+      }
+    }
+    fuser_block(F, p, "norm1", nullptr, R1, n_seq, L, mask, T, probs, p_outer, p_inner_stride, p_inner);
+    fuser_mlp(F, p, "norm2", R1);
+  }
+
+  // 3. final norm + token selection / averaging
+  if (c.fuser_kind == AFFT_FUSER_SA) {
+    // token 0 of every (b, t): fusion.py:362-364
+    F.layernorm(h->h, static_cast<long long>(n) * D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, 0, 0, 0, 0, T, T + 1,
+                pf, &pfb, D);
+  } else if (c.fuser_kind == AFFT_FUSER_SA_NOTOKEN) {
+    // mean over the modality tokens of LN(x): fusion.py:114-116
+    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, 1, n, n, 1, T, T + 1, pf, &pfb, D);
+  } else if (c.frame_level_token) {
+    // first T tokens of every clip: fusion.py:207-209
+    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, T, n * T, 0, 0, T, T + 1, pf, &pfb, D);
+  } else {
+    // mean over modalities per timestep: fusion.py:211-214
+    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, T, n * T, n, T, T, T + 1, pf, &pfb, D);
+  }
+}
+
+// dim_encoder -> GPT-2 -> dim_decoder -> classifiers over all B clips
+// (future_prediction.py:267-269,282-288; transformers GPT2Model)
+static void run_predictor(Fwd& F, const afft_io& io, int B) {
+  afft_handle* h = F.h;
+  const afft_config& c = h->cfg;
+  const int T = c.T, D = c.dim, G = c.gpt_dim, H = c.gpt_heads, hd = G / H;
+  const int R2 = B * T;
+  const std::string gp = "future_predictor.gpt_model.";
+  // g = z . Wenc^T + wpe[t]
+  F.gemm(h->zb, D, R2, "dim_encoder.weight", nullptr, ACT_NONE, F.V(gp + "wpe.weight"), G, T, h->g, G, nullptr, 0);
+  for (int i = 0; i < c.gpt_layers; ++i) {
+    const std::string p = gp + blk_name("h.", i, ".");
+    F.layernorm(h->g, G, R2, G, p + "ln_1", 1e-5f, &h->y2, nullptr, G);
+    QkvOut q = qkv_out(h->qkv2, F.strict, 0);
+    F.gemm(h->y2, G, R2, p + "attn.c_attn.weight", F.V(p + "attn.c_attn.bias"), ACT_NONE, nullptr, 0, 0, q.f32, 3 * G,
+           q.bp, 3 * G);
+    F.attention(h->qkv2, 3 * G, 0, G, 2 * G, B, T, H, hd, 1, T, h->att2, G, nullptr, 0, 0, 1);
+    F.gemm(h->att2, G, R2, p + "attn.c_proj.weight", F.V(p + "attn.c_proj.bias"), ACT_NONE, h->g, G, 0, h->g, G, nullptr,
+           0);
+    F.layernorm(h->g, G, R2, G, p + "ln_2", 1e-5f, &h->y2, nullptr, G);
+    F.gemm(h->y2, G, R2, p + "mlp.c_fc.weight", F.V(p + "mlp.c_fc.bias"), ACT_GELU_TANH, nullptr, 0, 0, nullptr, 0,
+           &h->f2, 4 * G);
+    F.gemm(h->f2, 4 * G, R2, p + "mlp.c_proj.weight", F.V(p + "mlp.c_proj.bias"), ACT_NONE, h->g, G, 0, h->g, G, nullptr,
+           0);
+  }
+  F.layernorm(h->g, G, R2, G, gp + "ln_f", 1e-5f, &h->y2, nullptr, G);
+  // z_hat[b, t] -> slot t + 1 of the [B, T+1, D] past_futures buffer (fp32 output + bf16 classifier input)
+  F.gemm(h->y2, G, R2, "dim_decoder.weight", nullptr, ACT_NONE, nullptr, 0, 0, io.past_futures, D, &h->pfb, D, T, T + 1, 1);
+  for (int k = 0; k < c.n_cls; ++k) {
+    const std::string p = std::string("classifiers.") + c.cls_name[k] + ".all-fused.1.";
+    F.gemm(h->pfb, D, B * (T + 1), p + "weight", F.V(p + "bias"), ACT_NONE, nullptr, 0, 0, io.logits[k], io.ld_logits[k],
+           nullptr, 0);
+  }
+}
+
+extern "C" int afft_forward(afft_handle* h, int32_t B, const afft_io* io, void* stream_) {
+  if (h == nullptr) return fail(AFFT_ERR_INVALID, "forward: null handle");
+  if (io == nullptr) return hfail(h, AFFT_ERR_INVALID, "forward: null io");
+  const afft_config& c = h->cfg;
+  if (B < 1 || B > c.max_batch) return hfail(h, AFFT_ERR_INVALID, "forward: B out of range [1, max_batch]");
+  for (int m = 0; m < c.n_mod; ++m)
+    if (io->feat[m] == nullptr) return hfail(h, AFFT_ERR_INVALID, "forward: null feature pointer");
+  if (io->orig_past == nullptr || io->past_futures == nullptr) return hfail(h, AFFT_ERR_INVALID, "forward: null output pointer");
+  for (int k = 0; k < c.n_cls; ++k) {
+    if (io->logits[k] == nullptr) return hfail(h, AFFT_ERR_INVALID, "forward: null logits pointer");
+    if (io->ld_logits[k] < c.cls_dim[k] || io->ld_logits[k] % 4 != 0)
+      return hfail(h, AFFT_ERR_INVALID, "forward: ld_logits must be a multiple of 4 and >= cls_dim");
+  }
+  if (h->w.size() != h->expected.size()) {
+    char buf[512];
+    int n = afft_missing_weights(h, buf, sizeof(buf));
+    return hfail(h, AFFT_ERR_MISSING, "forward: " + std::to_string(n) + " weights not registered, e.g. " + std::string(buf));
+  }
+  cudaError_t e = cudaSetDevice(c.device);
+  if (e != cudaSuccess) return hfail(h, AFFT_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+
+  Fwd F;
+  F.h = h;
+  F.stream = static_cast<cudaStream_t>(stream_);
+  F.strict = c.strict != 0;
+  h->launches = 0;
+  const int chunk = (h->fuser_chunk > 0) ? h->fuser_chunk : B;
+  for (int b0 = 0; b0 < B && F.ok(); b0 += chunk) run_fuser(F, *io, b0, std::min(chunk, B - b0));
+  if (F.ok()) run_predictor(F, *io, B);
+  return F.rc;
+}

@@ -1,0 +1,148 @@
+// Host-side launcher for gemm_bf16_tcgen05_kernel: builds the TMA tensor maps and picks the
+// tile shape.  No libcuda link dependency: cuTensorMapEncodeTiled is resolved at run time
+// through cudaGetDriverEntryPoint.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+#include <string>
+
+#include "gemm_sm100.cuh"
+
+namespace afft {
+
+struct GemmOperands {
+  const __nv_bfloat16* a;     // [M,K] row pitch lda (elements)
+  const __nv_bfloat16* a_lo;  // strict mode only
+  long long lda;
+  const __nv_bfloat16* w;     // [N,K] row pitch ldw
+  const __nv_bfloat16* w_lo;  // strict mode only
+  long long ldw;
+  int M, N, K;
+};
+
+inline PFN_cuTensorMapEncodeTiled_v12000 get_tensormap_encoder(std::string* err) {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  static std::string init_err;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) {
+      init_err = std::string("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: ") +
+                 cudaGetErrorString(e);
+      (void)cudaGetLastError();
+    } else {
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+  });
+  if (fn == nullptr && err != nullptr) *err = init_err;
+  return fn;
+}
+
+// bf16 matrix [rows, cols] with row pitch ld (elements) -> 2-D tiled map, box = 64 x box_rows,
+// SWIZZLE_128B, out-of-bounds elements read as zero.
+inline bool make_tmap_bf16(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld,
+                           int box_rows, std::string* err) {
+  auto enc = get_tensormap_encoder(err);
+  if (enc == nullptr) return false;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (ld * 2) % 16 != 0) {
+    if (err) *err = "TMA operand must be 16-B aligned with a 16-B multiple row pitch";
+    return false;
+  }
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box,
+                   estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r));
+    return false;
+  }
+  return true;
+}
+
+template <int BLOCK_N, int SPLIT>
+inline cudaError_t launch_gemm_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal,
+                                       const CUtensorMap& tbl, const GemmEpilogue& ep, int M, int N, int K,
+                                       int num_sms, cudaStream_t stream) {
+  using T = GemmTraits<BLOCK_N, SPLIT>;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT>;
+  static bool attr_set[64] = {false};  // per variant and device; benign race (idempotent)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  const int num_tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  kern<<<grid, kGemmThreads, T::kSmemBytes, stream>>>(ta, tb, tal, tbl, ep, M, N, K);
+  return cudaGetLastError();
+}
+
+inline int pick_block_n(int M, int N, int num_sms, int forced) {
+  if (forced == 128 || forced == 256) return forced;
+  // Fewest waves wins; ties go to the 256-wide tile (less A re-streaming through shared memory).
+  const long long m_tiles = (M + kBlockM - 1) / kBlockM;
+  const long long t256 = m_tiles * ((N + 255) / 256), t128 = m_tiles * ((N + 127) / 128);
+  const long long w256 = (t256 + num_sms - 1) / num_sms, w128 = (t128 + num_sms - 1) / num_sms;
+  // cost in units of "128x128 tile times"
+  return (w128 < 2 * w256) ? 128 : 256;
+}
+
+// Returns false and fills *err on failure.  force_block_n: 0 = auto.
+inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, bool strict, int force_block_n,
+                        int num_sms, cudaStream_t stream, std::string* err) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) {
+    if (err) *err = "gemm: empty problem";
+    return false;
+  }
+  if (strict && (g.a_lo == nullptr || g.w_lo == nullptr)) {
+    if (err) *err = "gemm: strict mode needs hi/lo operands";
+    return false;
+  }
+  auto misaligned = [](const void* p, long long ld, int elem) {
+    return p != nullptr && (((reinterpret_cast<uintptr_t>(p) & 15u) != 0) || ((ld * elem) % 16 != 0));
+  };
+  if (misaligned(ep.out_f32, ep.ld_f32, 4) || misaligned(ep.res, ep.ld_res, 4) ||
+      misaligned(ep.out_hi, ep.ld_bf16, 2) || misaligned(ep.out_lo, ep.ld_bf16, 2) ||
+      (ep.bias != nullptr && (reinterpret_cast<uintptr_t>(ep.bias) & 15u) != 0)) {
+    if (err) *err = "gemm: epilogue pointers must be 16-B aligned with 16-B multiple pitches";
+    return false;
+  }
+  const int bn = pick_block_n(g.M, g.N, num_sms, force_block_n);
+  CUtensorMap ta, tb, tal, tbl;
+  if (!make_tmap_bf16(&ta, g.a, g.M, g.K, g.lda, kBlockM, err)) return false;
+  if (!make_tmap_bf16(&tb, g.w, g.N, g.K, g.ldw, bn, err)) return false;
+  if (strict) {
+    if (!make_tmap_bf16(&tal, g.a_lo, g.M, g.K, g.lda, kBlockM, err)) return false;
+    if (!make_tmap_bf16(&tbl, g.w_lo, g.N, g.K, g.ldw, bn, err)) return false;
+  } else {
+    tal = ta;
+    tbl = tb;
+  }
+  cudaError_t e;
+  if (strict) {
+    e = (bn == 256) ? launch_gemm_variant<256, 3>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, stream)
+                    : launch_gemm_variant<128, 3>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, stream);
+  } else {
+    e = (bn == 256) ? launch_gemm_variant<256, 1>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, stream)
+                    : launch_gemm_variant<128, 1>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, stream);
+  }
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("gemm launch failed: ") + cudaGetErrorString(e);
+    return false;
+  }
+  return true;
+}
+
+}  // namespace afft

@@ -1,0 +1,398 @@
+// The non-GEMM kernels of the AFFT hot path.  All of them are HBM/L2-bandwidth or latency bound
+// (SURVEY.md section 8d), so they are plain SIMT kernels: 16-byte coalesced accesses, fp32 math,
+// warp-shuffle reductions, operands staged in shared memory where they are re-read.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace afft {
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat16 x = __float2bfloat16_rn(a), y = __float2bfloat16_rn(b);
+  return static_cast<uint32_t>(__bfloat16_as_ushort(x)) | (static_cast<uint32_t>(__bfloat16_as_ushort(y)) << 16);
+}
+// residual part of the hi/lo split: bf16(a - float(bf16(a)))
+__device__ __forceinline__ float bf16_residual(float a) {
+  return a - __bfloat162float(__float2bfloat16_rn(a));
+}
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> bf16 (hi [+ lo]) conversion, optionally transposing.  Used once per weight at load time
+// (Conv1D [in,out] -> K-major [out,in]) and per forward for feature inputs that feed a projection.
+// ------------------------------------------------------------------------------------------------
+__global__ void convert_f32_bf16_kernel(const float* __restrict__ src, long long lds, int rows, int cols,
+                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                        long long ldd) {
+  const long long total = static_cast<long long>(rows) * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+    const float v = src[r * lds + c];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[r * ldd + c] = h;
+    if (lo != nullptr) lo[r * ldd + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// dst[c, r] = src[r, c]   (src [rows, cols] pitch lds; dst [cols, rows] pitch ldd)
+__global__ void convert_transpose_f32_bf16_kernel(const float* __restrict__ src, long long lds, int rows,
+                                                  int cols, __nv_bfloat16* __restrict__ hi,
+                                                  __nv_bfloat16* __restrict__ lo, long long ldd) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? src[r * lds + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) {
+      const float v = tile[threadIdx.x][j];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi[c * ldd + r] = h;
+      if (lo != nullptr) lo[c * ldd + r] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (biased variance, affine), one warp per row, row in registers.
+// (reference: nn.LayerNorm eps=1e-6 in models/fusion.py:281 / transformerblock.py:132,134,
+//  eps=1e-5 in GPT-2 ln_1/ln_2/ln_f)
+// Outputs (each optional): y_f32, y_hi (bf16), y_lo (bf16 residual) at row r, pitch ldy; and an
+// "aux" copy of rows with r % aux_mod == 0 to row (r / aux_mod) * aux_stride of aux_f32 / aux_hi /
+// aux_lo (pitch ld_aux) - used to drop z[:, 0] into slot 0 of the past_futures buffer.
+// ------------------------------------------------------------------------------------------------
+struct LayerNormArgs {
+  const float* x;
+  long long ldx;
+  int in_group, in_stride;  // input row of output row r: (r / in_group) * in_stride + r % in_group (0: r)
+  int n_avg, avg_stride;    // output = mean over s < n_avg of LN(x[in_row + s * avg_stride])  (n_avg <= 1: plain LN)
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int rows, dim;
+  float* y_f32;
+  __nv_bfloat16* y_hi;
+  __nv_bfloat16* y_lo;
+  long long ldy;
+  int aux_mod, aux_stride;
+  float* aux_f32;
+  __nv_bfloat16* aux_hi;
+  __nv_bfloat16* aux_lo;
+  long long ld_aux;
+};
+
+template <int NV>  // NV float4 per lane: dim = 128 * NV
+__global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= a.rows) return;
+  long long irow = warp;
+  if (a.in_group > 0) irow = static_cast<long long>(warp / a.in_group) * a.in_stride + (warp % a.in_group);
+  const float inv_d = 1.0f / static_cast<float>(a.dim);
+  const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(a.beta);
+  const int n_avg = a.n_avg > 1 ? a.n_avg : 1;
+  float4 acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int sl = 0; sl < n_avg; ++sl) {
+    const float4* xr = reinterpret_cast<const float4*>(a.x + (irow + static_cast<long long>(sl) * a.avg_stride) * a.ldx);
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + a.eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.gamma != nullptr) g = __ldg(g4 + c4);
+      if (a.beta != nullptr) b = __ldg(b4 + c4);
+      acc[i].x += (v[i].x - mean) * rstd * g.x + b.x;
+      acc[i].y += (v[i].y - mean) * rstd * g.y + b.y;
+      acc[i].z += (v[i].z - mean) * rstd * g.z + b.z;
+      acc[i].w += (v[i].w - mean) * rstd * g.w + b.w;
+    }
+  }
+  const float inv_avg = 1.0f / static_cast<float>(n_avg);
+  const bool aux = a.aux_mod > 0 && (warp % a.aux_mod) == 0;
+  const long long arow = aux ? static_cast<long long>(warp / a.aux_mod) * a.aux_stride : 0;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;  // float4 index within the row
+    float4 y = acc[i];
+    if (n_avg > 1) {
+      y.x *= inv_avg; y.y *= inv_avg; y.z *= inv_avg; y.w *= inv_avg;
+    }
+    const uint2 hi = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+    const uint2 lo = make_uint2(pack_bf16x2(bf16_residual(y.x), bf16_residual(y.y)),
+                                pack_bf16x2(bf16_residual(y.z), bf16_residual(y.w)));
+    if (a.y_f32 != nullptr) reinterpret_cast<float4*>(a.y_f32 + warp * a.ldy)[c4] = y;
+    if (a.y_hi != nullptr) reinterpret_cast<uint2*>(a.y_hi + warp * a.ldy)[c4] = hi;
+    if (a.y_lo != nullptr) reinterpret_cast<uint2*>(a.y_lo + warp * a.ldy)[c4] = lo;
+    if (aux) {
+      if (a.aux_f32 != nullptr) reinterpret_cast<float4*>(a.aux_f32 + arow * a.ld_aux)[c4] = y;
+      if (a.aux_hi != nullptr) reinterpret_cast<uint2*>(a.aux_hi + arow * a.ld_aux)[c4] = hi;
+      if (a.aux_lo != nullptr) reinterpret_cast<uint2*>(a.aux_lo + arow * a.ld_aux)[c4] = lo;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Token assembly: builds the fp32 residual stream of a fuser from the per-modality feature
+// sequences (reference: models/fusion.py:338-353 SA-Fuser, :177-196 T-SA-Fuser, :262 CA-Fuser).
+//   slot s of (b, t) goes to row  b*n_slots*T + (layout == 0 ? t*n_slots + s : s*T + t)
+//   value = src_s[b, t, :]            (src_s == nullptr: slot is filled by a projection GEMM, skip)
+//         | token[(t % tok_mod), :]   (learned modality-agnostic token; tok_mod = 1 or T)
+//         + pos_emb[t, :] (optional) + mod_emb[s, :] (optional)
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxSlots = 8;
+struct AssembleArgs {
+  float* h;           // [B * n_slots * T, dim]
+  int B, T, dim, n_slots, layout;
+  const float* src[kMaxSlots];  // [B*T, dim] contiguous, or nullptr
+  int is_token[kMaxSlots];      // slot reads `token` instead of src
+  const float* token;           // [tok_mod, dim]
+  int tok_mod;
+  const float* pos_emb;  // [>=T, dim] or nullptr
+  const float* mod_emb;  // [n_slots, dim] or nullptr
+};
+
+__global__ void __launch_bounds__(256) assemble_tokens_kernel(const AssembleArgs a) {
+  const int d4 = a.dim / 4;
+  const long long total = static_cast<long long>(a.B) * a.T * a.n_slots * d4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % d4);
+    long long r = i / d4;
+    const int s = static_cast<int>(r % a.n_slots);
+    r /= a.n_slots;
+    const int t = static_cast<int>(r % a.T);
+    const int b = static_cast<int>(r / a.T);
+    float4 v;
+    if (a.is_token[s]) {
+      v = __ldg(reinterpret_cast<const float4*>(a.token + static_cast<long long>(t % a.tok_mod) * a.dim) + c4);
+    } else if (a.src[s] != nullptr) {
+      v = __ldg(reinterpret_cast<const float4*>(a.src[s] + (static_cast<long long>(b) * a.T + t) * a.dim) + c4);
+    } else {
+      continue;
+    }
+    if (a.pos_emb != nullptr) {
+      const float4 p = __ldg(reinterpret_cast<const float4*>(a.pos_emb + static_cast<long long>(t) * a.dim) + c4);
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    if (a.mod_emb != nullptr) {
+      const float4 p = __ldg(reinterpret_cast<const float4*>(a.mod_emb + static_cast<long long>(s) * a.dim) + c4);
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    const long long orow = static_cast<long long>(b) * a.n_slots * a.T +
+                           (a.layout == 0 ? static_cast<long long>(t) * a.n_slots + s
+                                          : static_cast<long long>(s) * a.T + t);
+    reinterpret_cast<float4*>(a.h + orow * a.dim)[c4] = v;
+  }
+}
+
+// table[t, :] = pos_emb[t, :] + (mod_emb ? mod_emb[:] : 0)   for t < T - the additive term a projected
+// modality receives through the GEMM residual input (T-SA-Fuser / CA-Fuser embeddings).
+__global__ void embed_table_kernel(float* __restrict__ table, const float* __restrict__ pos_emb,
+                                   const float* __restrict__ mod_emb, int T, int dim) {
+  const int total = T * dim;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    float v = (pos_emb != nullptr) ? pos_emb[i] : 0.f;
+    if (mod_emb != nullptr) v += mod_emb[i % dim];
+    table[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small multi-head attention: one CTA per (sequence, head); L <= 64 keys, head_dim 256 or 512.
+// K and V of the head are staged in shared memory once and re-read by every query row; each warp
+// owns query rows i = warp, warp + NW, ...; lanes split head_dim in 16-B chunks; scores are
+// reduced with warp shuffles; softmax in fp32.
+// (reference: models/transformerblock.py:24-33 and :64-74; transformers GPT-2 eager attention)
+//   mask 0: none | 1: causal (j <= i) | 2: block-causal, period T ((j % T) <= (i % T))
+//        | 3: diagonal masked (j != i)   [ModalTokenCMFuser cross_attn=True]
+// q/k/v element (seq, i, h, d) is at  base[(seq*L + i) * ld + h*HD + d].
+// probs (optional, fp32): probs[(seq / p_inner) * p_outer + (seq % p_inner) * p_inner_stride
+//                               + h*L*L + i*L + j]
+// ------------------------------------------------------------------------------------------------
+struct AttentionArgs {
+  const void* q;
+  const void* k;
+  const void* v;
+  long long ldq, ldk, ldv;
+  int n_seq, L, H;
+  float scale;
+  int mask, T;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  long long ldo;
+  float* probs;
+  long long p_outer, p_inner_stride;
+  int p_inner;
+};
+
+template <typename TIn, int HD>
+struct AttnTraits {
+  static constexpr int kVecElems = 16 / sizeof(TIn);        // elements per 16-B vector
+  static constexpr int kChunkElems = 32 * kVecElems;        // elements covered by one warp-wide vector load
+  static constexpr int kNV = HD / kChunkElems;              // vectors per lane
+  static constexpr int kPerLane = HD / 32;                  // elements per lane
+};
+
+template <typename TIn, int HD>
+__device__ __forceinline__ void load_row_regs(const TIn* row, int lane, float (&f)[HD / 32]) {
+  using A = AttnTraits<TIn, HD>;
+#pragma unroll
+  for (int c = 0; c < A::kNV; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + c * A::kChunkElems + lane * A::kVecElems);
+    if constexpr (sizeof(TIn) == 2) {
+      float t[8];
+      unpack_bf16x8(u, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[c * 8 + e] = t[e];
+    } else {
+      f[c * 4 + 0] = __uint_as_float(u.x);
+      f[c * 4 + 1] = __uint_as_float(u.y);
+      f[c * 4 + 2] = __uint_as_float(u.z);
+      f[c * 4 + 3] = __uint_as_float(u.w);
+    }
+  }
+}
+
+template <typename TIn, int HD>
+__global__ void __launch_bounds__(256) attention_small_kernel(const AttentionArgs a) {
+  using A = AttnTraits<TIn, HD>;
+  extern __shared__ uint4 smem_attn[];
+  TIn* ks = reinterpret_cast<TIn*>(smem_attn);
+  TIn* vs = ks + static_cast<size_t>(a.L) * HD;
+  const int seq = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int L = a.L;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const TIn* qg = reinterpret_cast<const TIn*>(a.q) + static_cast<long long>(seq) * L * a.ldq + h * HD;
+  const TIn* kg = reinterpret_cast<const TIn*>(a.k) + static_cast<long long>(seq) * L * a.ldk + h * HD;
+  const TIn* vg = reinterpret_cast<const TIn*>(a.v) + static_cast<long long>(seq) * L * a.ldv + h * HD;
+
+  // stage K, V (16-B vectors, coalesced)
+  constexpr int kVecPerRow = HD / A::kVecElems;
+  for (int i = threadIdx.x; i < L * kVecPerRow; i += blockDim.x) {
+    const int r = i / kVecPerRow, c = i % kVecPerRow;
+    reinterpret_cast<uint4*>(ks)[i] = *reinterpret_cast<const uint4*>(kg + r * a.ldk + c * A::kVecElems);
+    reinterpret_cast<uint4*>(vs)[i] = *reinterpret_cast<const uint4*>(vg + r * a.ldv + c * A::kVecElems);
+  }
+  __syncthreads();
+
+  for (int i = warp; i < L; i += nw) {
+    float q[A::kPerLane];
+    load_row_regs<TIn, HD>(qg + static_cast<long long>(i) * a.ldq, lane, q);
+    // scores: lane (j % 32) keeps s_j in slot j / 32
+    float s0 = -INFINITY, s1 = -INFINITY;
+    for (int j = 0; j < L; ++j) {
+      bool ok = true;
+      if (a.mask == 1) ok = (j <= i);
+      else if (a.mask == 2) ok = ((j % a.T) <= (i % a.T));
+      else if (a.mask == 3) ok = (j != i);
+      if (!ok) continue;  // warp-uniform
+      float kr[A::kPerLane];
+      load_row_regs<TIn, HD>(ks + static_cast<size_t>(j) * HD, lane, kr);
+      float d = 0.f;
+#pragma unroll
+      for (int e = 0; e < A::kPerLane; ++e) d = fmaf(q[e], kr[e], d);
+      d = warp_sum(d) * a.scale;
+      if (lane == (j & 31)) {
+        if (j < 32) s0 = d; else s1 = d;
+      }
+    }
+    const float mx = warp_max(fmaxf(s0, s1));
+    float p0 = (s0 == -INFINITY) ? 0.f : expf(s0 - mx);
+    float p1 = (s1 == -INFINITY) ? 0.f : expf(s1 - mx);
+    const float inv = 1.0f / warp_sum(p0 + p1);
+    p0 *= inv;
+    p1 *= inv;
+    if (a.probs != nullptr) {
+      float* pr = a.probs + static_cast<long long>(seq / a.p_inner) * a.p_outer +
+                  static_cast<long long>(seq % a.p_inner) * a.p_inner_stride +
+                  (static_cast<long long>(h) * L + i) * L;
+      if (lane < L) pr[lane] = p0;
+      if (lane + 32 < L) pr[lane + 32] = p1;
+    }
+    float o[A::kPerLane];
+#pragma unroll
+    for (int e = 0; e < A::kPerLane; ++e) o[e] = 0.f;
+    for (int j = 0; j < L; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, (j < 32) ? p0 : p1, j & 31);
+      if (pj == 0.f) continue;  // warp-uniform (masked keys)
+      float vr[A::kPerLane];
+      load_row_regs<TIn, HD>(vs + static_cast<size_t>(j) * HD, lane, vr);
+#pragma unroll
+      for (int e = 0; e < A::kPerLane; ++e) o[e] = fmaf(pj, vr[e], o[e]);
+    }
+    // write merged-head output row: element d of lane = chunk c, lane*kVecElems + e
+    const long long orow = (static_cast<long long>(seq) * L + i) * a.ldo + h * HD;
+#pragma unroll
+    for (int c = 0; c < A::kNV; ++c) {
+      constexpr int VE = A::kVecElems;
+      const int d0 = c * A::kChunkElems + lane * VE;
+      if constexpr (VE == 8) {
+        const float* oo = &o[c * 8];
+        uint4 hv = make_uint4(pack_bf16x2(oo[0], oo[1]), pack_bf16x2(oo[2], oo[3]), pack_bf16x2(oo[4], oo[5]),
+                              pack_bf16x2(oo[6], oo[7]));
+        *reinterpret_cast<uint4*>(a.out_hi + orow + d0) = hv;
+        if (a.out_lo != nullptr) {
+          uint4 lv = make_uint4(pack_bf16x2(bf16_residual(oo[0]), bf16_residual(oo[1])),
+                                pack_bf16x2(bf16_residual(oo[2]), bf16_residual(oo[3])),
+                                pack_bf16x2(bf16_residual(oo[4]), bf16_residual(oo[5])),
+                                pack_bf16x2(bf16_residual(oo[6]), bf16_residual(oo[7])));
+          *reinterpret_cast<uint4*>(a.out_lo + orow + d0) = lv;
+        }
+      } else {
+        const float* oo = &o[c * 4];
+        uint2 hv = make_uint2(pack_bf16x2(oo[0], oo[1]), pack_bf16x2(oo[2], oo[3]));
+        *reinterpret_cast<uint2*>(a.out_hi + orow + d0) = hv;
+        if (a.out_lo != nullptr) {
+          uint2 lv = make_uint2(pack_bf16x2(bf16_residual(oo[0]), bf16_residual(oo[1])),
+                                pack_bf16x2(bf16_residual(oo[2]), bf16_residual(oo[3])));
+          *reinterpret_cast<uint2*>(a.out_lo + orow + d0) = lv;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace afft

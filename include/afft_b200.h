@@ -1,0 +1,218 @@
+/*
+ * afft_b200 - C ABI of the B200-native AFFT fusion-and-anticipation forward path.
+ *
+ * The reference (zeyun-zhong/AFFT) is pure Python/PyTorch and has no FFI layer; the seam this
+ * library plugs into is the `models/` module API.  The Python shim classes
+ * in afft_b200/models/ keep the reference's constructor/forward signatures and parameter names
+ * and call the entry points below through ctypes.  Each entry point cites the reference code it
+ * replaces.
+ *
+ * Conventions
+ *  - every pointer named *_dev / in the io structs is DEVICE memory owned by the caller
+ *    (PyTorch's allocator); the library never frees it and only retains registered weights
+ *    (which it copies/packs into its own storage at afft_set_weight time).
+ *  - `stream` is a cudaStream_t passed as void*; work is enqueued on it, there is no hidden
+ *    synchronisation.
+ *  - every function returns an int status (AFFT_OK == 0); none throws or aborts.  The message for
+ *    the last failure is available from afft_last_error() (thread-local for the stateless ops,
+ *    per-handle for model calls).
+ *  - one handle per (device, model); re-entrant across handles (test.py:130 runs DataParallel
+ *    replicas from Python threads), not thread-safe within one handle.
+ *  - plain C types only: no torch / C++ types cross the boundary.
+ */
+#ifndef AFFT_B200_H_
+#define AFFT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFFT_OK 0
+#define AFFT_ERR_INVALID 1     /* bad argument / unsupported configuration */
+#define AFFT_ERR_CUDA 2        /* a CUDA runtime/driver call failed */
+#define AFFT_ERR_MISSING 3     /* forward called before all weights were registered */
+#define AFFT_ERR_UNSUPPORTED 4 /* device is not sm_100 */
+
+#define AFFT_MAX_MODS 8
+#define AFFT_MAX_CLS 4
+#define AFFT_NAME_LEN 32
+
+/* ------------------------------------------------------------------------------------------ */
+/* Library / device                                                                            */
+/* ------------------------------------------------------------------------------------------ */
+
+/* ABI version of this header (bumped on any struct change). */
+int afft_abi_version(void);
+
+/* Last error message of the calling thread (stateless ops) - never NULL. */
+const char* afft_last_error(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Stateless operators (one per library call the reference makes on the path)                  */
+/* ------------------------------------------------------------------------------------------ */
+
+enum { AFFT_ACT_NONE = 0, AFFT_ACT_GELU_ERF = 1, AFFT_ACT_GELU_TANH = 2 };
+
+/*
+ * C = epilogue(A . W^T): replaces torch.nn.Linear / transformers Conv1D
+ * (models/feature_mapping.py:60,74; models/transformerblock.py:21,34,85-87;
+ *  models/future_prediction.py:108,149,248,254,267,269; GPT-2 c_attn/c_proj/c_fc).
+ * A [M,K] and W [N,K] are bf16, K contiguous, 16-byte aligned with 16-byte multiple pitches.
+ * strict != 0: operands are hi/lo bf16 pairs and the product is hi.hi + hi.lo + lo.hi.
+ * Epilogue, in order: + bias[N] -> activation -> + residual -> stores.
+ * Output row of GEMM row r: (r / row_group) * row_stride + r % row_group + row_off
+ * (row_group == 0: r).  The residual is read at the same mapped row, or at row r % res_mod when
+ * res_mod > 0.
+ */
+typedef struct afft_gemm_desc {
+  const void* a_hi;
+  const void* a_lo; /* strict only */
+  int64_t lda;
+  const void* w_hi;
+  const void* w_lo; /* strict only */
+  int64_t ldw;
+  int32_t M, N, K;
+  int32_t strict;
+  const float* bias;
+  const float* res;
+  int64_t ld_res;
+  int32_t res_mod;
+  int32_t act;
+  float* out_f32;
+  int64_t ld_f32;
+  void* out_hi; /* bf16 */
+  void* out_lo; /* bf16, strict producers */
+  int64_t ld_bf16;
+  int32_t row_group, row_stride, row_off;
+  int32_t force_block_n; /* 0 = auto, 128 or 256 */
+} afft_gemm_desc;
+
+int afft_gemm(const afft_gemm_desc* d, void* stream);
+
+/* fp32 [rows, cols] (pitch lds) -> bf16 hi (+ lo when lo != NULL), pitch ldd; transpose != 0
+ * writes dst[c, r].  Weight packing (Conv1D [in,out] -> K-major) and feature inputs. */
+int afft_convert_bf16(const float* src, int64_t lds, int32_t rows, int32_t cols, void* hi, void* lo, int64_t ldd,
+                      int32_t transpose, void* stream);
+
+/* LayerNorm over the last dim: replaces nn.LayerNorm (models/fusion.py:281,362;
+ * models/transformerblock.py:132,134,157-161; GPT-2 ln_1/ln_2/ln_f).  dim in {512,1024,2048}. */
+typedef struct afft_layernorm_desc {
+  const float* x;
+  int64_t ldx;
+  int32_t in_group, in_stride; /* input row of output row r: (r / in_group)*in_stride + r % in_group (0: r) */
+  int32_t n_avg, avg_stride;   /* y = mean over s < n_avg of LN(x[in_row + s*avg_stride]) (<= 1: plain LN) */
+  const float* gamma; /* may be NULL (elementwise_affine=False) */
+  const float* beta;
+  float eps;
+  int32_t rows, dim;
+  float* y_f32; /* each output optional */
+  void* y_hi;
+  void* y_lo;
+  int64_t ldy;
+  int32_t aux_mod, aux_stride; /* rows with r % aux_mod == 0 are also written to aux row (r/aux_mod)*aux_stride */
+  float* aux_f32;
+  void* aux_hi;
+  void* aux_lo;
+  int64_t ld_aux;
+} afft_layernorm_desc;
+
+int afft_layernorm(const afft_layernorm_desc* d, void* stream);
+
+/* Small multi-head attention (L <= 64, head_dim 256 or 512): replaces the two bmm + softmax of
+ * models/transformerblock.py:24-33, :64-74 and GPT-2's eager attention.
+ * in_f32 != 0: q/k/v are fp32 (strict mode), else bf16.  Element (seq, i, h, d) of q is at
+ * q[(seq*L + i)*ldq + h*head_dim + d].  mask: 0 none, 1 causal, 2 block-causal with period T,
+ * 3 diagonal masked.  probs (optional, fp32) element (seq,h,i,j) is at
+ * probs[(seq / p_inner)*p_outer + (seq % p_inner)*p_inner_stride + (h*L + i)*L + j]. */
+typedef struct afft_attention_desc {
+  const void* q;
+  const void* k;
+  const void* v;
+  int64_t ldq, ldk, ldv;
+  int32_t in_f32;
+  int32_t n_seq, L, H, head_dim;
+  float scale;
+  int32_t mask, T;
+  void* out_hi;
+  void* out_lo;
+  int64_t ldo;
+  float* probs;
+  int64_t p_outer, p_inner_stride;
+  int32_t p_inner;
+} afft_attention_desc;
+
+int afft_attention(const afft_attention_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Model-level API: everything below BaseModel.future_predictor (models/base_model.py:59)      */
+/* ------------------------------------------------------------------------------------------ */
+
+enum {
+  AFFT_FUSER_SA = 0,       /* models.fusion.ModalTokenCMFuser        (fusion.py:273-365) */
+  AFFT_FUSER_SA_NOTOKEN = 1, /* models.fusion.CMFuser                (fusion.py:61-118)  */
+  AFFT_FUSER_TSA = 2,      /* models.fusion.TemporalCMFuser          (fusion.py:121-215) */
+  AFFT_FUSER_CA = 3        /* models.fusion.TemporalCrossAttentFuser (fusion.py:218-270) */
+};
+
+typedef struct afft_config {
+  int32_t fuser_kind;
+  int32_t T;                              /* timesteps per clip */
+  int32_t n_mod;                          /* modalities present, in fusion order (conf/config.yaml:41) */
+  char mod_name[AFFT_MAX_MODS][AFFT_NAME_LEN];
+  int32_t mod_dim[AFFT_MAX_MODS];         /* input feature width per modality */
+  int32_t dim;                            /* model.common_dim */
+  int32_t fuser_depth, fuser_heads;
+  int32_t modal_encoding, frame_level_token, cross_attn, norm_elementwise;
+  int32_t gpt_dim, gpt_layers, gpt_heads; /* fp_inter_dim, fp_layers, fp_heads */
+  int32_t n_cls;
+  char cls_name[AFFT_MAX_CLS][AFFT_NAME_LEN];
+  int32_t cls_dim[AFFT_MAX_CLS];
+  int32_t strict;                         /* 0: bf16 operands; 1: bf16x3 error-compensated GEMMs */
+  int32_t max_batch;                      /* workspace is sized for this many clips per call */
+  int32_t device;                         /* CUDA device ordinal */
+} afft_config;
+
+typedef struct afft_handle afft_handle;
+
+int afft_create(const afft_config* cfg, afft_handle** out);
+void afft_destroy(afft_handle* h);
+const char* afft_handle_error(const afft_handle* h);
+
+/* Bytes of device workspace + packed weights the handle holds (for capacity planning). */
+size_t afft_workspace_bytes(const afft_handle* h);
+size_t afft_weight_bytes(const afft_handle* h);
+
+/*
+ * Register one tensor of the reference state dict (train.py:55-103 key contract), name relative
+ * to "future_predictor." e.g. "fuser.blocks.0.attn.qkv.weight".  src_dev is fp32 device memory,
+ * contiguous, with the reference's shape (ndim <= 3).  Unknown names return AFFT_ERR_INVALID
+ * (the Python shim filters GPT-2's attn.bias / attn.masked_bias buffers).
+ */
+int afft_set_weight(afft_handle* h, const char* name, const float* src_dev, int32_t ndim, const int64_t* shape,
+                    void* stream);
+
+/* Number of tensors still missing; names are written, newline separated, into buf (may be NULL). */
+int afft_missing_weights(const afft_handle* h, char* buf, size_t buf_len);
+
+typedef struct afft_io {
+  const float* feat[AFFT_MAX_MODS]; /* [B, T, mod_dim[m]] fp32, fusion order */
+  float* orig_past;                 /* [B, T, dim]       fused features z                        */
+  float* past_futures;              /* [B, T+1, dim]     slots 0..T-1 = past_futures, T = future */
+  float* logits[AFFT_MAX_CLS];      /* [B, T+1, ld_logits] slots 0..T-1 = past_logits, T = logits */
+  int64_t ld_logits[AFFT_MAX_CLS];  /* row pitch in floats, multiple of 4, >= cls_dim            */
+  float* fuser_attn;                /* SA: [B, depth, T, H, n, n]; T-SA: [B, depth, H, nT, nT]; NULL = skip */
+} afft_io;
+
+/* One forward of CMFPEarly.forward (models/future_prediction.py:257-291) for B <= max_batch clips. */
+int afft_forward(afft_handle* h, int32_t B, const afft_io* io, void* stream);
+
+/* Kernels launched by the most recent afft_forward on this handle. */
+int afft_last_launch_count(const afft_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFFT_B200_H_ */
