@@ -1,0 +1,156 @@
+"""Mirror of reference models/fusion.py: the fusers as parameter containers with the reference's
+constructor signatures, parameter names, shapes and initialisation.
+
+Name map (reference models/fusion.py:3-9):  ModalTokenCMFuser = SA-Fuser, CMFuser = SA-Fuser without token,
+TemporalCMFuser = T-SA-Fuser, TemporalCrossAttentFuser = CA-Fuser.  Their arithmetic runs inside
+``afft_forward`` (afft_b200/csrc/afft_api.cu: run_fuser); ``afft_kind`` selects the native code path.
+"""
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from .. import _capi
+from .transformerblock import Block, DecoderBlock
+
+
+def _init_weights(m):
+    # reference models/fusion.py:21-27 (timm ViT init): trunc-normal(0.02) Linear weights, zero biases
+    if isinstance(m, nn.Linear):
+        nn.init.trunc_normal_(m.weight, std=.02)
+        if m.bias is not None:
+            nn.init.constant_(m.bias, 0)
+
+
+class _Fuser(nn.Module):
+    afft_kind = None
+
+    def forward(self, modal_feats, ordered_feature_list):
+        raise NotImplementedError(
+            f"{type(self).__name__} is executed inside the fused afft_forward() call of CMFPEarly "
+            "(no standalone PyTorch forward)")
+
+    def _check_rates(self, act_layer, mlp_ratio, qkv_bias, qk_scale):
+        if act_layer is not nn.GELU or mlp_ratio != 4. or qkv_bias or qk_scale is not None:
+            raise NotImplementedError("fused fuser supports act_layer=nn.GELU, mlp_ratio=4, qkv_bias=False, qk_scale=None")
+
+
+class ModalTokenCMFuser(_Fuser):
+    """SA-Fuser with modality token - reference models/fusion.py:273-365"""
+    afft_kind = _capi.FUSER_SA
+
+    def __init__(self, dim, depth=1, num_heads=4, mlp_ratio=4., qkv_bias=False, qk_scale=None, embd_drop_rate=0.,
+                 drop_rate=0., attn_drop_rate=0., drop_path_rate=0., act_layer=nn.GELU,
+                 norm_elementwise=True, cross_attn=False, modalities=None, modal_encoding=False,
+                 frame_level_token=False, temporal_sequence_length=None):
+        super().__init__()
+        self._check_rates(act_layer, mlp_ratio, qkv_bias, qk_scale)
+        norm_layer = partial(nn.LayerNorm, eps=1e-6, elementwise_affine=norm_elementwise)
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]
+        self.blocks = nn.ModuleList([
+            Block(dim=dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale,
+                  drop=drop_rate, attn_drop=attn_drop_rate, drop_path=dpr[i], act_layer=act_layer,
+                  norm_layer=norm_layer) for i in range(depth)])
+        self.norm = norm_layer(dim)
+        self.num_mods = len(modalities) + 1
+        self.modality_embedding = nn.Parameter(torch.zeros(1, self.num_mods, dim)) if modal_encoding else None
+        self.embd_drop = nn.Dropout(embd_drop_rate)
+        self.cross_attn = cross_attn
+        self.frame_level_token = frame_level_token
+        self.temporal_sequence_length = temporal_sequence_length
+        if not frame_level_token:
+            self.modal_token = nn.Parameter(torch.zeros(1, 1, dim))
+        else:
+            assert temporal_sequence_length is not None, "Temporal sequence length must be provided!"
+            self.modal_token = nn.Parameter(torch.zeros(1, temporal_sequence_length, dim))
+        nn.init.trunc_normal_(self.modal_token, std=.02)
+        if self.modality_embedding is not None:
+            nn.init.trunc_normal_(self.modality_embedding, std=.02)
+        self.apply(_init_weights)
+        self.dim, self.depth, self.num_heads = dim, depth, num_heads
+        self.norm_elementwise, self.modal_encoding = norm_elementwise, modal_encoding
+
+
+class CMFuser(_Fuser):
+    """SA-Fuser without modality token - reference models/fusion.py:61-118"""
+    afft_kind = _capi.FUSER_SA_NOTOKEN
+
+    def __init__(self, dim, depth=1, num_heads=4, mlp_ratio=4., qkv_bias=False, qk_scale=None, embd_drop_rate=0.,
+                 drop_rate=0., attn_drop_rate=0., drop_path_rate=0., act_layer=nn.GELU,
+                 norm_layer=partial(nn.LayerNorm, eps=1e-6), cross_attn=False):
+        super().__init__()
+        self._check_rates(act_layer, mlp_ratio, qkv_bias, qk_scale)
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]
+        self.blocks = nn.ModuleList([
+            Block(dim=dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale,
+                  drop=drop_rate, attn_drop=attn_drop_rate, drop_path=dpr[i], act_layer=act_layer,
+                  norm_layer=norm_layer) for i in range(depth)])
+        self.norm = norm_layer(dim)
+        self.embd_drop = nn.Dropout(embd_drop_rate)
+        self.cross_attn = cross_attn
+        self.apply(_init_weights)
+        self.dim, self.depth, self.num_heads = dim, depth, num_heads
+        self.norm_elementwise, self.modal_encoding, self.frame_level_token = True, False, False
+
+
+class TemporalCMFuser(_Fuser):
+    """T-SA-Fuser - reference models/fusion.py:121-215"""
+    afft_kind = _capi.FUSER_TSA
+
+    def __init__(self, dim, depth=1, num_heads=4, mlp_ratio=4., qkv_bias=False, qk_scale=None, embd_drop_rate=0.,
+                 drop_rate=0., attn_drop_rate=0., drop_path_rate=0., act_layer=nn.GELU,
+                 norm_layer=partial(nn.LayerNorm, eps=1e-6), modalities=None, modal_encoding=True,
+                 frame_level_token=False, temporal_sequence_length=None, max_position_embeddings=64):
+        super().__init__()
+        self._check_rates(act_layer, mlp_ratio, qkv_bias, qk_scale)
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]
+        self.blocks = nn.ModuleList([
+            Block(dim=dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale,
+                  drop=drop_rate, attn_drop=attn_drop_rate, drop_path=dpr[i], act_layer=act_layer,
+                  norm_layer=norm_layer) for i in range(depth)])
+        self.norm = norm_layer(dim)
+        self.num_mods = len(modalities) + 1 if frame_level_token else len(modalities)
+        self.modality_embedding = nn.Parameter(torch.zeros(self.num_mods, dim)) if modal_encoding else None
+        self.position_embeddings = nn.Embedding(max_position_embeddings, dim)
+        self.embd_drop = nn.Dropout(embd_drop_rate)
+        self.frame_level_token = frame_level_token
+        self.temporal_sequence_length = temporal_sequence_length
+        self.modal_token = None
+        if frame_level_token:
+            assert temporal_sequence_length is not None, "Temporal sequence length must be provided!"
+            self.modal_token = nn.Parameter(torch.zeros(1, temporal_sequence_length, dim))
+        if self.modal_token is not None:
+            nn.init.trunc_normal_(self.modal_token, std=.02)
+        if self.modality_embedding is not None:
+            nn.init.trunc_normal_(self.modality_embedding, std=.02)
+        self.apply(_init_weights)
+        self.dim, self.depth, self.num_heads = dim, depth, num_heads
+        self.norm_elementwise, self.modal_encoding, self.cross_attn = True, modal_encoding, False
+
+
+class TemporalCrossAttentFuser(_Fuser):
+    """CA-Fuser - reference models/fusion.py:218-270 (depth = number of modalities - 1)"""
+    afft_kind = _capi.FUSER_CA
+
+    def __init__(self, dim, modalities=None, num_heads=4, mlp_ratio=4., qkv_bias=False, qk_scale=None,
+                 embd_drop_rate=0., drop_rate=0., attn_drop_rate=0., drop_path_rate=0., act_layer=nn.GELU,
+                 norm_layer=partial(nn.LayerNorm, eps=1e-6), max_position_embeddings=128):
+        super().__init__()
+        self._check_rates(act_layer, mlp_ratio, qkv_bias, qk_scale)
+        depth = len(modalities) - 1
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]
+        self.blocks = nn.ModuleList([
+            DecoderBlock(dim=dim, mem_dim=None, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                         qk_scale=qk_scale, drop=drop_rate, attn_drop=attn_drop_rate, drop_path=dpr[i],
+                         act_layer=act_layer, norm_layer=norm_layer) for i in range(depth)])
+        self.norm = norm_layer(dim)
+        self.embd_drop = nn.Dropout(embd_drop_rate)
+        self.position_embeddings = nn.Embedding(max_position_embeddings, dim)
+        self.apply(_init_weights)
+        self.dim, self.depth, self.num_heads = dim, depth, num_heads
+        self.norm_elementwise, self.modal_encoding, self.frame_level_token, self.cross_attn = True, False, False, False
+
+
+class MATT(nn.Module):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("MATT score fusion (expts/05, SURVEY.md section 8f row N3) is not built yet")

@@ -1,0 +1,273 @@
+"""Mirror of reference models/future_prediction.py for the early-fusion path (CMFPEarly + BaseFuturePredictor).
+
+The module tree and parameter names equal the reference's (``mapping.<mod>.mapping.0``, ``fuser.*``,
+``dim_encoder``, ``dim_decoder``, ``future_predictor.gpt_model.*``, ``classifiers.<cls>.all-fused.1``), so
+checkpoints load with the reference's own ``init_model``.  ``CMFPEarly.forward`` hands the whole chain
+feature_mapping -> fuser -> dim_encoder -> GPT-2 -> dim_decoder -> classifiers to one native call.
+"""
+from __future__ import annotations
+
+import importlib
+import logging
+import math
+from collections.abc import Mapping
+from typing import Dict
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .. import _capi
+from ..engine import Engine
+
+PAST_LOGITS_PREFIX = 'past_'
+
+
+# ------------------------------------------------------------------------------------------------
+# config helpers (accept omegaconf DictConfig, plain dicts or attribute objects)
+# ------------------------------------------------------------------------------------------------
+def cfg_get(cfg, key, default=None):
+    if isinstance(cfg, Mapping):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+def cfg_items(cfg):
+    return cfg.items() if isinstance(cfg, Mapping) else vars(cfg).items()
+
+
+_TARGETS = {
+    "models.fusion.ModalTokenCMFuser": ("afft_b200.models.fusion", "ModalTokenCMFuser"),
+    "models.fusion.CMFuser": ("afft_b200.models.fusion", "CMFuser"),
+    "models.fusion.TemporalCMFuser": ("afft_b200.models.fusion", "TemporalCMFuser"),
+    "models.fusion.TemporalCrossAttentFuser": ("afft_b200.models.fusion", "TemporalCrossAttentFuser"),
+    "models.fusion.MATT": ("afft_b200.models.fusion", "MATT"),
+    "models.feature_mapping.Linear": ("afft_b200.models.feature_mapping", "Linear"),
+    "models.feature_mapping.GatedLinear": ("afft_b200.models.feature_mapping", "GatedLinear"),
+    "models.feature_mapping.NonLinear": ("afft_b200.models.feature_mapping", "NonLinear"),
+    "models.future_prediction.BaseFuturePredictor": ("afft_b200.models.future_prediction", "BaseFuturePredictor"),
+    "models.future_prediction.CMFPEarly": ("afft_b200.models.future_prediction", "CMFPEarly"),
+}
+
+
+def instantiate(cfg, *args, **kwargs):
+    """Minimal ``hydra.utils.instantiate``: resolve ``_target_`` (the reference's ``models.*`` names map onto
+    this package, anything else is imported as is) and call it with the remaining keys + kwargs."""
+    params = {k: v for k, v in cfg_items(cfg) if k not in ("_target_", "_recursive_")}
+    kwargs.pop("_recursive_", None)
+    params.update(kwargs)
+    target = cfg_get(cfg, "_target_")
+    if target.startswith("afft_b200.models."):
+        target = target[len("afft_b200."):]
+    if target in _TARGETS:
+        mod_name, cls_name = _TARGETS[target]
+    elif target.startswith("models."):
+        raise NotImplementedError(f"{target} is outside the hot path rebuilt here (SURVEY.md section 8f)")
+    else:
+        mod_name, cls_name = target.rsplit(".", 1)
+    return getattr(importlib.import_module(mod_name), cls_name)(*args, **params)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPT-2 parameter tree (transformers.GPT2Model layout, wte deleted - reference future_prediction.py:372-385)
+# ------------------------------------------------------------------------------------------------
+class Conv1D(nn.Module):
+    """transformers' Conv1D: y = x @ weight + bias with weight stored [in, out]."""
+
+    def __init__(self, nf, nx):
+        super().__init__()
+        self.nf = nf
+        self.weight = nn.Parameter(torch.empty(nx, nf))
+        self.bias = nn.Parameter(torch.zeros(nf))
+        nn.init.normal_(self.weight, std=0.02)
+
+
+class _GPT2Attention(nn.Module):
+    def __init__(self, n_embd, attn_pdrop, resid_pdrop):
+        super().__init__()
+        self.c_attn = Conv1D(3 * n_embd, n_embd)
+        self.c_proj = Conv1D(n_embd, n_embd)
+        self.attn_dropout = nn.Dropout(attn_pdrop)
+        self.resid_dropout = nn.Dropout(resid_pdrop)
+
+
+class _GPT2MLP(nn.Module):
+    def __init__(self, n_embd, resid_pdrop):
+        super().__init__()
+        self.c_fc = Conv1D(4 * n_embd, n_embd)
+        self.c_proj = Conv1D(n_embd, 4 * n_embd)
+        self.dropout = nn.Dropout(resid_pdrop)
+
+
+class _GPT2Block(nn.Module):
+    def __init__(self, n_embd, attn_pdrop, resid_pdrop, eps=1e-5):
+        super().__init__()
+        self.ln_1 = nn.LayerNorm(n_embd, eps=eps)
+        self.attn = _GPT2Attention(n_embd, attn_pdrop, resid_pdrop)
+        self.ln_2 = nn.LayerNorm(n_embd, eps=eps)
+        self.mlp = _GPT2MLP(n_embd, resid_pdrop)
+
+
+class _GPT2Model(nn.Module):
+    def __init__(self, n_embd, n_layer, n_head, n_positions, embd_pdrop, resid_pdrop, attn_pdrop):
+        super().__init__()
+        self.n_embd, self.n_layer, self.n_head, self.n_positions = n_embd, n_layer, n_head, n_positions
+        self.wpe = nn.Embedding(n_positions, n_embd)
+        nn.init.normal_(self.wpe.weight, std=0.02)
+        self.drop = nn.Dropout(embd_pdrop)
+        self.h = nn.ModuleList([_GPT2Block(n_embd, attn_pdrop, resid_pdrop) for _ in range(n_layer)])
+        self.ln_f = nn.LayerNorm(n_embd, eps=1e-5)
+        for blk in self.h:  # GPT-2's scaled init of the residual projections
+            nn.init.normal_(blk.attn.c_proj.weight, std=0.02 / math.sqrt(2 * n_layer))
+            nn.init.normal_(blk.mlp.c_proj.weight, std=0.02 / math.sqrt(2 * n_layer))
+
+
+class BaseFuturePredictor(nn.Module):
+    """reference models/future_prediction.py:354-415.  Holds the GPT-2 weights (gelu_new MLP, n_inner = 4 n_embd,
+    1024 positions, LayerNorm eps 1e-5 - the GPT2Config defaults the reference relies on)."""
+
+    def __init__(self, in_features, inter_dim=2048, n_layer=6, n_head=4, embd_pdrop=0.1, resid_pdrop=0.1,
+                 attn_pdrop=0.1, output_attentions=False, dimension_mapping=False):
+        super().__init__()
+        if dimension_mapping:
+            raise NotImplementedError("dimension_mapping inside GPT-2 is deprecated in the reference and not supported")
+        if output_attentions:
+            raise NotImplementedError("fp_output_attentions=true (visualisation only) is not supported")
+        self.in_features = in_features
+        self.output_attentions = output_attentions
+        self.encoder = nn.Identity()
+        self.decoder = nn.Identity()
+        self.gpt_model = _GPT2Model(inter_dim, n_layer, n_head, 1024, embd_pdrop, resid_pdrop, attn_pdrop)
+
+    def forward(self, feats, output_len: int = 1):
+        raise NotImplementedError("the GPT-2 future predictor is executed inside the fused afft_forward() call")
+
+
+# ------------------------------------------------------------------------------------------------
+# CMFPEarly
+# ------------------------------------------------------------------------------------------------
+class CMFPEarly(nn.Module):
+    """Early-fusion cross-modal future predictor - reference models/future_prediction.py:19-186,228-291.
+
+    strict=False: bf16 tensor-core operands, fp32 accumulation/residual/LayerNorm/softmax.
+    strict=True : error-compensated bf16x3 GEMMs (hi.hi + hi.lo + lo.hi), fp32 activations between kernels;
+                  this is the mode whose top-5 indices are required to be identical to the fp32 reference.
+    """
+
+    def __init__(self, model_cfg, num_classes, strict: bool = False, max_batch: int = 64):
+        super().__init__()
+        logger = logging.getLogger(__name__)
+        common = cfg_get(model_cfg, "common")
+        modal_dims = cfg_get(model_cfg, "modal_dims")
+        assert isinstance(modal_dims, Mapping), 'cfg.model.modal_dims must be a Dict!'
+        for flag in ("share_classifiers", "share_predictors"):
+            if not cfg_get(common, flag):
+                logger.warning("Enforcing %s for early CMFP.", flag)
+        if cfg_get(common, "modality_cls") or not cfg_get(common, "fusion_cls"):
+            raise NotImplementedError("CMFPEarly here supports modality_cls=false, fusion_cls=true (every shipped config)")
+        self.cfg = model_cfg
+        self.num_classes = dict(num_classes)
+        self.latent_dim = cfg_get(common, "in_features")
+        self.fp_inter_dim = cfg_get(common, "fp_inter_dim")
+        self.modality_dims = dict(modal_dims)
+        self.fp_output_len = cfg_get(common, "fp_output_len", 1)
+        if self.fp_output_len != 1:
+            raise NotImplementedError("fp_output_len > 1 (autoregressive roll-out, SURVEY.md section 8f row N1) is not built yet")
+        self.modal_feature_order = list(cfg_get(model_cfg, "modal_feature_order"))
+
+        self.mapping = nn.ModuleDict()
+        for mod, dim in self.modality_dims.items():  # reference :47-54
+            self.mapping[mod] = instantiate(cfg_get(model_cfg, "mapping"), in_features=dim, out_features=self.latent_dim)
+        self.fuser = instantiate(cfg_get(model_cfg, "fuser"))  # reference :74-76
+        if self.latent_dim == self.fp_inter_dim:
+            raise NotImplementedError("common_dim == fp_inter_dim (Identity dim_encoder) is not supported")
+        self.dim_encoder = nn.Linear(self.latent_dim, self.fp_inter_dim, bias=False)  # reference :245-255
+        self.dim_decoder = nn.Linear(self.fp_inter_dim, self.latent_dim, bias=False)
+        self.future_predictor = instantiate(cfg_get(model_cfg, "future_predictor"), in_features=self.fp_inter_dim,
+                                            dimension_mapping=False)  # reference :84-87
+        self.classifiers = nn.ModuleDict()  # reference :97-122 (shared classifier, fusion_cls only)
+        dropout = cfg_get(model_cfg, "dropout")
+        for cls_type, cls_dim in self.num_classes.items():
+            self.classifiers[cls_type] = nn.ModuleDict(
+                {'all-fused': nn.Sequential(nn.Dropout(dropout), nn.Linear(self.latent_dim, cls_dim))})
+
+        self.strict = strict
+        self.max_batch = max_batch
+        self.return_attentions = True
+        self._engines: Dict[tuple, Engine] = {}
+
+    # ---- reference helpers kept for API parity ----
+    @staticmethod
+    def ordered_feature_list(x_d: Dict[str, Tensor], feats_order):
+        return [x_d[m] for m in feats_order]
+
+    # ---- native path ----
+    def _named_weights(self) -> Dict[str, Tensor]:
+        return {n: p for n, p in self.named_parameters()}
+
+    def _engine(self, feats_order, T: int, B: int, device: torch.device) -> Engine:
+        key = (tuple(feats_order), T, str(device), bool(self.strict))
+        eng = self._engines.get(key)
+        if eng is not None and B > eng.max_batch:
+            eng.close()
+            eng = None
+        if eng is None:
+            f = self.fuser
+            gpt = self.future_predictor.gpt_model
+            eng = Engine(fuser_kind=f.afft_kind, T=T, mod_names=list(feats_order),
+                         mod_dims=[self.modality_dims[m] for m in feats_order], dim=self.latent_dim,
+                         fuser_depth=f.depth, fuser_heads=f.num_heads, modal_encoding=bool(f.modal_encoding),
+                         frame_level_token=bool(f.frame_level_token), cross_attn=bool(f.cross_attn),
+                         norm_elementwise=bool(f.norm_elementwise), gpt_dim=gpt.n_embd, gpt_layers=gpt.n_layer,
+                         gpt_heads=gpt.n_head, cls_names=list(self.num_classes.keys()),
+                         cls_dims=list(self.num_classes.values()), strict=bool(self.strict),
+                         max_batch=max(B, self.max_batch), device=device)
+            self._engines[key] = eng
+        return eng
+
+    def forward(self, feats: Dict[str, Tensor]) -> Dict[str, Dict[str, Tensor]]:
+        if self.training:
+            raise NotImplementedError("the fused path implements eval-mode forward only (call model.eval()); "
+                                      "training-mode dropout/DropPath and backward are not built yet")
+        feats_order = [mod for mod in self.modal_feature_order if mod in feats]  # reference :258
+        if set(feats_order) != set(self.modality_dims):
+            raise ValueError(f"features {sorted(feats)} do not match modal_dims {sorted(self.modality_dims)}")
+        first = feats[feats_order[0]]
+        shape = first.shape
+        assert all(feats[m].shape[:2] == shape[:2] for m in feats_order), \
+            'The shape of all inputs of the fusion module should be the same!'
+        B, T = shape[0], shape[1]
+        f = self.fuser
+        if getattr(f, "frame_level_token", False) and f.temporal_sequence_length is not None:
+            assert f.temporal_sequence_length == T, f"Temporal sequence length not valid {f.temporal_sequence_length} vs {T}"
+        eng = self._engine(feats_order, T, B, first.device)
+        eng.sync_weights(self._named_weights())
+        xs = [feats[m].to(torch.float32).contiguous() for m in feats_order]
+        z, pf, logits, attn = eng.forward(xs, want_attn=self.return_attentions)
+
+        out = {  # reference prepare_output :155-182 (views into the native output buffers)
+            'orig_past': {'all-fused': z},
+            'future': {'all-fused': pf[:, T:]},
+            'all-fused': {'all-fused': z[:, T - 1:]},
+            'past_futures': {'all-fused': pf[:, :T]},
+        }
+        for k, (cls, c) in enumerate(self.num_classes.items()):  # reference apply_classifier :144-153
+            out[f'{PAST_LOGITS_PREFIX}logits/{cls}'] = {'all-fused': logits[k][:, :T, :c]}
+            out[f'logits/{cls}'] = {'all-fused': logits[k][:, T:, :c]}
+        if attn is None:
+            attn = torch.zeros(B)  # CA-Fuser's dummy attention (reference fusion.py:269)
+        out['attentions'] = {'all-fused': {'modality_attns': attn, 'temporal_attns': {}}}
+        return out
+
+    def last_launch_count(self) -> int:
+        return max((e.launch_count() for e in self._engines.values()), default=0)
+
+
+class IndividualFuturePrediction(nn.Module):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("IndividualFuturePrediction (expts/00, SURVEY.md section 8f row N3) is not built yet")
+
+
+class CMFPScoreFusion(nn.Module):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("CMFPScoreFusion (expts/05, SURVEY.md section 8f row N3) is not built yet")
