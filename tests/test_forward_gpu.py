@@ -1,0 +1,188 @@
+"""GPU: the fused path (BaseModel -> CMFPEarly -> afft_forward through the C ABI) against
+  (a) the committed golden fixtures written from the reference module,
+  (b) the CPU oracle run here on fresh inputs,
+  (c) size-independent properties at the BASELINE batch sizes.
+
+Tolerances (logits have |max| ~ 2.2, std ~ 0.35 with the synthetic weights):
+  fast   mode (bf16 operands, fp32 accumulate/residual/LN/softmax): |dlogit| < 6e-2, features < 8e-2,
+         attention probabilities < 1e-2.  Top-5 identity is NOT required in this mode.
+  strict mode (bf16x3 error-compensated GEMMs): |dlogit| < 4e-4, features < 6e-4, probabilities < 5e-5 and
+         ordered top-5 indices identical to the fp32 reference on every clip.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from afft_b200 import _capi, configs, synthetic
+from afft_b200.models import BaseModel
+
+pytestmark = pytest.mark.gpu
+
+TOL = {False: dict(logits=6e-2, feat=8e-2, attn=1e-2), True: dict(logits=4e-4, feat=6e-4, attn=5e-5)}
+KW = dict(mixup_fn=None, target=None, target_subclips=None, target_subclips_ignore_index=None)
+_models = {}
+
+
+def _model(cfg_name, strict, max_batch=64):
+    key = (cfg_name, strict)
+    if key not in _models:
+        if len(_models) >= 3:
+            _models.pop(next(iter(_models)))
+        cfg, T, ncls, _ = configs.named_config(cfg_name)
+        m = BaseModel(cfg, ncls, {}, strict=strict, max_batch=max_batch)
+        m.load_state_dict(synthetic.synthetic_state_dict(m, seed=0))
+        _models[key] = m.to("cuda:0").eval()
+    return _models[key]
+
+
+def _run(model, feats):
+    with torch.no_grad():
+        out, _ = model({m: t.to("cuda:0") for m, t in feats.items()}, **KW)
+    torch.cuda.synchronize()
+    return out
+
+
+CASES = ["egtea_sa_b3", "ek100_sa_tsn_b2", "ek100_sa_tsn_relu_b2", "ek100_sa_tsn_wo_audio_b2", "ek100_sa_swin_b2",
+         "ek100_tsa_b2", "ek100_ca_b2", "ek100_sa_wo_token_b2"]
+
+
+@pytest.mark.parametrize("strict", [False, True])
+@pytest.mark.parametrize("case", CASES)
+def test_golden_parity(case, strict, golden_dir, golden_cases):
+    cfg_name, B, seed, family = golden_cases[case]
+    cfg, T, ncls, _ = configs.named_config(cfg_name)
+    model = _model(cfg_name, strict)
+    feats = synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=seed, family=family, six_d=True)
+    out = _run(model, feats)
+    gold = np.load(os.path.join(golden_dir, case + ".npz"))
+    tol = TOL[strict]
+
+    def err(t, ref):
+        a = t.float().cpu().numpy()
+        assert a.shape == ref.shape
+        assert not np.isnan(a).any()
+        return np.abs(a - ref).max()
+
+    assert err(out["logits/action"]["all-fused"], gold["logits"]) < tol["logits"]
+    assert err(out["past_logits/action"]["all-fused"][:1], gold["past_logits_clip0"]) < tol["logits"]
+    assert err(out["orig_past"]["all-fused"], gold["orig_past"]) < tol["feat"]
+    assert err(out["future"]["all-fused"], gold["future"]) < tol["feat"]
+    assert err(out["past_futures"]["all-fused"], gold["past_futures"]) < tol["feat"]
+    assert err(out["all-fused"]["all-fused"], gold["orig_past"][:, -1:]) < tol["feat"]
+    ma = out["attentions"]["all-fused"]["modality_attns"]
+    if gold["modality_attns"].ndim > 1:
+        assert err(ma, gold["modality_attns"]) < tol["attn"]
+    else:
+        assert ma.shape == (B,)
+    if strict:
+        t5 = out["logits/action"]["all-fused"][:, 0].topk(5, dim=-1).indices.cpu().numpy()
+        assert (t5 == gold["top5"]).all(), "ordered top-5 must be identical in strict mode"
+    assert model.future_predictor.last_launch_count() > 20  # native kernels, not a fallback
+
+
+@pytest.mark.parametrize("strict", [False, True])
+def test_against_oracle_fresh_inputs(strict):
+    """Same seeded inputs through the CUDA path and the CPU oracle (not a stored fixture)."""
+    from oracle import afft_oracle
+    cfg_name = "ek100_sa_tsn"
+    cfg, T, ncls, _ = configs.named_config(cfg_name)
+    model = _model(cfg_name, strict)
+    B = 5  # ragged: 5*18*5 = 450 fuser rows, 90 GPT rows - nothing is a tile multiple
+    feats = synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=4242, family="relu")
+    out = _run(model, feats)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref = afft_oracle.forward(sd, cfg, ncls, feats, dtype=torch.float32)
+    tol = TOL[strict]
+    for key, t in (("logits/action", tol["logits"]), ("past_logits/action", tol["logits"]), ("orig_past", tol["feat"]),
+                   ("future", tol["feat"]), ("past_futures", tol["feat"])):
+        d = (out[key]["all-fused"].cpu() - ref[key]["all-fused"]).abs().max().item()
+        assert d < t, (key, d)
+    if strict:
+        assert torch.equal(out["logits/action"]["all-fused"][:, 0].topk(5).indices.cpu(),
+                           afft_oracle.top5(ref["logits/action"]["all-fused"][:, 0]))
+        # every past step too (T * B rows of top-5)
+        assert torch.equal(out["past_logits/action"]["all-fused"].topk(5).indices.cpu(),
+                           afft_oracle.top5(ref["past_logits/action"]["all-fused"]))
+
+
+def test_properties_at_baseline_batch():
+    """Size-independent properties at the experiment file's batch size (B=32) and at B=256."""
+    cfg_name = "ek100_sa_tsn"
+    cfg, T, ncls, bs = configs.named_config(cfg_name)
+    model = _model(cfg_name, False)
+    for B in (bs, 256):
+        feats = synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=77)
+        out = _run(model, feats)
+        lg = out["logits/action"]["all-fused"]
+        assert lg.shape == (B, 1, 3806) and torch.isfinite(lg).all()
+        pl = out["past_logits/action"]["all-fused"]
+        assert pl.shape == (B, T, 3806) and torch.isfinite(pl).all()
+        pr = out["attentions"]["all-fused"]["modality_attns"]
+        assert pr.shape == (B, 6, T, 4, 5, 5)
+        assert (pr.sum(-1) - 1).abs().max().item() < 1e-5 and (pr >= 0).all()
+        # clips are independent units: a clip's result does not depend on its batch neighbours (bitwise)
+        sub = {m: f[8:16] for m, f in feats.items()}
+        out_sub = _run(model, sub)
+        assert torch.equal(out_sub["logits/action"]["all-fused"], lg[8:16])
+        assert torch.equal(out_sub["orig_past"]["all-fused"], out["orig_past"]["all-fused"][8:16])
+        # permutation equivariance over clips
+        perm = torch.randperm(B, generator=torch.Generator().manual_seed(B))
+        out_p = _run(model, {m: f[perm] for m, f in feats.items()})
+        assert torch.equal(out_p["logits/action"]["all-fused"], lg[perm.to(lg.device)])
+        # prepare_output identities (reference future_prediction.py:172-180)
+        assert torch.equal(out["past_futures"]["all-fused"][:, 0], out["orig_past"]["all-fused"][:, 0])
+        assert torch.equal(out["all-fused"]["all-fused"][:, 0], out["orig_past"]["all-fused"][:, T - 1])
+        # causality: perturbing the last timestep leaves earlier past logits untouched (bitwise)
+        f2 = {m: f.clone() for m, f in feats.items()}
+        for f in f2.values():
+            f[:, T - 1] = torch.randn(f[:, T - 1].shape, generator=torch.Generator().manual_seed(1))
+        out2 = _run(model, f2)
+        assert torch.equal(out2["past_logits/action"]["all-fused"][:, :T - 1], pl[:, :T - 1])
+        assert not torch.equal(out2["logits/action"]["all-fused"], lg)
+
+
+def test_edge_batches_and_regrowth():
+    cfg_name = "egtea_sa"
+    cfg, T, ncls, _ = configs.named_config(cfg_name)
+    m = BaseModel(cfg, ncls, {}, max_batch=4)
+    m.load_state_dict(synthetic.synthetic_state_dict(m, seed=0))
+    m = m.to("cuda:0").eval()
+    feats = synthetic.synthetic_features(cfg["modal_dims"], 9, T, seed=5)
+    full = _run(m, feats)["logits/action"]["all-fused"]  # B=9 > max_batch=4: the engine is rebuilt larger
+    one = _run(m, {k: v[:1] for k, v in feats.items()})["logits/action"]["all-fused"]  # B=1
+    assert full.shape == (9, 1, 106) and torch.equal(one, full[:1])
+    # weights are re-packed when parameters change (init_model after construction, optimizer steps)
+    with torch.no_grad():
+        m.future_predictor.classifiers["action"]["all-fused"][1].bias.add_(1.0)
+    shifted = _run(m, feats)["logits/action"]["all-fused"]
+    assert torch.allclose(shifted, full + 1.0, atol=1e-5)
+
+
+def test_fuser_chunking_is_equivalent(monkeypatch):
+    cfg_name = "egtea_sa"
+    cfg, T, ncls, _ = configs.named_config(cfg_name)
+    feats = synthetic.synthetic_features(cfg["modal_dims"], 13, T, seed=6)
+    outs = []
+    for chunk in ("0", "4"):
+        monkeypatch.setenv("AFFT_FUSER_CHUNK", chunk)
+        m = BaseModel(cfg, ncls, {})
+        m.load_state_dict(synthetic.synthetic_state_dict(m, seed=0))
+        outs.append(_run(m.to("cuda:0").eval(), feats))
+    for k in ("logits/action", "past_logits/action", "orig_past", "past_futures"):
+        assert torch.equal(outs[0][k]["all-fused"], outs[1][k]["all-fused"]), k
+    assert torch.equal(outs[0]["attentions"]["all-fused"]["modality_attns"], outs[1]["attentions"]["all-fused"]["modality_attns"])
+
+
+def test_input_validation_on_device():
+    cfg, T, ncls, _ = configs.named_config("egtea_sa")
+    m = _model("egtea_sa", False)
+    good = synthetic.synthetic_features(cfg["modal_dims"], 2, T, seed=1, six_d=True)
+    bad = dict(good)
+    bad["rgb"] = torch.zeros(2, T, 512, 1, 1, 1)
+    with pytest.raises(_capi.AfftError):
+        _run(m, bad)
+    with pytest.raises(AssertionError):
+        _run(m, {"rgb": good["rgb"], "flow": good["flow"][:, :T - 1]})

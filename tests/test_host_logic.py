@@ -1,0 +1,148 @@
+"""CPU: host-side mirror of the reference models/ API - module tree, state-dict key contract, config handling,
+crop/shape glue and error behaviour.  No native compute."""
+import json
+import os
+
+import pytest
+import torch
+
+from afft_b200 import _capi, configs, synthetic
+from afft_b200.models import BaseModel
+from afft_b200.models import future_prediction as fp
+
+
+@pytest.mark.parametrize("name", configs.CONFIG_NAMES)
+def test_state_dict_contract_matches_reference(name, golden_dir):
+    """Same parameter names and shapes as the reference module (train.py:55-103 init_model contract);
+    tests/golden/param_names_*.json was written from the reference's named_parameters()."""
+    cfg, T, ncls, _ = configs.named_config(name)
+    model = BaseModel(cfg, ncls, {})
+    ours = {k: list(v.shape) for k, v in model.named_parameters()}
+    ref = json.load(open(os.path.join(golden_dir, f"param_names_{name}.json")))
+    assert ours == ref
+
+
+def test_flops_per_clip_match_survey():
+    expect = {"egtea_sa": 3.609, "ek100_sa_tsn": 24.773, "ek100_sa_tsn_wo_audio": 22.055, "ek100_sa_swin": 22.022,
+              "ek100_tsa": 13.766, "ek100_ca": 7.223}
+    for name, gf in expect.items():
+        cfg, T, ncls, _ = configs.named_config(name)
+        assert abs(configs.gemm_flops_per_clip(cfg, T, ncls) / 1e9 - gf) < 5e-4
+
+
+def test_checkpoint_with_gpt2_buffers_loads_non_strict():
+    """Checkpoints written with transformers 4.18 carry attn.bias / attn.masked_bias buffers."""
+    cfg, T, ncls, _ = configs.named_config("egtea_sa")
+    model = BaseModel(cfg, ncls, {})
+    sd = synthetic.synthetic_state_dict(model, seed=3)
+    sd["future_predictor.future_predictor.gpt_model.h.0.attn.bias"] = torch.ones(1, 1, 1024, 1024)
+    sd["future_predictor.future_predictor.gpt_model.h.0.attn.masked_bias"] = torch.tensor(-1e4)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert missing == [] and len(unexpected) == 2
+    assert torch.equal(model.state_dict()["future_predictor.dim_encoder.weight"], sd["future_predictor.dim_encoder.weight"])
+
+
+def test_class_mappings_become_buffers():
+    cfg, T, ncls, _ = configs.named_config("egtea_sa")
+    m = BaseModel(cfg, ncls, {("action", "verb"): torch.ones(106, 19)})
+    assert "cls_map_action_verb" in dict(m.named_buffers())
+
+
+class _Recorder(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.seen = []
+
+    def forward(self, feats):
+        self.seen.append({k: v.clone() for k, v in feats.items()})
+        B = next(iter(feats.values())).shape[0]
+        x = torch.stack([v.sum(dim=(1, 2)) for v in feats.values()]).sum(0)
+        return {"logits/action": {"all-fused": x.reshape(B, 1, 1).expand(B, 1, 4).clone()},
+                "attentions": {"all-fused": {"modality_attns": torch.zeros(B), "temporal_attns": {}}}}
+
+
+def _glue_model():
+    cfg, T, ncls, _ = configs.named_config("egtea_sa")
+    m = BaseModel(cfg, ncls, {})
+    m.future_predictor = _Recorder()
+    return m.eval(), T
+
+
+def test_basemodel_glue_6d_input():
+    m, T = _glue_model()
+    B = 3
+    x = {"rgb": torch.randn(B, T, 1024, 1, 1, 1), "flow": torch.randn(B, T, 1024, 1, 1, 1)}
+    out, tgt = m(x, mixup_fn=None, target=None, target_subclips=None, target_subclips_ignore_index=None)
+    seen = m.future_predictor.seen[0]
+    assert seen["rgb"].shape == (B, T, 1024) and torch.equal(seen["rgb"], x["rgb"].reshape(B, T, 1024))
+    assert tgt == {"target": None, "target_subclips": None, "target_subclips_ignore_index": None}
+    assert out["logits/action"]["all-fused"].shape == (B, 1, 4)
+
+
+def test_basemodel_glue_spatial_mean_and_crops():
+    m, T = _glue_model()
+    B = 2
+    # (B, #clips, #crops=3, C, T'=1, H=2, W=2): spatial mean, crops averaged (reference base_model.py:40-46,100-117)
+    x = {"rgb": torch.randn(B, T, 3, 1024, 1, 2, 2), "flow": torch.randn(B, T, 1, 1024, 1, 2, 2)}
+    out, _ = m(dict(x), mixup_fn=None, target=None, target_subclips=None, target_subclips_ignore_index=None)
+    assert len(m.future_predictor.seen) == 3
+    exp0 = x["rgb"][:, :, 0].mean(dim=(-1, -2)).permute(0, 1, 3, 2).flatten(1, 2)
+    assert torch.allclose(m.future_predictor.seen[0]["rgb"], exp0)
+    per_crop = [s["rgb"].sum(dim=(1, 2)) + s["flow"].sum(dim=(1, 2)) for s in m.future_predictor.seen]
+    assert torch.allclose(out["logits/action"]["all-fused"][:, 0, 0], torch.stack(per_crop).mean(0), rtol=1e-5, atol=1e-3)
+    with pytest.raises(NotImplementedError):
+        m({"rgb": torch.zeros(2, 3)})
+
+
+def test_mixup_hook_is_called():
+    m, T = _glue_model()
+    calls = []
+
+    def mix(feats, target, target_subclips):
+        calls.append(1)
+        return feats, "t", "ts", "ig"
+    x = {"rgb": torch.randn(1, T, 1024, 1, 1, 1), "flow": torch.randn(1, T, 1024, 1, 1, 1)}
+    _, tgt = m(x, mixup_fn=mix, target=None, target_subclips=None, target_subclips_ignore_index=None)
+    assert calls and tgt == {"target": "t", "target_subclips": "ts", "target_subclips_ignore_index": "ig"}
+
+
+def test_error_behaviour():
+    cfg, T, ncls, _ = configs.named_config("egtea_sa")
+    model = BaseModel(cfg, ncls, {})
+    x = {"rgb": torch.zeros(1, T, 1024, 1, 1, 1), "flow": torch.zeros(1, T, 1024, 1, 1, 1)}
+    with pytest.raises(NotImplementedError):  # training mode is not implemented: loud, not silent
+        model.train()(dict(x))
+    with pytest.raises(_capi.AfftError):  # CPU tensors: there is no CPU fallback
+        model.eval()(dict(x))
+    with pytest.raises(ValueError):
+        model.eval()({"rgb": torch.zeros(1, T, 1024, 1, 1, 1)})
+    bad = configs.named_config("egtea_sa")[0]
+    bad["common"]["fp_output_len"] = 2
+    with pytest.raises(NotImplementedError):
+        BaseModel(bad, ncls, {})
+    bad = configs.named_config("egtea_sa")[0]
+    bad["mapping"]["_target_"] = "models.feature_mapping.GatedLinear"
+    with pytest.raises(NotImplementedError):
+        BaseModel(bad, ncls, {})
+
+
+def test_instantiate_accepts_attribute_configs():
+    class NS(dict):
+        __getattr__ = dict.__getitem__
+    lin = fp.instantiate(NS(_target_="models.feature_mapping.Linear", use_layernorm=False, sparse_mapping=True),
+                         in_features=352, out_features=1024)
+    assert lin.mapping[0].weight.shape == (1024, 352)
+    ident = fp.instantiate({"_target_": "models.feature_mapping.Linear"}, in_features=1024, out_features=1024)
+    assert isinstance(ident.mapping[0], torch.nn.Identity)
+    assert isinstance(fp.instantiate({"_target_": "torch.nn.Identity"}), torch.nn.Identity)
+
+
+def test_synthetic_weights_are_deterministic():
+    cfg, T, ncls, _ = configs.named_config("egtea_sa")
+    m = BaseModel(cfg, ncls, {})
+    a = synthetic.synthetic_state_dict(m, seed=0)
+    b = synthetic.synthetic_state_dict(m, seed=0)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    f1 = synthetic.synthetic_features(cfg["modal_dims"], 2, T, seed=9)
+    f2 = synthetic.synthetic_features(cfg["modal_dims"], 2, T, seed=9)
+    assert all(torch.equal(f1[k], f2[k]) for k in f1)

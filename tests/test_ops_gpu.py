@@ -1,0 +1,188 @@
+"""GPU: each stateless operator of the C ABI against a plain torch reference of the same op
+(float64 matmul / F.layer_norm / softmax attention).  Tolerances are stated per case."""
+import pytest
+import torch
+
+from afft_b200 import _capi as capi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def _randn(gen, dev, *shape, scale=1.0):
+    return (torch.randn(*shape, generator=gen) * scale).to(dev)
+
+
+def _mm(a, w):
+    return (a.double() @ w.double().t()).float()
+
+
+# bf16 operands are exact inputs; the only error is fp32 accumulation order: ~1e-5 at K=1024, scale |out|~1
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (128, 256, 64, 256), (1000, 1024, 1024, 0), (90, 3072, 1024, 0),
+                                      (18, 2048, 1024, 0), (576, 1024, 352, 0), (300, 3806, 1024, 0), (131, 106, 1024, 0),
+                                      (1, 1024, 1024, 0), (4608, 2048, 8192, 128), (2304, 8192, 2048, 256)])
+def test_gemm_plain(dev, M, N, K, bn):
+    g = torch.Generator().manual_seed(M * 7 + N)
+    a = _randn(g, dev, M, K).bfloat16()
+    w = _randn(g, dev, N, K, scale=0.05).bfloat16()
+    ld = (N + 3) // 4 * 4
+    out = torch.full((M, ld), float("nan"), device=dev)
+    capi.gemm(a, w, out_f32=out, force_block_n=bn)
+    ref = _mm(a, w)
+    assert not torch.isnan(out[:, :N]).any()
+    assert (out[:, :N] - ref).abs().max().item() < 2e-4 * max(1.0, (K / 1024) ** 0.5) * 3
+    if ld > N:
+        assert torch.isnan(out[:, N:]).all()  # padding columns are never written
+
+
+def test_gemm_epilogues(dev):
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 777, 1024, 1024
+    a = _randn(g, dev, M, K).bfloat16()
+    w = _randn(g, dev, N, K, scale=0.05).bfloat16()
+    bias, res = _randn(g, dev, N), _randn(g, dev, M, N)
+    ref0 = _mm(a, w)
+    F = torch.nn.functional
+    out_f = torch.zeros(M, N, device=dev)
+    capi.gemm(a, w, bias=bias, act=capi.ACT_GELU_ERF, out_f32=out_f)
+    assert (out_f - F.gelu(ref0 + bias)).abs().max().item() < 1e-4  # erf approx 1.5e-7 + accumulation order
+    capi.gemm(a, w, bias=bias, act=capi.ACT_GELU_TANH, out_f32=out_f)
+    assert (out_f - F.gelu(ref0 + bias, approximate="tanh")).abs().max().item() < 1e-4
+    out_b = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    capi.gemm(a, w, bias=bias, act=capi.ACT_GELU_ERF, out_hi=out_b)
+    assert torch.equal(out_b, F.gelu(ref0 + bias).bfloat16()) or \
+        (out_b.float() - F.gelu(ref0 + bias)).abs().max().item() < 4e-2  # one bf16 ulp at |x|<8
+    h = res.clone()
+    capi.gemm(a, w, bias=bias, res=h, out_f32=h)  # in-place residual stream update
+    assert (h - (ref0 + bias + res)).abs().max().item() < 1e-4
+    T = 7
+    pos = _randn(g, dev, T, N)
+    outm = torch.zeros(M // T * (T + 1) + T + 1, N, device=dev)
+    capi.gemm(a, w, res=pos, res_mod=T, out_f32=outm, row_map=(T, T + 1, 1))
+    r = torch.arange(M, device=dev)
+    assert (outm[(r // T) * (T + 1) + r % T + 1] - (ref0 + pos[r % T])).abs().max().item() < 1e-4
+    slots = 5
+    hbuf = torch.zeros(M * slots, N, device=dev)
+    capi.gemm(a, w, out_f32=hbuf.view(M, slots * N)[:, 2 * N:3 * N])
+    assert (hbuf.view(M, slots, N)[:, 2] - ref0).abs().max().item() < 1e-4
+    assert hbuf.view(M, slots, N)[:, [0, 1, 3, 4]].abs().max().item() == 0.0
+    Nc = 3806
+    wc = _randn(g, dev, Nc, K, scale=0.05).bfloat16()
+    bc = torch.zeros(Nc + 16, device=dev)[:Nc]
+    bc.copy_(_randn(g, dev, Nc))
+    oc = torch.full((M, 3808), 7.0, device=dev)
+    capi.gemm(a, wc, bias=bc, out_f32=oc)
+    assert (oc[:, :Nc] - (_mm(a, wc) + bc)).abs().max().item() < 1e-4
+    assert (oc[:, Nc:] == 7.0).all()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(256, 256, 1024, 128), (777, 1024, 1024, 256), (300, 3806, 1024, 0), (576, 1024, 352, 0)])
+def test_gemm_strict_bf16x3(dev, M, N, K, bn):
+    """hi.hi + hi.lo + lo.hi: fp32 inputs reproduced to ~2^-16 relative per product."""
+    g = torch.Generator().manual_seed(M + N)
+    a32, w32 = _randn(g, dev, M, K), _randn(g, dev, N, K, scale=0.05)
+    a_hi, a_lo = capi.split_bf16(a32)
+    w_hi, w_lo = capi.split_bf16(w32)
+    assert torch.equal(a_hi, a32.bfloat16())
+    assert (a_hi.float() + a_lo.float() - a32).abs().max().item() < 2e-5 * a32.abs().max().item()
+    ld = (N + 3) // 4 * 4
+    out = torch.zeros(M, ld, device=dev)
+    capi.gemm(a_hi, w_hi, a_lo=a_lo, w_lo=w_lo, out_f32=out, force_block_n=bn)
+    ref = _mm(a32, w32)
+    assert (out[:, :N] - ref).abs().max().item() < 2e-4
+    oh = torch.zeros(M, ld, device=dev, dtype=torch.bfloat16)
+    ol = torch.zeros(M, ld, device=dev, dtype=torch.bfloat16)
+    capi.gemm(a_hi, w_hi, a_lo=a_lo, w_lo=w_lo, out_hi=oh, out_lo=ol, force_block_n=bn)
+    assert ((oh.float() + ol.float())[:, :N] - ref).abs().max().item() < 2e-4
+
+
+def test_gemm_rejects_bad_arguments(dev):
+    a = torch.zeros(128, 64, device=dev, dtype=torch.bfloat16)
+    w = torch.zeros(128, 64, device=dev, dtype=torch.bfloat16)
+    with pytest.raises(capi.AfftError):
+        capi.gemm(a, w)  # no output
+    with pytest.raises(capi.AfftError):
+        capi.gemm(a, w, out_f32=torch.zeros(128, 130, device=dev)[:, 1:129])  # misaligned pitch/pointer
+    with pytest.raises(capi.AfftError):  # TMA needs 16-B multiple operand pitches
+        capi.gemm(torch.zeros(128, 68, device=dev, dtype=torch.bfloat16)[:, :64], w, out_f32=torch.zeros(128, 128, device=dev))
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("dim,eps", [(1024, 1e-6), (2048, 1e-5), (512, 1e-6)])
+def test_layernorm(dev, dim, eps):
+    g = torch.Generator().manual_seed(dim)
+    rows = 1237
+    x = _randn(g, dev, rows, dim) * 3 + 0.5
+    gm, bt = _randn(g, dev, dim), _randn(g, dev, dim)
+    yf = torch.zeros(rows, dim, device=dev)
+    yh = torch.zeros(rows, dim, device=dev, dtype=torch.bfloat16)
+    yl = torch.zeros(rows, dim, device=dev, dtype=torch.bfloat16)
+    capi.layernorm(x, gm, bt, eps, y_f32=yf, y_hi=yh, y_lo=yl)
+    ref = torch.nn.functional.layer_norm(x.double(), (dim,), gm.double(), bt.double(), eps).float()
+    assert (yf - ref).abs().max().item() < 2e-5
+    assert torch.equal(yh, yf.bfloat16())
+    assert (yh.float() + yl.float() - ref).abs().max().item() < 2e-4
+    capi.layernorm(x, None, None, eps, y_f32=yf)  # elementwise_affine=False
+    assert (yf - torch.nn.functional.layer_norm(x, (dim,), None, None, eps)).abs().max().item() < 2e-5
+
+
+def test_layernorm_row_maps(dev):
+    g = torch.Generator().manual_seed(3)
+    B, T, n, dim = 5, 6, 4, 1024
+    x = _randn(g, dev, B * T * n, dim)
+    gm, bt = _randn(g, dev, dim), _randn(g, dev, dim)
+    F = torch.nn.functional
+    yf = torch.zeros(B * T, dim, device=dev)
+    aux = torch.zeros(B * (T + 1), dim, device=dev)
+    capi.layernorm(x, gm, bt, 1e-6, rows=B * T, ldx=n * dim, y_f32=yf, aux=(T, T + 1), aux_f32=aux)
+    ref = F.layer_norm(x.view(B * T, n, dim)[:, 0], (dim,), gm, bt, 1e-6)
+    assert (yf - ref).abs().max().item() < 2e-5
+    assert (aux.view(B, T + 1, dim)[:, 0] - ref.view(B, T, dim)[:, 0]).abs().max().item() < 2e-5
+    assert aux.view(B, T + 1, dim)[:, 1:].abs().max().item() == 0
+    capi.layernorm(x, gm, bt, 1e-6, rows=B * T, ldx=dim, y_f32=yf, in_map=(1, n), avg=(n, 1))
+    assert (yf - F.layer_norm(x.view(B * T, n, dim), (dim,), gm, bt, 1e-6).mean(1)).abs().max().item() < 2e-5
+    # T-SA layout: first T tokens of each clip's n*T-token sequence
+    capi.layernorm(x, gm, bt, 1e-6, rows=B * T, ldx=dim, y_f32=yf, in_map=(T, n * T))
+    assert (yf - F.layer_norm(x.view(B, n * T, dim)[:, :T].reshape(B * T, dim), (dim,), gm, bt, 1e-6)).abs().max().item() < 2e-5
+
+
+def _ref_attn(qkv, n_seq, L, H, hd, mask, T):
+    dev = qkv.device
+    x = qkv.float().view(n_seq, L, 3, H, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = x[0], x[1], x[2]
+    s = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    i = torch.arange(L, device=dev)[:, None]
+    j = torch.arange(L, device=dev)[None, :]
+    if mask == 1:
+        s = s.masked_fill(j > i, float("-inf"))
+    elif mask == 2:
+        s = s.masked_fill((j % T) > (i % T), float("-inf"))
+    elif mask == 3:
+        s = s.masked_fill(j == i, float("-inf"))
+    p = s.softmax(-1)
+    return (p @ v).transpose(1, 2).reshape(n_seq * L, H * hd), p
+
+
+@pytest.mark.parametrize("n_seq,L,H,hd,mask,T,dt", [
+    (36, 5, 4, 256, 0, 1, torch.bfloat16), (7, 18, 4, 512, 1, 18, torch.bfloat16), (3, 50, 4, 256, 2, 10, torch.bfloat16),
+    (36, 5, 4, 256, 3, 1, torch.float32), (7, 18, 4, 512, 1, 18, torch.float32), (3, 50, 4, 256, 2, 10, torch.float32),
+    (2, 1, 4, 256, 0, 1, torch.bfloat16), (2, 64, 4, 256, 1, 64, torch.bfloat16)])
+def test_attention(dev, n_seq, L, H, hd, mask, T, dt):
+    g = torch.Generator().manual_seed(L * 31 + hd)
+    D = H * hd
+    qkv = _randn(g, dev, n_seq * L, 3 * D).to(dt)
+    oh = torch.zeros(n_seq * L, D, device=dev, dtype=torch.bfloat16)
+    ol = torch.zeros(n_seq * L, D, device=dev, dtype=torch.bfloat16)
+    probs = torch.zeros(n_seq, H, L, L, device=dev)
+    capi.attention(qkv, n_seq, L, H, hd, mask=mask, T=T, out_hi=oh, out_lo=ol, probs=probs, p_outer=H * L * L)
+    ro, rp = _ref_attn(qkv, n_seq, L, H, hd, mask, T)
+    assert (oh.float() + ol.float() - ro).abs().max().item() < 2e-4
+    assert (probs - rp).abs().max().item() < 2e-5
+    assert (probs.sum(-1) - 1).abs().max().item() < 1e-5
+    with pytest.raises(capi.AfftError):
+        capi.attention(qkv, n_seq, 65, H, hd, out_hi=oh)
