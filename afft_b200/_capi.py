@@ -92,11 +92,23 @@ class IO(C.Structure):
     ]
 
 
+class ProfileRec(C.Structure):
+    _fields_ = [("cat", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("ms", C.c_float)]
+
+
+AFFT_MAX_PROFILE_RECS = 256
+
+
+class Profile(C.Structure):
+    _fields_ = [("n", C.c_int32), ("recs", ProfileRec * AFFT_MAX_PROFILE_RECS)]
+
+
 # every symbol include/afft_b200.h declares
 EXPORTED_SYMBOLS = [
     "afft_abi_version", "afft_last_error", "afft_gemm", "afft_convert_bf16", "afft_layernorm", "afft_attention",
     "afft_create", "afft_destroy", "afft_handle_error", "afft_workspace_bytes", "afft_weight_bytes",
     "afft_set_weight", "afft_missing_weights", "afft_forward", "afft_last_launch_count",
+    "afft_profile_enable", "afft_profile_read",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -132,8 +144,11 @@ def lib() -> C.CDLL:
     l.afft_missing_weights.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     l.afft_forward.argtypes = [C.c_void_p, C.c_int32, C.POINTER(IO), C.c_void_p]
     l.afft_last_launch_count.argtypes = [C.c_void_p]
+    l.afft_profile_enable.argtypes = [C.c_void_p, C.c_int32]
+    l.afft_profile_read.argtypes = [C.c_void_p, C.POINTER(Profile)]
     for name in ("afft_gemm", "afft_convert_bf16", "afft_layernorm", "afft_attention", "afft_create",
-                 "afft_set_weight", "afft_missing_weights", "afft_forward", "afft_last_launch_count"):
+                 "afft_set_weight", "afft_missing_weights", "afft_forward", "afft_last_launch_count",
+                 "afft_profile_enable", "afft_profile_read"):
         getattr(l, name).restype = C.c_int
     if l.afft_abi_version() != ABI_VERSION:
         raise AfftError(f"ABI mismatch: library {l.afft_abi_version()} vs binding {ABI_VERSION}; rebuild the extension")

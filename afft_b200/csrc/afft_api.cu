@@ -278,6 +278,10 @@ struct afft_handle {
   void* qkv2 = nullptr;
   int launches = 0;
   int fuser_chunk = 0;
+  // optional per-launch event timing
+  bool profile = false;
+  std::vector<cudaEvent_t> ev;  // 2 per record
+  afft_profile prof;
 };
 
 static int hfail(afft_handle* h, int code, const std::string& msg) {
@@ -475,6 +479,7 @@ extern "C" void afft_destroy(afft_handle* h) {
     if (kv.second.f32) cudaFree(kv.second.f32);
   }
   if (h->ws) cudaFree(h->ws);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
 }
 
@@ -587,6 +592,17 @@ struct Fwd {
     }
     if (r == AFFT_OK) ++h->launches;
   }
+  // event pair around one launch when profiling is on
+  int prof_begin(int cat, int M = 0, int N = 0, int K = 0) {
+    if (!h->profile || h->prof.n >= AFFT_MAX_PROFILE_RECS) return -1;
+    const int i = h->prof.n++;
+    h->prof.recs[i] = {cat, M, N, K, 0.f};
+    cudaEventRecord(h->ev[2 * i], stream);
+    return i;
+  }
+  void prof_end(int i) {
+    if (i >= 0) cudaEventRecord(h->ev[2 * i + 1], stream);
+  }
 
   // out = epilogue(A . W^T)
   void gemm(const PairBuf& A, long long lda, int M, const std::string& wname, const float* bias, int act,
@@ -621,7 +637,9 @@ struct Fwd {
     d.row_group = row_group;
     d.row_stride = row_stride;
     d.row_off = row_off;
+    const int pi = prof_begin(AFFT_CAT_GEMM, d.M, d.N, d.K);
     check(run_gemm(d, h->num_sms, stream));
+    prof_end(pi);
   }
 
   void layernorm(const float* x, long long ldx, int rows, int dim, const std::string& name, float eps, const PairBuf* yb,
@@ -651,7 +669,9 @@ struct Fwd {
     a.aux_hi = aux_b ? aux_b->hi : nullptr;
     a.aux_lo = aux_b ? aux_b->lo : nullptr;
     a.ld_aux = ld_aux;
+    const int pi = prof_begin(AFFT_CAT_LAYERNORM);
     check(run_layernorm(a, stream));
+    prof_end(pi);
   }
 
   // q/k/v live in one buffer of row pitch ld (elements) at column offsets qo/ko/vo
@@ -678,28 +698,36 @@ struct Fwd {
     a.p_outer = p_outer;
     a.p_inner_stride = p_inner_stride;
     a.p_inner = p_inner > 0 ? p_inner : 1;
+    const int pi = prof_begin(AFFT_CAT_ATTENTION);
     check(run_attention(a, hd, strict, stream));
+    prof_end(pi);
   }
 
   void convert(const float* src, long long lds, int rows, int cols, const PairBuf& dst, long long ldd) {
     if (!ok()) return;
+    const int pi = prof_begin(AFFT_CAT_OTHER);
     check(run_convert(src, lds, rows, cols, dst.hi, dst.lo, ldd, 0, stream));
+    prof_end(pi);
   }
 
   void assemble(const AssembleArgs& a) {
     if (!ok()) return;
     const long long total = static_cast<long long>(a.B) * a.T * a.n_slots * (a.dim / 4);
     const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    const int pi = prof_begin(AFFT_CAT_OTHER);
     assemble_tokens_kernel<<<blocks, 256, 0, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     check(e == cudaSuccess ? AFFT_OK : cuda_fail("assemble launch", e));
+    prof_end(pi);
   }
 
   void embed_table(float* table, const float* pos, const float* mod, int T, int dim) {
     if (!ok()) return;
+    const int pi = prof_begin(AFFT_CAT_OTHER);
     embed_table_kernel<<<(T * dim + 255) / 256, 256, 0, stream>>>(table, pos, mod, T, dim);
     cudaError_t e = cudaGetLastError();
     check(e == cudaSuccess ? AFFT_OK : cuda_fail("embed_table launch", e));
+    prof_end(pi);
   }
 };
 
@@ -955,8 +983,36 @@ extern "C" int afft_forward(afft_handle* h, int32_t B, const afft_io* io, void* 
   F.stream = static_cast<cudaStream_t>(stream_);
   F.strict = c.strict != 0;
   h->launches = 0;
+  h->prof.n = 0;
   const int chunk = (h->fuser_chunk > 0) ? h->fuser_chunk : B;
   for (int b0 = 0; b0 < B && F.ok(); b0 += chunk) run_fuser(F, *io, b0, std::min(chunk, B - b0));
   if (F.ok()) run_predictor(F, *io, B);
   return F.rc;
+}
+
+extern "C" int afft_profile_enable(afft_handle* h, int32_t enable) {
+  if (h == nullptr) return fail(AFFT_ERR_INVALID, "profile_enable: null handle");
+  if (enable && h->ev.empty()) {
+    cudaError_t e = cudaSetDevice(h->cfg.device);
+    if (e != cudaSuccess) return hfail(h, AFFT_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    h->ev.resize(2 * AFFT_MAX_PROFILE_RECS);
+    for (auto& ev : h->ev) {
+      e = cudaEventCreate(&ev);
+      if (e != cudaSuccess) return hfail(h, AFFT_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e));
+    }
+  }
+  h->profile = enable != 0;
+  h->prof.n = 0;
+  return AFFT_OK;
+}
+
+extern "C" int afft_profile_read(afft_handle* h, afft_profile* out) {
+  if (h == nullptr || out == nullptr) return fail(AFFT_ERR_INVALID, "profile_read: null argument");
+  for (int i = 0; i < h->prof.n; ++i) {
+    cudaError_t e = cudaEventSynchronize(h->ev[2 * i + 1]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&h->prof.recs[i].ms, h->ev[2 * i], h->ev[2 * i + 1]);
+    if (e != cudaSuccess) return hfail(h, AFFT_ERR_CUDA, std::string("profile_read: ") + cudaGetErrorString(e));
+  }
+  *out = h->prof;
+  return AFFT_OK;
 }

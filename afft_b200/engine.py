@@ -135,6 +135,15 @@ class Engine:
         _capi.check(self.lib.afft_forward(self.handle, B, C.byref(io), _capi.current_stream_ptr(self.device)),
                     self.handle)
 
+    def profile_enable(self, on: bool = True):
+        _capi.check(self.lib.afft_profile_enable(self.handle, int(on)), self.handle)
+
+    def profile_read(self):
+        """[(category, M, N, K, ms)] of the most recent forward (categories: 0 GEMM, 1 LN, 2 attention, 3 other)."""
+        p = _capi.Profile()
+        _capi.check(self.lib.afft_profile_read(self.handle, C.byref(p)), self.handle)
+        return [(r.cat, r.M, r.N, r.K, r.ms) for r in p.recs[:p.n]]
+
     def launch_count(self) -> int:
         return int(self.lib.afft_last_launch_count(self.handle))
 

@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""Benchmark of the AFFT fusion-and-anticipation forward path (BASELINE.json metric: SA-Fuser EK100 forward
+clips/sec on B200, fraction of the bf16 tensor-core roofline, next to the host-CPU path).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+A "step" is one forward of the hot path over one batch of synthetic clips per GPU (weak scaling: the
+per-GPU batch is fixed, clips are sharded data-parallel, no data-path collective).  One JSON line is printed
+by rank 0.  See DESIGN.md section "Measurement" for how each field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from afft_b200 import configs, synthetic  # noqa: E402
+from afft_b200 import dist as adist  # noqa: E402
+
+METRIC = "SA-Fuser EK100 forward clips/sec"
+UNIT = "clips/s"
+KW = dict(mixup_fn=None, target=None, target_subclips=None, target_subclips_ignore_index=None)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"burst": p["bf16_tflops"], "sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"burst": 1590.0, "sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while a timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.01):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            # CUDA_VISIBLE_DEVICES remapping: resolve by UUID of the torch device
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            h = None
+            for cand in (f"GPU-{uuid}", uuid):
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                    break
+                except Exception:  # noqa: BLE001
+                    continue
+            self._h = h if h is not None else pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self._nvml = None
+
+    def _loop(self):
+        nv = self._nvml
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mask = get_reasons(self._h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self._nvml is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_forward_timer(cfg, T, ncls, batch, steps, warmup, budget_s=240.0):
+    """Times oracle.forward (the CPU restatement of the reference path, pinned to the reference module) on all
+    host cores.  Returns (clips/s, cores, description)."""
+    from afft_b200.models import BaseModel
+    from oracle import afft_oracle  # bench.py's cpu_baseline / --impl reference legs may execute the oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    afft_oracle.ATEN_OPS = True  # issue the same ATen library calls as the reference module (fair CPU timing)
+    torch.manual_seed(0)
+    model = BaseModel(cfg, ncls, {})  # random-init weights of the architecture (CPU tensors; no native call)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    feats = synthetic.synthetic_features(cfg["modal_dims"], batch, T, seed=1000)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        afft_oracle.forward(sd, cfg, ncls, feats)
+        first = time.perf_counter() - t0
+        if first * (steps + warmup) > budget_s:  # keep the whole run bounded
+            steps = max(1, int(budget_s / first) - warmup)
+        for _ in range(max(0, warmup - 1)):
+            afft_oracle.forward(sd, cfg, ncls, feats)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            afft_oracle.forward(sd, cfg, ncls, feats)
+        dt = time.perf_counter() - t0
+    cpu_name = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    cpu_name = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    desc = f"{steps} forwards of {batch} clips, fp32 torch CPU ops, {cores} threads on {cpu_name}"
+    return batch * steps / dt, cores, desc, steps, dt
+
+
+def run_reference(args):
+    rank, _, world = adist.env_world()
+    if rank != 0:
+        return
+    cfg, T, ncls, eval_bs = configs.named_config(args.config)
+    batch = args.cpu_batch or eval_bs
+    value, cores, desc, steps, dt = cpu_forward_timer(cfg, T, ncls, batch, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": round(1e3 * dt / steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, cfg, T, batch, "reference algorithm on host CPU"),
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cfg, T, batch, how, ncls=None):
+    return {"workload": f"{args.config}: SA-Fuser EK100 R-TSN+O+AU+F 4h_18s (expts/01_SA-Fuser_ek100_val_TSN.txt)"
+            if args.config == "ek100_sa_tsn" else args.config,
+            "clips_per_gpu_per_step": batch, "T": T, "modal_dims": cfg["modal_dims"],
+            "gemm_gflop_per_clip": round(configs.gemm_flops_per_clip(cfg, T, ncls or configs.named_config(args.config)[2]) / 1e9, 3),
+            "weights": "random init (torch.manual_seed(0))", "parallelism": f"dp{args.gpus} (clips sharded, no collective)",
+            "path": how,
+            "l2": "no explicit flush: per-step working set (772 MB bf16 weights + >1 GB activations) exceeds the 126 MB L2; "
+                  "4 input buffer sets are rotated"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_afft(args):
+    from afft_b200 import _capi
+    from afft_b200.models import BaseModel
+
+    rank, local_rank, world = adist.init()
+    if world != args.gpus and rank == 0:
+        print(f"[bench] note: WORLD_SIZE={world} but --gpus={args.gpus}; using WORLD_SIZE", file=sys.stderr)
+    n_gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); the hot path has no CPU fallback. "
+                         "Use --impl reference for the CPU arm.")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _capi.lib()  # fail loudly if the extension is not built
+    cfg, T, ncls, eval_bs = configs.named_config(args.config)
+    B = args.batch
+    peaks = load_peaks()
+    flops_per_clip = configs.gemm_flops_per_clip(cfg, T, ncls)
+
+    torch.manual_seed(0)
+    model = BaseModel(cfg, ncls, {}, strict=args.strict, max_batch=B).to(dev).eval()
+    head = model.future_predictor
+    order = [m for m in cfg["modal_feature_order"] if m in cfg["modal_dims"]]
+
+    # ---- device-resident inputs: NBUF rotating sets ----
+    NBUF = 4
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    dev_sets = [{m: torch.randn(B, T, cfg["modal_dims"][m], 1, 1, 1, device=dev, generator=g) for m in order}
+                for _ in range(NBUF)]
+    with torch.no_grad():
+        out, _ = model(dict(dev_sets[0]), **KW)  # builds the engine, packs the weights
+    torch.cuda.synchronize()
+    eng = next(iter(head._engines.values()))
+    launches_per_fwd = eng.launch_count()
+
+    # persistent output buffers + io structs for the lowest-overhead call (C ABI with raw pointers)
+    D = cfg["common_dim"]
+    C = list(ncls.values())[0]
+    ldc = (C + 3) // 4 * 4
+    n_tok, H1 = eng.n_slots, eng.fuser_heads
+    if eng.fuser_kind == _capi.FUSER_TSA:
+        attn_buf = torch.empty(B, eng.fuser_depth, H1, n_tok * T, n_tok * T, device=dev)
+    elif eng.fuser_kind == _capi.FUSER_CA:
+        attn_buf = None
+    else:
+        attn_buf = torch.empty(B, eng.fuser_depth, T, H1, n_tok, n_tok, device=dev)
+    bufs = dict(orig=torch.empty(B, T, D, device=dev), pf=torch.empty(B, T + 1, D, device=dev),
+                logits=torch.empty(B, T + 1, ldc, device=dev), attn=attn_buf)
+    ios = []
+    for s in dev_sets:
+        io = _capi.IO()
+        for i, m in enumerate(order):
+            io.feat[i] = s[m].data_ptr()
+        io.orig_past, io.past_futures = bufs["orig"].data_ptr(), bufs["pf"].data_ptr()
+        io.logits[0], io.ld_logits[0] = bufs["logits"].data_ptr(), ldc
+        io.fuser_attn = bufs["attn"].data_ptr() if bufs["attn"] is not None else None
+        ios.append(io)
+
+    def step(i):
+        eng.forward_into(ios[i % NBUF], B)
+
+    # ---- value: device-resident inputs, CUDA events, max over ranks ----
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    adist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    with sampler:
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+    adist.barrier()
+    ms_total = adist.max_over_ranks(e0.elapsed_time(e1), dev)
+    ms_per_step = ms_total / args.steps
+    value = n_gpus * B * args.steps / (ms_total / 1e3)
+
+    # ---- e2e: public API, pinned host inputs, H2D + forward + D2H of the consumed logits every step ----
+    host_sets = [{m: torch.randn(B, T, cfg["modal_dims"][m], 1, 1, 1).pin_memory() for m in order} for _ in range(2)]
+    h2d_bytes = sum(t.numel() * 4 for t in host_sets[0].values())
+    d2h_bytes = B * C * 4
+    host_out = torch.empty(B, C).pin_memory()
+    copy_stream = torch.cuda.Stream(dev)
+    main_stream = torch.cuda.current_stream(dev)
+    head.return_attentions = True
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            d = {m: t.to(dev, non_blocking=True) for m, t in host_sets[i % 2].items()}
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return d, ev
+
+    def e2e_loop(n):
+        nxt = prefetch(0)
+        for i in range(n):
+            d, ev = nxt
+            main_stream.wait_event(ev)
+            if i + 1 < n:
+                nxt = prefetch(i + 1)  # overlaps the next batch's H2D with this batch's compute
+            with torch.no_grad():
+                o, _ = model(d, **KW)  # the call test.py:82 makes
+            for t in d.values():
+                t.record_stream(main_stream)
+            host_out.copy_(o["logits/action"]["all-fused"][:, 0, :], non_blocking=True)  # test.py:86
+            main_stream.synchronize()
+
+    e2e_loop(max(2, args.warmup))
+    adist.barrier()
+    with sampler:
+        e0.record()
+        e2e_loop(args.steps)
+        e1.record()
+        torch.cuda.synchronize()
+    adist.barrier()
+    e2e_ms = adist.max_over_ranks(e0.elapsed_time(e1), dev)
+    e2e_value = n_gpus * B * args.steps / (e2e_ms / 1e3)
+
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM): per-launch CUDA events, separate pass ----
+    eng.profile_enable(True)
+    agg = {0: [0.0, 0], 1: [0.0, 0], 2: [0.0, 0], 3: [0.0, 0]}
+    gemm_flops = 0.0
+    by_shape = {}
+    PSTEPS = 3
+    for i in range(PSTEPS):
+        step(i)
+        torch.cuda.synchronize()
+        for cat, M, N, K, ms in eng.profile_read():
+            agg[cat][0] += ms
+            agg[cat][1] += 1
+            if cat == 0:
+                gemm_flops += 2.0 * M * N * K
+                s = by_shape.setdefault((M, N, K), [0.0, 0])
+                s[0] += ms
+                s[1] += 1
+    eng.profile_enable(False)
+    gemm_ms = agg[0][0]
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    kernel_ms_total = sum(v[0] for v in agg.values())
+    step_tflops = value / n_gpus * flops_per_clip / 1e12
+
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, cfg, T, B, "afft_forward (C ABI), " + ("strict bf16x3" if args.strict else "bf16 operands / fp32 accumulate")),
+        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(e2e_ms / args.steps, 4),
+                "api": "afft_b200.models.BaseModel.__call__ (test.py:72-86 pattern), pinned host inputs, double-buffered H2D"},
+        "gpu_launches": launches_per_fwd * args.steps,
+        "launches_per_step": launches_per_fwd,
+        "clocks": sampler.summary(),
+        "roofline": {
+            "bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": round(achieved, 1),
+            "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": round(achieved / peaks["sustained"], 4),
+            "peak_kind": "bf16_tflops_sustained, " + peaks["source"], "frac_of_burst": round(achieved / peaks["burst"], 4),
+            "traffic": None,
+            "launches_per_step": agg[0][1] // PSTEPS, "gemm_ms_per_step": round(gemm_ms / PSTEPS, 4),
+            "gemm_share_of_kernel_time": round(gemm_ms / kernel_ms_total, 4) if kernel_ms_total else None,
+            "whole_step_tflops": round(step_tflops, 1), "whole_step_frac": round(step_tflops / peaks["sustained"], 4),
+            "whole_step_frac_of_burst": round(step_tflops / peaks["burst"], 4),
+            "other_kernels_ms_per_step": {"layernorm": round(agg[1][0] / PSTEPS, 4), "attention": round(agg[2][0] / PSTEPS, 4),
+                                          "assembly_convert": round(agg[3][0] / PSTEPS, 4)},
+        },
+    }
+    if args.verbose and rank == 0:
+        for (M, N, K), (ms, n) in sorted(by_shape.items(), key=lambda kv: -kv[1][0]):
+            print(f"[gemm] M={M} N={N} K={K} launches/step={n // PSTEPS} ms/launch={ms / n:.4f} "
+                  f"TFLOP/s={2.0 * M * N * K / (ms / n) / 1e9:.0f}", file=sys.stderr)
+
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        # parity of exactly this build on a small sample, and the CPU baseline, in the same run
+        from oracle import afft_oracle
+        pb = 4
+        pf = synthetic.synthetic_features(cfg["modal_dims"], pb, T, seed=31)
+        with torch.no_grad():
+            o, _ = model({m: t.reshape(pb, T, -1, 1, 1, 1).to(dev) for m, t in pf.items()}, **KW)
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        ref = afft_oracle.forward(sd, cfg, ncls, pf)
+        got = o["logits/action"]["all-fused"].cpu()
+        line["parity_sample"] = {
+            "clips": pb, "max_abs_dlogit_vs_oracle_fp32": round((got - ref["logits/action"]["all-fused"]).abs().max().item(), 6),
+            "top5_identical_clips": int((got[:, 0].topk(5).indices == afft_oracle.top5(ref["logits/action"]["all-fused"][:, 0])).all(-1).sum()),
+            "mode": "strict" if args.strict else "bf16"}
+        del sd
+        v, cores, desc, _, _ = cpu_forward_timer(cfg, T, ncls, args.cpu_batch or eval_bs, 3, 1, budget_s=60.0)
+        line["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    adist.shutdown()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["afft", "reference"], default="afft")
+    ap.add_argument("--config", default="ek100_sa_tsn", choices=configs.CONFIG_NAMES)
+    ap.add_argument("--batch", type=int, default=256, help="clips per GPU per step")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="clips per CPU forward (default: the experiment's eval batch)")
+    ap.add_argument("--strict", action="store_true", help="bf16x3 error-compensated GEMMs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.warmup = max(args.warmup, 1)
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)  # timing rule: at least 3 warm-up steps
+        run_afft(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define AFFT_API __attribute__((visibility("default")))
+#else
+#define AFFT_API
+#endif
+
 #define AFFT_OK 0
 #define AFFT_ERR_INVALID 1     /* bad argument / unsupported configuration */
 #define AFFT_ERR_CUDA 2        /* a CUDA runtime/driver call failed */
@@ -45,10 +51,10 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------ */
 
 /* ABI version of this header (bumped on any struct change). */
-int afft_abi_version(void);
+AFFT_API int afft_abi_version(void);
 
 /* Last error message of the calling thread (stateless ops) - never NULL. */
-const char* afft_last_error(void);
+AFFT_API const char* afft_last_error(void);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Stateless operators (one per library call the reference makes on the path)                  */
@@ -90,11 +96,11 @@ typedef struct afft_gemm_desc {
   int32_t force_block_n; /* 0 = auto, 128 or 256 */
 } afft_gemm_desc;
 
-int afft_gemm(const afft_gemm_desc* d, void* stream);
+AFFT_API int afft_gemm(const afft_gemm_desc* d, void* stream);
 
 /* fp32 [rows, cols] (pitch lds) -> bf16 hi (+ lo when lo != NULL), pitch ldd; transpose != 0
  * writes dst[c, r].  Weight packing (Conv1D [in,out] -> K-major) and feature inputs. */
-int afft_convert_bf16(const float* src, int64_t lds, int32_t rows, int32_t cols, void* hi, void* lo, int64_t ldd,
+AFFT_API int afft_convert_bf16(const float* src, int64_t lds, int32_t rows, int32_t cols, void* hi, void* lo, int64_t ldd,
                       int32_t transpose, void* stream);
 
 /* LayerNorm over the last dim: replaces nn.LayerNorm (models/fusion.py:281,362;
@@ -119,7 +125,7 @@ typedef struct afft_layernorm_desc {
   int64_t ld_aux;
 } afft_layernorm_desc;
 
-int afft_layernorm(const afft_layernorm_desc* d, void* stream);
+AFFT_API int afft_layernorm(const afft_layernorm_desc* d, void* stream);
 
 /* Small multi-head attention (L <= 64, head_dim 256 or 512): replaces the two bmm + softmax of
  * models/transformerblock.py:24-33, :64-74 and GPT-2's eager attention.
@@ -144,7 +150,7 @@ typedef struct afft_attention_desc {
   int32_t p_inner;
 } afft_attention_desc;
 
-int afft_attention(const afft_attention_desc* d, void* stream);
+AFFT_API int afft_attention(const afft_attention_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Model-level API: everything below BaseModel.future_predictor (models/base_model.py:59)      */
@@ -177,13 +183,13 @@ typedef struct afft_config {
 
 typedef struct afft_handle afft_handle;
 
-int afft_create(const afft_config* cfg, afft_handle** out);
-void afft_destroy(afft_handle* h);
-const char* afft_handle_error(const afft_handle* h);
+AFFT_API int afft_create(const afft_config* cfg, afft_handle** out);
+AFFT_API void afft_destroy(afft_handle* h);
+AFFT_API const char* afft_handle_error(const afft_handle* h);
 
 /* Bytes of device workspace + packed weights the handle holds (for capacity planning). */
-size_t afft_workspace_bytes(const afft_handle* h);
-size_t afft_weight_bytes(const afft_handle* h);
+AFFT_API size_t afft_workspace_bytes(const afft_handle* h);
+AFFT_API size_t afft_weight_bytes(const afft_handle* h);
 
 /*
  * Register one tensor of the reference state dict (train.py:55-103 key contract), name relative
@@ -191,11 +197,11 @@ size_t afft_weight_bytes(const afft_handle* h);
  * contiguous, with the reference's shape (ndim <= 3).  Unknown names return AFFT_ERR_INVALID
  * (the Python shim filters GPT-2's attn.bias / attn.masked_bias buffers).
  */
-int afft_set_weight(afft_handle* h, const char* name, const float* src_dev, int32_t ndim, const int64_t* shape,
+AFFT_API int afft_set_weight(afft_handle* h, const char* name, const float* src_dev, int32_t ndim, const int64_t* shape,
                     void* stream);
 
 /* Number of tensors still missing; names are written, newline separated, into buf (may be NULL). */
-int afft_missing_weights(const afft_handle* h, char* buf, size_t buf_len);
+AFFT_API int afft_missing_weights(const afft_handle* h, char* buf, size_t buf_len);
 
 typedef struct afft_io {
   const float* feat[AFFT_MAX_MODS]; /* [B, T, mod_dim[m]] fp32, fusion order */
@@ -207,10 +213,29 @@ typedef struct afft_io {
 } afft_io;
 
 /* One forward of CMFPEarly.forward (models/future_prediction.py:257-291) for B <= max_batch clips. */
-int afft_forward(afft_handle* h, int32_t B, const afft_io* io, void* stream);
+AFFT_API int afft_forward(afft_handle* h, int32_t B, const afft_io* io, void* stream);
 
 /* Kernels launched by the most recent afft_forward on this handle. */
-int afft_last_launch_count(const afft_handle* h);
+AFFT_API int afft_last_launch_count(const afft_handle* h);
+
+/*
+ * Optional per-launch timing (CUDA events recorded on the caller's stream around every kernel of the next
+ * forwards).  Used by bench.py for the roofline of the GEMM kernel; off by default (no events recorded).
+ * afft_profile_read synchronises on the recorded events and returns the records of the most recent forward.
+ */
+enum { AFFT_CAT_GEMM = 0, AFFT_CAT_LAYERNORM = 1, AFFT_CAT_ATTENTION = 2, AFFT_CAT_OTHER = 3 };
+#define AFFT_MAX_PROFILE_RECS 256
+typedef struct afft_profile_rec {
+  int32_t cat;
+  int32_t M, N, K; /* GEMM shape (0 for other kernels) */
+  float ms;
+} afft_profile_rec;
+typedef struct afft_profile {
+  int32_t n;
+  afft_profile_rec recs[AFFT_MAX_PROFILE_RECS];
+} afft_profile;
+AFFT_API int afft_profile_enable(afft_handle* h, int32_t enable);
+AFFT_API int afft_profile_read(afft_handle* h, afft_profile* out);
 
 #ifdef __cplusplus
 }

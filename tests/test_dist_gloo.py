@@ -1,0 +1,59 @@
+"""CPU: the N>1 host logic (contiguous clip sharding, barrier, max-over-ranks timing) with world_size 2 on gloo."""
+import os
+import socket
+import subprocess
+import sys
+
+from afft_b200 import dist as adist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, json
+sys.path.insert(0, os.environ["AFFT_ROOT"])
+import torch
+from afft_b200 import dist as adist
+rank, local_rank, world = adist.init(backend="gloo")
+assert world == 2
+lo, hi = adist.shard_bounds(37, rank, world)
+adist.barrier()
+t = adist.max_over_ranks(1.0 + rank, device="cpu")          # slowest rank wins
+n = adist.sum_over_ranks(hi - lo, device="cpu")              # all clips covered exactly once
+# the sharded "forward": each rank processes its contiguous slice; results must tile the batch
+x = torch.arange(37, dtype=torch.float64)
+part = (x[lo:hi] * 2).sum().item()
+total = adist.sum_over_ranks(part, device="cpu")
+print(json.dumps({"rank": rank, "lo": lo, "hi": hi, "tmax": t, "n": n, "total": total}), flush=True)
+adist.shutdown()
+'''
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 7, 32, 37, 256):
+        for world in (1, 2, 3, 8):
+            spans = [adist.shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_world_size_2_gloo(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, AFFT_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = []
+    for p in procs:
+        o, e = p.communicate(timeout=180)
+        assert p.returncode == 0, e[-2000:]
+        outs.append(o)
+    import json
+    recs = sorted((json.loads(o.strip().splitlines()[-1]) for o in outs), key=lambda r: r["rank"])
+    assert (recs[0]["lo"], recs[0]["hi"], recs[1]["lo"], recs[1]["hi"]) == (0, 19, 19, 37)
+    assert recs[0]["tmax"] == recs[1]["tmax"] == 2.0
+    assert recs[0]["n"] == 37 and recs[0]["total"] == float(sum(range(37)) * 2)

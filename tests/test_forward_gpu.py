@@ -38,6 +38,8 @@ def _model(cfg_name, strict, max_batch=64):
 
 
 def _run(model, feats):
+    # the loader's layout is (B, T, C, 1, 1, 1); accept (B, T, C) for brevity in tests
+    feats = {m: (t.reshape(*t.shape, 1, 1, 1) if t.ndim == 3 else t) for m, t in feats.items()}
     with torch.no_grad():
         out, _ = model({m: t.to("cuda:0") for m, t in feats.items()}, **KW)
     torch.cuda.synchronize()

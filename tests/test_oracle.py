@@ -100,3 +100,18 @@ def test_oracle_matches_live_reference():
     for k in ("logits/action", "past_logits/action", "orig_past", "future", "past_futures", "all-fused"):
         assert (out[k]["all-fused"] - ref[k]["all-fused"]).abs().max().item() < 1e-12, k
     assert (out["attentions"]["all-fused"]["modality_attns"] - ref["attentions"]["all-fused"]["modality_attns"]).abs().max() < 1e-13
+
+
+def test_aten_spelling_agrees_with_elementary_spelling():
+    """bench.py times the oracle with ATEN_OPS=True (the reference's own library calls); same numbers."""
+    cfg, T, ncls, _ = configs.named_config("egtea_sa")
+    sd = _weights("egtea_sa")
+    feats = synthetic.synthetic_features(cfg["modal_dims"], 2, T, seed=8)
+    a = afft_oracle.forward(sd, cfg, ncls, feats)
+    afft_oracle.ATEN_OPS = True
+    try:
+        b = afft_oracle.forward(sd, cfg, ncls, feats)
+    finally:
+        afft_oracle.ATEN_OPS = False
+    for k in ("logits/action", "past_logits/action", "orig_past", "past_futures"):
+        assert (a[k]["all-fused"] - b[k]["all-fused"]).abs().max().item() < 2e-5
