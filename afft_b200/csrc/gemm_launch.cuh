@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -68,12 +69,12 @@ inline bool make_tmap_bf16(CUtensorMap* out, const void* ptr, long long rows, lo
   return true;
 }
 
-template <int BLOCK_N, int SPLIT>
+template <int BLOCK_N, int SPLIT, int EPI>
 inline cudaError_t launch_gemm_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal,
                                        const CUtensorMap& tbl, const GemmEpilogue& ep, int M, int N, int K,
-                                       int num_sms, cudaStream_t stream) {
+                                       int num_sms, const GemmSched& sched, cudaStream_t stream) {
   using T = GemmTraits<BLOCK_N, SPLIT>;
-  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT>;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT, EPI>;
   static bool attr_set[64] = {false};  // per variant and device; benign race (idempotent)
   int dev = 0;
   cudaGetDevice(&dev);
@@ -85,7 +86,7 @@ inline cudaError_t launch_gemm_variant(const CUtensorMap& ta, const CUtensorMap&
   }
   const int num_tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  kern<<<grid, kGemmThreads, T::kSmemBytes, stream>>>(ta, tb, tal, tbl, ep, M, N, K);
+  kern<<<grid, kGemmThreads, T::kSmemBytes, stream>>>(ta, tb, tal, tbl, ep, M, N, K, sched);
   return cudaGetLastError();
 }
 
@@ -95,8 +96,29 @@ inline int pick_block_n(int M, int N, int num_sms, int forced) {
   const long long m_tiles = (M + kBlockM - 1) / kBlockM;
   const long long t256 = m_tiles * ((N + 255) / 256), t128 = m_tiles * ((N + 127) / 128);
   const long long w256 = (t256 + num_sms - 1) / num_sms, w128 = (t128 + num_sms - 1) / num_sms;
-  // cost in units of "128x128 tile times"
-  return (w128 < 2 * w256) ? 128 : 256;
+  // A 128-wide tile costs ~0.62 of a 256-wide one (measured: its main loop re-streams A through shared
+  // memory twice as often per flop), so it only pays when it removes a mostly empty last wave.
+  return (w128 * 0.62 < w256 * 1.0) ? 128 : 256;
+}
+
+inline unsigned long long policy_from_env(const char* name, unsigned long long dflt) {
+  const char* v = getenv(name);
+  if (v == nullptr) return dflt;
+  if (v[0] == 'f') return ptx::kEvictFirst;
+  if (v[0] == 'l') return ptx::kEvictLast;
+  return ptx::kEvictNormal;
+}
+
+inline const GemmSched& default_sched() {
+  static const GemmSched s = [] {
+    GemmSched g;
+    const char* o = getenv("AFFT_GEMM_ORDER");  // "m" = m-fastest, default n-fastest
+    g.n_fastest = (o != nullptr && o[0] == 'm') ? 0 : 1;
+    g.policy_a = policy_from_env("AFFT_GEMM_HINT_A", ptx::kEvictFirst);   // activations: streamed once
+    g.policy_b = policy_from_env("AFFT_GEMM_HINT_B", ptx::kEvictNormal);  // weights: hot for the whole launch
+    return g;
+  }();
+  return s;
 }
 
 // Returns false and fills *err on failure.  force_block_n: 0 = auto.
@@ -130,14 +152,31 @@ inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, bool stri
     tal = ta;
     tbl = tb;
   }
-  cudaError_t e;
+  // epilogue variant: the combinations the forward path uses are compiled with constant flags
+  const int code = epi_code(ep.act, ep.res != nullptr, ep.out_f32 != nullptr, ep.out_hi != nullptr);
+  const bool lo_ok = (ep.out_hi == nullptr) || ((ep.out_lo != nullptr) == strict);  // specialised kernels tie lo to SPLIT
+  cudaError_t e = cudaErrorInvalidValue;
+#define AFFT_LAUNCH(BN, SP, EP) e = launch_gemm_variant<BN, SP, EP>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, default_sched(), stream)
+#define AFFT_DISPATCH_EPI(BN, SP)                                                            \
+  do {                                                                                       \
+    if (!lo_ok) { AFFT_LAUNCH(BN, SP, EPI_GENERIC); break; }                                 \
+    switch (code) {                                                                          \
+      case epi_code(ACT_NONE, false, false, true): AFFT_LAUNCH(BN, SP, epi_code(ACT_NONE, false, false, true)); break;          \
+      case epi_code(ACT_NONE, false, true, false): AFFT_LAUNCH(BN, SP, epi_code(ACT_NONE, false, true, false)); break;          \
+      case epi_code(ACT_NONE, true, true, false): AFFT_LAUNCH(BN, SP, epi_code(ACT_NONE, true, true, false)); break;            \
+      case epi_code(ACT_GELU_ERF, false, false, true): AFFT_LAUNCH(BN, SP, epi_code(ACT_GELU_ERF, false, false, true)); break;  \
+      case epi_code(ACT_GELU_TANH, false, false, true): AFFT_LAUNCH(BN, SP, epi_code(ACT_GELU_TANH, false, false, true)); break; \
+      case epi_code(ACT_NONE, false, true, true): AFFT_LAUNCH(BN, SP, epi_code(ACT_NONE, false, true, true)); break;            \
+      default: AFFT_LAUNCH(BN, SP, EPI_GENERIC); break;                                      \
+    }                                                                                        \
+  } while (0)
   if (strict) {
-    e = (bn == 256) ? launch_gemm_variant<256, 3>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, stream)
-                    : launch_gemm_variant<128, 3>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, stream);
+    if (bn == 256) AFFT_DISPATCH_EPI(256, 3); else AFFT_DISPATCH_EPI(128, 3);
   } else {
-    e = (bn == 256) ? launch_gemm_variant<256, 1>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, stream)
-                    : launch_gemm_variant<128, 1>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, stream);
+    if (bn == 256) AFFT_DISPATCH_EPI(256, 1); else AFFT_DISPATCH_EPI(128, 1);
   }
+#undef AFFT_DISPATCH_EPI
+#undef AFFT_LAUNCH
   if (e != cudaSuccess) {
     if (err) *err = std::string("gemm launch failed: ") + cudaGetErrorString(e);
     return false;

@@ -14,8 +14,9 @@
 //                               buffered (2 x BLOCK_N columns) so the epilogue of tile i overlaps
 //                               the main loop of tile i+1
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue       tcgen05.ld 32x32b -> registers -> bias / GELU / residual / casts ->
-//                               global.  Each warp owns one 32-lane TMEM quadrant = 32 output rows.
+//   warps 4..11 epilogue       tcgen05.ld 32x32b -> registers -> swizzled smem transposition -> bias / GELU /
+//                               residual / casts -> coalesced 16-B global accesses.  Two warps per 32-lane
+//                               TMEM quadrant (= 32 output rows), interleaved over 32-column slabs.
 //
 // SPLIT == 3 is the "strict" mode: both operands are given as bf16 hi/lo
 // pairs (x = hi + lo to ~16 mantissa bits) and the kernel accumulates hi.hi + hi.lo + lo.hi into
@@ -31,7 +32,8 @@ namespace afft {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kNumEpilogueWarps = 8;   // two per TMEM lane quadrant
+constexpr int kGemmThreads = 128 + 32 * kNumEpilogueWarps;
 
 enum : int { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_GELU_TANH = 2 };
 
@@ -53,6 +55,13 @@ struct GemmEpilogue {
   int row_group, row_stride, row_off;
 };
 
+// Tile order and L2 policy.  n_fastest: consecutive tiles share the A (activation) row block and sweep the
+// N tiles of the (small, L2-resident) weight, so every activation tile is fetched from DRAM once.
+struct GemmSched {
+  int n_fastest;
+  unsigned long long policy_a, policy_b;
+};
+
 template <int BLOCK_N, int SPLIT>
 struct GemmTraits {
   static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N must be 128 or 256");
@@ -64,131 +73,197 @@ struct GemmTraits {
   static constexpr int kStages = (SPLIT == 3) ? (BLOCK_N == 256 ? 2 : 3) : (BLOCK_N == 256 ? 4 : 6);
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
   static constexpr uint32_t kBarrierBytes = 256;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;  // +align slack
+  // per epilogue warp: one 32 x 32 fp32 transposition tile (4 KB, 16-B chunks XOR-swizzled by row)
+  static constexpr uint32_t kStagingBytes = kNumEpilogueWarps * 4096;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;  // +align slack
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
 // --------------------------------------------------------------------------------------------
-// Activation functions (fp32).  erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7) so the epilogue
-// stays well under the tensor-core time of a K=1024 tile; tanh via exp.
+// Activation functions (fp32 in, fp32 out), written against the MUFU approximations directly so that an
+// element costs ~16 (erf) / ~8 (tanh) issue slots: at K = 1024 the tensor core finishes a 128x256 tile
+// in 8192 cycles = 0.25 cycle per element, and the epilogue has to keep up with that.
 // --------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {
-  // 0.5 x (1 + erf(x / sqrt 2))   (torch.nn.GELU default; reference models/transformerblock.py:79)
+  // x * Phi(x), Phi(x) = 0.5 erfc(-x / sqrt 2)   (torch.nn.GELU default; reference models/transformerblock.py:79)
+  // erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1 / (1 + p z)   Abramowitz-Stegun 7.1.26,
+  // |error| < 1.5e-7.  q = 0.5 erfc(|x| / sqrt 2);  Phi = x < 0 ? q : 1 - q.
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = __expf(-z * z);
-  const float erf_abs = fmaf(-p, e, 1.0f);  // erf(|x|/sqrt2)
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
+  const float t = mufu_rcp(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  const float e = mufu_ex2((z * -1.4426950408889634f) * z);  // exp(-z^2)
+  const float q = (p * t) * e;
+  const float phi = (x < 0.f) ? q : 1.0f - q;
+  return x * phi;
 }
 
 __device__ __forceinline__ float gelu_tanh(float x) {
-  // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))   (HF "gelu_new", GPT-2 MLP)
-  const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
-  // tanh(u) = 1 - 2 / (1 + exp(2u)); exp overflow -> inf -> tanh = 1, underflow -> -1: both exact.
-  const float e = __expf(2.0f * u);
-  const float th = 1.0f - __fdividef(2.0f, 1.0f + e);
-  return 0.5f * x * (1.0f + th);
+  // 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3)   (HF "gelu_new", GPT-2 MLP)
+  // = x * sigmoid(2u) = x - x / (1 + exp(2u));  exp -> inf gives x, exp -> 0 gives 0: both limits exact.
+  const float k0 = 2.0f * 0.7978845608028654f * 1.4426950408889634f;  // 2 sqrt(2/pi) log2(e)
+  const float w = fmaf(k0 * 0.044715f, x * x, k0);
+  const float e = mufu_ex2(x * w);
+  const float r = mufu_rcp(1.0f + e);
+  return fmaf(-x, r, x);
 }
 
 // --------------------------------------------------------------------------------------------
-// Epilogue for one thread: one output row, 32 consecutive columns starting at n0.
+// Epilogue variants.  The combinations the forward path uses are compiled with their flags as
+// constants (the 8-row unrolled epilogue of the all-runtime version is ~60 KB of SASS and thrashes
+// the instruction cache - ncu: stall_no_inst dominated); EPI_GENERIC keeps every flag at run time
+// for the stateless afft_gemm() entry point.
+//   bit 0-1 activation, bit 2 residual, bit 3 fp32 output, bit 4 bf16 output (+ lo when SPLIT == 3)
 // --------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_row32(const GemmEpilogue& ep, float (&x)[32], int row, long long orow,
-                                               int n0, int N) {
-  const bool full = (n0 + 32 <= N);
+constexpr int EPI_GENERIC = -1;
+constexpr int epi_code(int act, bool res, bool f32, bool bf16) {
+  return act | (res ? 4 : 0) | (f32 ? 8 : 0) | (bf16 ? 16 : 0);
+}
+
+template <int EPI, int SPLIT>
+struct EpiFlags {
+  static constexpr bool kGeneric = EPI < 0;
+  __device__ static __forceinline__ int act(const GemmEpilogue& ep) { return kGeneric ? ep.act : (EPI & 3); }
+  __device__ static __forceinline__ bool res(const GemmEpilogue& ep) { return kGeneric ? ep.res != nullptr : (EPI & 4) != 0; }
+  __device__ static __forceinline__ bool f32(const GemmEpilogue& ep) { return kGeneric ? ep.out_f32 != nullptr : (EPI & 8) != 0; }
+  __device__ static __forceinline__ bool bf16(const GemmEpilogue& ep) { return kGeneric ? ep.out_hi != nullptr : (EPI & 16) != 0; }
+  __device__ static __forceinline__ bool lo(const GemmEpilogue& ep) { return kGeneric ? ep.out_lo != nullptr : (SPLIT == 3); }
+};
+
+__device__ __forceinline__ uint32_t pack2_bf16_rn(float a, float b) {  // a -> low half
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16_hi_f32(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
+
+template <int EPI, int SPLIT>
+__device__ __forceinline__ float4 epilogue_math(const GemmEpilogue& ep, float4 x, const float4& bias4) {
+  using F = EpiFlags<EPI, SPLIT>;
+  x.x += bias4.x;
+  x.y += bias4.y;
+  x.z += bias4.z;
+  x.w += bias4.w;
+  const int act = F::act(ep);
+  if (act == ACT_GELU_ERF) {
+    x.x = gelu_erf(x.x);
+    x.y = gelu_erf(x.y);
+    x.z = gelu_erf(x.z);
+    x.w = gelu_erf(x.w);
+  } else if (act == ACT_GELU_TANH) {
+    x.x = gelu_tanh(x.x);
+    x.y = gelu_tanh(x.y);
+    x.z = gelu_tanh(x.z);
+    x.w = gelu_tanh(x.w);
+  }
+  return x;
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 x;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr));
+  return x;
+}
+
+// One 32-row x 32-column slab, interior case: every row < M and every column < N, so no predicates.
+// Lane (sub_row, chunk) handles rows sub_row + 4 i (i < 8), columns col .. col + 3.
+template <int EPI, int SPLIT>
+__device__ __forceinline__ void epilogue_slab_full(const GemmEpilogue& ep, uint32_t stage, int sub_row, int chunk,
+                                                   int row0, int col, const long long (&orow)[8], const float4& bias4) {
+  using F = EpiFlags<EPI, SPLIT>;
+  float4 x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = i * 4 + sub_row;
+    x[i] = lds128(stage + static_cast<uint32_t>(rl) * 128u + static_cast<uint32_t>((chunk ^ (rl & 7)) * 16));
+  }
+  if (F::res(ep)) {
+    // all residual loads are issued before any store: the residual may alias the output (in-place stream)
+    float4 r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long rrow = (ep.res_mod > 0) ? static_cast<long long>((row0 + i * 4 + sub_row) % ep.res_mod) : orow[i];
+      r[i] = *reinterpret_cast<const float4*>(ep.res + rrow * ep.ld_res + col);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      x[i] = epilogue_math<EPI, SPLIT>(ep, x[i], bias4);
+      x[i].x += r[i].x;
+      x[i].y += r[i].y;
+      x[i].z += r[i].z;
+      x[i].w += r[i].w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = epilogue_math<EPI, SPLIT>(ep, x[i], bias4);
+  }
+  if (F::f32(ep)) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(ep.out_f32 + orow[i] * ep.ld_f32 + col) = x[i];
+  }
+  if (F::bf16(ep)) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t h01 = pack2_bf16_rn(x[i].x, x[i].y), h23 = pack2_bf16_rn(x[i].z, x[i].w);
+      *reinterpret_cast<uint2*>(ep.out_hi + orow[i] * ep.ld_bf16 + col) = make_uint2(h01, h23);
+      if (F::lo(ep)) {
+        const uint32_t l01 = pack2_bf16_rn(x[i].x - bf16_lo_f32(h01), x[i].y - bf16_hi_f32(h01));
+        const uint32_t l23 = pack2_bf16_rn(x[i].z - bf16_lo_f32(h23), x[i].w - bf16_hi_f32(h23));
+        *reinterpret_cast<uint2*>(ep.out_lo + orow[i] * ep.ld_bf16 + col) = make_uint2(l01, l23);
+      }
+    }
+  }
+}
+
+// Edge slab (partial rows and/or columns): element-wise predicates; kept out of line so the interior path
+// stays small in the instruction cache.
+template <int EPI, int SPLIT>
+__device__ __noinline__ void epilogue_slab_edge(const GemmEpilogue& ep, uint32_t stage, int sub_row, int chunk, int row0,
+                                                int col, int M, int N) {
+  using F = EpiFlags<EPI, SPLIT>;
+  if (col >= N) return;
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
   if (ep.bias != nullptr) {
-    if (full) {
-      const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b = __ldg(b4 + j);
-        x[4 * j + 0] += b.x;
-        x[4 * j + 1] += b.y;
-        x[4 * j + 2] += b.z;
-        x[4 * j + 3] += b.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < N) x[j] += __ldg(ep.bias + n0 + j);
-    }
+    for (int e = 0; e < 4; ++e)
+      if (col + e < N) bias[e] = __ldg(ep.bias + col + e);
   }
-  if (ep.act == ACT_GELU_ERF) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
-  } else if (ep.act == ACT_GELU_TANH) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = gelu_tanh(x[j]);
-  }
-  if (ep.res != nullptr) {
+  const float4 bias4 = make_float4(bias[0], bias[1], bias[2], bias[3]);
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    const int rl = i * 4 + sub_row;
+    const int row = row0 + rl;
+    if (row >= M) break;
+    long long orow = row;
+    if (ep.row_group > 0)
+      orow = static_cast<long long>(row / ep.row_group) * ep.row_stride + (row % ep.row_group) + ep.row_off;
+    float4 x4 = lds128(stage + static_cast<uint32_t>(rl) * 128u + static_cast<uint32_t>((chunk ^ (rl & 7)) * 16));
+    x4 = epilogue_math<EPI, SPLIT>(ep, x4, bias4);
+    float x[4] = {x4.x, x4.y, x4.z, x4.w};
     const long long rrow = (ep.res_mod > 0) ? static_cast<long long>(row % ep.res_mod) : orow;
-    const float* rp = ep.res + rrow * ep.ld_res + n0;
-    if (full) {
-      const float4* r4 = reinterpret_cast<const float4*>(rp);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 r = r4[j];
-        x[4 * j + 0] += r.x;
-        x[4 * j + 1] += r.y;
-        x[4 * j + 2] += r.z;
-        x[4 * j + 3] += r.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < N) x[j] += rp[j];
-    }
-  }
-  if (ep.out_f32 != nullptr) {
-    float* op = ep.out_f32 + orow * ep.ld_f32 + n0;
-    if (full) {
-      float4* o4 = reinterpret_cast<float4*>(op);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o4[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < N) op[j] = x[j];
-    }
-  }
-  if (ep.out_hi != nullptr) {
-    __nv_bfloat16* hp = ep.out_hi + orow * ep.ld_bf16 + n0;
-    __nv_bfloat16* lp = (ep.out_lo != nullptr) ? ep.out_lo + orow * ep.ld_bf16 + n0 : nullptr;
-    if (full) {
-      uint32_t hw[16], lw[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * j]);
-        const __nv_bfloat16 h1 = __float2bfloat16_rn(x[2 * j + 1]);
-        hw[j] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
-                (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * j] - __bfloat162float(h0));
-        const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * j + 1] - __bfloat162float(h1));
-        lw[j] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
-                (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
-      }
-      uint4* h4 = reinterpret_cast<uint4*>(hp);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) h4[j] = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
-      if (lp != nullptr) {
-        uint4* l4 = reinterpret_cast<uint4*>(lp);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) l4[j] = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (n0 + j < N) {
-          const __nv_bfloat16 h = __float2bfloat16_rn(x[j]);
-          hp[j] = h;
-          if (lp != nullptr) lp[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h));
-        }
+    for (int e = 0; e < 4; ++e) {
+      if (col + e >= N) break;
+      float v = x[e];
+      if (F::res(ep)) v += ep.res[rrow * ep.ld_res + col + e];
+      if (F::f32(ep)) ep.out_f32[orow * ep.ld_f32 + col + e] = v;
+      if (F::bf16(ep)) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        ep.out_hi[orow * ep.ld_bf16 + col + e] = h;
+        if (F::lo(ep)) ep.out_lo[orow * ep.ld_bf16 + col + e] = __float2bfloat16_rn(v - __bfloat162float(h));
       }
     }
   }
@@ -197,17 +272,18 @@ __device__ __forceinline__ void epilogue_row32(const GemmEpilogue& ep, float (&x
 // --------------------------------------------------------------------------------------------
 // The kernel
 // --------------------------------------------------------------------------------------------
-template <int BLOCK_N, int SPLIT>
+template <int BLOCK_N, int SPLIT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                          const __grid_constant__ CUtensorMap tm_a_lo,
                          const __grid_constant__ CUtensorMap tm_b_lo, const GemmEpilogue ep, const int M,
-                         const int N, const int K) {
+                         const int N, const int K, const GemmSched sched) {
   using T = GemmTraits<BLOCK_N, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_raw_u32 = ptx::smem_u32(smem_raw);
   const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;  // SWIZZLE_128B tiles: 1024-B aligned
-  const uint32_t bar_base = smem_base + T::kStages * T::kStageBytes;
+  const uint32_t staging_base = smem_base + T::kStages * T::kStageBytes;
+  const uint32_t bar_base = staging_base + T::kStagingBytes;
   auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
   auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (T::kStages + s); };
   auto tmem_full_bar = [&](uint32_t a) { return bar_base + 8u * (2 * T::kStages + a); };
@@ -238,7 +314,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     }
     for (uint32_t a = 0; a < 2; ++a) {
       ptx::mbar_init(tmem_full_bar(a), 1);   // tcgen05.commit
-      ptx::mbar_init(tmem_empty_bar(a), 4);  // one arrive per epilogue warp
+      ptx::mbar_init(tmem_empty_bar(a), kNumEpilogueWarps);  // one arrive per epilogue warp
     }
     ptx::fence_mbar_init();
   }
@@ -253,23 +329,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_idx = tile % num_m;
-        const int n_idx = tile / num_m;
+        const int m_idx = sched.n_fastest ? tile / num_n : tile % num_m;
+        const int n_idx = sched.n_fastest ? tile % num_n : tile / num_m;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * T::kStageBytes;
           const uint32_t b_dst = a_dst + T::kABytes;
           const uint32_t fb = full_bar(stage);
           ptx::mbar_arrive_expect_tx(fb, T::kStageBytes);
-          // Activations stream through once per n-tile column; weights are re-read by every
-          // m-tile: keep weights in L2 preferentially.
-          ptx::tma_load_2d(a_dst, &tm_a, fb, kb * kBlockK, m_idx * kBlockM, ptx::kEvictNormal);
-          ptx::tma_load_2d(b_dst, &tm_b, fb, kb * kBlockK, n_idx * BLOCK_N, ptx::kEvictLast);
+          ptx::tma_load_2d(a_dst, &tm_a, fb, kb * kBlockK, m_idx * kBlockM, sched.policy_a);
+          ptx::tma_load_2d(b_dst, &tm_b, fb, kb * kBlockK, n_idx * BLOCK_N, sched.policy_b);
           if (SPLIT == 3) {
             const uint32_t a_lo_dst = b_dst + T::kBBytes;
             const uint32_t b_lo_dst = a_lo_dst + T::kABytes;
-            ptx::tma_load_2d(a_lo_dst, &tm_a_lo, fb, kb * kBlockK, m_idx * kBlockM, ptx::kEvictNormal);
-            ptx::tma_load_2d(b_lo_dst, &tm_b_lo, fb, kb * kBlockK, n_idx * BLOCK_N, ptx::kEvictLast);
+            ptx::tma_load_2d(a_lo_dst, &tm_a_lo, fb, kb * kBlockK, m_idx * kBlockM, sched.policy_a);
+            ptx::tma_load_2d(b_lo_dst, &tm_b_lo, fb, kb * kBlockK, n_idx * BLOCK_N, sched.policy_b);
           }
           if (++stage == T::kStages) {
             stage = 0;
@@ -325,32 +399,56 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     }
   } else if (warp >= 4) {
     // ======================= epilogue =======================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // Two warps per TMEM lane quadrant (warp % 4), interleaved over the 32-column slabs of the tile.
+    // A slab is read from TMEM row-per-thread, transposed through a private swizzled smem tile, and
+    // leaves as fully coalesced 16-byte accesses: each warp instruction covers 4 rows x 128 B.
+    const int quad = warp & 3;
+    const int egrp = (warp - 4) >> 2;
+    const int sub_row = lane >> 3;  // row within a group of 4
+    const int chunk = lane & 7;     // 16-byte chunk = 4 fp32 columns
+    const uint32_t stage = staging_base + static_cast<uint32_t>(warp - 4) * 4096u;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_idx = tile % num_m;
-      const int n_idx = tile / num_m;
+      const int m_idx = sched.n_fastest ? tile / num_n : tile % num_m;
+      const int n_idx = sched.n_fastest ? tile % num_n : tile / num_m;
+      const int row0 = m_idx * kBlockM + quad * 32;
+      const bool rows_full = (row0 + 32 <= M);
+      long long orow[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = row0 + i * 4 + sub_row;
+        orow[i] = r;
+        if (ep.row_group > 0)
+          orow[i] = static_cast<long long>(r / ep.row_group) * ep.row_stride + (r % ep.row_group) + ep.row_off;
+      }
       ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
       ptx::tcgen05_fence_after();
-      const int row = m_idx * kBlockM + quad * 32 + lane;
-      const bool row_ok = row < M;
-      long long orow = row;
-      if (ep.row_group > 0)
-        orow = static_cast<long long>(row / ep.row_group) * ep.row_stride + (row % ep.row_group) + ep.row_off;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = egrp; c < BLOCK_N / 32; c += kNumEpilogueWarps / 4) {
         const int n0 = n_idx * BLOCK_N + c * 32;
         if (n0 >= N) break;  // warp-uniform
         uint32_t v[32];
         ptx::tmem_ld_32x32(t_row + c * 32, v);
         ptx::tmem_ld_wait();
-        if (row_ok) {
-          float x[32];
+        // own row (= lane) -> staging, 16-B chunk j at position j ^ (lane & 7): conflict-free
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-          epilogue_row32(ep, x, row, orow, n0, N);
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = stage + static_cast<uint32_t>(lane) * 128u + static_cast<uint32_t>((j ^ (lane & 7)) * 16);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * j]), "r"(v[4 * j + 1]),
+                       "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                       : "memory");
         }
+        __syncwarp();
+        const int col = n0 + chunk * 4;
+        if (rows_full && n0 + 32 <= N) {
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+          epilogue_slab_full<EPI, SPLIT>(ep, stage, sub_row, chunk, row0, col, orow, bias4);
+        } else {
+          epilogue_slab_edge<EPI, SPLIT>(ep, stage, sub_row, chunk, row0, col, M, N);
+        }
+        __syncwarp();  // staging tile is rewritten by the next slab
       }
       ptx::tcgen05_fence_before();
       __syncwarp();
