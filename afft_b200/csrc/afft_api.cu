@@ -126,15 +126,22 @@ static int run_layernorm(const LayerNormArgs& a, cudaStream_t stream) {
   if (a.x == nullptr || a.rows <= 0) return fail(AFFT_ERR_INVALID, "layernorm: bad argument");
   if (a.dim % 128 != 0) return fail(AFFT_ERR_INVALID, "layernorm: dim must be a multiple of 128");
   const int blocks = (a.rows + 7) / 8;  // 8 warps (rows) per 256-thread block
+  const bool avg = a.n_avg > 1;
+#define AFFT_LN(NV)                                                        \
+  case NV:                                                                 \
+    if (avg) layernorm_kernel<NV, true><<<blocks, 256, 0, stream>>>(a);   \
+    else layernorm_kernel<NV, false><<<blocks, 256, 0, stream>>>(a);      \
+    break;
   switch (a.dim / 128) {
-    case 2: layernorm_kernel<2><<<blocks, 256, 0, stream>>>(a); break;
-    case 4: layernorm_kernel<4><<<blocks, 256, 0, stream>>>(a); break;
-    case 6: layernorm_kernel<6><<<blocks, 256, 0, stream>>>(a); break;
-    case 8: layernorm_kernel<8><<<blocks, 256, 0, stream>>>(a); break;
-    case 12: layernorm_kernel<12><<<blocks, 256, 0, stream>>>(a); break;
-    case 16: layernorm_kernel<16><<<blocks, 256, 0, stream>>>(a); break;
+    AFFT_LN(2)
+    AFFT_LN(4)
+    AFFT_LN(6)
+    AFFT_LN(8)
+    AFFT_LN(12)
+    AFFT_LN(16)
     default: return fail(AFFT_ERR_INVALID, "layernorm: unsupported dim (256, 512, 768, 1024, 1536, 2048)");
   }
+#undef AFFT_LN
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail("layernorm launch", e);
   return AFFT_OK;
@@ -189,11 +196,31 @@ static int launch_attention(const AttentionArgs& a, cudaStream_t stream) {
   return AFFT_OK;
 }
 
+template <typename TIn>
+static int launch_attention_tokens(const AttentionArgs& a, cudaStream_t stream) {
+  const int warps = a.n_seq * a.H;
+  const int blocks = (warps + 3) / 4;
+  switch (a.L) {
+    case 2: attention_tokens_kernel<TIn, 2><<<blocks, 128, 0, stream>>>(a); break;
+    case 3: attention_tokens_kernel<TIn, 3><<<blocks, 128, 0, stream>>>(a); break;
+    case 4: attention_tokens_kernel<TIn, 4><<<blocks, 128, 0, stream>>>(a); break;
+    case 5: attention_tokens_kernel<TIn, 5><<<blocks, 128, 0, stream>>>(a); break;
+    case 6: attention_tokens_kernel<TIn, 6><<<blocks, 128, 0, stream>>>(a); break;
+    default: return fail(AFFT_ERR_INVALID, "attention_tokens: L must be in [2, 6]");
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("attention_tokens launch", e);
+  return AFFT_OK;
+}
+
 static int run_attention(const AttentionArgs& a, int head_dim, bool in_f32, cudaStream_t stream) {
   if (a.q == nullptr || a.k == nullptr || a.v == nullptr || a.out_hi == nullptr)
     return fail(AFFT_ERR_INVALID, "attention: null pointer");
   if (a.L < 1 || a.L > 64) return fail(AFFT_ERR_INVALID, "attention: sequence length must be in [1, 64]");
   if (a.n_seq <= 0 || a.H <= 0) return fail(AFFT_ERR_INVALID, "attention: empty problem");
+  // few modality tokens per timestep (SA-Fuser): register-resident warp-per-(timestep, head) kernel
+  if (head_dim == 256 && a.L >= 2 && a.L <= 6 && (a.mask == 0 || a.mask == 3))
+    return in_f32 ? launch_attention_tokens<float>(a, stream) : launch_attention_tokens<bf16>(a, stream);
   if (head_dim == 256) return in_f32 ? launch_attention<float, 256>(a, stream) : launch_attention<bf16, 256>(a, stream);
   if (head_dim == 512) return in_f32 ? launch_attention<float, 512>(a, stream) : launch_attention<bf16, 512>(a, stream);
   return fail(AFFT_ERR_INVALID, "attention: head_dim must be 256 or 512");

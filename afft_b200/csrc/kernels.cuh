@@ -108,7 +108,26 @@ struct LayerNormArgs {
   long long ld_aux;
 };
 
-template <int NV>  // NV float4 per lane: dim = 128 * NV
+__device__ __forceinline__ void ln_store(const LayerNormArgs& a, int row, bool aux, long long arow, int c4, const float4& y) {
+  const uint2 hi = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+  if (a.y_f32 != nullptr) reinterpret_cast<float4*>(a.y_f32 + row * a.ldy)[c4] = y;
+  if (a.y_hi != nullptr) reinterpret_cast<uint2*>(a.y_hi + row * a.ldy)[c4] = hi;
+  if (a.y_lo != nullptr)
+    reinterpret_cast<uint2*>(a.y_lo + row * a.ldy)[c4] =
+        make_uint2(pack_bf16x2(bf16_residual(y.x), bf16_residual(y.y)), pack_bf16x2(bf16_residual(y.z), bf16_residual(y.w)));
+  if (aux) {
+    if (a.aux_f32 != nullptr) reinterpret_cast<float4*>(a.aux_f32 + arow * a.ld_aux)[c4] = y;
+    if (a.aux_hi != nullptr) reinterpret_cast<uint2*>(a.aux_hi + arow * a.ld_aux)[c4] = hi;
+    if (a.aux_lo != nullptr)
+      reinterpret_cast<uint2*>(a.aux_lo + arow * a.ld_aux)[c4] =
+          make_uint2(pack_bf16x2(bf16_residual(y.x), bf16_residual(y.y)), pack_bf16x2(bf16_residual(y.z), bf16_residual(y.w)));
+  }
+}
+
+// NV float4 per lane: dim = 128 * NV.  AVG = false: plain LayerNorm of one row per warp (the hot case: the row
+// lives in NV float4 registers, one 16-B load per lane per 512 B, all loads in flight before the reductions).
+// AVG = true: mean over n_avg normalised rows (CMFuser / T-SA-Fuser without frame-level token).
+template <int NV, bool AVG>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs a) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -118,15 +137,19 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs a) {
   const float inv_d = 1.0f / static_cast<float>(a.dim);
   const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
   const float4* b4 = reinterpret_cast<const float4*>(a.beta);
-  const int n_avg = a.n_avg > 1 ? a.n_avg : 1;
-  float4 acc[NV];
+  const bool aux = a.aux_mod > 0 && (warp % a.aux_mod) == 0;
+  const long long arow = aux ? static_cast<long long>(warp / a.aux_mod) * a.aux_stride : 0;
+  const int n_avg = (AVG && a.n_avg > 1) ? a.n_avg : 1;
+  float4 acc[AVG ? NV : 1];
+  if (AVG) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < NV; ++i) acc[AVG ? i : 0] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int sl = 0; sl < n_avg; ++sl) {
     const float4* xr = reinterpret_cast<const float4*>(a.x + (irow + static_cast<long long>(sl) * a.avg_stride) * a.ldx);
     float4 v[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+    for (int i = 0; i < NV; ++i) v[i] = __ldg(xr + lane + 32 * i);
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -144,32 +167,26 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs a) {
       float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
       if (a.gamma != nullptr) g = __ldg(g4 + c4);
       if (a.beta != nullptr) b = __ldg(b4 + c4);
-      acc[i].x += (v[i].x - mean) * rstd * g.x + b.x;
-      acc[i].y += (v[i].y - mean) * rstd * g.y + b.y;
-      acc[i].z += (v[i].z - mean) * rstd * g.z + b.z;
-      acc[i].w += (v[i].w - mean) * rstd * g.w + b.w;
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g.x + b.x;
+      y.y = (v[i].y - mean) * rstd * g.y + b.y;
+      y.z = (v[i].z - mean) * rstd * g.z + b.z;
+      y.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (AVG) {
+        float4& t = acc[AVG ? i : 0];
+        t.x += y.x; t.y += y.y; t.z += y.z; t.w += y.w;
+      } else {
+        ln_store(a, warp, aux, arow, c4, y);
+      }
     }
   }
-  const float inv_avg = 1.0f / static_cast<float>(n_avg);
-  const bool aux = a.aux_mod > 0 && (warp % a.aux_mod) == 0;
-  const long long arow = aux ? static_cast<long long>(warp / a.aux_mod) * a.aux_stride : 0;
+  if (AVG) {
+    const float inv_avg = 1.0f / static_cast<float>(n_avg);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c4 = lane + 32 * i;  // float4 index within the row
-    float4 y = acc[i];
-    if (n_avg > 1) {
+    for (int i = 0; i < NV; ++i) {
+      float4 y = acc[AVG ? i : 0];
       y.x *= inv_avg; y.y *= inv_avg; y.z *= inv_avg; y.w *= inv_avg;
-    }
-    const uint2 hi = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
-    const uint2 lo = make_uint2(pack_bf16x2(bf16_residual(y.x), bf16_residual(y.y)),
-                                pack_bf16x2(bf16_residual(y.z), bf16_residual(y.w)));
-    if (a.y_f32 != nullptr) reinterpret_cast<float4*>(a.y_f32 + warp * a.ldy)[c4] = y;
-    if (a.y_hi != nullptr) reinterpret_cast<uint2*>(a.y_hi + warp * a.ldy)[c4] = hi;
-    if (a.y_lo != nullptr) reinterpret_cast<uint2*>(a.y_lo + warp * a.ldy)[c4] = lo;
-    if (aux) {
-      if (a.aux_f32 != nullptr) reinterpret_cast<float4*>(a.aux_f32 + arow * a.ld_aux)[c4] = y;
-      if (a.aux_hi != nullptr) reinterpret_cast<uint2*>(a.aux_hi + arow * a.ld_aux)[c4] = hi;
-      if (a.aux_lo != nullptr) reinterpret_cast<uint2*>(a.aux_lo + arow * a.ld_aux)[c4] = lo;
+      ln_store(a, warp, aux, arow, lane + 32 * i, y);
     }
   }
 }
@@ -392,6 +409,98 @@ __global__ void __launch_bounds__(256) attention_small_kernel(const AttentionArg
         }
       }
     }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// SA-Fuser attention: L <= 6 modality tokens per timestep, head_dim 256 (reference models/fusion.py:358-360 ->
+// transformerblock.py:24-33).  One warp per (timestep, head), everything in registers: the 3 L rows of the head
+// (q, k, v) are fetched with 16-byte loads that are all in flight before the first use, the L x L scores are
+// reduced with warp shuffles, softmax in fp32, P.V accumulated in registers.  No shared memory, no block sync.
+// ------------------------------------------------------------------------------------------------
+template <typename TIn, int HD>
+__device__ __forceinline__ void store_row_regs(__nv_bfloat16* out_hi, __nv_bfloat16* out_lo, long long off, int lane,
+                                               const float (&o)[HD / 32]) {
+  using A = AttnTraits<TIn, HD>;
+#pragma unroll
+  for (int c = 0; c < A::kNV; ++c) {
+    constexpr int VE = A::kVecElems;
+    const int d0 = c * A::kChunkElems + lane * VE;
+    if constexpr (VE == 8) {
+      const float* oo = &o[c * 8];
+      *reinterpret_cast<uint4*>(out_hi + off + d0) = make_uint4(pack_bf16x2(oo[0], oo[1]), pack_bf16x2(oo[2], oo[3]),
+                                                                 pack_bf16x2(oo[4], oo[5]), pack_bf16x2(oo[6], oo[7]));
+      if (out_lo != nullptr)
+        *reinterpret_cast<uint4*>(out_lo + off + d0) =
+            make_uint4(pack_bf16x2(bf16_residual(oo[0]), bf16_residual(oo[1])), pack_bf16x2(bf16_residual(oo[2]), bf16_residual(oo[3])),
+                       pack_bf16x2(bf16_residual(oo[4]), bf16_residual(oo[5])), pack_bf16x2(bf16_residual(oo[6]), bf16_residual(oo[7])));
+    } else {
+      const float* oo = &o[c * 4];
+      *reinterpret_cast<uint2*>(out_hi + off + d0) = make_uint2(pack_bf16x2(oo[0], oo[1]), pack_bf16x2(oo[2], oo[3]));
+      if (out_lo != nullptr)
+        *reinterpret_cast<uint2*>(out_lo + off + d0) =
+            make_uint2(pack_bf16x2(bf16_residual(oo[0]), bf16_residual(oo[1])), pack_bf16x2(bf16_residual(oo[2]), bf16_residual(oo[3])));
+    }
+  }
+}
+
+template <typename TIn, int L>
+__global__ void __launch_bounds__(128) attention_tokens_kernel(const AttentionArgs a) {
+  constexpr int HD = 256;
+  constexpr int PL = HD / 32;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= a.n_seq * a.H) return;
+  const int lane = threadIdx.x & 31;
+  const int seq = gw / a.H, h = gw % a.H;
+  const TIn* qg = reinterpret_cast<const TIn*>(a.q) + static_cast<long long>(seq) * L * a.ldq + h * HD;
+  const TIn* kg = reinterpret_cast<const TIn*>(a.k) + static_cast<long long>(seq) * L * a.ldk + h * HD;
+  const TIn* vg = reinterpret_cast<const TIn*>(a.v) + static_cast<long long>(seq) * L * a.ldv + h * HD;
+  float q[L][PL], k[L][PL], v[L][PL];
+#pragma unroll
+  for (int i = 0; i < L; ++i) load_row_regs<TIn, HD>(qg + static_cast<long long>(i) * a.ldq, lane, q[i]);
+#pragma unroll
+  for (int i = 0; i < L; ++i) load_row_regs<TIn, HD>(kg + static_cast<long long>(i) * a.ldk, lane, k[i]);
+#pragma unroll
+  for (int i = 0; i < L; ++i) load_row_regs<TIn, HD>(vg + static_cast<long long>(i) * a.ldv, lane, v[i]);
+  float* pr = nullptr;
+  if (a.probs != nullptr)
+    pr = a.probs + static_cast<long long>(seq / a.p_inner) * a.p_outer +
+         static_cast<long long>(seq % a.p_inner) * a.p_inner_stride + static_cast<long long>(h) * L * L;
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    float s[L];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      float d = 0.f;
+#pragma unroll
+      for (int e = 0; e < PL; ++e) d = fmaf(q[i][e], k[j][e], d);
+      d = warp_sum(d) * a.scale;
+      if (a.mask == 3 && j == i) d = -INFINITY;  // diagonal masked (cross_attn=True)
+      s[j] = d;
+      mx = fmaxf(mx, d);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      s[j] = (s[j] == -INFINITY) ? 0.f : expf(s[j] - mx);
+      sum += s[j];
+    }
+    const float inv = 1.0f / sum;
+    float o[PL];
+#pragma unroll
+    for (int e = 0; e < PL; ++e) o[e] = 0.f;
+    float mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      const float p = s[j] * inv;
+      if (lane == j) mine = p;
+#pragma unroll
+      for (int e = 0; e < PL; ++e) o[e] = fmaf(p, v[j][e], o[e]);
+    }
+    if (pr != nullptr && lane < L) pr[i * L + lane] = mine;
+    store_row_regs<TIn, HD>(a.out_hi, a.out_lo, (static_cast<long long>(seq) * L + i) * a.ldo + h * HD, lane, o);
   }
 }
 

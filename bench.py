@@ -314,7 +314,11 @@ def run_afft(args):
     for i in range(PSTEPS):
         step(i)
         torch.cuda.synchronize()
-        for cat, M, N, K, ms in eng.profile_read():
+        recs = eng.profile_read()
+        if args.verbose and rank == 0 and i == PSTEPS - 1:
+            names = {0: "gemm", 1: "ln", 2: "attn", 3: "other"}
+            print("[launches] " + " ".join(f"{names[c]}:{ms * 1e3:.0f}" for c, _, _, _, ms in recs), file=sys.stderr)
+        for cat, M, N, K, ms in recs:
             agg[cat][0] += ms
             agg[cat][1] += 1
             if cat == 0:
