@@ -90,6 +90,28 @@ inline cudaError_t launch_gemm_variant(const CUtensorMap& ta, const CUtensorMap&
   return cudaGetLastError();
 }
 
+template <int SPLIT, int EPI>
+inline cudaError_t launch_gemm_2cta_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal,
+                                            const CUtensorMap& tbl, const GemmEpilogue& ep, int M, int N, int K,
+                                            int num_sms, const GemmSched& sched, cudaStream_t stream) {
+  using T = Gemm2Traits<SPLIT>;
+  auto kern = gemm_bf16_tcgen05_2cta_kernel<SPLIT, EPI>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  const int num_tiles = ((M + 255) / 256) * ((N + 255) / 256);
+  int clusters = num_sms / 2;
+  if (num_tiles < clusters) clusters = num_tiles;
+  kern<<<2 * clusters, kGemmThreads, T::kSmemBytes, stream>>>(ta, tb, tal, tbl, ep, M, N, K, sched);  // __cluster_dims__(2)
+  return cudaGetLastError();
+}
+
 inline int pick_block_n(int M, int N, int num_sms, int forced) {
   if (forced == 128 || forced == 256) return forced;
   // Fewest waves wins; ties go to the 256-wide tile (less A re-streaming through shared memory).
@@ -141,13 +163,18 @@ inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, bool stri
     if (err) *err = "gemm: epilogue pointers must be 16-B aligned with 16-B multiple pitches";
     return false;
   }
-  const int bn = pick_block_n(g.M, g.N, num_sms, force_block_n);
+  int bn = pick_block_n(g.M, g.N, num_sms, force_block_n);
+  // CTA pairs (cta_group::2, 256 x 256 tiles) whenever the 256-wide tile is chosen and there is enough work
+  static const int use_2cta_env = [] { const char* v = getenv("AFFT_GEMM_2CTA"); return v == nullptr ? 1 : atoi(v); }();
+  const bool use_2cta = (force_block_n == 512) || (use_2cta_env != 0 && force_block_n == 0 && bn == 256 && g.M > 128);
+  if (force_block_n == 512) bn = 256;
+  const int b_box_rows = use_2cta ? 128 : bn;  // each CTA of a pair loads half of the 256-row weight tile
   CUtensorMap ta, tb, tal, tbl;
   if (!make_tmap_bf16(&ta, g.a, g.M, g.K, g.lda, kBlockM, err)) return false;
-  if (!make_tmap_bf16(&tb, g.w, g.N, g.K, g.ldw, bn, err)) return false;
+  if (!make_tmap_bf16(&tb, g.w, g.N, g.K, g.ldw, b_box_rows, err)) return false;
   if (strict) {
     if (!make_tmap_bf16(&tal, g.a_lo, g.M, g.K, g.lda, kBlockM, err)) return false;
-    if (!make_tmap_bf16(&tbl, g.w_lo, g.N, g.K, g.ldw, bn, err)) return false;
+    if (!make_tmap_bf16(&tbl, g.w_lo, g.N, g.K, g.ldw, b_box_rows, err)) return false;
   } else {
     tal = ta;
     tbl = tb;
@@ -156,7 +183,9 @@ inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, bool stri
   const int code = epi_code(ep.act, ep.res != nullptr, ep.out_f32 != nullptr, ep.out_hi != nullptr);
   const bool lo_ok = (ep.out_hi == nullptr) || ((ep.out_lo != nullptr) == strict);  // specialised kernels tie lo to SPLIT
   cudaError_t e = cudaErrorInvalidValue;
-#define AFFT_LAUNCH(BN, SP, EP) e = launch_gemm_variant<BN, SP, EP>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, default_sched(), stream)
+#define AFFT_LAUNCH(BN, SP, EP)                                                                                       \
+  e = (BN == 512) ? launch_gemm_2cta_variant<SP, EP>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, default_sched(), stream) \
+                  : launch_gemm_variant<(BN == 512 ? 256 : BN), SP, EP>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, default_sched(), stream)
 #define AFFT_DISPATCH_EPI(BN, SP)                                                            \
   do {                                                                                       \
     if (!lo_ok) { AFFT_LAUNCH(BN, SP, EPI_GENERIC); break; }                                 \
@@ -171,9 +200,9 @@ inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, bool stri
     }                                                                                        \
   } while (0)
   if (strict) {
-    if (bn == 256) AFFT_DISPATCH_EPI(256, 3); else AFFT_DISPATCH_EPI(128, 3);
+    if (use_2cta) AFFT_DISPATCH_EPI(512, 3); else if (bn == 256) AFFT_DISPATCH_EPI(256, 3); else AFFT_DISPATCH_EPI(128, 3);
   } else {
-    if (bn == 256) AFFT_DISPATCH_EPI(256, 1); else AFFT_DISPATCH_EPI(128, 1);
+    if (use_2cta) AFFT_DISPATCH_EPI(512, 1); else if (bn == 256) AFFT_DISPATCH_EPI(256, 1); else AFFT_DISPATCH_EPI(128, 1);
   }
 #undef AFFT_DISPATCH_EPI
 #undef AFFT_LAUNCH

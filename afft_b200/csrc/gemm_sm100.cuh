@@ -466,4 +466,227 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   }
 }
 
+
+// --------------------------------------------------------------------------------------------
+// 2-CTA variant: a CTA pair (cluster of 2 = the two SMs of a TPC) computes one 256 x 256 tile with
+// tcgen05.mma.cta_group::2 (M = 256).  Each CTA loads its own 128 rows of A and HALF of the B tile
+// (128 of the 256 weight rows), so a K slab costs 32 KB of L2->SM traffic per SM instead of 48 KB:
+// the main loop of the 1-CTA kernel is bound by that traffic (96 B/clk/SM at full tensor rate).
+//   - both CTAs run a TMA producer; all transaction bytes are signalled on the LEADER's full barrier
+//   - the leader's MMA thread issues for the pair; tcgen05.commit multicasts the slot-free / accumulator-ready
+//     arrivals to both CTAs
+//   - each CTA's epilogue warps drain their own 128 x 256 TMEM accumulator and arrive (remotely for the peer)
+//     on the leader's tmem-empty barrier
+// --------------------------------------------------------------------------------------------
+template <int SPLIT>
+struct Gemm2Traits {
+  static constexpr int kPairs = (SPLIT == 3) ? 2 : 1;
+  static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;       // 128 rows of A
+  static constexpr uint32_t kBBytes = 128 * kBlockK * 2;           // this CTA's half of the 256-row B tile
+  static constexpr uint32_t kStageBytes = kPairs * (kABytes + kBBytes);
+  static constexpr int kStages = (SPLIT == 3) ? 3 : 6;
+  static constexpr uint32_t kTmemCols = 512;                       // 2 accumulators x 256 columns
+  static constexpr uint32_t kBarrierBytes = 256;
+  static constexpr uint32_t kStagingBytes = kNumEpilogueWarps * 4096;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
+};
+
+template <int SPLIT, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                              const __grid_constant__ CUtensorMap tm_a_lo,
+                              const __grid_constant__ CUtensorMap tm_b_lo, const GemmEpilogue ep, const int M,
+                              const int N, const int K, const GemmSched sched) {
+  using T = Gemm2Traits<SPLIT>;
+  constexpr int BLOCK_N = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_raw_u32 = ptx::smem_u32(smem_raw);
+  const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
+  const uint32_t staging_base = smem_base + T::kStages * T::kStageBytes;
+  const uint32_t bar_base = staging_base + T::kStagingBytes;
+  auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (T::kStages + s); };
+  auto tmem_full_bar = [&](uint32_t a) { return bar_base + 8u * (2 * T::kStages + a); };
+  auto tmem_empty_bar = [&](uint32_t a) { return bar_base + 8u * (2 * T::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * T::kStages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();  // 0 = leader
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_m = (M + 255) / 256;
+  const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + kBlockK - 1) / kBlockK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_a);
+    ptx::prefetch_tensormap(&tm_b);
+    if (SPLIT == 3) {
+      ptx::prefetch_tensormap(&tm_a_lo);
+      ptx::prefetch_tensormap(&tm_b_lo);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (uint32_t s = 0; s < T::kStages; ++s) {
+      ptx::mbar_init(full_bar(s), 2);   // leader's arrive.expect_tx + the peer producer's remote arrive
+      ptx::mbar_init(empty_bar(s), 1);  // tcgen05.commit (multicast from the leader)
+    }
+    for (uint32_t a = 0; a < 2; ++a) {
+      ptx::mbar_init(tmem_full_bar(a), 1);                        // tcgen05.commit (multicast)
+      ptx::mbar_init(tmem_empty_bar(a), 2 * kNumEpilogueWarps);   // epilogue warps of both CTAs
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc_2cta<T::kTmemCols>(tmem_slot);
+  ptx::tcgen05_fence_before();
+  ptx::cluster_sync();  // barriers of both CTAs initialised before any remote arrive / multicast commit
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ======================= TMA producer (both CTAs) =======================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_idx = sched.n_fastest ? tile / num_n : tile % num_m;
+        const int n_idx = sched.n_fastest ? tile % num_n : tile / num_m;
+        const int a_row = m_idx * 256 + static_cast<int>(rank) * 128;
+        const int b_row = n_idx * BLOCK_N + static_cast<int>(rank) * 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = smem_base + stage * T::kStageBytes;
+          const uint32_t b_dst = a_dst + T::kABytes;
+          const uint32_t fb_leader = ptx::mapa(full_bar(stage), 0);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * T::kStageBytes);
+          else ptx::mbar_arrive_cluster(fb_leader);
+          ptx::tma_load_2d_2cta(a_dst, &tm_a, fb_leader, kb * kBlockK, a_row, sched.policy_a);
+          ptx::tma_load_2d_2cta(b_dst, &tm_b, fb_leader, kb * kBlockK, b_row, sched.policy_b);
+          if (SPLIT == 3) {
+            const uint32_t a_lo_dst = b_dst + T::kBBytes;
+            const uint32_t b_lo_dst = a_lo_dst + T::kABytes;
+            ptx::tma_load_2d_2cta(a_lo_dst, &tm_a_lo, fb_leader, kb * kBlockK, a_row, sched.policy_a);
+            ptx::tma_load_2d_2cta(b_lo_dst, &tm_b_lo, fb_leader, kb * kBlockK, b_row, sched.policy_b);
+          }
+          if (++stage == T::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (leader CTA only) =======================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(256, BLOCK_N);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        ptx::mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+        ptx::tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tcgen05_fence_after();
+          const uint32_t a_src = smem_base + stage * T::kStageBytes;
+          const uint32_t b_src = a_src + T::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            ptx::umma_bf16_ss_2cta(d_tmem, ptx::make_smem_desc_sw128(a_src + k * (kUmmaK * 2)),
+                                   ptx::make_smem_desc_sw128(b_src + k * (kUmmaK * 2)), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if (SPLIT == 3) {
+            const uint32_t a_lo_src = b_src + T::kBBytes;
+            const uint32_t b_lo_src = a_lo_src + T::kABytes;
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              ptx::umma_bf16_ss_2cta(d_tmem, ptx::make_smem_desc_sw128(a_src + k * (kUmmaK * 2)),
+                                     ptx::make_smem_desc_sw128(b_lo_src + k * (kUmmaK * 2)), idesc, 1u);
+            }
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              ptx::umma_bf16_ss_2cta(d_tmem, ptx::make_smem_desc_sw128(a_lo_src + k * (kUmmaK * 2)),
+                                     ptx::make_smem_desc_sw128(b_src + k * (kUmmaK * 2)), idesc, 1u);
+            }
+          }
+          ptx::umma_commit_2cta(empty_bar(stage), 0b11);  // frees the slot in both CTAs
+          if (++stage == T::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        ptx::umma_commit_2cta(tmem_full_bar(acc), 0b11);  // accumulators of both CTAs complete
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================= epilogue (both CTAs, own 128 rows) =======================
+    const int quad = warp & 3;
+    const int egrp = (warp - 4) >> 2;
+    const int sub_row = lane >> 3;
+    const int chunk = lane & 7;
+    const uint32_t stage = staging_base + static_cast<uint32_t>(warp - 4) * 4096u;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_idx = sched.n_fastest ? tile / num_n : tile % num_m;
+      const int n_idx = sched.n_fastest ? tile % num_n : tile / num_m;
+      const int row0 = m_idx * 256 + static_cast<int>(rank) * 128 + quad * 32;
+      const bool rows_full = (row0 + 32 <= M);
+      long long orow[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = row0 + i * 4 + sub_row;
+        orow[i] = r;
+        if (ep.row_group > 0)
+          orow[i] = static_cast<long long>(r / ep.row_group) * ep.row_stride + (r % ep.row_group) + ep.row_off;
+      }
+      ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
+      ptx::tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c = egrp; c < BLOCK_N / 32; c += kNumEpilogueWarps / 4) {
+        const int n0 = n_idx * BLOCK_N + c * 32;
+        if (n0 >= N) break;
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(t_row + c * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = stage + static_cast<uint32_t>(lane) * 128u + static_cast<uint32_t>((j ^ (lane & 7)) * 16);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * j]), "r"(v[4 * j + 1]),
+                       "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                       : "memory");
+        }
+        __syncwarp();
+        const int col = n0 + chunk * 4;
+        if (row0 < M) {
+          if (rows_full && n0 + 32 <= N) {
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ep.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+            epilogue_slab_full<EPI, SPLIT>(ep, stage, sub_row, chunk, row0, col, orow, bias4);
+          } else {
+            epilogue_slab_edge<EPI, SPLIT>(ep, stage, sub_row, chunk, row0, col, M, N);
+          }
+        }
+        __syncwarp();
+      }
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(tmem_empty_bar(acc), 0));
+      acc ^= 1u;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  ptx::tcgen05_fence_before();
+  ptx::cluster_sync();  // the peer may still be arriving on / reading this CTA's shared memory and TMEM
+  if (warp == 2) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc_2cta<T::kTmemCols>(tmem_base);
+  }
+}
+
 }  // namespace afft

@@ -11,7 +11,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["gemm_basic", "gemm_shapes", "gemm_epilogue", "gemm_strict", "layernorm", "attention", "gemm_perf"]
+GROUPS = ["gemm_2cta", "gemm_basic", "gemm_shapes", "gemm_epilogue", "gemm_strict", "layernorm", "attention", "gemm_perf"]
 
 
 def _ref_mm(a, w):
@@ -35,8 +35,10 @@ def run_group(name):
             rec.update(extra)
         print(json.dumps(rec), flush=True)
 
-    if name in ("gemm_basic", "gemm_shapes"):
-        shapes = [(128, 128, 64, 128), (128, 256, 64, 256), (128, 256, 128, 256), (256, 512, 1024, 256)] if name == "gemm_basic" else [
+    if name in ("gemm_basic", "gemm_shapes", "gemm_2cta"):
+        shapes = [(256, 256, 64, 512), (256, 256, 128, 512), (256, 512, 1024, 512), (1000, 1024, 1024, 512), (300, 3806, 1024, 512),
+                  (131, 106, 1024, 512), (576, 1024, 352, 512), (4608, 2048, 8192, 512), (23040, 3072, 1024, 512),
+                  (18, 2048, 1024, 512)] if name == "gemm_2cta" else [(128, 128, 64, 128), (128, 256, 64, 256), (128, 256, 128, 256), (256, 512, 1024, 256)] if name == "gemm_basic" else [
             (1000, 1024, 1024, 0), (90, 3072, 1024, 0), (18, 2048, 1024, 0), (576, 1024, 352, 0), (300, 3806, 1024, 0),
             (5760, 1024, 4096, 0), (4608, 8192, 2048, 256), (4608, 2048, 8192, 128), (23040, 3072, 1024, 0), (131, 106, 1024, 0)]
         for (M, N, K, bn) in shapes:
@@ -213,7 +215,7 @@ def run_group(name):
             print(json.dumps({"group": name, "case": f"M{M}_N{N}_K{K}_bn{bn}_{'strict' if strict else 'bf16'}_{epi}",
                               "ms": round(ms, 4), "tflops": round(tf, 1), "cublas_ms": round(ms_ref, 4),
                               "cublas_tflops": round(2.0 * M * N * K / ms_ref / 1e9, 1), "ok": True}), flush=True)
-        for bn in (256, 128):
+        for bn in (512, 256):
             bench(23040, 3072, 1024, bn)
             bench(23040, 4096, 1024, bn, epi="gelu")
             bench(23040, 1024, 4096, bn, epi="res")
@@ -222,8 +224,9 @@ def run_group(name):
             bench(4608, 2048, 8192, bn, epi="res")
             bench(4608, 6144, 2048, bn)
         bench(8192, 8192, 8192, 256)
+        bench(8192, 8192, 8192, 512)
         bench(23040, 4096, 1024, 256, strict=True)
-        bench(23040, 4096, 1024, 128, strict=True)
+        bench(23040, 4096, 1024, 512, strict=True)
     else:
         raise SystemExit(f"unknown group {name}")
 
