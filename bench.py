@@ -327,6 +327,11 @@ def run_afft(args):
                 s[0] += ms
                 s[1] += 1
     eng.profile_enable(False)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(tpath) and args.config == "ek100_sa_tsn" and B == 256 and not args.strict:
+        with open(tpath) as f:  # dram read+write bytes per GEMM launch from the committed ncu capture of this workload
+            traffic = round(json.load(f)["traffic_bytes_per_launch_avg"])
     gemm_ms = agg[0][0]
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     kernel_ms_total = sum(v[0] for v in agg.values())
@@ -344,10 +349,11 @@ def run_afft(args):
         "launches_per_step": launches_per_fwd,
         "clocks": sampler.summary(),
         "roofline": {
-            "bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": round(achieved, 1),
+            "bound": "tensor", "kernel": "gemm_bf16_tcgen05_2cta_kernel / gemm_bf16_tcgen05_kernel", "achieved": round(achieved, 1),
             "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": round(achieved / peaks["sustained"], 4),
             "peak_kind": "bf16_tflops_sustained, " + peaks["source"], "frac_of_burst": round(achieved / peaks["burst"], 4),
-            "traffic": None,
+            "traffic": traffic, "traffic_note": "dram bytes per GEMM launch, avg over the 52 launches of a forward (profiles/r01_gemm_traffic.json)",
+            "algorithmic_flop_per_launch_avg": round(gemm_flops / max(1, agg[0][1])),
             "launches_per_step": agg[0][1] // PSTEPS, "gemm_ms_per_step": round(gemm_ms / PSTEPS, 4),
             "gemm_share_of_kernel_time": round(gemm_ms / kernel_ms_total, 4) if kernel_ms_total else None,
             "whole_step_tflops": round(step_tflops, 1), "whole_step_frac": round(step_tflops / peaks["sustained"], 4),
