@@ -213,6 +213,25 @@ static int launch_attention_tokens(const AttentionArgs& a, cudaStream_t stream) 
   return AFFT_OK;
 }
 
+template <int HD>
+static int launch_attention_mma(const AttentionArgs& a, cudaStream_t stream) {
+  auto kern = attention_mma_kernel<HD>;
+  constexpr int smem = AttnMmaSmem<HD>::kBytes;
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_fail("attention_mma smem attribute", e);
+    configured[dev] = true;
+  }
+  kern<<<a.n_seq * a.H, 128, smem, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("attention_mma launch", e);
+  return AFFT_OK;
+}
+
 static int run_attention(const AttentionArgs& a, int head_dim, bool in_f32, cudaStream_t stream) {
   if (a.q == nullptr || a.k == nullptr || a.v == nullptr || a.out_hi == nullptr)
     return fail(AFFT_ERR_INVALID, "attention: null pointer");
@@ -221,6 +240,12 @@ static int run_attention(const AttentionArgs& a, int head_dim, bool in_f32, cuda
   // few modality tokens per timestep (SA-Fuser): register-resident warp-per-(timestep, head) kernel
   if (head_dim == 256 && a.L >= 2 && a.L <= 6 && (a.mask == 0 || a.mask == 3))
     return in_f32 ? launch_attention_tokens<float>(a, stream) : launch_attention_tokens<bf16>(a, stream);
+  // short sequences with bf16 inputs (GPT-2 predictor, CA-Fuser): tensor-core (mma.sync) kernel
+  static const int use_mma = [] { const char* v = getenv("AFFT_ATTN_MMA"); return v == nullptr ? 1 : atoi(v); }();
+  if (use_mma && !in_f32 && a.out_lo == nullptr && a.L > 6 && a.L <= 32 && (a.mask == 0 || a.mask == 1)) {
+    if (head_dim == 256) return launch_attention_mma<256>(a, stream);
+    if (head_dim == 512) return launch_attention_mma<512>(a, stream);
+  }
   if (head_dim == 256) return in_f32 ? launch_attention<float, 256>(a, stream) : launch_attention<bf16, 256>(a, stream);
   if (head_dim == 512) return in_f32 ? launch_attention<float, 512>(a, stream) : launch_attention<bf16, 512>(a, stream);
   return fail(AFFT_ERR_INVALID, "attention: head_dim must be 256 or 512");

@@ -504,4 +504,183 @@ __global__ void __launch_bounds__(128) attention_tokens_kernel(const AttentionAr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Causal / full attention over a short sequence (L <= 32) with head_dim 256 or 512, bf16 inputs: the GPT-2
+// future predictor (18 x 18 causal, head_dim 512; transformers eager attention) and the CA-Fuser's causal
+// self/cross attention (10 x 10, head_dim 256; reference models/transformerblock.py:24-33,64-74).
+// CUDA cores cannot do 2 * 18 * 18 * 512 MACs per (clip, head) inside the kernel's HBM time (~12 us per launch
+// at B = 256), so Q.K^T and P.V run on the tensor cores with warp-level mma.sync.m16n8k16 (bf16 in, fp32
+// accumulate): one CTA (4 warps) per (sequence, head); Q, K, V rows staged once in padded shared memory
+// (ldmatrix conflict-free), scores and softmax in fp32, P re-quantised to bf16 for the second product, the
+// output tile staged through shared memory and written with coalesced 16-byte stores.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int HD>
+struct AttnMmaSmem {
+  static constexpr int kLP = 32;                  // padded sequence length (two m16 tiles)
+  static constexpr int kRowBytes = HD * 2 + 16;   // odd multiple of 16 B: ldmatrix rows hit distinct banks
+  static constexpr int kTileBytes = kLP * kRowBytes;
+  static constexpr int kSStride = 33;             // fp32 scores [32][33]
+  static constexpr int kPRowBytes = 80;           // bf16 probabilities [32][32] + pad (5 x 16 B)
+  static constexpr int kBytes = 3 * kTileBytes + kLP * kSStride * 4 + kLP * kPRowBytes;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs a) {
+  using S = AttnMmaSmem<HD>;
+  extern __shared__ uint4 smem_attn[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(smem_attn);
+  const uint32_t sq = static_cast<uint32_t>(__cvta_generic_to_shared(base));
+  const uint32_t sk = sq + S::kTileBytes, sv = sk + S::kTileBytes;
+  float* ss = reinterpret_cast<float*>(base + 3 * S::kTileBytes);
+  uint8_t* sp_ptr = base + 3 * S::kTileBytes + S::kLP * S::kSStride * 4;
+  const uint32_t sp = sv + S::kTileBytes + S::kLP * S::kSStride * 4;
+
+  const int seq = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int L = a.L;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const __nv_bfloat16* qg = reinterpret_cast<const __nv_bfloat16*>(a.q) + static_cast<long long>(seq) * L * a.ldq + h * HD;
+  const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(a.k) + static_cast<long long>(seq) * L * a.ldk + h * HD;
+  const __nv_bfloat16* vg = reinterpret_cast<const __nv_bfloat16*>(a.v) + static_cast<long long>(seq) * L * a.ldv + h * HD;
+
+  // ---- stage rows < L of Q, K, V with cp.async (every 16-byte copy in flight at once) ----
+  // Pad rows of Q and K only produce scores that are never read; pad rows of V meet zero probabilities but must
+  // be finite (0 * NaN), so they are zero-filled.
+  constexpr int kVecPerRow = HD / 8;             // 16-byte vectors per row
+  constexpr int kRowsPerPass = 128 / kVecPerRow;  // rows covered by the CTA per pass (2 for HD 512, 4 for 256)
+  {
+    const int c = tid % kVecPerRow;
+    const int r0 = tid / kVecPerRow;
+    const __nv_bfloat16* qp = qg + static_cast<long long>(r0) * a.ldq + c * 8;
+    const __nv_bfloat16* kp = kg + static_cast<long long>(r0) * a.ldk + c * 8;
+    const __nv_bfloat16* vp = vg + static_cast<long long>(r0) * a.ldv + c * 8;
+    uint32_t dst = sq + r0 * S::kRowBytes + c * 16;
+    for (int r = r0; r < L; r += kRowsPerPass) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(qp) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + S::kTileBytes), "l"(kp) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 2 * S::kTileBytes), "l"(vp) : "memory");
+      qp += kRowsPerPass * a.ldq;
+      kp += kRowsPerPass * a.ldk;
+      vp += kRowsPerPass * a.ldv;
+      dst += kRowsPerPass * S::kRowBytes;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int r = L + r0; r < S::kLP; r += kRowsPerPass)
+      *reinterpret_cast<uint4*>(base + 2 * S::kTileBytes + r * S::kRowBytes + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int g8 = lane >> 2, t4 = lane & 3;
+  // ---- S = Q K^T: warp -> (query tile mt, key half nh), each a 16 x 16 block over the full head_dim ----
+  {
+    const int mt = warp >> 1, nh = warp & 1;
+    const bool skip = (nh * 16 >= L) || (mt * 16 >= L) || (a.mask == 1 && nh * 16 > mt * 16 + 15);
+    if (!skip) {
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      const uint32_t a_addr = sq + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * S::kRowBytes + (lane >> 4) * 16;
+      const uint32_t b_addr = sk + (nh * 16 + (lane & 7) + (lane >> 4) * 8) * S::kRowBytes + ((lane >> 3) & 1) * 16;
+#pragma unroll 4
+      for (int ks = 0; ks < HD / 16; ++ks) {
+        uint32_t af[4], bf[4];
+        ldmatrix_x4(a_addr + ks * 32, af);
+        ldmatrix_x4(b_addr + ks * 32, bf);
+        mma_bf16_16816(acc[0], af, bf[0], bf[1]);
+        mma_bf16_16816(acc[1], af, bf[2], bf[3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        float* r0 = ss + (mt * 16 + g8) * S::kSStride + nh * 16 + nt * 8 + t4 * 2;
+        r0[0] = acc[nt][0];
+        r0[1] = acc[nt][1];
+        r0[8 * S::kSStride] = acc[nt][2];
+        r0[8 * S::kSStride + 1] = acc[nt][3];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- softmax rows (fp32), P -> bf16 ----
+  for (int i = warp; i < S::kLP; i += 4) {
+    float p = 0.f;
+    if (i < L) {
+      const bool ok = (lane < L) && (a.mask != 1 || lane <= i);
+      const float sc = ok ? ss[i * S::kSStride + lane] * a.scale : -INFINITY;
+      const float mx = warp_max(sc);
+      p = ok ? expf(sc - mx) : 0.f;
+      p *= 1.0f / warp_sum(p);
+      if (a.probs != nullptr && lane < L)
+        a.probs[static_cast<long long>(seq / a.p_inner) * a.p_outer + static_cast<long long>(seq % a.p_inner) * a.p_inner_stride +
+                (static_cast<long long>(h) * L + i) * L + lane] = p;
+    }
+    reinterpret_cast<__nv_bfloat16*>(sp_ptr + i * S::kPRowBytes)[lane] = __float2bfloat16_rn(p);
+  }
+  __syncthreads();
+
+  // ---- O = P V: warp -> HD / 4 output dims; output tile staged in the (now free) Q region ----
+  {
+    const int ksteps = (L + 15) / 16;
+    uint32_t pa[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        ldmatrix_x4(sp + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * S::kPRowBytes + ks * 32 + (lane >> 4) * 16, pa[mt][ks]);
+#pragma unroll 2
+    for (int np = 0; np < HD / 4 / 16; ++np) {
+      const int n0 = warp * (HD / 4) + np * 16;
+      float acc[2][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        if (ks < ksteps) {
+          uint32_t vf[4];
+          ldmatrix_x4_trans(sv + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * S::kRowBytes + (n0 + (lane >> 4) * 8) * 2, vf);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            mma_bf16_16816(acc[mt][0], pa[mt][ks], vf[0], vf[1]);
+            mma_bf16_16816(acc[mt][1], pa[mt][ks], vf[2], vf[3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          uint8_t* o0 = base + (mt * 16 + g8) * S::kRowBytes + (n0 + nt * 8 + t4 * 2) * 2;
+          *reinterpret_cast<uint32_t*>(o0) = pack_bf16x2(acc[mt][nt][0], acc[mt][nt][1]);
+          *reinterpret_cast<uint32_t*>(o0 + 8 * S::kRowBytes) = pack_bf16x2(acc[mt][nt][2], acc[mt][nt][3]);
+        }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < L * kVecPerRow; i += 128) {
+    const int r = i / kVecPerRow, c = i % kVecPerRow;
+    *reinterpret_cast<uint4*>(a.out_hi + (static_cast<long long>(seq) * L + r) * a.ldo + h * HD + c * 8) =
+        *reinterpret_cast<const uint4*>(base + r * S::kRowBytes + c * 16);
+  }
+}
+
 }  // namespace afft
