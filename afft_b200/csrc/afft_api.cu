@@ -127,10 +127,13 @@ static int run_layernorm(const LayerNormArgs& a, cudaStream_t stream) {
   if (a.dim % 128 != 0) return fail(AFFT_ERR_INVALID, "layernorm: dim must be a multiple of 128");
   const int blocks = (a.rows + 7) / 8;  // 8 warps (rows) per 256-thread block
   const bool avg = a.n_avg > 1;
-#define AFFT_LN(NV)                                                        \
-  case NV:                                                                 \
-    if (avg) layernorm_kernel<NV, true><<<blocks, 256, 0, stream>>>(a);   \
-    else layernorm_kernel<NV, false><<<blocks, 256, 0, stream>>>(a);      \
+  const bool fast = !avg && a.gamma != nullptr && a.beta != nullptr && a.y_hi != nullptr && a.y_f32 == nullptr &&
+                    a.y_lo == nullptr && a.aux_mod == 0;
+#define AFFT_LN(NV)                                                                 \
+  case NV:                                                                          \
+    if (fast) layernorm_kernel<NV, false, true><<<blocks, 256, 0, stream>>>(a);     \
+    else if (avg) layernorm_kernel<NV, true><<<blocks, 256, 0, stream>>>(a);        \
+    else layernorm_kernel<NV, false><<<blocks, 256, 0, stream>>>(a);                \
     break;
   switch (a.dim / 128) {
     AFFT_LN(2)
@@ -213,6 +216,26 @@ static int launch_attention_tokens(const AttentionArgs& a, cudaStream_t stream) 
   return AFFT_OK;
 }
 
+template <int L>
+static int launch_attention_tokens_mma(const AttentionArgs& a, cudaStream_t stream) {
+  auto kern = attention_tokens_mma_kernel<L>;
+  const int smem = a.H * 3 * 16 * (256 * 2 + 16);
+  static int configured[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (smem > configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_fail("attention_tokens_mma smem attribute", e);
+    configured[dev] = smem;
+  }
+  constexpr int G = 16 / L;
+  kern<<<(a.n_seq + G - 1) / G, 32 * a.H, smem, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("attention_tokens_mma launch", e);
+  return AFFT_OK;
+}
+
 template <int HD>
 static int launch_attention_mma(const AttentionArgs& a, cudaStream_t stream) {
   auto kern = attention_mma_kernel<HD>;
@@ -237,11 +260,22 @@ static int run_attention(const AttentionArgs& a, int head_dim, bool in_f32, cuda
     return fail(AFFT_ERR_INVALID, "attention: null pointer");
   if (a.L < 1 || a.L > 64) return fail(AFFT_ERR_INVALID, "attention: sequence length must be in [1, 64]");
   if (a.n_seq <= 0 || a.H <= 0) return fail(AFFT_ERR_INVALID, "attention: empty problem");
-  // few modality tokens per timestep (SA-Fuser): register-resident warp-per-(timestep, head) kernel
-  if (head_dim == 256 && a.L >= 2 && a.L <= 6 && (a.mask == 0 || a.mask == 3))
-    return in_f32 ? launch_attention_tokens<float>(a, stream) : launch_attention_tokens<bf16>(a, stream);
-  // short sequences with bf16 inputs (GPT-2 predictor, CA-Fuser): tensor-core (mma.sync) kernel
   static const int use_mma = [] { const char* v = getenv("AFFT_ATTN_MMA"); return v == nullptr ? 1 : atoi(v); }();
+  // few modality tokens per timestep (SA-Fuser): tensor-core kernel for bf16 inputs, register-resident
+  // warp-per-(timestep, head) kernel for fp32 inputs (strict mode)
+  if (head_dim == 256 && a.L >= 2 && a.L <= 6 && (a.mask == 0 || a.mask == 3)) {
+    if (use_mma && !in_f32 && a.out_lo == nullptr && a.H <= 8) {
+      switch (a.L) {
+        case 2: return launch_attention_tokens_mma<2>(a, stream);
+        case 3: return launch_attention_tokens_mma<3>(a, stream);
+        case 4: return launch_attention_tokens_mma<4>(a, stream);
+        case 5: return launch_attention_tokens_mma<5>(a, stream);
+        default: return launch_attention_tokens_mma<6>(a, stream);
+      }
+    }
+    return in_f32 ? launch_attention_tokens<float>(a, stream) : launch_attention_tokens<bf16>(a, stream);
+  }
+  // short sequences with bf16 inputs (GPT-2 predictor, CA-Fuser): tensor-core (mma.sync) kernel
   if (use_mma && !in_f32 && a.out_lo == nullptr && a.L > 6 && a.L <= 32 && (a.mask == 0 || a.mask == 1)) {
     if (head_dim == 256) return launch_attention_mma<256>(a, stream);
     if (head_dim == 512) return launch_attention_mma<512>(a, stream);

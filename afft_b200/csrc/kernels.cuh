@@ -23,9 +23,9 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  const __nv_bfloat16 x = __float2bfloat16_rn(a), y = __float2bfloat16_rn(b);
-  return static_cast<uint32_t>(__bfloat16_as_ushort(x)) | (static_cast<uint32_t>(__bfloat16_as_ushort(y)) << 16);
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {  // a -> low half; one F2FP instruction
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
 }
 // residual part of the hi/lo split: bf16(a - float(bf16(a)))
 __device__ __forceinline__ float bf16_residual(float a) {
@@ -127,7 +127,8 @@ __device__ __forceinline__ void ln_store(const LayerNormArgs& a, int row, bool a
 // NV float4 per lane: dim = 128 * NV.  AVG = false: plain LayerNorm of one row per warp (the hot case: the row
 // lives in NV float4 registers, one 16-B load per lane per 512 B, all loads in flight before the reductions).
 // AVG = true: mean over n_avg normalised rows (CMFuser / T-SA-Fuser without frame-level token).
-template <int NV, bool AVG>
+// FAST = true is the hot instantiation (bf16 output only, affine, no aux scatter): no per-vector null checks.
+template <int NV, bool AVG, bool FAST = false>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs a) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -165,14 +166,16 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs a) {
     for (int i = 0; i < NV; ++i) {
       const int c4 = lane + 32 * i;
       float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a.gamma != nullptr) g = __ldg(g4 + c4);
-      if (a.beta != nullptr) b = __ldg(b4 + c4);
+      if (FAST || a.gamma != nullptr) g = __ldg(g4 + c4);
+      if (FAST || a.beta != nullptr) b = __ldg(b4 + c4);
       float4 y;
-      y.x = (v[i].x - mean) * rstd * g.x + b.x;
-      y.y = (v[i].y - mean) * rstd * g.y + b.y;
-      y.z = (v[i].z - mean) * rstd * g.z + b.z;
-      y.w = (v[i].w - mean) * rstd * g.w + b.w;
-      if (AVG) {
+      y.x = fmaf((v[i].x - mean) * rstd, g.x, b.x);
+      y.y = fmaf((v[i].y - mean) * rstd, g.y, b.y);
+      y.z = fmaf((v[i].z - mean) * rstd, g.z, b.z);
+      y.w = fmaf((v[i].w - mean) * rstd, g.w, b.w);
+      if (FAST) {
+        reinterpret_cast<uint2*>(a.y_hi + warp * a.ldy)[c4] = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+      } else if (AVG) {
         float4& t = acc[AVG ? i : 0];
         t.x += y.x; t.y += y.y; t.z += y.z; t.w += y.w;
       } else {
@@ -680,6 +683,136 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs 
     const int r = i / kVecPerRow, c = i % kVecPerRow;
     *reinterpret_cast<uint4*>(a.out_hi + (static_cast<long long>(seq) * L + r) * a.ldo + h * HD + c * 8) =
         *reinterpret_cast<const uint4*>(base + r * S::kRowBytes + c * 16);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// SA-Fuser attention on the tensor cores (bf16 inputs): the register kernel above needs ~1700 instructions per
+// (timestep, head) and is issue-bound at twice the kernel's HBM time (ncu).  Here one warp handles G = 16 / L
+// consecutive timesteps of one head as ONE 16 x 16 mma tile: S = Q K^T over the G*L token rows (16 k-steps of
+// m16n8k16), block-diagonal mask (a token only sees the tokens of its own timestep), softmax on the accumulator
+// fragments, P.V with one k-step per 8 output dims.  Rows are staged per warp with cp.async; no block barrier.
+// ------------------------------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(256) attention_tokens_mma_kernel(const AttentionArgs a) {
+  constexpr int HD = 256;
+  constexpr int G = 16 / L;
+  constexpr int RB = HD * 2 + 16;  // padded row: odd multiple of 16 B
+  constexpr int TILE = 16 * RB;
+  extern __shared__ uint4 smem_attn[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = warp;  // one warp per head
+  const int seq0 = blockIdx.x * G;
+  const int n_t = (a.n_seq - seq0) < G ? (a.n_seq - seq0) : G;
+  const int nrows = n_t * L;
+  uint8_t* wbase = reinterpret_cast<uint8_t*>(smem_attn) + warp * 3 * TILE;
+  const uint32_t sq = static_cast<uint32_t>(__cvta_generic_to_shared(wbase));
+  const uint32_t sk = sq + TILE, sv = sk + TILE;
+  const long long row0 = static_cast<long long>(seq0) * L;
+  const __nv_bfloat16* qg = reinterpret_cast<const __nv_bfloat16*>(a.q) + row0 * a.ldq + h * HD + lane * 8;
+  const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(a.k) + row0 * a.ldk + h * HD + lane * 8;
+  const __nv_bfloat16* vg = reinterpret_cast<const __nv_bfloat16*>(a.v) + row0 * a.ldv + h * HD + lane * 8;
+  {
+    uint32_t dst = sq + lane * 16;
+    for (int r = 0; r < nrows; ++r) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(qg) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + TILE), "l"(kg) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 2 * TILE), "l"(vg) : "memory");
+      qg += a.ldq;
+      kg += a.ldk;
+      vg += a.ldv;
+      dst += RB;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // pad rows: V must be finite (it meets zero probabilities); Q / K pad rows only feed masked scores, but keep
+    // them finite as well so no NaN ever enters the accumulators
+    for (int r = nrows; r < 16; ++r) {
+      *reinterpret_cast<uint4*>(wbase + r * RB + lane * 16) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(wbase + TILE + r * RB + lane * 16) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(wbase + 2 * TILE + r * RB + lane * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncwarp();
+
+  const int g8 = lane >> 2, t4 = lane & 3;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  {
+    const uint32_t a_addr = sq + ((lane & 7) + ((lane >> 3) & 1) * 8) * RB + (lane >> 4) * 16;
+    const uint32_t b_addr = sk + ((lane & 7) + (lane >> 4) * 8) * RB + ((lane >> 3) & 1) * 16;
+#pragma unroll 4
+    for (int ks = 0; ks < HD / 16; ++ks) {
+      uint32_t af[4], bf[4];
+      ldmatrix_x4(a_addr + ks * 32, af);
+      ldmatrix_x4(b_addr + ks * 32, bf);
+      mma_bf16_16816(acc[0], af, bf[0], bf[1]);
+      mma_bf16_16816(acc[1], af, bf[2], bf[3]);
+    }
+  }
+  // softmax on the fragments: this thread holds rows g8 and g8 + 8, columns nt * 8 + 2 * t4 + {0, 1}
+  float p[2][4];  // [row half][nt * 2 + e]
+#pragma unroll
+  for (int rh = 0; rh < 2; ++rh) {
+    const int i = g8 + rh * 8;
+    float sc[4];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = (c >> 1) * 8 + t4 * 2 + (c & 1);
+      const bool ok = (i < nrows) && (j < nrows) && (i / L == j / L) && !(a.mask == 3 && i == j);
+      sc[c] = ok ? acc[c >> 1][rh * 2 + (c & 1)] * a.scale : -INFINITY;
+      mx = fmaxf(mx, sc[c]);
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      p[rh][c] = (sc[c] == -INFINITY) ? 0.f : expf(sc[c] - mx);
+      sum += p[rh][c];
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) p[rh][c] *= inv;
+    if (a.probs != nullptr && i < nrows) {
+      const int seq = seq0 + i / L, ii = i % L;
+      float* pr = a.probs + static_cast<long long>(seq / a.p_inner) * a.p_outer +
+                  static_cast<long long>(seq % a.p_inner) * a.p_inner_stride + (static_cast<long long>(h) * L + ii) * L;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = (c >> 1) * 8 + t4 * 2 + (c & 1);
+        if (j < nrows && j / L == i / L) pr[j % L] = p[rh][c];
+      }
+    }
+  }
+  uint32_t pa[4];
+  pa[0] = pack_bf16x2(p[0][0], p[0][1]);
+  pa[1] = pack_bf16x2(p[1][0], p[1][1]);
+  pa[2] = pack_bf16x2(p[0][2], p[0][3]);
+  pa[3] = pack_bf16x2(p[1][2], p[1][3]);
+  __syncwarp();  // every lane is done reading Q before the region is reused for the output tile
+#pragma unroll 4
+  for (int np = 0; np < HD / 16; ++np) {
+    uint32_t vf[4];
+    ldmatrix_x4_trans(sv + ((lane & 7) + ((lane >> 3) & 1) * 8) * RB + (np * 16 + (lane >> 4) * 8) * 2, vf);
+    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    mma_bf16_16816(o[0], pa, vf[0], vf[1]);
+    mma_bf16_16816(o[1], pa, vf[2], vf[3]);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      uint8_t* o0 = wbase + g8 * RB + (np * 16 + nt * 8 + t4 * 2) * 2;
+      *reinterpret_cast<uint32_t*>(o0) = pack_bf16x2(o[nt][0], o[nt][1]);
+      *reinterpret_cast<uint32_t*>(o0 + 8 * RB) = pack_bf16x2(o[nt][2], o[nt][3]);
+    }
+  }
+  __syncwarp();
+  __nv_bfloat16* og = a.out_hi + row0 * a.ldo + h * HD + lane * 8;
+  for (int r = 0; r < nrows; ++r) {
+    *reinterpret_cast<uint4*>(og) = *reinterpret_cast<const uint4*>(wbase + r * RB + lane * 16);
+    og += a.ldo;
   }
 }
 
