@@ -107,8 +107,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
   p = fmaf(p, t, 0.5f * 0.254829592f);
   const float e = mufu_ex2((z * -1.4426950408889634f) * z);  // exp(-z^2)
   const float q = (p * t) * e;
-  const float phi = (x < 0.f) ? q : 1.0f - q;
-  return x * phi;
+  // x >= 0: x (1 - q);  x < 0: x q = -|x| q   =>   relu(x) - |x| q for both signs
+  return fmaf(-fabsf(x), q, fmaxf(x, 0.f));
 }
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -178,11 +178,36 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return x;
 }
 
+// Per-tile row pointers of the tensors the epilogue touches (column 0 of each of this lane's 8 rows), so that the
+// per-slab address is one 64-bit add per row and tensor.
+struct EpiRowPtrs {
+  float* f32[8];
+  const float* res[8];
+  __nv_bfloat16* hi[8];
+  __nv_bfloat16* lo[8];
+};
+
+template <int EPI, int SPLIT>
+__device__ __forceinline__ void epilogue_row_ptrs(const GemmEpilogue& ep, int row0, int sub_row, EpiRowPtrs& P) {
+  using F = EpiFlags<EPI, SPLIT>;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = row0 + i * 4 + sub_row;
+    long long orow = r;
+    if (ep.row_group > 0)
+      orow = static_cast<long long>(r / ep.row_group) * ep.row_stride + (r % ep.row_group) + ep.row_off;
+    if (F::f32(ep)) P.f32[i] = ep.out_f32 + orow * ep.ld_f32;
+    if (F::res(ep)) P.res[i] = ep.res + ((ep.res_mod > 0) ? static_cast<long long>(r % ep.res_mod) : orow) * ep.ld_res;
+    if (F::bf16(ep)) P.hi[i] = ep.out_hi + orow * ep.ld_bf16;
+    if (F::bf16(ep) && F::lo(ep)) P.lo[i] = ep.out_lo + orow * ep.ld_bf16;
+  }
+}
+
 // One 32-row x 32-column slab, interior case: every row < M and every column < N, so no predicates.
 // Lane (sub_row, chunk) handles rows sub_row + 4 i (i < 8), columns col .. col + 3.
 template <int EPI, int SPLIT>
-__device__ __forceinline__ void epilogue_slab_full(const GemmEpilogue& ep, uint32_t stage, int sub_row, int chunk,
-                                                   int row0, int col, const long long (&orow)[8], const float4& bias4) {
+__device__ __forceinline__ void epilogue_slab_full(const GemmEpilogue& ep, uint32_t stage, int sub_row, int chunk, int col,
+                                                   const EpiRowPtrs& P, const float4& bias4) {
   using F = EpiFlags<EPI, SPLIT>;
   float4 x[8];
 #pragma unroll
@@ -194,10 +219,7 @@ __device__ __forceinline__ void epilogue_slab_full(const GemmEpilogue& ep, uint3
     // all residual loads are issued before any store: the residual may alias the output (in-place stream)
     float4 r[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const long long rrow = (ep.res_mod > 0) ? static_cast<long long>((row0 + i * 4 + sub_row) % ep.res_mod) : orow[i];
-      r[i] = *reinterpret_cast<const float4*>(ep.res + rrow * ep.ld_res + col);
-    }
+    for (int i = 0; i < 8; ++i) r[i] = *reinterpret_cast<const float4*>(P.res[i] + col);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       x[i] = epilogue_math<EPI, SPLIT>(ep, x[i], bias4);
@@ -212,17 +234,17 @@ __device__ __forceinline__ void epilogue_slab_full(const GemmEpilogue& ep, uint3
   }
   if (F::f32(ep)) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(ep.out_f32 + orow[i] * ep.ld_f32 + col) = x[i];
+    for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(P.f32[i] + col) = x[i];
   }
   if (F::bf16(ep)) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const uint32_t h01 = pack2_bf16_rn(x[i].x, x[i].y), h23 = pack2_bf16_rn(x[i].z, x[i].w);
-      *reinterpret_cast<uint2*>(ep.out_hi + orow[i] * ep.ld_bf16 + col) = make_uint2(h01, h23);
+      *reinterpret_cast<uint2*>(P.hi[i] + col) = make_uint2(h01, h23);
       if (F::lo(ep)) {
         const uint32_t l01 = pack2_bf16_rn(x[i].x - bf16_lo_f32(h01), x[i].y - bf16_hi_f32(h01));
         const uint32_t l23 = pack2_bf16_rn(x[i].z - bf16_lo_f32(h23), x[i].w - bf16_hi_f32(h23));
-        *reinterpret_cast<uint2*>(ep.out_lo + orow[i] * ep.ld_bf16 + col) = make_uint2(l01, l23);
+        *reinterpret_cast<uint2*>(P.lo[i] + col) = make_uint2(l01, l23);
       }
     }
   }
@@ -413,14 +435,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       const int n_idx = sched.n_fastest ? tile % num_n : tile / num_m;
       const int row0 = m_idx * kBlockM + quad * 32;
       const bool rows_full = (row0 + 32 <= M);
-      long long orow[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = row0 + i * 4 + sub_row;
-        orow[i] = r;
-        if (ep.row_group > 0)
-          orow[i] = static_cast<long long>(r / ep.row_group) * ep.row_stride + (r % ep.row_group) + ep.row_off;
-      }
+      EpiRowPtrs rp;
+      epilogue_row_ptrs<EPI, SPLIT>(ep, row0, sub_row, rp);
       ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
@@ -444,7 +460,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         if (rows_full && n0 + 32 <= N) {
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ep.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-          epilogue_slab_full<EPI, SPLIT>(ep, stage, sub_row, chunk, row0, col, orow, bias4);
+          epilogue_slab_full<EPI, SPLIT>(ep, stage, sub_row, chunk, col, rp, bias4);
         } else {
           epilogue_slab_edge<EPI, SPLIT>(ep, stage, sub_row, chunk, row0, col, M, N);
         }
@@ -635,14 +651,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
       const int n_idx = sched.n_fastest ? tile % num_n : tile / num_m;
       const int row0 = m_idx * 256 + static_cast<int>(rank) * 128 + quad * 32;
       const bool rows_full = (row0 + 32 <= M);
-      long long orow[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = row0 + i * 4 + sub_row;
-        orow[i] = r;
-        if (ep.row_group > 0)
-          orow[i] = static_cast<long long>(r / ep.row_group) * ep.row_stride + (r % ep.row_group) + ep.row_off;
-      }
+      EpiRowPtrs rp;
+      epilogue_row_ptrs<EPI, SPLIT>(ep, row0, sub_row, rp);
       ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
@@ -666,7 +676,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
           if (rows_full && n0 + 32 <= N) {
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ep.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-            epilogue_slab_full<EPI, SPLIT>(ep, stage, sub_row, chunk, row0, col, orow, bias4);
+            epilogue_slab_full<EPI, SPLIT>(ep, stage, sub_row, chunk, col, rp, bias4);
           } else {
             epilogue_slab_edge<EPI, SPLIT>(ep, stage, sub_row, chunk, row0, col, M, N);
           }

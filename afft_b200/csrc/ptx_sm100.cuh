@@ -62,8 +62,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1ll << 31)) {
+    if ((++spins & 0x3ffu) == 0 && clock64() - t0 > (1ll << 31)) {
       printf("afft: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, bar, parity);
       __trap();
