@@ -19,7 +19,7 @@ AFFT_OK = 0
 AFFT_MAX_MODS = 8
 AFFT_MAX_CLS = 4
 AFFT_NAME_LEN = 32
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH = 0, 1, 2
 FUSER_SA, FUSER_SA_NOTOKEN, FUSER_TSA, FUSER_CA = 0, 1, 2, 3
@@ -50,7 +50,7 @@ class LayerNormDesc(C.Structure):
         ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
         ("rows", C.c_int32), ("dim", C.c_int32),
         ("y_f32", C.c_void_p), ("y_hi", C.c_void_p), ("y_lo", C.c_void_p), ("ldy", C.c_int64),
-        ("aux_mod", C.c_int32), ("aux_stride", C.c_int32),
+        ("aux_mod", C.c_int32), ("aux_stride", C.c_int32), ("aux_rem", C.c_int32),
         ("aux_f32", C.c_void_p), ("aux_hi", C.c_void_p), ("aux_lo", C.c_void_p), ("ld_aux", C.c_int64),
     ]
 
@@ -79,7 +79,7 @@ class Config(C.Structure):
         ("n_cls", C.c_int32),
         ("cls_name", (C.c_char * AFFT_NAME_LEN) * AFFT_MAX_CLS),
         ("cls_dim", C.c_int32 * AFFT_MAX_CLS),
-        ("strict", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32),
+        ("strict", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32), ("fp_output_len", C.c_int32),
     ]
 
 
@@ -108,7 +108,7 @@ EXPORTED_SYMBOLS = [
     "afft_abi_version", "afft_last_error", "afft_gemm", "afft_convert_bf16", "afft_layernorm", "afft_attention",
     "afft_create", "afft_destroy", "afft_handle_error", "afft_workspace_bytes", "afft_weight_bytes",
     "afft_set_weight", "afft_missing_weights", "afft_forward", "afft_last_launch_count",
-    "afft_profile_enable", "afft_profile_read",
+    "afft_profile_enable", "afft_profile_read", "afft_marginalize_topk",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -144,6 +144,9 @@ def lib() -> C.CDLL:
     l.afft_missing_weights.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     l.afft_forward.argtypes = [C.c_void_p, C.c_int32, C.POINTER(IO), C.c_void_p]
     l.afft_last_launch_count.argtypes = [C.c_void_p]
+    l.afft_marginalize_topk.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    l.afft_marginalize_topk.restype = C.c_int
     l.afft_profile_enable.argtypes = [C.c_void_p, C.c_int32]
     l.afft_profile_read.argtypes = [C.c_void_p, C.POINTER(Profile)]
     for name in ("afft_gemm", "afft_convert_bf16", "afft_layernorm", "afft_attention", "afft_create",
@@ -217,7 +220,8 @@ def layernorm(x, gamma, beta, eps, *, rows=None, ldx=None, y_f32=None, y_hi=None
     d.rows, d.dim = (rows if rows is not None else x.shape[0]), x.shape[-1]
     first = next(t for t in (y_f32, y_hi, y_lo) if t is not None)
     d.y_f32, d.y_hi, d.y_lo, d.ldy = ptr(y_f32), ptr(y_hi), ptr(y_lo), first.stride(0)
-    d.aux_mod, d.aux_stride = aux
+    d.aux_mod, d.aux_stride = aux[0], aux[1]
+    d.aux_rem = aux[2] if len(aux) > 2 else 0
     d.aux_f32, d.aux_hi, d.aux_lo = ptr(aux_f32), ptr(aux_hi), ptr(aux_lo)
     fa = next((t for t in (aux_f32, aux_hi, aux_lo) if t is not None), None)
     d.ld_aux = fa.stride(0) if fa is not None else 0

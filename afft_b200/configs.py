@@ -62,6 +62,11 @@ def model_cfg(modal_dims: Dict[str, int], *, fuser: str = "SA-Fuser", depth: int
     }
 
 
+def _with_output_len(cfg: Dict, n: int) -> Dict:
+    cfg["common"]["fp_output_len"] = n
+    return cfg
+
+
 # name -> (cfg.model, T, num_classes, eval batch size of the experiment file)
 def named_config(name: str):
     ek4 = {"rgb": 1024, "objects": 352, "audio": 1024, "flow": 1024}
@@ -82,6 +87,9 @@ def named_config(name: str):
         "ek100_ca": (lambda: model_cfg(ek4, fuser="CA-Fuser"), 10, {"action": 3806}, 16),
         # expts/02_SA-Fuser_wo_token_ek100_train.txt
         "ek100_sa_wo_token": (lambda: model_cfg(ek4, fuser="SA-Fuser_wo_token"), 10, {"action": 3806}, 16),
+        # model.common.fp_output_len=3 on the EGTEA model: autoregressive roll-out (future_prediction.py:395-412)
+        "egtea_sa_rollout3": (lambda: _with_output_len(model_cfg({"rgb": 1024, "flow": 1024}, depth=2, fp_layers=2), 3),
+                              10, {"action": 106}, 32),
     }
     if name not in table:
         raise KeyError(f"unknown config {name}; have {sorted(table)}")

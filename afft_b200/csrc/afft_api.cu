@@ -34,7 +34,7 @@ static int cuda_fail(const char* what, cudaError_t e) {
   return fail(AFFT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-extern "C" int afft_abi_version(void) { return 1; }
+extern "C" int afft_abi_version(void) { return 2; }
 extern "C" const char* afft_last_error(void) { return g_err.c_str(); }
 
 static int device_sm_count(int* out) {
@@ -169,6 +169,7 @@ extern "C" int afft_layernorm(const afft_layernorm_desc* d, void* stream) {
   a.y_lo = static_cast<bf16*>(d->y_lo);
   a.ldy = d->ldy;
   a.aux_mod = d->aux_mod;
+  a.aux_rem = d->aux_rem;
   a.aux_stride = d->aux_stride;
   a.aux_f32 = d->aux_f32;
   a.aux_hi = static_cast<bf16*>(d->aux_hi);
@@ -310,6 +311,36 @@ extern "C" int afft_attention(const afft_attention_desc* d, void* stream) {
   return run_attention(a, d->head_dim, d->in_f32 != 0, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int afft_marginalize_topk(const float* logits, int64_t ld, int32_t B, int32_t A, const int32_t* verb_of,
+                                     const int32_t* noun_of, int32_t n_verb, int32_t n_noun, float* probs, float* verb,
+                                     float* noun, int32_t* topk, int32_t K, void* stream) {
+  if (logits == nullptr || verb_of == nullptr || noun_of == nullptr || verb == nullptr || noun == nullptr)
+    return fail(AFFT_ERR_INVALID, "marginalize: null pointer");
+  if (B <= 0 || A <= 0 || n_verb <= 0 || n_noun <= 0 || ld < A) return fail(AFFT_ERR_INVALID, "marginalize: bad sizes");
+  if (n_verb + n_noun > 8192) return fail(AFFT_ERR_INVALID, "marginalize: too many verb + noun classes (max 8192)");
+  if (topk != nullptr && (K < 1 || K > 16 || K > n_verb || K > n_noun || K > A))
+    return fail(AFFT_ERR_INVALID, "marginalize: K must be in [1, 16] and <= every class count");
+  MarginalizeArgs a;
+  a.logits = logits;
+  a.ld = ld;
+  a.B = B;
+  a.A = A;
+  a.verb_of = verb_of;
+  a.noun_of = noun_of;
+  a.n_verb = n_verb;
+  a.n_noun = n_noun;
+  a.probs = probs;
+  a.verb = verb;
+  a.noun = noun;
+  a.topk = topk;
+  a.K = K;
+  const size_t smem = static_cast<size_t>(n_verb + n_noun) * 4 + 32 * 8 + 16 * 4;
+  marginalize_topk_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("marginalize launch", e);
+  return AFFT_OK;
+}
+
 // ================================================================================================
 // model-level
 // ================================================================================================
@@ -362,6 +393,12 @@ struct afft_handle {
   float* g = nullptr;
   PairBuf y2, att2, f2, pfb;
   void* qkv2 = nullptr;
+  // autoregressive roll-out (fp_output_len > 1)
+  std::vector<void*> qkv_layer;   // per GPT-2 layer: prompt q|k|v [B*T, 3G]   (the KV cache)
+  std::vector<void*> qkv_new;     // per layer: generated positions [B*(O-1), 3G]
+  float* gn = nullptr;            // [B, G] residual stream of the position being generated
+  float* hid = nullptr;           // [B, G] last hidden state (post ln_f), fed back as the next input
+  PairBuf yn, attn_n, fn;         // [B, G], [B, G], [B, 4G]
   int launches = 0;
   int fuser_chunk = 0;
   // optional per-launch event timing
@@ -482,6 +519,8 @@ extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
   for (int m = 0; m < c.n_mod; ++m)
     if (c.mod_dim[m] < 8 || c.mod_dim[m] % 8 != 0) return fail(AFFT_ERR_INVALID, "create: modality dims must be multiples of 8");
   if (c.fuser_kind == AFFT_FUSER_CA && c.n_mod < 2) return fail(AFFT_ERR_INVALID, "create: CA-Fuser needs >= 2 modalities");
+  if (c.fp_output_len < 1 || c.T + c.fp_output_len - 1 > 1024)
+    return fail(AFFT_ERR_INVALID, "create: fp_output_len must be >= 1 and T + fp_output_len - 1 <= 1024 (GPT-2 positions)");
 
   cudaError_t e = cudaSetDevice(c.device);
   if (e != cudaSuccess) return cuda_fail("cudaSetDevice", e);
@@ -509,7 +548,8 @@ extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
   // ---- workspace ----
   const bool strict = c.strict != 0;
   const size_t B = c.max_batch, T = c.T, D = c.dim, G = c.gpt_dim;
-  const size_t R2 = B * T, R1 = R2 * h->n_slots, RP = B * (T + 1);
+  const size_t OL = c.fp_output_len;
+  const size_t R2 = B * T, R1 = R2 * h->n_slots, RP = B * (T + OL);
   struct Req {
     void** dst;
     size_t bytes;
@@ -539,6 +579,19 @@ extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
   want_pair(h->f2, R2 * 4 * G);
   want(&h->qkv2, R2 * 3 * G * (strict ? 4 : 2));
   want_pair(h->pfb, RP * D);
+  if (OL > 1) {
+    h->qkv_layer.assign(c.gpt_layers, nullptr);
+    h->qkv_new.assign(c.gpt_layers, nullptr);
+    for (int l = 0; l < c.gpt_layers; ++l) {
+      want(&h->qkv_layer[l], R2 * 3 * G * (strict ? 4 : 2));
+      want(&h->qkv_new[l], B * (OL - 1) * 3 * G * (strict ? 4 : 2));
+    }
+    want(reinterpret_cast<void**>(&h->gn), B * G * 4);
+    want(reinterpret_cast<void**>(&h->hid), B * G * 4);
+    want_pair(h->yn, B * G);
+    want_pair(h->attn_n, B * G);
+    want_pair(h->fn, B * 4 * G);
+  }
   size_t total = 0;
   for (auto& r : reqs) total += r.bytes;
   e = cudaMalloc(reinterpret_cast<void**>(&h->ws), total);
@@ -731,7 +784,7 @@ struct Fwd {
   void layernorm(const float* x, long long ldx, int rows, int dim, const std::string& name, float eps, const PairBuf* yb,
                  float* y_f32, long long ldy, int in_group = 0, int in_stride = 0, int n_avg = 0, int avg_stride = 0,
                  int aux_mod = 0, int aux_stride = 0, float* aux_f32 = nullptr, const PairBuf* aux_b = nullptr,
-                 long long ld_aux = 0) {
+                 long long ld_aux = 0, int aux_rem = 0) {
     if (!ok()) return;
     LayerNormArgs a;
     a.x = x;
@@ -750,6 +803,7 @@ struct Fwd {
     a.y_lo = yb ? yb->lo : nullptr;
     a.ldy = ldy;
     a.aux_mod = aux_mod;
+    a.aux_rem = aux_rem;
     a.aux_stride = aux_stride;
     a.aux_f32 = aux_f32;
     a.aux_hi = aux_b ? aux_b->hi : nullptr;
@@ -804,6 +858,44 @@ struct Fwd {
     assemble_tokens_kernel<<<blocks, 256, 0, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     check(e == cudaSuccess ? AFFT_OK : cuda_fail("assemble launch", e));
+    prof_end(pi);
+  }
+
+  void add_row_vector(float* out, const float* in, const float* vec, int rows, int dim) {
+    if (!ok()) return;
+    const int pi = prof_begin(AFFT_CAT_OTHER);
+    add_row_vector_kernel<<<(rows * dim + 255) / 256, 256, 0, stream>>>(out, in, vec, rows, dim);
+    cudaError_t e = cudaGetLastError();
+    check(e == cudaSuccess ? AFFT_OK : cuda_fail("add_row_vector launch", e));
+    prof_end(pi);
+  }
+
+  void decode_attention(const void* cache, const void* fresh, long long ld, int B, int T, int H, int hd, int n_new,
+                        int n_new_max, const PairBuf& out) {
+    if (!ok()) return;
+    DecodeAttnArgs a;
+    a.cache = cache;
+    a.fresh = fresh;
+    a.ld = ld;
+    a.B = B;
+    a.T = T;
+    a.H = H;
+    a.n_new = n_new;
+    a.n_new_max = n_new_max;
+    a.scale = 1.0f / sqrtf(static_cast<float>(hd));
+    a.out_hi = out.hi;
+    a.out_lo = out.lo;
+    const int blocks = (B * H + 3) / 4;
+    const int pi = prof_begin(AFFT_CAT_ATTENTION);
+    if (hd == 512) {
+      if (strict) attention_decode_kernel<float, 512><<<blocks, 128, 0, stream>>>(a);
+      else attention_decode_kernel<bf16, 512><<<blocks, 128, 0, stream>>>(a);
+    } else {
+      if (strict) attention_decode_kernel<float, 256><<<blocks, 128, 0, stream>>>(a);
+      else attention_decode_kernel<bf16, 256><<<blocks, 128, 0, stream>>>(a);
+    }
+    cudaError_t e = cudaGetLastError();
+    check(e == cudaSuccess ? AFFT_OK : cuda_fail("decode attention launch", e));
     prof_end(pi);
   }
 
@@ -865,8 +957,9 @@ static void run_fuser(Fwd& F, const afft_io& io, int b0, int nb) {
   const afft_config& c = h->cfg;
   const int T = c.T, D = c.dim, n = h->n_slots, H = c.fuser_heads, depth = c.fuser_depth;
   const int R2 = nb * T;
+  const int S = T + c.fp_output_len;                                  // slots per clip in past_futures / logits
   const long long zoff = static_cast<long long>(b0) * T * D;          // into orig_past / zb
-  const long long poff = static_cast<long long>(b0) * (T + 1) * D;    // into past_futures / pfb
+  const long long poff = static_cast<long long>(b0) * S * D;          // into past_futures / pfb
   PairBuf zb = {h->zb.hi + zoff, h->zb.lo ? h->zb.lo + zoff : nullptr};
   PairBuf pfb = {h->pfb.hi + poff, h->pfb.lo ? h->pfb.lo + poff : nullptr};
   float* orig_past = io.orig_past + zoff;
@@ -915,7 +1008,7 @@ static void run_fuser(Fwd& F, const afft_io& io, int b0, int nb) {
              D, nullptr, 0);
       fuser_mlp(F, p, "norm_mlp", R2);
     }
-    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, 0, 0, 0, 0, T, T + 1, pf, &pfb, D);
+    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, 0, 0, 0, 0, T, S, pf, &pfb, D);
     return;
   }
 
@@ -994,37 +1087,42 @@ static void run_fuser(Fwd& F, const afft_io& io, int b0, int nb) {
   // 3. final norm + token selection / averaging
   if (c.fuser_kind == AFFT_FUSER_SA) {
     // token 0 of every (b, t): fusion.py:362-364
-    F.layernorm(h->h, static_cast<long long>(n) * D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, 0, 0, 0, 0, T, T + 1,
+    F.layernorm(h->h, static_cast<long long>(n) * D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, 0, 0, 0, 0, T, S,
                 pf, &pfb, D);
   } else if (c.fuser_kind == AFFT_FUSER_SA_NOTOKEN) {
     // mean over the modality tokens of LN(x): fusion.py:114-116
-    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, 1, n, n, 1, T, T + 1, pf, &pfb, D);
+    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, 1, n, n, 1, T, S, pf, &pfb, D);
   } else if (c.frame_level_token) {
     // first T tokens of every clip: fusion.py:207-209
-    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, T, n * T, 0, 0, T, T + 1, pf, &pfb, D);
+    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, T, n * T, 0, 0, T, S, pf, &pfb, D);
   } else {
     // mean over modalities per timestep: fusion.py:211-214
-    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, T, n * T, n, T, T, T + 1, pf, &pfb, D);
+    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, T, n * T, n, T, T, S, pf, &pfb, D);
   }
 }
 
 // dim_encoder -> GPT-2 -> dim_decoder -> classifiers over all B clips
-// (future_prediction.py:267-269,282-288; transformers GPT2Model)
+// (future_prediction.py:267-269,282-288; transformers GPT2Model).
+// With fp_output_len = O > 1 the predictor is rolled out O - 1 more positions with its KV cache
+// (future_prediction.py:395-412): z_hat has T + O - 1 rows per clip.
 static void run_predictor(Fwd& F, const afft_io& io, int B) {
   afft_handle* h = F.h;
   const afft_config& c = h->cfg;
   const int T = c.T, D = c.dim, G = c.gpt_dim, H = c.gpt_heads, hd = G / H;
+  const int OL = c.fp_output_len, S = T + OL;
   const int R2 = B * T;
   const std::string gp = "future_predictor.gpt_model.";
+  const float* wpe = F.V(gp + "wpe.weight");
   // g = z . Wenc^T + wpe[t]
-  F.gemm(h->zb, D, R2, "dim_encoder.weight", nullptr, ACT_NONE, F.V(gp + "wpe.weight"), G, T, h->g, G, nullptr, 0);
+  F.gemm(h->zb, D, R2, "dim_encoder.weight", nullptr, ACT_NONE, wpe, G, T, h->g, G, nullptr, 0);
   for (int i = 0; i < c.gpt_layers; ++i) {
     const std::string p = gp + blk_name("h.", i, ".");
+    void* qkv = (OL > 1) ? h->qkv_layer[i] : h->qkv2;  // kept per layer when it is the KV cache of a roll-out
     F.layernorm(h->g, G, R2, G, p + "ln_1", 1e-5f, &h->y2, nullptr, G);
-    QkvOut q = qkv_out(h->qkv2, F.strict, 0);
+    QkvOut q = qkv_out(qkv, F.strict, 0);
     F.gemm(h->y2, G, R2, p + "attn.c_attn.weight", F.V(p + "attn.c_attn.bias"), ACT_NONE, nullptr, 0, 0, q.f32, 3 * G,
            q.bp, 3 * G);
-    F.attention(h->qkv2, 3 * G, 0, G, 2 * G, B, T, H, hd, 1, T, h->att2, G, nullptr, 0, 0, 1);
+    F.attention(qkv, 3 * G, 0, G, 2 * G, B, T, H, hd, 1, T, h->att2, G, nullptr, 0, 0, 1);
     F.gemm(h->att2, G, R2, p + "attn.c_proj.weight", F.V(p + "attn.c_proj.bias"), ACT_NONE, h->g, G, 0, h->g, G, nullptr,
            0);
     F.layernorm(h->g, G, R2, G, p + "ln_2", 1e-5f, &h->y2, nullptr, G);
@@ -1033,12 +1131,37 @@ static void run_predictor(Fwd& F, const afft_io& io, int B) {
     F.gemm(h->f2, 4 * G, R2, p + "mlp.c_proj.weight", F.V(p + "mlp.c_proj.bias"), ACT_NONE, h->g, G, 0, h->g, G, nullptr,
            0);
   }
-  F.layernorm(h->g, G, R2, G, gp + "ln_f", 1e-5f, &h->y2, nullptr, G);
-  // z_hat[b, t] -> slot t + 1 of the [B, T+1, D] past_futures buffer (fp32 output + bf16 classifier input)
-  F.gemm(h->y2, G, R2, "dim_decoder.weight", nullptr, ACT_NONE, nullptr, 0, 0, io.past_futures, D, &h->pfb, D, T, T + 1, 1);
+  if (OL > 1)  // also keep the last position's hidden state (fp32): it is the next input embedding
+    F.layernorm(h->g, G, R2, G, gp + "ln_f", 1e-5f, &h->y2, nullptr, G, 0, 0, 0, 0, T, 1, h->hid, nullptr, G, T - 1);
+  else
+    F.layernorm(h->g, G, R2, G, gp + "ln_f", 1e-5f, &h->y2, nullptr, G);
+  // z_hat[b, t] -> slot t + 1 of the [B, S, D] past_futures buffer (fp32 output + bf16 classifier input)
+  F.gemm(h->y2, G, R2, "dim_decoder.weight", nullptr, ACT_NONE, nullptr, 0, 0, io.past_futures, D, &h->pfb, D, T, S, 1);
+
+  for (int k = 1; k < OL; ++k) {
+    const int pos = T + k - 1;  // position id of the token being generated (future_prediction.py:398-399)
+    F.add_row_vector(h->gn, h->hid, wpe + static_cast<long long>(pos) * G, B, G);
+    for (int i = 0; i < c.gpt_layers; ++i) {
+      const std::string p = gp + blk_name("h.", i, ".");
+      F.layernorm(h->gn, G, B, G, p + "ln_1", 1e-5f, &h->yn, nullptr, G);
+      QkvOut q = qkv_out(h->qkv_new[i], F.strict, 0);
+      F.gemm(h->yn, G, B, p + "attn.c_attn.weight", F.V(p + "attn.c_attn.bias"), ACT_NONE, nullptr, 0, 0, q.f32, 3 * G,
+             q.bp, 3 * G, 1, OL - 1, k - 1);
+      F.decode_attention(h->qkv_layer[i], h->qkv_new[i], 3 * G, B, T, H, hd, k, OL - 1, h->attn_n);
+      F.gemm(h->attn_n, G, B, p + "attn.c_proj.weight", F.V(p + "attn.c_proj.bias"), ACT_NONE, h->gn, G, 0, h->gn, G,
+             nullptr, 0);
+      F.layernorm(h->gn, G, B, G, p + "ln_2", 1e-5f, &h->yn, nullptr, G);
+      F.gemm(h->yn, G, B, p + "mlp.c_fc.weight", F.V(p + "mlp.c_fc.bias"), ACT_GELU_TANH, nullptr, 0, 0, nullptr, 0, &h->fn,
+             4 * G);
+      F.gemm(h->fn, 4 * G, B, p + "mlp.c_proj.weight", F.V(p + "mlp.c_proj.bias"), ACT_NONE, h->gn, G, 0, h->gn, G, nullptr,
+             0);
+    }
+    F.layernorm(h->gn, G, B, G, gp + "ln_f", 1e-5f, &h->yn, h->hid, G);
+    F.gemm(h->yn, G, B, "dim_decoder.weight", nullptr, ACT_NONE, nullptr, 0, 0, io.past_futures, D, &h->pfb, D, 1, S, T + k);
+  }
   for (int k = 0; k < c.n_cls; ++k) {
     const std::string p = std::string("classifiers.") + c.cls_name[k] + ".all-fused.1.";
-    F.gemm(h->pfb, D, B * (T + 1), p + "weight", F.V(p + "bias"), ACT_NONE, nullptr, 0, 0, io.logits[k], io.ld_logits[k],
+    F.gemm(h->pfb, D, B * S, p + "weight", F.V(p + "bias"), ACT_NONE, nullptr, 0, 0, io.logits[k], io.ld_logits[k],
            nullptr, 0);
   }
 }

@@ -101,7 +101,7 @@ struct LayerNormArgs {
   __nv_bfloat16* y_hi;
   __nv_bfloat16* y_lo;
   long long ldy;
-  int aux_mod, aux_stride;
+  int aux_mod, aux_stride, aux_rem;  // rows with r % aux_mod == aux_rem are also written to aux row (r / aux_mod) * aux_stride
   float* aux_f32;
   __nv_bfloat16* aux_hi;
   __nv_bfloat16* aux_lo;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs a) {
   const float inv_d = 1.0f / static_cast<float>(a.dim);
   const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
   const float4* b4 = reinterpret_cast<const float4*>(a.beta);
-  const bool aux = a.aux_mod > 0 && (warp % a.aux_mod) == 0;
+  const bool aux = a.aux_mod > 0 && (warp % a.aux_mod) == a.aux_rem;
   const long long arow = aux ? static_cast<long long>(warp / a.aux_mod) * a.aux_stride : 0;
   const int n_avg = (AVG && a.n_avg > 1) ? a.n_avg : 1;
   float4 acc[AVG ? NV : 1];
@@ -814,6 +814,169 @@ __global__ void __launch_bounds__(256) attention_tokens_mma_kernel(const Attenti
     *reinterpret_cast<uint4*>(og) = *reinterpret_cast<const uint4*>(wbase + r * RB + lane * 16);
     og += a.ldo;
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Logit post-processing (reference challenge.py:196-210 marginalize_verb_noun and
+// common/utils.py:19-42 top-k ranking): per clip  p = softmax(action logits);  verb[v] = sum_{a: verb(a)=v} p[a],
+// noun[n] likewise (the reference multiplies by the 0/1 matrices class_mappings[('verb','action')] /
+// [('noun','action')], which have exactly one 1 per action row);  top-K indices of action / verb / noun scores.
+// One CTA per clip; verb/noun accumulators in shared memory; K rounds of block arg-max (ties -> lower index).
+// ------------------------------------------------------------------------------------------------
+struct MarginalizeArgs {
+  const float* logits;  // [B, ld]
+  long long ld;
+  int B, A;
+  const int* verb_of;  // [A]
+  const int* noun_of;  // [A]
+  int n_verb, n_noun;
+  float* probs;  // [B, A] or nullptr
+  float* verb;   // [B, n_verb]
+  float* noun;   // [B, n_noun]
+  int* topk;     // [B, 3, K]: action, verb, noun
+  int K;
+};
+
+__device__ __forceinline__ void block_argmax(float& v, int& idx, float* red_v, int* red_i) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  __syncthreads();
+  if (lane == 0) { red_v[warp] = v; red_i[warp] = idx; }
+  __syncthreads();
+  v = (lane < nw) ? red_v[lane] : -INFINITY;
+  idx = (lane < nw) ? red_i[lane] : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+}
+
+__device__ __forceinline__ void block_topk(const float* vals, int n, int K, int* out, float* red_v, int* red_i, int* chosen) {
+  for (int k = 0; k < K; ++k) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      bool taken = false;
+      for (int j = 0; j < k; ++j) taken |= (chosen[j] == i);
+      const float v = vals[i];
+      if (!taken && (v > best || (v == best && i < bi))) { best = v; bi = i; }
+    }
+    block_argmax(best, bi, red_v, red_i);
+    if (threadIdx.x == 0) { chosen[k] = bi; out[k] = bi; }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) marginalize_topk_kernel(const MarginalizeArgs a) {
+  extern __shared__ float smem_mg[];
+  float* sv = smem_mg;            // [n_verb]
+  float* sn = sv + a.n_verb;      // [n_noun]
+  float* red_v = sn + a.n_noun;   // [32]
+  int* red_i = reinterpret_cast<int*>(red_v + 32);
+  int* chosen = red_i + 32;       // [K]
+  const int b = blockIdx.x;
+  const float* lg = a.logits + b * a.ld;
+  for (int i = threadIdx.x; i < a.n_verb + a.n_noun; i += blockDim.x) sv[i] = 0.f;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < a.A; i += blockDim.x) mx = fmaxf(mx, lg[i]);
+  int dummy = 0;
+  block_argmax(mx, dummy, red_v, red_i);
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < a.A; i += blockDim.x) sum += expf(lg[i] - mx);
+  sum = warp_sum(sum);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red_v[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = (threadIdx.x & 31) < (blockDim.x >> 5) ? red_v[threadIdx.x & 31] : 0.f;
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.A; i += blockDim.x) {
+    const float p = expf(lg[i] - mx) * inv;
+    if (a.probs != nullptr) a.probs[static_cast<long long>(b) * a.A + i] = p;
+    atomicAdd(&sv[a.verb_of[i]], p);
+    atomicAdd(&sn[a.noun_of[i]], p);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.n_verb; i += blockDim.x) a.verb[static_cast<long long>(b) * a.n_verb + i] = sv[i];
+  for (int i = threadIdx.x; i < a.n_noun; i += blockDim.x) a.noun[static_cast<long long>(b) * a.n_noun + i] = sn[i];
+  if (a.topk != nullptr) {
+    int* out = a.topk + static_cast<long long>(b) * 3 * a.K;
+    block_topk(lg, a.A, a.K, out, red_v, red_i, chosen);  // softmax is monotone: rank the logits
+    block_topk(sv, a.n_verb, a.K, out + a.K, red_v, red_i, chosen);
+    block_topk(sn, a.n_noun, a.K, out + 2 * a.K, red_v, red_i, chosen);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Autoregressive roll-out of the future predictor (fp_output_len > 1; reference models/future_prediction.py:
+// 395-412: the last hidden state is fed back as the next input embedding, GPT-2 runs one position with its KV
+// cache).  Two small kernels: the position-embedding add for the fed-back row, and single-query attention over
+// the cached keys/values of the T prompt positions plus the positions generated so far (online softmax).
+// ------------------------------------------------------------------------------------------------
+__global__ void add_row_vector_kernel(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ vec,
+                                      int rows, int dim) {
+  const int total = rows * dim;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) out[i] = in[i] + vec[i % dim];
+}
+
+struct DecodeAttnArgs {
+  const void* cache;   // [B * T, ld] rows (b, t): q | k | v of the prompt positions
+  const void* fresh;   // [B * n_new_max, ld] rows (b, s): q | k | v of generated positions; the query is row (b, n_new - 1)
+  long long ld;        // 3 * H * HD
+  int B, T, H, n_new, n_new_max;
+  float scale;
+  __nv_bfloat16* out_hi;  // [B, H * HD]
+  __nv_bfloat16* out_lo;
+};
+
+template <typename TIn, int HD>
+__global__ void __launch_bounds__(128) attention_decode_kernel(const DecodeAttnArgs a) {
+  constexpr int PL = HD / 32;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= a.B * a.H) return;
+  const int lane = threadIdx.x & 31;
+  const int b = gw / a.H, h = gw % a.H;
+  const long long D = static_cast<long long>(a.H) * HD;
+  const TIn* cache = reinterpret_cast<const TIn*>(a.cache);
+  const TIn* fresh = reinterpret_cast<const TIn*>(a.fresh);
+  float q[PL];
+  load_row_regs<TIn, HD>(fresh + (static_cast<long long>(b) * a.n_new_max + a.n_new - 1) * a.ld + h * HD, lane, q);
+  float m = -INFINITY, l = 0.f, o[PL];
+#pragma unroll
+  for (int e = 0; e < PL; ++e) o[e] = 0.f;
+  const int n_keys = a.T + a.n_new;
+  for (int j = 0; j < n_keys; ++j) {
+    const TIn* row = (j < a.T) ? cache + (static_cast<long long>(b) * a.T + j) * a.ld
+                               : fresh + (static_cast<long long>(b) * a.n_new_max + (j - a.T)) * a.ld;
+    float kr[PL], vr[PL];
+    load_row_regs<TIn, HD>(row + D + h * HD, lane, kr);
+    load_row_regs<TIn, HD>(row + 2 * D + h * HD, lane, vr);
+    float d = 0.f;
+#pragma unroll
+    for (int e = 0; e < PL; ++e) d = fmaf(q[e], kr[e], d);
+    const float sc = warp_sum(d) * a.scale;
+    const float m_new = fmaxf(m, sc);
+    const float corr = expf(m - m_new);  // exp(-inf) = 0 on the first key
+    const float p = expf(sc - m_new);
+    l = l * corr + p;
+#pragma unroll
+    for (int e = 0; e < PL; ++e) o[e] = fmaf(p, vr[e], o[e] * corr);
+    m = m_new;
+  }
+  const float inv = 1.0f / l;
+#pragma unroll
+  for (int e = 0; e < PL; ++e) o[e] *= inv;
+  store_row_regs<TIn, HD>(a.out_hi, a.out_lo, static_cast<long long>(b) * D + h * HD, lane, o);
 }
 
 }  // namespace afft

@@ -21,7 +21,7 @@ class Engine:
     def __init__(self, *, fuser_kind: int, T: int, mod_names: List[str], mod_dims: List[int], dim: int,
                  fuser_depth: int, fuser_heads: int, modal_encoding: bool, frame_level_token: bool, cross_attn: bool,
                  norm_elementwise: bool, gpt_dim: int, gpt_layers: int, gpt_heads: int, cls_names: List[str],
-                 cls_dims: List[int], strict: bool, max_batch: int, device: torch.device):
+                 cls_dims: List[int], strict: bool, max_batch: int, device: torch.device, fp_output_len: int = 1):
         if device.type != "cuda":
             raise _capi.AfftError("afft_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
         self.lib = _capi.lib()
@@ -31,6 +31,7 @@ class Engine:
         self.cls_names, self.cls_dims = list(cls_names), list(cls_dims)
         self.fuser_kind, self.fuser_depth, self.fuser_heads = fuser_kind, fuser_depth, fuser_heads
         self.frame_level_token = frame_level_token
+        self.fp_output_len = fp_output_len
         cfg = _capi.Config()
         cfg.fuser_kind, cfg.T, cfg.n_mod = fuser_kind, T, len(mod_names)
         for i, (n, d) in enumerate(zip(mod_names, mod_dims)):
@@ -45,6 +46,7 @@ class Engine:
             cfg.cls_name[i].value = n.encode()
             cfg.cls_dim[i] = d
         cfg.strict, cfg.max_batch = int(strict), max_batch
+        cfg.fp_output_len = fp_output_len
         cfg.device = device.index if device.index is not None else torch.cuda.current_device()
         self.cfg = cfg
         h = C.c_void_p()
@@ -99,7 +101,7 @@ class Engine:
 
     def forward(self, feats: List[torch.Tensor], want_attn: bool = True):
         """feats: per modality (fusion order) (B, T, C_m) fp32 contiguous CUDA tensors.
-        Returns (orig_past (B,T,D), past_futures_buf (B,T+1,D), [logits_buf (B,T+1,ld)], attn or None)."""
+        Returns (orig_past (B,T,D), past_futures_buf (B,T+O,D), [logits_buf (B,T+O,ld)], attn or None), O = fp_output_len."""
         B = feats[0].shape[0]
         T, D, dev = self.T, self.dim, self.device
         io = _capi.IO()
@@ -110,11 +112,12 @@ class Engine:
                 raise _capi.AfftError(f"feature {self.mod_names[i]} has shape {tuple(f.shape)}, expected {(B, T, self.mod_dims[i])}")
             io.feat[i] = f.data_ptr()
         orig_past = torch.empty(B, T, D, device=dev, dtype=torch.float32)
-        pf = torch.empty(B, T + 1, D, device=dev, dtype=torch.float32)
+        S = T + self.fp_output_len
+        pf = torch.empty(B, S, D, device=dev, dtype=torch.float32)
         logits = []
         for k, c in enumerate(self.cls_dims):
             ld = (c + 3) // 4 * 4
-            buf = torch.empty(B, T + 1, ld, device=dev, dtype=torch.float32)
+            buf = torch.empty(B, S, ld, device=dev, dtype=torch.float32)
             logits.append(buf)
             io.logits[k] = buf.data_ptr()
             io.ld_logits[k] = ld

@@ -170,9 +170,9 @@ class CMFPEarly(nn.Module):
         self.latent_dim = cfg_get(common, "in_features")
         self.fp_inter_dim = cfg_get(common, "fp_inter_dim")
         self.modality_dims = dict(modal_dims)
-        self.fp_output_len = cfg_get(common, "fp_output_len", 1)
-        if self.fp_output_len != 1:
-            raise NotImplementedError("fp_output_len > 1 (autoregressive roll-out, SURVEY.md section 8f row N1) is not built yet")
+        self.fp_output_len = int(cfg_get(common, "fp_output_len", 1))
+        if self.fp_output_len < 1:
+            raise ValueError("fp_output_len must be >= 1")
         self.modal_feature_order = list(cfg_get(model_cfg, "modal_feature_order"))
 
         self.mapping = nn.ModuleDict()
@@ -206,7 +206,7 @@ class CMFPEarly(nn.Module):
         return {n: p for n, p in self.named_parameters()}
 
     def _engine(self, feats_order, T: int, B: int, device: torch.device) -> Engine:
-        key = (tuple(feats_order), T, str(device), bool(self.strict))
+        key = (tuple(feats_order), T, str(device), bool(self.strict), self.fp_output_len)
         eng = self._engines.get(key)
         if eng is not None and B > eng.max_batch:
             eng.close()
@@ -221,7 +221,7 @@ class CMFPEarly(nn.Module):
                          norm_elementwise=bool(f.norm_elementwise), gpt_dim=gpt.n_embd, gpt_layers=gpt.n_layer,
                          gpt_heads=gpt.n_head, cls_names=list(self.num_classes.keys()),
                          cls_dims=list(self.num_classes.values()), strict=bool(self.strict),
-                         max_batch=max(B, self.max_batch), device=device)
+                         max_batch=max(B, self.max_batch), device=device, fp_output_len=self.fp_output_len)
             self._engines[key] = eng
         return eng
 

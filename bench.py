@@ -230,8 +230,8 @@ def run_afft(args):
         attn_buf = None
     else:
         attn_buf = torch.empty(B, eng.fuser_depth, T, H1, n_tok, n_tok, device=dev)
-    bufs = dict(orig=torch.empty(B, T, D, device=dev), pf=torch.empty(B, T + 1, D, device=dev),
-                logits=torch.empty(B, T + 1, ldc, device=dev), attn=attn_buf)
+    bufs = dict(orig=torch.empty(B, T, D, device=dev), pf=torch.empty(B, T + eng.fp_output_len, D, device=dev),
+                logits=torch.empty(B, T + eng.fp_output_len, ldc, device=dev), attn=attn_buf)
     ios = []
     for s in dev_sets:
         io = _capi.IO()

@@ -118,7 +118,7 @@ typedef struct afft_layernorm_desc {
   void* y_hi;
   void* y_lo;
   int64_t ldy;
-  int32_t aux_mod, aux_stride; /* rows with r % aux_mod == 0 are also written to aux row (r/aux_mod)*aux_stride */
+  int32_t aux_mod, aux_stride, aux_rem; /* rows with r % aux_mod == aux_rem are also written to aux row (r/aux_mod)*aux_stride */
   float* aux_f32;
   void* aux_hi;
   void* aux_lo;
@@ -152,6 +152,15 @@ typedef struct afft_attention_desc {
 
 AFFT_API int afft_attention(const afft_attention_desc* d, void* stream);
 
+/* Logit post-processing (the step right after the path): softmax over the action logits,
+ * verb/noun marginalisation and top-K ranking - replaces challenge.py:196-210 (scipy softmax + two matmuls with the
+ * 0/1 class_mappings matrices) and the argsort ranking of common/utils.py:19-42.  verb_of/noun_of [A] int32 give the
+ * verb / noun class of every action (the column of the single 1 in each row of the mapping matrices).
+ * probs may be NULL; topk [B, 3, K] int32 (action, verb, noun; K <= 16) may be NULL. */
+AFFT_API int afft_marginalize_topk(const float* logits, int64_t ld, int32_t B, int32_t A, const int32_t* verb_of,
+                                   const int32_t* noun_of, int32_t n_verb, int32_t n_noun, float* probs, float* verb,
+                                   float* noun, int32_t* topk, int32_t K, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Model-level API: everything below BaseModel.future_predictor (models/base_model.py:59)      */
 /* ------------------------------------------------------------------------------------------ */
@@ -179,6 +188,7 @@ typedef struct afft_config {
   int32_t strict;                         /* 0: bf16 operands; 1: bf16x3 error-compensated GEMMs */
   int32_t max_batch;                      /* workspace is sized for this many clips per call */
   int32_t device;                         /* CUDA device ordinal */
+  int32_t fp_output_len;                  /* model.common.fp_output_len: future steps rolled out (>= 1) */
 } afft_config;
 
 typedef struct afft_handle afft_handle;
@@ -206,8 +216,8 @@ AFFT_API int afft_missing_weights(const afft_handle* h, char* buf, size_t buf_le
 typedef struct afft_io {
   const float* feat[AFFT_MAX_MODS]; /* [B, T, mod_dim[m]] fp32, fusion order */
   float* orig_past;                 /* [B, T, dim]       fused features z                        */
-  float* past_futures;              /* [B, T+1, dim]     slots 0..T-1 = past_futures, T = future */
-  float* logits[AFFT_MAX_CLS];      /* [B, T+1, ld_logits] slots 0..T-1 = past_logits, T = logits */
+  float* past_futures;              /* [B, T+O, dim]     slots 0..T-1 = past_futures, T.. = future (O = fp_output_len) */
+  float* logits[AFFT_MAX_CLS];      /* [B, T+O, ld_logits] slots 0..T-1 = past_logits, T.. = logits */
   int64_t ld_logits[AFFT_MAX_CLS];  /* row pitch in floats, multiple of 4, >= cls_dim            */
   float* fuser_attn;                /* SA: [B, depth, T, H, n, n]; T-SA: [B, depth, H, nT, nT]; NULL = skip */
 } afft_io;

@@ -258,10 +258,11 @@ def _ca_fuser(feats: List[torch.Tensor], w: _W, fcfg):
 # ------------------------------------------------------------------------------------------------
 # GPT-2 (transformers GPT2Model, restated)
 # ------------------------------------------------------------------------------------------------
-def _gpt2(x, w: _W, n_layer, n_head):
-    B, T, G = x.shape
-    h = x + w("wpe.weight")[:T]
-    mask = _causal_mask(T, x.dtype)
+def _gpt2_once(emb, w: _W, n_layer, n_head):
+    """GPT2Model on input embeddings that already include the position embeddings."""
+    B, T, G = emb.shape
+    h = emb
+    mask = _causal_mask(T, emb.dtype)
     for i in range(n_layer):
         wl = w.sub(f"h.{i}.")
         y = _ln(h, wl("ln_1.weight"), wl("ln_1.bias"), 1e-5)
@@ -275,6 +276,23 @@ def _gpt2(x, w: _W, n_layer, n_head):
         h = h + _conv1d(_gelu_new(_conv1d(y, wl("mlp.c_fc.weight"), wl("mlp.c_fc.bias"))), wl("mlp.c_proj.weight"),
                         wl("mlp.c_proj.bias"))
     return _ln(h, w("ln_f.weight"), w("ln_f.bias"), 1e-5)
+
+
+def _gpt2(x, w: _W, n_layer, n_head, output_len=1):
+    """BaseFuturePredictor.forward (future_prediction.py:387-415).  output_len > 1: the last hidden state is fed
+    back as the next input embedding at position T + k - 1 (:398-412).  The reference runs that single position
+    against its KV cache; because attention is causal that equals re-running the extended sequence, which is
+    what this checker does."""
+    B, T, G = x.shape
+    wpe = w("wpe.weight")
+    emb = x + wpe[:T]
+    hidden = _gpt2_once(emb, w, n_layer, n_head)
+    outs = [hidden]
+    for k in range(1, output_len):
+        emb = torch.cat([emb, hidden[:, -1:] + wpe[T + k - 1]], dim=1)
+        hidden = _gpt2_once(emb, w, n_layer, n_head)
+        outs.append(hidden[:, -1:])
+    return torch.cat(outs, dim=1)  # (B, T + output_len - 1, G)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -314,7 +332,8 @@ def forward(state_dict: Dict[str, torch.Tensor], cfg: Dict, num_classes: Dict[st
     enc = w("dim_encoder.weight", optional=True)
     dec = w("dim_decoder.weight", optional=True)
     z_enc = z if enc is None else _linear(z, enc)  # future_prediction.py:267
-    g = _gpt2(z_enc, w.sub("future_predictor.gpt_model."), cfg["common"]["fp_layers"], cfg["common"]["fp_heads"])
+    g = _gpt2(z_enc, w.sub("future_predictor.gpt_model."), cfg["common"]["fp_layers"], cfg["common"]["fp_heads"],
+              cfg["common"].get("fp_output_len", 1))
     z_hat = g if dec is None else _linear(g, dec)  # future_prediction.py:269
 
     out = {  # prepare_output, future_prediction.py:155-182
@@ -334,3 +353,16 @@ def forward(state_dict: Dict[str, torch.Tensor], cfg: Dict, num_classes: Dict[st
 def top5(logits: torch.Tensor) -> torch.Tensor:
     """Ordered top-5 class indices per row (the quantity test.py / challenge.py consume)."""
     return logits.topk(5, dim=-1).indices
+
+
+def marginalize_verb_noun(logits: torch.Tensor, verb_in_action: torch.Tensor, noun_in_action: torch.Tensor, k: int = 5):
+    """Restatement of reference challenge.py:196-210 (softmax over action logits, marginalisation with the 0/1
+    class_mappings matrices of datasets/epic_kitchens.py:87-106) and the ranking of common/utils.py:19-42
+    (`scores.argsort()[:, ::-1][:, :k]`).  Returns verb scores, noun scores, and top-k indices (action, verb, noun)."""
+    probs = _softmax(logits.double()).float()
+    verb = probs @ verb_in_action.float()
+    noun = probs @ noun_in_action.float()
+
+    def rank(x):
+        return torch.argsort(x, dim=-1, descending=True, stable=True)[:, :k]
+    return verb, noun, torch.stack([rank(logits), rank(verb), rank(noun)], dim=1), probs

@@ -35,6 +35,7 @@ CASES = [
     ("ek100_tsa_b2", "ek100_tsa", 2, 123, "randn"),
     ("ek100_ca_b2", "ek100_ca", 2, 123, "randn"),
     ("ek100_sa_wo_token_b2", "ek100_sa_wo_token", 2, 123, "randn"),
+    ("egtea_sa_rollout3_b3", "egtea_sa_rollout3", 3, 123, "randn"),
 ]
 
 
@@ -53,9 +54,12 @@ def flatten_outputs(out):
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])  # optional: regenerate just these cases (merged into oracle_pin.json)
     pin = {}
     names_written = set()
     for case, cfg_name, B, seed, family in CASES:
+        if only and case not in only:
+            continue
         cfg, T, ncls, _ = configs.named_config(cfg_name)
         model = ref_shim.build_reference_model(cfg, ncls)
         sd = synthetic.synthetic_state_dict(model, seed=0)
@@ -105,7 +109,13 @@ def main():
             with open(os.path.join(HERE, f"param_names_{cfg_name}.json"), "w") as f:
                 json.dump({n: list(p.shape) for n, p in model.named_parameters()}, f, indent=0)
 
-    with open(os.path.join(HERE, "oracle_pin.json"), "w") as f:
+    pin_path = os.path.join(HERE, "oracle_pin.json")
+    if only and os.path.exists(pin_path):
+        with open(pin_path) as f:
+            old = json.load(f)
+        old["pin"].update(pin)
+        pin = old["pin"]
+    with open(pin_path, "w") as f:
         json.dump({"generated_with": {"torch": torch.__version__, "transformers": __import__("transformers").__version__,
                                       "reference": ref_shim.REFERENCE_ROOT},
                    "cases": {c: list(x) for c, *x in CASES}, "pin": pin}, f, indent=1)

@@ -117,8 +117,8 @@ def test_error_behaviour():
     with pytest.raises(ValueError):
         model.eval()({"rgb": torch.zeros(1, T, 1024, 1, 1, 1)})
     bad = configs.named_config("egtea_sa")[0]
-    bad["common"]["fp_output_len"] = 2
-    with pytest.raises(NotImplementedError):
+    bad["common"]["fp_output_len"] = 0
+    with pytest.raises(ValueError):
         BaseModel(bad, ncls, {})
     bad = configs.named_config("egtea_sa")[0]
     bad["mapping"]["_target_"] = "models.feature_mapping.GatedLinear"

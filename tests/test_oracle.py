@@ -29,7 +29,7 @@ def _weights(cfg_name):
 
 
 CASES = ["egtea_sa_b3", "ek100_sa_tsn_b2", "ek100_sa_tsn_relu_b2", "ek100_sa_tsn_wo_audio_b2", "ek100_sa_swin_b2",
-         "ek100_tsa_b2", "ek100_ca_b2", "ek100_sa_wo_token_b2"]
+         "ek100_tsa_b2", "ek100_ca_b2", "ek100_sa_wo_token_b2", "egtea_sa_rollout3_b3"]
 
 
 @pytest.mark.parametrize("case", CASES)

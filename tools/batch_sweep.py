@@ -29,8 +29,8 @@ D, C = cfg["common_dim"], list(ncls.values())[0]
 ldc = (C + 3) // 4 * 4
 n_tok, H1 = eng.n_slots, eng.fuser_heads
 orig = torch.empty(BMAX, T, D, device=dev)
-pf = torch.empty(BMAX, T + 1, D, device=dev)
-logits = torch.empty(BMAX, T + 1, ldc, device=dev)
+pf = torch.empty(BMAX, T + eng.fp_output_len, D, device=dev)
+logits = torch.empty(BMAX, T + eng.fp_output_len, ldc, device=dev)
 attn = torch.empty(BMAX, eng.fuser_depth, T, H1, n_tok, n_tok, device=dev)
 io = _capi.IO()
 for i, m in enumerate(order):
