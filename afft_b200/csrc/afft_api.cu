@@ -237,10 +237,10 @@ static int launch_attention_tokens_mma(const AttentionArgs& a, cudaStream_t stre
   return AFFT_OK;
 }
 
-template <int HD>
+template <int HD, int LP>
 static int launch_attention_mma(const AttentionArgs& a, cudaStream_t stream) {
-  auto kern = attention_mma_kernel<HD>;
-  constexpr int smem = AttnMmaSmem<HD>::kBytes;
+  auto kern = attention_mma_kernel<HD, LP>;
+  constexpr int smem = AttnMmaSmem<HD, LP>::kBytes;
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -277,9 +277,13 @@ static int run_attention(const AttentionArgs& a, int head_dim, bool in_f32, cuda
     return in_f32 ? launch_attention_tokens<float>(a, stream) : launch_attention_tokens<bf16>(a, stream);
   }
   // short sequences with bf16 inputs (GPT-2 predictor, CA-Fuser): tensor-core (mma.sync) kernel
-  if (use_mma && !in_f32 && a.out_lo == nullptr && a.L > 6 && a.L <= 32 && (a.mask == 0 || a.mask == 1)) {
-    if (head_dim == 256) return launch_attention_mma<256>(a, stream);
-    if (head_dim == 512) return launch_attention_mma<512>(a, stream);
+  if (use_mma && !in_f32 && a.out_lo == nullptr && a.L > 6 && a.mask >= 0 && a.mask <= 2) {
+    if (a.L <= 32) {
+      if (head_dim == 256) return launch_attention_mma<256, 32>(a, stream);
+      if (head_dim == 512) return launch_attention_mma<512, 32>(a, stream);
+    } else if (head_dim == 256) {  // T-SA-Fuser: up to 64 tokens, block-causal
+      return launch_attention_mma<256, 64>(a, stream);
+    }
   }
   if (head_dim == 256) return in_f32 ? launch_attention<float, 256>(a, stream) : launch_attention<bf16, 256>(a, stream);
   if (head_dim == 512) return in_f32 ? launch_attention<float, 512>(a, stream) : launch_attention<bf16, 512>(a, stream);

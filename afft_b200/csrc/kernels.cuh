@@ -535,19 +535,20 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int HD>
+template <int HD, int LP>
 struct AttnMmaSmem {
-  static constexpr int kLP = 32;                  // padded sequence length (two m16 tiles)
+  static constexpr int kLP = LP;                  // padded sequence length (LP / 16 m16 tiles): 32 or 64
   static constexpr int kRowBytes = HD * 2 + 16;   // odd multiple of 16 B: ldmatrix rows hit distinct banks
   static constexpr int kTileBytes = kLP * kRowBytes;
-  static constexpr int kSStride = 33;             // fp32 scores [32][33]
-  static constexpr int kPRowBytes = 80;           // bf16 probabilities [32][32] + pad (5 x 16 B)
+  static constexpr int kSStride = LP + 1;         // fp32 scores [LP][LP + 1]
+  static constexpr int kPRowBytes = LP * 2 + 16;  // bf16 probabilities [LP][LP] + pad
   static constexpr int kBytes = 3 * kTileBytes + kLP * kSStride * 4 + kLP * kPRowBytes;
 };
 
-template <int HD>
+template <int HD, int LP>
 __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs a) {
-  using S = AttnMmaSmem<HD>;
+  using S = AttnMmaSmem<HD, LP>;
+  constexpr int MT = LP / 16;  // 16-row tiles
   extern __shared__ uint4 smem_attn[];
   uint8_t* base = reinterpret_cast<uint8_t*>(smem_attn);
   const uint32_t sq = static_cast<uint32_t>(__cvta_generic_to_shared(base));
@@ -585,91 +586,110 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs 
       dst += kRowsPerPass * S::kRowBytes;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    for (int r = L + r0; r < S::kLP; r += kRowsPerPass)
+    for (int r = L + r0; r < S::kLP; r += kRowsPerPass) {
+      *reinterpret_cast<uint4*>(base + r * S::kRowBytes + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(base + S::kTileBytes + r * S::kRowBytes + c * 16) = make_uint4(0u, 0u, 0u, 0u);
       *reinterpret_cast<uint4*>(base + 2 * S::kTileBytes + r * S::kRowBytes + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
 
   const int g8 = lane >> 2, t4 = lane & 3;
-  // ---- S = Q K^T: warp -> (query tile mt, key half nh), each a 16 x 16 block over the full head_dim ----
-  {
-    const int mt = warp >> 1, nh = warp & 1;
-    const bool skip = (nh * 16 >= L) || (mt * 16 >= L) || (a.mask == 1 && nh * 16 > mt * 16 + 15);
-    if (!skip) {
-      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-      const uint32_t a_addr = sq + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * S::kRowBytes + (lane >> 4) * 16;
-      const uint32_t b_addr = sk + (nh * 16 + (lane & 7) + (lane >> 4) * 8) * S::kRowBytes + ((lane >> 3) & 1) * 16;
+  // ---- S = Q K^T: 16 x 16 blocks (query tile mt, key tile nb) over the full head_dim, dealt round-robin to warps ----
+  for (int blk = warp; blk < MT * MT; blk += 4) {
+    const int mt = blk / MT, nb = blk % MT;
+    const bool skip = (nb * 16 >= L) || (mt * 16 >= L) || (a.mask == 1 && nb * 16 > mt * 16 + 15);
+    if (skip) continue;
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const uint32_t a_addr = sq + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * S::kRowBytes + (lane >> 4) * 16;
+    const uint32_t b_addr = sk + (nb * 16 + (lane & 7) + (lane >> 4) * 8) * S::kRowBytes + ((lane >> 3) & 1) * 16;
 #pragma unroll 4
-      for (int ks = 0; ks < HD / 16; ++ks) {
-        uint32_t af[4], bf[4];
-        ldmatrix_x4(a_addr + ks * 32, af);
-        ldmatrix_x4(b_addr + ks * 32, bf);
-        mma_bf16_16816(acc[0], af, bf[0], bf[1]);
-        mma_bf16_16816(acc[1], af, bf[2], bf[3]);
-      }
+    for (int ks = 0; ks < HD / 16; ++ks) {
+      uint32_t af[4], bf[4];
+      ldmatrix_x4(a_addr + ks * 32, af);
+      ldmatrix_x4(b_addr + ks * 32, bf);
+      mma_bf16_16816(acc[0], af, bf[0], bf[1]);
+      mma_bf16_16816(acc[1], af, bf[2], bf[3]);
+    }
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        float* r0 = ss + (mt * 16 + g8) * S::kSStride + nh * 16 + nt * 8 + t4 * 2;
-        r0[0] = acc[nt][0];
-        r0[1] = acc[nt][1];
-        r0[8 * S::kSStride] = acc[nt][2];
-        r0[8 * S::kSStride + 1] = acc[nt][3];
-      }
+    for (int nt = 0; nt < 2; ++nt) {
+      float* r0 = ss + (mt * 16 + g8) * S::kSStride + nb * 16 + nt * 8 + t4 * 2;
+      r0[0] = acc[nt][0];
+      r0[1] = acc[nt][1];
+      r0[8 * S::kSStride] = acc[nt][2];
+      r0[8 * S::kSStride + 1] = acc[nt][3];
     }
   }
   __syncthreads();
 
-  // ---- softmax rows (fp32), P -> bf16 ----
+  // ---- softmax rows (fp32), P -> bf16.  mask 1: j <= i; mask 2: (j % T) <= (i % T); mask 0: none ----
   for (int i = warp; i < S::kLP; i += 4) {
-    float p = 0.f;
+    float p[LP / 32];
+#pragma unroll
+    for (int c = 0; c < LP / 32; ++c) p[c] = 0.f;
     if (i < L) {
-      const bool ok = (lane < L) && (a.mask != 1 || lane <= i);
-      const float sc = ok ? ss[i * S::kSStride + lane] * a.scale : -INFINITY;
-      const float mx = warp_max(sc);
-      p = ok ? expf(sc - mx) : 0.f;
-      p *= 1.0f / warp_sum(p);
-      if (a.probs != nullptr && lane < L)
-        a.probs[static_cast<long long>(seq / a.p_inner) * a.p_outer + static_cast<long long>(seq % a.p_inner) * a.p_inner_stride +
-                (static_cast<long long>(h) * L + i) * L + lane] = p;
+      float sc[LP / 32];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < LP / 32; ++c) {
+        const int j = lane + 32 * c;
+        const bool ok = (j < L) && (a.mask == 0 || (a.mask == 1 && j <= i) || (a.mask == 2 && (j % a.T) <= (i % a.T)));
+        sc[c] = ok ? ss[i * S::kSStride + j] * a.scale : -INFINITY;
+        mx = fmaxf(mx, sc[c]);
+      }
+      mx = warp_max(mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < LP / 32; ++c) {
+        p[c] = (sc[c] == -INFINITY) ? 0.f : expf(sc[c] - mx);
+        sum += p[c];
+      }
+      const float inv = 1.0f / warp_sum(sum);
+#pragma unroll
+      for (int c = 0; c < LP / 32; ++c) {
+        p[c] *= inv;
+        const int j = lane + 32 * c;
+        if (a.probs != nullptr && j < L)
+          a.probs[static_cast<long long>(seq / a.p_inner) * a.p_outer + static_cast<long long>(seq % a.p_inner) * a.p_inner_stride +
+                  (static_cast<long long>(h) * L + i) * L + j] = p[c];
+      }
     }
-    reinterpret_cast<__nv_bfloat16*>(sp_ptr + i * S::kPRowBytes)[lane] = __float2bfloat16_rn(p);
+#pragma unroll
+    for (int c = 0; c < LP / 32; ++c)
+      reinterpret_cast<__nv_bfloat16*>(sp_ptr + i * S::kPRowBytes)[lane + 32 * c] = __float2bfloat16_rn(p[c]);
   }
   __syncthreads();
 
   // ---- O = P V: warp -> HD / 4 output dims; output tile staged in the (now free) Q region ----
   {
     const int ksteps = (L + 15) / 16;
-    uint32_t pa[2][2][4];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks)
-        ldmatrix_x4(sp + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * S::kPRowBytes + ks * 32 + (lane >> 4) * 16, pa[mt][ks]);
-#pragma unroll 2
+#pragma unroll 1
     for (int np = 0; np < HD / 4 / 16; ++np) {
       const int n0 = warp * (HD / 4) + np * 16;
-      float acc[2][2][4];
+      float acc[MT][2][4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
+      for (int ks = 0; ks < MT; ++ks) {
         if (ks < ksteps) {
           uint32_t vf[4];
           ldmatrix_x4_trans(sv + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * S::kRowBytes + (n0 + (lane >> 4) * 8) * 2, vf);
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            mma_bf16_16816(acc[mt][0], pa[mt][ks], vf[0], vf[1]);
-            mma_bf16_16816(acc[mt][1], pa[mt][ks], vf[2], vf[3]);
+          for (int mt = 0; mt < MT; ++mt) {
+            uint32_t pa[4];
+            ldmatrix_x4(sp + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * S::kPRowBytes + ks * 32 + (lane >> 4) * 16, pa);
+            mma_bf16_16816(acc[mt][0], pa, vf[0], vf[1]);
+            mma_bf16_16816(acc[mt][1], pa, vf[2], vf[3]);
           }
         }
       }
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
           uint8_t* o0 = base + (mt * 16 + g8) * S::kRowBytes + (n0 + nt * 8 + t4 * 2) * 2;
@@ -685,7 +705,6 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs 
         *reinterpret_cast<const uint4*>(base + r * S::kRowBytes + c * 16);
   }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // SA-Fuser attention on the tensor cores (bf16 inputs): the register kernel above needs ~1700 instructions per

@@ -174,7 +174,9 @@ def _ref_attn(qkv, n_seq, L, H, hd, mask, T):
     (2, 1, 4, 256, 0, 1, torch.bfloat16), (2, 64, 4, 256, 1, 64, torch.bfloat16), (5, 10, 4, 256, 1, 10, torch.bfloat16),
     (5, 32, 4, 512, 1, 32, torch.bfloat16), (5, 16, 4, 256, 0, 16, torch.bfloat16), (3, 7, 4, 512, 1, 7, torch.bfloat16),
     (37, 3, 4, 256, 0, 1, torch.bfloat16), (37, 4, 4, 256, 0, 1, torch.bfloat16), (38, 5, 4, 256, 3, 1, torch.bfloat16),
-    (7, 6, 4, 256, 0, 1, torch.bfloat16), (9, 2, 4, 256, 0, 1, torch.bfloat16), (36, 5, 8, 256, 0, 1, torch.bfloat16)])
+    (7, 6, 4, 256, 0, 1, torch.bfloat16), (9, 2, 4, 256, 0, 1, torch.bfloat16), (36, 5, 8, 256, 0, 1, torch.bfloat16),
+    (3, 40, 4, 256, 2, 8, torch.bfloat16), (2, 64, 4, 256, 2, 16, torch.bfloat16), (2, 33, 4, 256, 0, 33, torch.bfloat16),
+    (2, 40, 4, 512, 1, 40, torch.bfloat16)])
 def test_attention(dev, n_seq, L, H, hd, mask, T, dt):
     g = torch.Generator().manual_seed(L * 31 + hd)
     D = H * hd
@@ -186,7 +188,8 @@ def test_attention(dev, n_seq, L, H, hd, mask, T, dt):
     ro, rp = _ref_attn(qkv, n_seq, L, H, hd, mask, T)
     # bf16 inputs with 6 < L <= 32 run on the tensor-core kernel: P is re-quantised to bf16 for P.V and the
     # output has no lo part (2^-9 relative on |v| ~ 3); everything else is fp32 math + hi/lo outputs.
-    mma_path = dt == torch.bfloat16 and ((6 < L <= 32 and mask in (0, 1)) or (2 <= L <= 6 and hd == 256 and mask in (0, 3)))
+    mma_path = dt == torch.bfloat16 and ((6 < L <= 32 and mask in (0, 1, 2)) or (32 < L <= 64 and hd == 256 and mask in (0, 1, 2))
+                                         or (2 <= L <= 6 and hd == 256 and mask in (0, 3)))
     if mma_path:
         assert (oh.float() - ro).abs().max().item() < 3e-2
     else:
