@@ -109,6 +109,7 @@ EXPORTED_SYMBOLS = [
     "afft_create", "afft_destroy", "afft_handle_error", "afft_workspace_bytes", "afft_weight_bytes",
     "afft_set_weight", "afft_missing_weights", "afft_forward", "afft_last_launch_count",
     "afft_profile_enable", "afft_profile_read", "afft_marginalize_topk",
+    "afft_transpose_bf16", "afft_layernorm_bwd", "afft_gelu_fwd", "afft_gelu_bwd", "afft_colsum", "afft_attention_bwd",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -147,6 +148,16 @@ def lib() -> C.CDLL:
     l.afft_marginalize_topk.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     l.afft_marginalize_topk.restype = C.c_int
+    l.afft_transpose_bf16.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+    l.afft_layernorm_bwd.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.afft_gelu_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    l.afft_gelu_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    l.afft_colsum.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    l.afft_attention_bwd.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_int32, C.c_float, C.c_void_p]
+    for _n in ("afft_transpose_bf16", "afft_layernorm_bwd", "afft_gelu_fwd", "afft_gelu_bwd", "afft_colsum", "afft_attention_bwd"):
+        getattr(l, _n).restype = C.c_int
     l.afft_profile_enable.argtypes = [C.c_void_p, C.c_int32]
     l.afft_profile_read.argtypes = [C.c_void_p, C.POINTER(Profile)]
     for name in ("afft_gemm", "afft_convert_bf16", "afft_layernorm", "afft_attention", "afft_create",

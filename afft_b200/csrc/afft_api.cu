@@ -18,6 +18,7 @@
 
 #include "gemm_launch.cuh"
 #include "kernels.cuh"
+#include "kernels_train.cuh"
 
 using namespace afft;
 typedef __nv_bfloat16 bf16;
@@ -343,6 +344,80 @@ extern "C" int afft_marginalize_topk(const float* logits, int64_t ld, int32_t B,
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail("marginalize launch", e);
   return AFFT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// training-step operators
+// ------------------------------------------------------------------------------------------------
+static int launch_check(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(what, e);
+  return AFFT_OK;
+}
+
+extern "C" int afft_transpose_bf16(const void* src, int64_t lds, int32_t rows, int32_t cols, void* dst, int64_t ldd,
+                                   void* stream) {
+  if (src == nullptr || dst == nullptr || rows <= 0 || cols <= 0) return fail(AFFT_ERR_INVALID, "transpose: bad argument");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_bf16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(src), lds, rows, cols,
+                                                                              static_cast<bf16*>(dst), ldd);
+  return launch_check("transpose launch");
+}
+
+extern "C" int afft_layernorm_bwd(const float* x, int64_t ldx, const float* gamma, float eps, const float* dy, int64_t lddy,
+                                  int32_t rows, int32_t dim, float* dx, int64_t lddx, float* dgamma, float* dbeta,
+                                  void* stream) {
+  if (x == nullptr || dy == nullptr || dx == nullptr || rows <= 0) return fail(AFFT_ERR_INVALID, "layernorm_bwd: bad argument");
+  if ((dgamma == nullptr) != (dbeta == nullptr)) return fail(AFFT_ERR_INVALID, "layernorm_bwd: dgamma and dbeta go together");
+  LayerNormBwdArgs a{x, ldx, gamma, eps, dy, lddy, rows, dim, dx, lddx, dgamma, dbeta};
+  const int blocks = std::min((rows + 7) / 8, 148 * 2);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dim / 128) {
+    case 4: layernorm_bwd_kernel<4><<<blocks, 256, 0, st>>>(a); break;
+    case 8: layernorm_bwd_kernel<8><<<blocks, 256, 0, st>>>(a); break;
+    case 16: layernorm_bwd_kernel<16><<<blocks, 256, 0, st>>>(a); break;
+    default: return fail(AFFT_ERR_INVALID, "layernorm_bwd: dim must be 512, 1024 or 2048");
+  }
+  if (dim % 128 != 0) return fail(AFFT_ERR_INVALID, "layernorm_bwd: dim must be a multiple of 128");
+  return launch_check("layernorm_bwd launch");
+}
+
+extern "C" int afft_gelu_fwd(const float* x, float* y, int64_t n, int32_t kind, void* stream) {
+  if (x == nullptr || y == nullptr || n <= 0 || (kind != 1 && kind != 2)) return fail(AFFT_ERR_INVALID, "gelu_fwd: bad argument");
+  const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 16));
+  gelu_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, kind);
+  return launch_check("gelu_fwd launch");
+}
+
+extern "C" int afft_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n, int32_t kind, void* stream) {
+  if (x == nullptr || dy == nullptr || dx == nullptr || n <= 0 || (kind != 1 && kind != 2))
+    return fail(AFFT_ERR_INVALID, "gelu_bwd: bad argument");
+  const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 16));
+  gelu_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, dx, n, kind);
+  return launch_check("gelu_bwd launch");
+}
+
+extern "C" int afft_colsum(const float* x, int64_t ld, int32_t rows, int32_t cols, float* out, void* stream) {
+  if (x == nullptr || out == nullptr || rows <= 0 || cols <= 0) return fail(AFFT_ERR_INVALID, "colsum: bad argument");
+  dim3 grid((cols + 127) / 128, std::min(rows, 64));
+  colsum_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, rows, cols, out);
+  return launch_check("colsum launch");
+}
+
+extern "C" int afft_attention_bwd(const float* qkv, int64_t ld, const float* probs, const float* d_out, int64_t ldo,
+                                  float* dqkv, int32_t n_seq, int32_t L, int32_t H, int32_t head_dim, float scale,
+                                  void* stream) {
+  if (qkv == nullptr || probs == nullptr || d_out == nullptr || dqkv == nullptr) return fail(AFFT_ERR_INVALID, "attention_bwd: null pointer");
+  if (L < 1 || L > 64 || n_seq <= 0 || H <= 0 || head_dim <= 0) return fail(AFFT_ERR_INVALID, "attention_bwd: bad sizes");
+  const size_t smem = (static_cast<size_t>(4) * L * head_dim + 2 * L * L) * sizeof(float);
+  if (smem > 227 * 1024) return fail(AFFT_ERR_INVALID, "attention_bwd: sequence too long for shared memory");
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return cuda_fail("attention_bwd smem attribute", e);
+  }
+  AttentionBwdArgs a{qkv, ld, probs, d_out, ldo, dqkv, n_seq, L, H, head_dim, scale};
+  attention_bwd_kernel<<<n_seq * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  return launch_check("attention_bwd launch");
 }
 
 // ================================================================================================

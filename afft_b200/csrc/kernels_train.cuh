@@ -1,0 +1,230 @@
+// Backward-pass kernels for the training step (BASELINE config 5; reference train.py:234-262 runs
+// loss.backward() through the same modules).  The dense contractions of the backward pass (dgrad = dY.W and
+// wgrad = dY^T.X) reuse the tcgen05 GEMM on transposed bf16 operands; what lives here are the HBM-bound pieces
+// autograd would otherwise run as ATen kernels: operand transposition, LayerNorm backward, GELU forward/backward,
+// the backward of the small attentions, and the bias-gradient column sum.  All fp32 in / fp32 out.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace afft {
+
+// dst[c, r] = src[r, c], bf16 -> bf16 (src [rows, cols] pitch lds, dst [cols, rows] pitch ldd)
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, long long lds, int rows, int cols,
+                                      __nv_bfloat16* __restrict__ dst, long long ldd) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? src[r * lds + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) dst[c * ldd + r] = tile[threadIdx.x][j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  xhat = (x - mean) * rstd (recomputed), g = dy * gamma:
+//   dx = rstd * (g - mean(g) - xhat * mean(g * xhat));  dgamma += sum_rows dy * xhat;  dbeta += sum_rows dy
+// One warp per row (grid-stride), per-lane partial dgamma/dbeta in registers, one atomicAdd per element per block.
+// ------------------------------------------------------------------------------------------------
+struct LayerNormBwdArgs {
+  const float* x;
+  long long ldx;
+  const float* gamma;  // may be nullptr (no affine)
+  float eps;
+  const float* dy;
+  long long lddy;
+  int rows, dim;
+  float* dx;
+  long long lddx;
+  float* dgamma;  // accumulated (+=); may be nullptr
+  float* dbeta;
+};
+
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LayerNormBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  const float inv_d = 1.0f / static_cast<float>(a.dim);
+  float4 pg[NV], pb[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) pg[i] = pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int row = gw; row < a.rows; row += nw) {
+    const float4* xr = reinterpret_cast<const float4*>(a.x + row * a.ldx);
+    const float4* dyr = reinterpret_cast<const float4*>(a.dy + row * a.lddy);
+    float4 v[NV], d[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i] = xr[lane + 32 * i];
+      d[i] = dyr[lane + 32 * i];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + a.eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xhat
+      pg[i].x += d[i].x * v[i].x; pg[i].y += d[i].y * v[i].y; pg[i].z += d[i].z * v[i].z; pg[i].w += d[i].w * v[i].w;
+      pb[i].x += d[i].x; pb[i].y += d[i].y; pb[i].z += d[i].z; pb[i].w += d[i].w;
+      if (a.gamma != nullptr) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma) + lane + 32 * i);
+        d[i].x *= g.x; d[i].y *= g.y; d[i].z *= g.z; d[i].w *= g.w;  // g = dy * gamma
+      }
+      sg += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+      sgx += (d[i].x * v[i].x + d[i].y * v[i].y) + (d[i].z * v[i].z + d[i].w * v[i].w);
+    }
+    const float mg = warp_sum(sg) * inv_d, mgx = warp_sum(sgx) * inv_d;
+    float4* dxr = reinterpret_cast<float4*>(a.dx + row * a.lddx);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 o;
+      o.x = rstd * (d[i].x - mg - v[i].x * mgx);
+      o.y = rstd * (d[i].y - mg - v[i].y * mgx);
+      o.z = rstd * (d[i].z - mg - v[i].z * mgx);
+      o.w = rstd * (d[i].w - mg - v[i].w * mgx);
+      dxr[lane + 32 * i] = o;
+    }
+  }
+  if (a.dgamma != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      atomicAdd(a.dgamma + c + 0, pg[i].x); atomicAdd(a.dgamma + c + 1, pg[i].y);
+      atomicAdd(a.dgamma + c + 2, pg[i].z); atomicAdd(a.dgamma + c + 3, pg[i].w);
+      atomicAdd(a.dbeta + c + 0, pb[i].x); atomicAdd(a.dbeta + c + 1, pb[i].y);
+      atomicAdd(a.dbeta + c + 2, pb[i].z); atomicAdd(a.dbeta + c + 3, pb[i].w);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GELU forward / backward (elementwise, fp32).  kind 1: erf (nn.GELU), kind 2: tanh (HF gelu_new).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_fwd_exact(float x, int kind) {
+  if (kind == 1) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(u));
+}
+__device__ __forceinline__ float gelu_grad_exact(float x, int kind) {
+  if (kind == 1) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+  }
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  const float t = tanhf(u);
+  const float du = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x * x);
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+}
+__global__ void gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int kind) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = gelu_fwd_exact(x[i], kind);
+}
+__global__ void gelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
+                                long long n, int kind) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dx[i] = dy[i] * gelu_grad_exact(x[i], kind);
+}
+
+// out[c] += sum_r x[r, c]   (bias gradients)
+__global__ void colsum_kernel(const float* __restrict__ x, long long ld, int rows, int cols, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) s += x[r * ld + c];
+  atomicAdd(out + c, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward of the small attentions (SA-Fuser 5x5, GPT-2 18x18 causal, ...): one CTA per (sequence, head).
+//   dV_j = sum_i P_ij dO_i;  dP_ij = dO_i . V_j;  dS_ij = P_ij (dP_ij - sum_j P_ij dP_ij) * scale;
+//   dQ_i = sum_j dS_ij K_j;  dK_j = sum_i dS_ij Q_i.       Masked entries have P = 0, hence dS = 0.
+// q/k/v fp32 at qkv[(seq*L + i)*ld + {0, D, 2D} + h*HD + d]; probs fp32 [n_seq, H, L, L]; dO fp32 [rows, D];
+// dqkv fp32 with the layout of qkv.
+// ------------------------------------------------------------------------------------------------
+struct AttentionBwdArgs {
+  const float* qkv;
+  long long ld;
+  const float* probs;
+  const float* d_out;
+  long long ldo;
+  float* dqkv;
+  int n_seq, L, H, HD;
+  float scale;
+};
+
+__global__ void __launch_bounds__(256) attention_bwd_kernel(const AttentionBwdArgs a) {
+  extern __shared__ float smem_ab[];
+  const int L = a.L, HD = a.HD;
+  const long long D = static_cast<long long>(a.H) * HD;
+  float* sq = smem_ab;
+  float* sk = sq + L * HD;
+  float* sv = sk + L * HD;
+  float* sdo = sv + L * HD;
+  float* sp = sdo + L * HD;   // [L][L]
+  float* sds = sp + L * L;    // [L][L]
+  const int seq = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const float* base = a.qkv + static_cast<long long>(seq) * L * a.ld + h * HD;
+  for (int i = threadIdx.x; i < L * HD; i += blockDim.x) {
+    const int r = i / HD, d = i % HD;
+    sq[i] = base[r * a.ld + d];
+    sk[i] = base[r * a.ld + D + d];
+    sv[i] = base[r * a.ld + 2 * D + d];
+    sdo[i] = a.d_out[(static_cast<long long>(seq) * L + r) * a.ldo + h * HD + d];
+  }
+  const float* pg = a.probs + (static_cast<long long>(seq) * a.H + h) * L * L;
+  for (int i = threadIdx.x; i < L * L; i += blockDim.x) sp[i] = pg[i];
+  __syncthreads();
+  // dP (stored in sds)
+  for (int ij = threadIdx.x; ij < L * L; ij += blockDim.x) {
+    const int i = ij / L, j = ij % L;
+    float acc = 0.f;
+    if (sp[ij] != 0.f) {
+      const float* o = sdo + i * HD;
+      const float* v = sv + j * HD;
+      for (int d = 0; d < HD; ++d) acc = fmaf(o[d], v[d], acc);
+    }
+    sds[ij] = acc;
+  }
+  __syncthreads();
+  // dS = P * (dP - rowsum(P * dP)) * scale, one thread per row
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    float rs = 0.f;
+    for (int j = 0; j < L; ++j) rs = fmaf(sp[i * L + j], sds[i * L + j], rs);
+    for (int j = 0; j < L; ++j) sds[i * L + j] = sp[i * L + j] * (sds[i * L + j] - rs) * a.scale;
+  }
+  __syncthreads();
+  float* dbase = a.dqkv + static_cast<long long>(seq) * L * a.ld + h * HD;
+  for (int id = threadIdx.x; id < L * HD; id += blockDim.x) {
+    const int r = id / HD, d = id % HD;
+    float dq = 0.f, dk = 0.f, dv = 0.f;
+    for (int j = 0; j < L; ++j) {
+      dq = fmaf(sds[r * L + j], sk[j * HD + d], dq);   // dQ_r = sum_j dS_rj K_j
+      dk = fmaf(sds[j * L + r], sq[j * HD + d], dk);   // dK_r = sum_i dS_ir Q_i
+      dv = fmaf(sp[j * L + r], sdo[j * HD + d], dv);   // dV_r = sum_i P_ir dO_i
+    }
+    dbase[r * a.ld + d] = dq;
+    dbase[r * a.ld + D + d] = dk;
+    dbase[r * a.ld + 2 * D + d] = dv;
+  }
+}
+
+}  // namespace afft

@@ -227,8 +227,11 @@ class CMFPEarly(nn.Module):
 
     def forward(self, feats: Dict[str, Tensor]) -> Dict[str, Dict[str, Tensor]]:
         if self.training:
-            raise NotImplementedError("the fused path implements eval-mode forward only (call model.eval()); "
-                                      "training-mode dropout/DropPath and backward are not built yet")
+            # training step (BASELINE config 5): differentiable path built from the same native kernels
+            from ..train import forward_train
+            if next(iter(feats.values())).device.type != "cuda":
+                raise _capi.AfftError("afft_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
+            return forward_train(self, feats)
         feats_order = [mod for mod in self.modal_feature_order if mod in feats]  # reference :258
         if set(feats_order) != set(self.modality_dims):
             raise ValueError(f"features {sorted(feats)} do not match modal_dims {sorted(self.modality_dims)}")

@@ -162,6 +162,25 @@ AFFT_API int afft_marginalize_topk(const float* logits, int64_t ld, int32_t B, i
                                    float* noun, int32_t* topk, int32_t K, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Training-step operators (BASELINE config 5: forward + backward; reference train.py:234-262 relies on autograd   */
+/* through nn.Linear / nn.LayerNorm / nn.GELU / softmax attention).  dgrad and wgrad are afft_gemm calls on       */
+/* transposed bf16 operands; these are the remaining backward kernels.  fp32 in / fp32 out.                       */
+/* ------------------------------------------------------------------------------------------ */
+AFFT_API int afft_transpose_bf16(const void* src, int64_t lds, int32_t rows, int32_t cols, void* dst, int64_t ldd, void* stream);
+/* dx = LayerNorm backward; dgamma / dbeta are ACCUMULATED (+=) and may be NULL (together with gamma). */
+AFFT_API int afft_layernorm_bwd(const float* x, int64_t ldx, const float* gamma, float eps, const float* dy, int64_t lddy,
+                                int32_t rows, int32_t dim, float* dx, int64_t lddx, float* dgamma, float* dbeta, void* stream);
+/* kind: AFFT_ACT_GELU_ERF or AFFT_ACT_GELU_TANH */
+AFFT_API int afft_gelu_fwd(const float* x, float* y, int64_t n, int32_t kind, void* stream);
+AFFT_API int afft_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n, int32_t kind, void* stream);
+/* out[c] += sum over rows of x[r, c] (bias gradient) */
+AFFT_API int afft_colsum(const float* x, int64_t ld, int32_t rows, int32_t cols, float* out, void* stream);
+/* Backward of afft_attention for fp32 q|k|v (layout as afft_attention_desc with ldq = ldk = ldv = ld, q at column 0,
+ * k at H*head_dim, v at 2*H*head_dim); probs [n_seq, H, L, L] as written by the forward; d_out [n_seq*L, ldo]. */
+AFFT_API int afft_attention_bwd(const float* qkv, int64_t ld, const float* probs, const float* d_out, int64_t ldo, float* dqkv,
+                                int32_t n_seq, int32_t L, int32_t H, int32_t head_dim, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Model-level API: everything below BaseModel.future_predictor (models/base_model.py:59)      */
 /* ------------------------------------------------------------------------------------------ */
 

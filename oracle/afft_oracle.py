@@ -123,7 +123,8 @@ class _W:
             if optional:
                 return None
             raise KeyError(k)
-        return self.sd[k].detach().to(self.dtype)
+        t = self.sd[k]
+        return t.to(self.dtype) if t.requires_grad else t.detach().to(self.dtype)  # keeps autograd for gradient checks
 
     def sub(self, p):
         return _W(self.sd, self.prefix + p, self.dtype)

@@ -110,7 +110,7 @@ def test_error_behaviour():
     cfg, T, ncls, _ = configs.named_config("egtea_sa")
     model = BaseModel(cfg, ncls, {})
     x = {"rgb": torch.zeros(1, T, 1024, 1, 1, 1), "flow": torch.zeros(1, T, 1024, 1, 1, 1)}
-    with pytest.raises(NotImplementedError):  # training mode is not implemented: loud, not silent
+    with pytest.raises(_capi.AfftError):  # CPU tensors in training mode: there is no CPU fallback
         model.train()(dict(x))
     with pytest.raises(_capi.AfftError):  # CPU tensors: there is no CPU fallback
         model.eval()(dict(x))
