@@ -389,8 +389,77 @@ def run_afft(args):
     adist.shutdown()
 
 
+# ------------------------------------------------------------------------------------------------
+# training-step arm (BASELINE config 5): fwd + bwd + NCCL gradient all-reduce (DDP) + SGD-nesterov step
+# ------------------------------------------------------------------------------------------------
+def run_train(args):
+    from afft_b200 import _capi
+    from afft_b200 import train as atrain
+    from afft_b200.models import BaseModel
+
+    rank, local_rank, world = adist.init()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --mode train needs CUDA devices (B200)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _capi.lib()
+    cfg, T, ncls, _ = configs.named_config(args.config if args.config != "ek100_sa_tsn" else "ek100_sa_swin")
+    B = args.batch if args.batch != 256 else 16  # expts/01_SA-Fuser_ek100_train.txt:7: 16 clips per GPU
+    C = list(ncls.values())[0]
+    torch.manual_seed(0)
+    model = BaseModel(cfg, ncls, {}).to(dev).train()
+    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if world > 1 else model
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, nesterov=True, weight_decay=1e-6)  # expts/01 :48-52
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    sets = [{m: torch.randn(B, T, d, 1, 1, 1, device=dev, generator=g) for m, d in cfg["modal_dims"].items()} for _ in range(2)]
+    target = torch.randint(0, C, (B, 1), device=dev, generator=g)
+    target_sub = torch.randint(0, C, (B, T), device=dev, generator=g)
+
+    def step(i):
+        opt.zero_grad(set_to_none=True)
+        out, _ = ddp(dict(sets[i % 2]), **KW)
+        loss = atrain.reference_losses(out, target, target_sub)["total"]
+        loss.backward()  # DDP: bucketed NCCL all-reduce overlapped with the remaining backward
+        opt.step()
+        return loss
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    torch.cuda.synchronize()
+    adist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    with sampler:
+        e0.record()
+        for i in range(args.steps):
+            loss = step(i)
+        e1.record()
+        torch.cuda.synchronize()
+    adist.barrier()
+    ms_total = adist.max_over_ranks(e0.elapsed_time(e1), dev)
+    n_params = sum(p.numel() for p in model.parameters())
+    flops_per_clip = 3.0 * configs.gemm_flops_per_clip(cfg, T, ncls)
+    value = world * B * args.steps / (ms_total / 1e3)
+    line = {
+        "metric": "SA-Fuser EK100 training step clips/sec (fwd + bwd + gradient all-reduce + SGD)", "value": round(value, 1),
+        "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "mode": "train",
+        "config": {"workload": "ek100_sa_swin training step (expts/01_SA-Fuser_ek100_train.txt: T=16, 4 modalities, SGD-nesterov)",
+                   "clips_per_gpu_per_step": B, "T": T, "params": n_params, "grad_allreduce_bytes": 4 * n_params if world > 1 else 0,
+                   "allreduce": "torch DDP bucketed NCCL all-reduce overlapped with backward" if world > 1 else "none (1 GPU)",
+                   "gemm_gflop_per_clip_fwd_bwd": round(flops_per_clip / 1e9, 2), "final_loss": round(float(loss), 4)},
+        "achieved_tflops": round(value * flops_per_clip / 1e12, 1),
+        "clocks": sampler.summary(),
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    adist.shutdown()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", choices=["infer", "train"], default="infer")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
@@ -402,7 +471,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.mode == "train":
+        run_train(args)
+    elif args.impl == "reference":
         args.warmup = max(args.warmup, 1)
         run_reference(args)
     else:
