@@ -130,11 +130,11 @@ static int run_layernorm(const LayerNormArgs& a, cudaStream_t stream) {
   const bool avg = a.n_avg > 1;
   const bool fast = !avg && a.gamma != nullptr && a.beta != nullptr && a.y_hi != nullptr && a.y_f32 == nullptr &&
                     a.y_lo == nullptr && a.aux_mod == 0;
-#define AFFT_LN(NV)                                                                 \
-  case NV:                                                                          \
-    if (fast) layernorm_kernel<NV, false, true><<<blocks, 256, 0, stream>>>(a);     \
-    else if (avg) layernorm_kernel<NV, true><<<blocks, 256, 0, stream>>>(a);        \
-    else layernorm_kernel<NV, false><<<blocks, 256, 0, stream>>>(a);                \
+#define AFFT_LN(NV)                                                                                          \
+  case NV:                                                                                                   \
+    if (fast) launch_pdl(layernorm_kernel<NV, false, true>, dim3(blocks), dim3(256), 0, stream, a);          \
+    else if (avg) launch_pdl(layernorm_kernel<NV, true, false>, dim3(blocks), dim3(256), 0, stream, a);      \
+    else launch_pdl(layernorm_kernel<NV, false, false>, dim3(blocks), dim3(256), 0, stream, a);              \
     break;
   switch (a.dim / 128) {
     AFFT_LN(2)
@@ -232,8 +232,7 @@ static int launch_attention_tokens_mma(const AttentionArgs& a, cudaStream_t stre
     configured[dev] = smem;
   }
   constexpr int G = 16 / L;
-  kern<<<(a.n_seq + G - 1) / G, 32 * a.H, smem, stream>>>(a);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(kern, dim3((a.n_seq + G - 1) / G), dim3(32 * a.H), smem, stream, a);
   if (e != cudaSuccess) return cuda_fail("attention_tokens_mma launch", e);
   return AFFT_OK;
 }
@@ -251,8 +250,7 @@ static int launch_attention_mma(const AttentionArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return cuda_fail("attention_mma smem attribute", e);
     configured[dev] = true;
   }
-  kern<<<a.n_seq * a.H, 128, smem, stream>>>(a);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(kern, dim3(a.n_seq * a.H), dim3(128), smem, stream, a);
   if (e != cudaSuccess) return cuda_fail("attention_mma launch", e);
   return AFFT_OK;
 }

@@ -69,6 +69,28 @@ inline bool make_tmap_bf16(CUtensorMap* out, const void* ptr, long long rows, lo
   return true;
 }
 
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* v = getenv("AFFT_PDL"); return v == nullptr || atoi(v) != 0; }();
+  return on;
+}
+
+// Launch with the programmatic-stream-serialization attribute (the kernel must call griddepcontrol.wait before
+// touching data produced by its predecessor).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int BLOCK_N, int SPLIT, int EPI>
 inline cudaError_t launch_gemm_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal,
                                        const CUtensorMap& tbl, const GemmEpilogue& ep, int M, int N, int K,
@@ -86,8 +108,7 @@ inline cudaError_t launch_gemm_variant(const CUtensorMap& ta, const CUtensorMap&
   }
   const int num_tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  kern<<<grid, kGemmThreads, T::kSmemBytes, stream>>>(ta, tb, tal, tbl, ep, M, N, K, sched);
-  return cudaGetLastError();
+  return launch_pdl(kern, dim3(grid), dim3(kGemmThreads), T::kSmemBytes, stream, ta, tb, tal, tbl, ep, M, N, K, sched);
 }
 
 template <int SPLIT, int EPI>
@@ -108,8 +129,8 @@ inline cudaError_t launch_gemm_2cta_variant(const CUtensorMap& ta, const CUtenso
   const int num_tiles = ((M + 255) / 256) * ((N + 255) / 256);
   int clusters = num_sms / 2;
   if (num_tiles < clusters) clusters = num_tiles;
-  kern<<<2 * clusters, kGemmThreads, T::kSmemBytes, stream>>>(ta, tb, tal, tbl, ep, M, N, K, sched);  // __cluster_dims__(2)
-  return cudaGetLastError();
+  // __cluster_dims__(2) is compiled into the kernel
+  return launch_pdl(kern, dim3(2 * clusters), dim3(kGemmThreads), T::kSmemBytes, stream, ta, tb, tal, tbl, ep, M, N, K, sched);
 }
 
 inline int pick_block_n(int M, int N, int num_sms, int forced) {

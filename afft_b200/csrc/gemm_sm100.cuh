@@ -314,6 +314,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
 
+  ptx::griddep_launch();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_m = (M + kBlockM - 1) / kBlockM;
@@ -345,6 +346,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  ptx::griddep_wait();  // operands / residual written by the previous kernel are visible from here on
 
   if (warp == 0) {
     // ======================= TMA producer =======================
@@ -528,6 +530,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
   const uint32_t tmem_slot = bar_base + 8u * (2 * T::kStages + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
 
+  ptx::griddep_launch();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();  // 0 = leader
@@ -562,6 +565,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
   ptx::cluster_sync();  // barriers of both CTAs initialised before any remote arrive / multicast commit
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  ptx::griddep_wait();  // operands / residual written by the previous kernel are visible from here on
 
   if (warp == 0) {
     // ======================= TMA producer (both CTAs) =======================

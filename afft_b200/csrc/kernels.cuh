@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ptx_sm100.cuh"
+
 namespace afft {
 
 // ------------------------------------------------------------------------------------------------
@@ -130,6 +132,8 @@ __device__ __forceinline__ void ln_store(const LayerNormArgs& a, int row, bool a
 // FAST = true is the hot instantiation (bf16 output only, affine, no aux scatter): no per-vector null checks.
 template <int NV, bool AVG, bool FAST = false>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs a) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= a.rows) return;
@@ -557,6 +561,8 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs 
   uint8_t* sp_ptr = base + 3 * S::kTileBytes + S::kLP * S::kSStride * 4;
   const uint32_t sp = sv + S::kTileBytes + S::kLP * S::kSStride * 4;
 
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const int seq = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int L = a.L;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -720,6 +726,8 @@ __global__ void __launch_bounds__(256) attention_tokens_mma_kernel(const Attenti
   constexpr int RB = HD * 2 + 16;  // padded row: odd multiple of 16 B
   constexpr int TILE = 16 * RB;
   extern __shared__ uint4 smem_attn[];
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = warp;  // one warp per head
   const int seq0 = blockIdx.x * G;

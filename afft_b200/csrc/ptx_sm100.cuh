@@ -23,6 +23,16 @@ __device__ __forceinline__ uint32_t lane_id() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still running.  griddep_launch() lets the NEXT kernel start early;
+// griddep_wait() blocks until the PREVIOUS grid has completed and its writes are visible - everything before it
+// (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail.  Both are no-ops when the
+// kernel was launched without the attribute.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
