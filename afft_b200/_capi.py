@@ -19,10 +19,10 @@ AFFT_OK = 0
 AFFT_MAX_MODS = 8
 AFFT_MAX_CLS = 4
 AFFT_NAME_LEN = 32
-ABI_VERSION = 2
+ABI_VERSION = 3
 
-ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH = 0, 1, 2
-FUSER_SA, FUSER_SA_NOTOKEN, FUSER_TSA, FUSER_CA = 0, 1, 2, 3
+ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH, ACT_RELU, ACT_GATE = 0, 1, 2, 3, 4
+FUSER_SA, FUSER_SA_NOTOKEN, FUSER_TSA, FUSER_CA, FUSER_NONE = 0, 1, 2, 3, 4
 
 
 class AfftError(RuntimeError):
@@ -108,7 +108,7 @@ EXPORTED_SYMBOLS = [
     "afft_abi_version", "afft_last_error", "afft_gemm", "afft_convert_bf16", "afft_layernorm", "afft_attention",
     "afft_create", "afft_destroy", "afft_handle_error", "afft_workspace_bytes", "afft_weight_bytes",
     "afft_set_weight", "afft_missing_weights", "afft_forward", "afft_last_launch_count",
-    "afft_profile_enable", "afft_profile_read", "afft_marginalize_topk",
+    "afft_profile_enable", "afft_profile_read", "afft_marginalize_topk", "afft_score_fusion",
     "afft_transpose_bf16", "afft_layernorm_bwd", "afft_gelu_fwd", "afft_gelu_bwd", "afft_colsum", "afft_attention_bwd",
 ]
 
@@ -148,6 +148,9 @@ def lib() -> C.CDLL:
     l.afft_marginalize_topk.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     l.afft_marginalize_topk.restype = C.c_int
+    l.afft_score_fusion.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_void_p), C.c_int64, C.c_int32, C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    l.afft_score_fusion.restype = C.c_int
     l.afft_transpose_bf16.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
     l.afft_layernorm_bwd.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -255,3 +258,19 @@ def attention(qkv, n_seq, L, H, head_dim, *, mask=0, T=1, out_hi, out_lo=None, p
     d.out_hi, d.out_lo, d.ldo = ptr(out_hi), ptr(out_lo), out_hi.stride(0)
     d.probs, d.p_outer, d.p_inner_stride, d.p_inner = ptr(probs), p_outer, p_inner_stride, p_inner
     check(lib().afft_attention(C.byref(d), current_stream_ptr(qkv.device)))
+
+
+def score_fusion(attn_logits, logits=None, n_cols=0, *, attn=None, out=None):
+    """p = softmax(attn_logits[:, :M]); out[:, :n_cols] = sum_i p[:, i] * logits[i][:, :n_cols] (all fp32, 2-D).
+    With logits=None only the softmax is written to ``attn`` [rows, M]."""
+    M = attn.shape[1] if attn is not None else len(logits)
+    rows = attn_logits.shape[0]
+    arr = (C.c_void_p * 8)()
+    ld_l = 0
+    if logits is not None:
+        for i, t in enumerate(logits):
+            arr[i] = ptr(t)
+        ld_l = logits[0].stride(0)
+    check(lib().afft_score_fusion(ptr(attn_logits), attn_logits.stride(0), M, arr if logits is not None else None, ld_l, rows,
+                                  n_cols, ptr(attn), ptr(out), out.stride(0) if out is not None else 0,
+                                  current_stream_ptr(attn_logits.device)))

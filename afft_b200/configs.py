@@ -62,6 +62,31 @@ def model_cfg(modal_dims: Dict[str, int], *, fuser: str = "SA-Fuser", depth: int
     }
 
 
+_MAPPINGS = {  # conf/model/mapping/*.yaml
+    "linear": {"_target_": "models.feature_mapping.Linear", "use_layernorm": False, "sparse_mapping": True},
+    "gatedlinear": {"_target_": "models.feature_mapping.GatedLinear", "use_layernorm": True},
+    "nonlinear": {"_target_": "models.feature_mapping.NonLinear", "use_layernorm": True, "activation": "relu"},
+}
+
+
+def _with_mapping(cfg: Dict, name: str, **overrides) -> Dict:
+    cfg["mapping"] = dict(_MAPPINGS[name], **overrides)
+    return cfg
+
+
+def _unimodal_heads(cfg: Dict, head: str) -> Dict:
+    """expts/00 (model/CMFP=individual) and expts/05 (model/CMFP=scorefusion, model/fuser=MATT): per-modality
+    predictors and classifiers, no fused classifier."""
+    cfg["common"].update(share_classifiers=False, share_predictors=False, modality_cls=True, fusion_cls=False)
+    if head == "individual":
+        cfg["CMFP"] = {"_target_": "models.future_prediction.IndividualFuturePrediction", "model_cfg": None}
+    else:
+        cfg["CMFP"] = {"_target_": "models.future_prediction.CMFPScoreFusion", "model_cfg": None}
+        cfg["fuser"] = {"_target_": "models.fusion.MATT", "modal_dims": dict(cfg["modal_dims"]),
+                        "dim": cfg["common"]["in_features"], "drop_rate": 0.8}  # conf/model/fuser/MATT.yaml
+    return cfg
+
+
 def _with_output_len(cfg: Dict, n: int) -> Dict:
     cfg["common"]["fp_output_len"] = n
     return cfg
@@ -90,6 +115,19 @@ def named_config(name: str):
         # model.common.fp_output_len=3 on the EGTEA model: autoregressive roll-out (future_prediction.py:395-412)
         "egtea_sa_rollout3": (lambda: _with_output_len(model_cfg({"rgb": 1024, "flow": 1024}, depth=2, fp_layers=2), 3),
                               10, {"action": 106}, 32),
+        # expts/00_RGB_TSN_ek100_train.txt (model/CMFP=individual), here with a second, 352-wide modality
+        "ek100_individual": (lambda: _unimodal_heads(model_cfg({"rgb": 1024, "objects": 352}, fp_layers=2), "individual"),
+                             10, {"action": 3806}, 16),
+        # expts/05_MATT_ek100_train.txt (model/CMFP=scorefusion, model/fuser=MATT, fp_layers=2)
+        "ek100_matt": (lambda: _unimodal_heads(model_cfg(ek4, fp_layers=2), "scorefusion"), 10, {"action": 3806}, 16),
+        # conf/model/mapping/gatedlinear.yaml and nonlinear.yaml on a shallow SA-Fuser model
+        "ek100_sa_gatedlinear": (lambda: _with_mapping(model_cfg(ek3, depth=2, fp_layers=2), "gatedlinear"),
+                                 10, {"action": 3806}, 16),
+        "ek100_sa_nonlinear": (lambda: _with_mapping(model_cfg(ek3, depth=2, fp_layers=2), "nonlinear"),
+                               10, {"action": 3806}, 16),
+        # Linear mapping with use_layernorm=true, sparse_mapping=false (feature_mapping.py:58-67)
+        "ek100_sa_linear_ln": (lambda: _with_mapping(model_cfg(ek3, depth=2, fp_layers=2), "linear", use_layernorm=True,
+                                                     sparse_mapping=False), 10, {"action": 3806}, 16),
     }
     if name not in table:
         raise KeyError(f"unknown config {name}; have {sorted(table)}")

@@ -35,7 +35,7 @@ static int cuda_fail(const char* what, cudaError_t e) {
   return fail(AFFT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-extern "C" int afft_abi_version(void) { return 2; }
+extern "C" int afft_abi_version(void) { return 3; }
 extern "C" const char* afft_last_error(void) { return g_err.c_str(); }
 
 static int device_sm_count(int* out) {
@@ -88,6 +88,8 @@ static int run_gemm(const afft_gemm_desc& d, int num_sms, cudaStream_t stream) {
   ep.row_off = d.row_off;
   if (g.a == nullptr || g.w == nullptr) return fail(AFFT_ERR_INVALID, "gemm: null operand");
   if (ep.out_f32 == nullptr && ep.out_hi == nullptr) return fail(AFFT_ERR_INVALID, "gemm: no output");
+  if (ep.act < ACT_NONE || ep.act > ACT_GATE) return fail(AFFT_ERR_INVALID, "gemm: unknown activation");
+  if (ep.act == ACT_GATE && ep.res == nullptr) return fail(AFFT_ERR_INVALID, "gemm: AFFT_ACT_GATE needs the gated operand in res");
   std::string err;
   if (!launch_gemm(g, ep, d.strict != 0, d.force_block_n, num_sms, stream, &err)) return fail(AFFT_ERR_CUDA, err);
   return AFFT_OK;
@@ -344,6 +346,44 @@ extern "C" int afft_marginalize_topk(const float* logits, int64_t ld, int32_t B,
   return AFFT_OK;
 }
 
+extern "C" int afft_score_fusion(const float* attn_logits, int64_t ld_a, int32_t n_mod, const float* const* logits,
+                                 int64_t ld_l, int32_t rows, int32_t C, float* attn, float* out, int64_t ld_o, void* stream) {
+  if (attn_logits == nullptr) return fail(AFFT_ERR_INVALID, "score_fusion: null attn_logits");
+  if (n_mod < 1 || n_mod > 8 || rows < 1 || rows > 65535 || ld_a < n_mod) return fail(AFFT_ERR_INVALID, "score_fusion: bad sizes");
+  const bool softmax_only = (out == nullptr);  // only the modality attention is wanted (MATT.forward)
+  if (softmax_only && attn == nullptr) return fail(AFFT_ERR_INVALID, "score_fusion: no output");
+  if (softmax_only) C = 0;
+  ScoreFusionArgs a;
+  a.attn_logits = attn_logits;
+  a.ld_a = ld_a;
+  a.M = n_mod;
+  for (int i = 0; i < 8; ++i) a.logits[i] = nullptr;
+  if (!softmax_only) {
+    const int64_t c4 = (static_cast<int64_t>(C) + 3) / 4 * 4;
+    if (logits == nullptr || C < 1) return fail(AFFT_ERR_INVALID, "score_fusion: null logits / bad class count");
+    if (ld_l < c4 || ld_o < c4 || ld_l % 4 != 0 || ld_o % 4 != 0)
+      return fail(AFFT_ERR_INVALID, "score_fusion: logits pitches must be multiples of 4 floats and >= ceil4(C)");
+    for (int i = 0; i < n_mod; ++i) {
+      a.logits[i] = logits[i];
+      if (a.logits[i] == nullptr || (reinterpret_cast<uintptr_t>(a.logits[i]) & 15) != 0)
+        return fail(AFFT_ERR_INVALID, "score_fusion: logits pointers must be non-null and 16-byte aligned");
+    }
+    if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return fail(AFFT_ERR_INVALID, "score_fusion: out must be 16-byte aligned");
+  }
+  a.ld_l = ld_l;
+  a.rows = rows;
+  a.C = C;
+  a.attn = attn;
+  a.out = out;
+  a.ld_o = ld_o;
+  const int quads = (C + 3) / 4;
+  dim3 grid(std::max(1, (quads + 255) / 256), rows);
+  score_fusion_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("score_fusion launch", e);
+  return AFFT_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // training-step operators
 // ------------------------------------------------------------------------------------------------
@@ -512,6 +552,7 @@ static void build_expected(afft_handle* h) {
     if (c.mod_dim[m] != c.dim) gemm(std::string("mapping.") + c.mod_name[m] + ".mapping.0.weight", D, c.mod_dim[m]);
 
   const int n_slots = h->n_slots;
+  const bool has_fuser = c.fuser_kind != AFFT_FUSER_NONE;
   const bool affine = (c.fuser_kind == AFFT_FUSER_SA) ? (c.norm_elementwise != 0) : true;
   if (c.fuser_kind == AFFT_FUSER_SA) {
     vec("fuser.modal_token", c.frame_level_token ? c.T : 1, D);
@@ -523,7 +564,7 @@ static void build_expected(afft_handle* h) {
   } else if (c.fuser_kind == AFFT_FUSER_CA) {
     table("fuser.position_embeddings.weight", D);
   }
-  for (int i = 0; i < c.fuser_depth; ++i) {
+  for (int i = 0; has_fuser && i < c.fuser_depth; ++i) {
     const std::string p = blk_name("fuser.blocks.", i, ".");
     if (c.fuser_kind == AFFT_FUSER_CA) {
       ln(p + "norm_self", D, true);
@@ -547,7 +588,7 @@ static void build_expected(afft_handle* h) {
     gemm(p + "mlp.mlp.2.weight", D, 4 * D);
     vec(p + "mlp.mlp.2.bias", 1, D);
   }
-  ln("fuser.norm", D, affine);
+  if (has_fuser) ln("fuser.norm", D, affine);
   if (c.dim != c.gpt_dim) {
     gemm("dim_encoder.weight", G, D);
     gemm("dim_decoder.weight", D, G);
@@ -581,15 +622,21 @@ extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
   if (cfg == nullptr || out == nullptr) return fail(AFFT_ERR_INVALID, "create: null argument");
   *out = nullptr;
   const afft_config& c = *cfg;
-  if (c.fuser_kind < 0 || c.fuser_kind > 3) return fail(AFFT_ERR_INVALID, "create: unknown fuser_kind");
+  if (c.fuser_kind < 0 || c.fuser_kind > AFFT_FUSER_NONE) return fail(AFFT_ERR_INVALID, "create: unknown fuser_kind");
+  const bool no_fuser = c.fuser_kind == AFFT_FUSER_NONE;
   if (c.n_mod < 1 || c.n_mod > AFFT_MAX_MODS - 1) return fail(AFFT_ERR_INVALID, "create: n_mod out of range");
   if (c.n_cls < 1 || c.n_cls > AFFT_MAX_CLS) return fail(AFFT_ERR_INVALID, "create: n_cls out of range");
   if (c.T < 1 || c.T > 64) return fail(AFFT_ERR_INVALID, "create: T must be in [1, 64]");
   if (c.max_batch < 1) return fail(AFFT_ERR_INVALID, "create: max_batch must be >= 1");
-  if (c.dim % 128 != 0 || c.gpt_dim % 128 != 0) return fail(AFFT_ERR_INVALID, "create: dim and gpt_dim must be multiples of 128");
-  if (c.fuser_heads < 1 || c.gpt_heads < 1 || c.dim % c.fuser_heads != 0 || c.gpt_dim % c.gpt_heads != 0)
+  if (no_fuser) {
+    if (c.n_mod != 1 || c.mod_dim[0] != c.dim) return fail(AFFT_ERR_INVALID, "create: AFFT_FUSER_NONE takes one modality of width dim");
+    if (c.dim % 8 != 0 || c.gpt_dim % 128 != 0) return fail(AFFT_ERR_INVALID, "create: dim must be a multiple of 8 and gpt_dim of 128");
+  } else if (c.dim % 128 != 0 || c.gpt_dim % 128 != 0) {
+    return fail(AFFT_ERR_INVALID, "create: dim and gpt_dim must be multiples of 128");
+  }
+  if (c.gpt_heads < 1 || c.gpt_dim % c.gpt_heads != 0 || (!no_fuser && (c.fuser_heads < 1 || c.dim % c.fuser_heads != 0)))
     return fail(AFFT_ERR_INVALID, "create: heads must divide dims");
-  const int hd1 = c.dim / c.fuser_heads, hd2 = c.gpt_dim / c.gpt_heads;
+  const int hd1 = no_fuser ? 256 : c.dim / c.fuser_heads, hd2 = c.gpt_dim / c.gpt_heads;
   if ((hd1 != 256 && hd1 != 512) || (hd2 != 256 && hd2 != 512))
     return fail(AFFT_ERR_INVALID, "create: head_dim must be 256 or 512");
   if (c.dim == c.gpt_dim) return fail(AFFT_ERR_INVALID, "create: common_dim == fp_inter_dim (Identity encoder) is not supported");
@@ -637,11 +684,13 @@ extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
     want(reinterpret_cast<void**>(&pb.hi), elems * 2);
     if (strict) want(reinterpret_cast<void**>(&pb.lo), elems * 2);
   };
-  want(reinterpret_cast<void**>(&h->h), R1 * D * 4);
-  want_pair(h->y, R1 * D);
-  want_pair(h->att, R1 * D);
-  want_pair(h->f, R1 * 4 * D);
-  want(&h->qkv, R1 * 3 * D * (strict ? 4 : 2));
+  if (!no_fuser) {
+    want(reinterpret_cast<void**>(&h->h), R1 * D * 4);
+    want_pair(h->y, R1 * D);
+    want_pair(h->att, R1 * D);
+    want_pair(h->f, R1 * 4 * D);
+    want(&h->qkv, R1 * 3 * D * (strict ? 4 : 2));
+  }
   for (int m = 0; m < c.n_mod; ++m)
     if (c.mod_dim[m] != c.dim) want_pair(h->xin[m], R2 * c.mod_dim[m]);
   if (c.fuser_kind == AFFT_FUSER_CA) {
@@ -1044,6 +1093,23 @@ static void run_fuser(Fwd& F, const afft_io& io, int b0, int nb) {
   const float* feat[AFFT_MAX_MODS];
   for (int m = 0; m < c.n_mod; ++m) feat[m] = io.feat[m] + static_cast<long long>(b0) * T * c.mod_dim[m];
 
+  if (c.fuser_kind == AFFT_FUSER_NONE) {
+    // no fusion (future_prediction.py:203-204): z = the modality's features.  bf16 copy for dim_encoder, fp32 copy into
+    // orig_past, and frame 0 into slot 0 of past_futures (fp32 + the classifier's bf16 operand) - prepare_output :172-176.
+    F.convert(feat[0], D, R2, D, zb, D);
+    if (F.ok()) {
+      const size_t row4 = static_cast<size_t>(D) * 4, row2 = static_cast<size_t>(D) * 2;
+      cudaError_t e = cudaMemcpyAsync(orig_past, feat[0], static_cast<size_t>(R2) * row4, cudaMemcpyDeviceToDevice, F.stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(pf, S * row4, feat[0], T * row4, row4, nb, cudaMemcpyDeviceToDevice, F.stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(pfb.hi, S * row2, zb.hi, T * row2, row2, nb, cudaMemcpyDeviceToDevice, F.stream);
+      if (e == cudaSuccess && zb.lo != nullptr)
+        e = cudaMemcpy2DAsync(pfb.lo, S * row2, zb.lo, T * row2, row2, nb, cudaMemcpyDeviceToDevice, F.stream);
+      if (e != cudaSuccess) F.check(cuda_fail("stage features", e));
+    }
+    return;
+  }
   if (c.fuser_kind == AFFT_FUSER_CA) {
     // x = rgb + pos; mems = others + pos  (fusion.py:262-264)
     const float* pos = F.V("fuser.position_embeddings.weight");

@@ -209,7 +209,7 @@ inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, bool stri
                   : launch_gemm_variant<(BN == 512 ? 256 : BN), SP, EP>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, default_sched(), stream)
 #define AFFT_DISPATCH_EPI(BN, SP)                                                            \
   do {                                                                                       \
-    if (!lo_ok) { AFFT_LAUNCH(BN, SP, EPI_GENERIC); break; }                                 \
+    if (!lo_ok || ep.act > ACT_GELU_TANH) { AFFT_LAUNCH(BN, SP, EPI_GENERIC); break; }                               \
     switch (code) {                                                                          \
       case epi_code(ACT_NONE, false, false, true): AFFT_LAUNCH(BN, SP, epi_code(ACT_NONE, false, false, true)); break;          \
       case epi_code(ACT_NONE, false, true, false): AFFT_LAUNCH(BN, SP, epi_code(ACT_NONE, false, true, false)); break;          \

@@ -35,7 +35,7 @@ constexpr int kUmmaK = 16;
 constexpr int kNumEpilogueWarps = 8;   // two per TMEM lane quadrant
 constexpr int kGemmThreads = 128 + 32 * kNumEpilogueWarps;
 
-enum : int { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_GELU_TANH = 2 };
+enum : int { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_GELU_TANH = 2, ACT_RELU = 3, ACT_GATE = 4 };
 
 // Everything the epilogue may do with an accumulator tile.  Pointers may be null (= skip).
 // Row r of the GEMM is written to row  orow(r) = (r / row_group) * row_stride + r % row_group + row_off
@@ -127,6 +127,7 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 // the instruction cache - ncu: stall_no_inst dominated); EPI_GENERIC keeps every flag at run time
 // for the stateless afft_gemm() entry point.
 //   bit 0-1 activation, bit 2 residual, bit 3 fp32 output, bit 4 bf16 output (+ lo when SPLIT == 3)
+// ACT_RELU / ACT_GATE (ablation mappings, MATT) exist in the generic variant only.
 // --------------------------------------------------------------------------------------------
 constexpr int EPI_GENERIC = -1;
 constexpr int epi_code(int act, bool res, bool f32, bool bf16) {
@@ -168,8 +169,25 @@ __device__ __forceinline__ float4 epilogue_math(const GemmEpilogue& ep, float4 x
     x.y = gelu_tanh(x.y);
     x.z = gelu_tanh(x.z);
     x.w = gelu_tanh(x.w);
+  } else if (F::kGeneric && act == ACT_RELU) {
+    x.x = fmaxf(x.x, 0.f);
+    x.y = fmaxf(x.y, 0.f);
+    x.z = fmaxf(x.z, 0.f);
+    x.w = fmaxf(x.w, 0.f);
+  } else if (F::kGeneric && act == ACT_GATE) {
+    x.x = 1.0f / (1.0f + __expf(-x.x));
+    x.y = 1.0f / (1.0f + __expf(-x.y));
+    x.z = 1.0f / (1.0f + __expf(-x.z));
+    x.w = 1.0f / (1.0f + __expf(-x.w));
   }
   return x;
+}
+
+// residual combine: + for the residual stream, * for ACT_GATE (the "residual" is the gated value)
+template <int EPI, int SPLIT>
+__device__ __forceinline__ float epilogue_combine(const GemmEpilogue& ep, float x, float r) {
+  if (EpiFlags<EPI, SPLIT>::kGeneric && ep.act == ACT_GATE) return x * r;
+  return x + r;
 }
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -223,10 +241,10 @@ __device__ __forceinline__ void epilogue_slab_full(const GemmEpilogue& ep, uint3
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       x[i] = epilogue_math<EPI, SPLIT>(ep, x[i], bias4);
-      x[i].x += r[i].x;
-      x[i].y += r[i].y;
-      x[i].z += r[i].z;
-      x[i].w += r[i].w;
+      x[i].x = epilogue_combine<EPI, SPLIT>(ep, x[i].x, r[i].x);
+      x[i].y = epilogue_combine<EPI, SPLIT>(ep, x[i].y, r[i].y);
+      x[i].z = epilogue_combine<EPI, SPLIT>(ep, x[i].z, r[i].z);
+      x[i].w = epilogue_combine<EPI, SPLIT>(ep, x[i].w, r[i].w);
     }
   } else {
 #pragma unroll
@@ -280,7 +298,7 @@ __device__ __noinline__ void epilogue_slab_edge(const GemmEpilogue& ep, uint32_t
     for (int e = 0; e < 4; ++e) {
       if (col + e >= N) break;
       float v = x[e];
-      if (F::res(ep)) v += ep.res[rrow * ep.ld_res + col + e];
+      if (F::res(ep)) v = epilogue_combine<EPI, SPLIT>(ep, v, ep.res[rrow * ep.ld_res + col + e]);
       if (F::f32(ep)) ep.out_f32[orow * ep.ld_f32 + col + e] = v;
       if (F::bf16(ep)) {
         const __nv_bfloat16 h = __float2bfloat16_rn(v);

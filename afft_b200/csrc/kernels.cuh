@@ -1006,4 +1006,63 @@ __global__ void __launch_bounds__(128) attention_decode_kernel(const DecodeAttnA
   store_row_regs<TIn, HD>(a.out_hi, a.out_lo, static_cast<long long>(b) * D + h * HD, lane, o);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Score fusion (reference models/fusion.py:57 softmax over MATT's outputs; models/future_prediction.py:341-350):
+//   p[r, :] = softmax(attn_logits[r, :M]);  out[r, c] = sum_i p[r, i] * logits_i[r, c]
+// HBM-bound: one pass over the M logit tensors, float4 accesses (pitches are multiples of 4 floats).
+// ------------------------------------------------------------------------------------------------
+struct ScoreFusionArgs {
+  const float* attn_logits;
+  long long ld_a;
+  int M;
+  const float* logits[8];
+  long long ld_l;
+  int rows, C;
+  float* attn;  // [rows, M] or nullptr
+  float* out;
+  long long ld_o;
+};
+
+__global__ void __launch_bounds__(256) score_fusion_kernel(const ScoreFusionArgs a) {
+  const int r = blockIdx.y;
+  float p[8];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    p[i] = (i < a.M) ? a.attn_logits[r * a.ld_a + i] : -INFINITY;
+    mx = fmaxf(mx, p[i]);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    p[i] = (i < a.M) ? __expf(p[i] - mx) : 0.f;
+    sum += p[i];
+  }
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p[i] *= inv;
+  if (a.attn != nullptr && blockIdx.x == 0 && threadIdx.x < a.M) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i == static_cast<int>(threadIdx.x)) v = p[i];
+    a.attn[static_cast<long long>(r) * a.M + threadIdx.x] = v;
+  }
+  const int quads = (a.C + 3) / 4;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < a.M) {
+        const float4 v = *reinterpret_cast<const float4*>(a.logits[i] + r * a.ld_l + q * 4);
+        acc.x = fmaf(p[i], v.x, acc.x);
+        acc.y = fmaf(p[i], v.y, acc.y);
+        acc.z = fmaf(p[i], v.z, acc.z);
+        acc.w = fmaf(p[i], v.w, acc.w);
+      }
+    }
+    *reinterpret_cast<float4*>(a.out + r * a.ld_o + q * 4) = acc;
+  }
+}
+
 }  // namespace afft

@@ -123,7 +123,7 @@ class Engine:
             io.ld_logits[k] = ld
         io.orig_past, io.past_futures = orig_past.data_ptr(), pf.data_ptr()
         attn = None
-        if want_attn and self.fuser_kind != _capi.FUSER_CA:
+        if want_attn and self.fuser_kind not in (_capi.FUSER_CA, _capi.FUSER_NONE):
             n, H = self.n_slots, self.fuser_heads
             if self.fuser_kind == _capi.FUSER_TSA:
                 attn = torch.empty(B, self.fuser_depth, H, n * T, n * T, device=dev, dtype=torch.float32)

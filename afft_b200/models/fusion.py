@@ -10,7 +10,7 @@ from functools import partial
 import torch
 import torch.nn as nn
 
-from .. import _capi
+from .. import _capi, hostops
 from .transformerblock import Block, DecoderBlock
 
 
@@ -152,5 +152,36 @@ class TemporalCrossAttentFuser(_Fuser):
 
 
 class MATT(nn.Module):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("MATT score fusion (expts/05, SURVEY.md section 8f row N3) is not built yet")
+    """Modality attention of RULSTM - reference models/fusion.py:35-58: a 3-layer MLP over the concatenated mapped
+    features whose softmax weights the per-modality classification scores (CMFPScoreFusion).  The three linears
+    (ReLU in the GEMM epilogue) and the softmax are library kernels (afft_gemm, afft_score_fusion)."""
+
+    def __init__(self, modal_dims, dim=None, drop_rate=0.8):
+        super().__init__()
+        num_modality = len(modal_dims)
+        in_size = dim * num_modality if dim else sum(modal_dims.values())
+        self.matt = nn.Sequential(nn.Linear(in_size, int(in_size / 4)), nn.ReLU(), nn.Dropout(drop_rate),
+                                  nn.Linear(int(in_size / 4), int(in_size / 8)), nn.ReLU(), nn.Dropout(drop_rate),
+                                  nn.Linear(int(in_size / 8), num_modality))
+        self.num_modality = num_modality
+        self.strict = False
+        self.__dict__["_wcache"] = hostops.WeightCache()
+
+    def attn_logits(self, modal_feats, ordered_feature_list):
+        """The pre-softmax modality scores, (B*S, num_modality) fp32 (row pitch padded to 4)."""
+        if self.training:
+            raise NotImplementedError("MATT: the training-step path is not built for score fusion")
+        x = torch.cat(ordered_feature_list(modal_feats), dim=2)
+        x = x.reshape(-1, x.shape[-1]).to(torch.float32)
+        cache = self.__dict__["_wcache"]
+        for idx, act in ((0, _capi.ACT_RELU), (3, _capi.ACT_RELU), (6, _capi.ACT_NONE)):
+            lin = self.matt[idx]
+            x = hostops.dense(x, lin.weight, lin.bias, cache, strict=self.strict, act=act)
+        return x
+
+    def forward(self, modal_feats, ordered_feature_list):
+        first = next(iter(modal_feats.values()))
+        scores = self.attn_logits(modal_feats, ordered_feature_list)
+        attn = torch.empty(scores.shape[0], self.num_modality, device=scores.device, dtype=torch.float32)
+        _capi.score_fusion(scores, attn=attn)
+        return attn.reshape(first.shape[0], first.shape[1], self.num_modality)

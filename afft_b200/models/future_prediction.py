@@ -47,6 +47,8 @@ _TARGETS = {
     "models.feature_mapping.NonLinear": ("afft_b200.models.feature_mapping", "NonLinear"),
     "models.future_prediction.BaseFuturePredictor": ("afft_b200.models.future_prediction", "BaseFuturePredictor"),
     "models.future_prediction.CMFPEarly": ("afft_b200.models.future_prediction", "CMFPEarly"),
+    "models.future_prediction.IndividualFuturePrediction": ("afft_b200.models.future_prediction", "IndividualFuturePrediction"),
+    "models.future_prediction.CMFPScoreFusion": ("afft_b200.models.future_prediction", "CMFPScoreFusion"),
 }
 
 
@@ -202,8 +204,14 @@ class CMFPEarly(nn.Module):
         return [x_d[m] for m in feats_order]
 
     # ---- native path ----
+    def _fused_mapping(self, mod: str) -> bool:
+        return bool(getattr(self.mapping[mod], "fused_in_forward", False))
+
     def _named_weights(self) -> Dict[str, Tensor]:
-        return {n: p for n, p in self.named_parameters()}
+        # mappings that run ahead of afft_forward (feature_mapping.py ablation variants) keep their weights in Python
+        skip = tuple(f"mapping.{m}." for m in self.mapping if not self._fused_mapping(m))
+        return {n: p for n, p in self.named_parameters() if not n.startswith(skip)} if skip else \
+            {n: p for n, p in self.named_parameters()}
 
     def _engine(self, feats_order, T: int, B: int, device: torch.device) -> Engine:
         key = (tuple(feats_order), T, str(device), bool(self.strict), self.fp_output_len)
@@ -215,7 +223,8 @@ class CMFPEarly(nn.Module):
             f = self.fuser
             gpt = self.future_predictor.gpt_model
             eng = Engine(fuser_kind=f.afft_kind, T=T, mod_names=list(feats_order),
-                         mod_dims=[self.modality_dims[m] for m in feats_order], dim=self.latent_dim,
+                         mod_dims=[self.modality_dims[m] if self._fused_mapping(m) else self.latent_dim
+                                   for m in feats_order], dim=self.latent_dim,
                          fuser_depth=f.depth, fuser_heads=f.num_heads, modal_encoding=bool(f.modal_encoding),
                          frame_level_token=bool(f.frame_level_token), cross_attn=bool(f.cross_attn),
                          norm_elementwise=bool(f.norm_elementwise), gpt_dim=gpt.n_embd, gpt_layers=gpt.n_layer,
@@ -245,7 +254,13 @@ class CMFPEarly(nn.Module):
             assert f.temporal_sequence_length == T, f"Temporal sequence length not valid {f.temporal_sequence_length} vs {T}"
         eng = self._engine(feats_order, T, B, first.device)
         eng.sync_weights(self._named_weights())
-        xs = [feats[m].to(torch.float32).contiguous() for m in feats_order]
+        xs = []
+        for m in feats_order:
+            x = feats[m].to(torch.float32).contiguous()
+            if not self._fused_mapping(m):  # ablation mapping: library kernels ahead of the fused call
+                self.mapping[m].strict = bool(self.strict)
+                x = self.mapping[m](x).contiguous()
+            xs.append(x)
         z, pf, logits, attn = eng.forward(xs, want_attn=self.return_attentions)
 
         out = {  # reference prepare_output :155-182 (views into the native output buffers)
@@ -266,11 +281,171 @@ class CMFPEarly(nn.Module):
         return max((e.launch_count() for e in self._engines.values()), default=0)
 
 
-class IndividualFuturePrediction(nn.Module):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("IndividualFuturePrediction (expts/00, SURVEY.md section 8f row N3) is not built yet")
+# ------------------------------------------------------------------------------------------------
+# per-modality heads: IndividualFuturePrediction, CMFPScoreFusion
+# ------------------------------------------------------------------------------------------------
+class _UnimodalPrediction(nn.Module):
+    """What reference IndividualFuturePrediction and CMFPScoreFusion share (models/future_prediction.py:57-95,97-122,
+    203-214): per modality a bias-free dim_encoder / dim_decoder around a (shared or private) GPT-2 predictor and a
+    classifier on the modality's own width.  One native handle per modality (AFFT_FUSER_NONE) runs
+    dim_encoder -> GPT-2 -> dim_decoder -> prepare_output -> classifier."""
+
+    def _init_common(self, model_cfg, num_classes, strict, max_batch):
+        common = cfg_get(model_cfg, "common")
+        modal_dims = cfg_get(model_cfg, "modal_dims")
+        assert isinstance(modal_dims, Mapping), 'cfg.model.modal_dims must be a Dict!'
+        self.cfg = model_cfg
+        self.num_classes = dict(num_classes)
+        self.latent_dim = cfg_get(common, "in_features")
+        self.fp_inter_dim = cfg_get(common, "fp_inter_dim")
+        self.modality_dims = dict(modal_dims)
+        self.common_predictor = bool(cfg_get(common, "share_predictors"))
+        self.common_classifier = bool(cfg_get(common, "share_classifiers"))
+        self.fp_output_len = int(cfg_get(common, "fp_output_len", 1))
+        self.modal_feature_order = list(cfg_get(model_cfg, "modal_feature_order"))
+        self.strict, self.max_batch = strict, max_batch
+        self._engines: Dict[tuple, Engine] = {}
+
+    def _init_future_predictor(self, model_cfg):  # reference :78-95
+        for d in self.modality_dims.values():
+            if d == self.fp_inter_dim:
+                raise NotImplementedError("modality width == fp_inter_dim (Identity dim_encoder) is not supported")
+        self.dim_encoder = nn.ModuleDict({m: nn.Linear(d, self.fp_inter_dim, bias=False) for m, d in self.modality_dims.items()})
+        self.dim_decoder = nn.ModuleDict({m: nn.Linear(self.fp_inter_dim, d, bias=False) for m, d in self.modality_dims.items()})
+        fp_cfg = cfg_get(model_cfg, "future_predictor")
+        if self.common_predictor:
+            self.future_predictor = instantiate(fp_cfg, in_features=self.fp_inter_dim, dimension_mapping=False)
+        else:
+            self.future_predictor = nn.ModuleDict({m: instantiate(fp_cfg, in_features=self.fp_inter_dim, dimension_mapping=False)
+                                                   for m in self.modality_dims})
+
+    def _init_classifiers(self, model_cfg):  # reference :97-122 with modality_cls=true, fusion_cls=false
+        dropout = cfg_get(model_cfg, "dropout")
+        self.classifiers = nn.ModuleDict()
+        for cls_type, cls_dim in self.num_classes.items():
+            shared = nn.Sequential(nn.Dropout(dropout), nn.Linear(self.latent_dim, cls_dim)) if self.common_classifier else None
+            self.classifiers[cls_type] = nn.ModuleDict(
+                {m: shared if shared is not None else nn.Sequential(nn.Dropout(dropout), nn.Linear(d, cls_dim))
+                 for m, d in self.modality_dims.items()})
+
+    def _predictor(self, mod):
+        return self.future_predictor if self.common_predictor else self.future_predictor[mod]
+
+    def _weights_for(self, mod) -> Dict[str, Tensor]:
+        """This modality's tensors under the names a fused-head handle expects (include/afft_b200.h)."""
+        w = {"dim_encoder.weight": self.dim_encoder[mod].weight, "dim_decoder.weight": self.dim_decoder[mod].weight}
+        for n, p in self._predictor(mod).named_parameters():
+            w["future_predictor." + n] = p
+        for cls in self.num_classes:
+            lin = self.classifiers[cls][mod][1]
+            w[f"classifiers.{cls}.all-fused.1.weight"] = lin.weight
+            w[f"classifiers.{cls}.all-fused.1.bias"] = lin.bias
+        return w
+
+    def _run_modality(self, mod, x: Tensor):
+        """-> (past_futures buffer (B, T+O, C_mod): slot 0 = x[:, 0], slots 1.. = predictions; [logits buffers (B, T+O, ld)])"""
+        if self.training:
+            raise NotImplementedError(f"{type(self).__name__}: the training-step path is built for CMFPEarly + SA-Fuser only")
+        if x.device.type != "cuda":
+            raise _capi.AfftError("afft_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
+        B, T, d = x.shape
+        key = (mod, T, str(x.device), bool(self.strict), self.fp_output_len)
+        eng = self._engines.get(key)
+        if eng is not None and B > eng.max_batch:
+            eng.close()
+            eng = None
+        if eng is None:
+            gpt = self._predictor(mod).gpt_model
+            eng = Engine(fuser_kind=_capi.FUSER_NONE, T=T, mod_names=[mod], mod_dims=[d], dim=d, fuser_depth=0,
+                         fuser_heads=1, modal_encoding=False, frame_level_token=False, cross_attn=False,
+                         norm_elementwise=True, gpt_dim=gpt.n_embd, gpt_layers=gpt.n_layer, gpt_heads=gpt.n_head,
+                         cls_names=list(self.num_classes.keys()), cls_dims=list(self.num_classes.values()),
+                         strict=bool(self.strict), max_batch=max(B, self.max_batch), device=x.device,
+                         fp_output_len=self.fp_output_len)
+            self._engines[key] = eng
+        eng.sync_weights(self._weights_for(mod))
+        _, pf, logits, _ = eng.forward([x.to(torch.float32).contiguous()], want_attn=False)
+        return pf, logits
+
+    def _unimodal_outputs(self, z: Dict[str, Tensor]):
+        """prepare_output (:155-182) + apply_classifier (:144-153) per modality, as views into the native buffers."""
+        out = {'orig_past': dict(z), 'future': {}, 'all-fused': {}, 'past_futures': {}}
+        for cls in self.num_classes:
+            out[f'{PAST_LOGITS_PREFIX}logits/{cls}'] = {}
+            out[f'logits/{cls}'] = {}
+        bufs = {}
+        for mod, x in z.items():
+            T = x.shape[1]
+            pf, logits = self._run_modality(mod, x)
+            bufs[mod] = (pf, logits)
+            out['past_futures'][mod] = pf[:, :T]
+            out['future'][mod] = pf[:, T:]
+            for k, (cls, c) in enumerate(self.num_classes.items()):
+                out[f'{PAST_LOGITS_PREFIX}logits/{cls}'][mod] = logits[k][:, :T, :c]
+                out[f'logits/{cls}'][mod] = logits[k][:, T:, :c]
+        return out, bufs
+
+    def last_launch_count(self) -> int:
+        return sum(e.launch_count() for e in self._engines.values())
 
 
-class CMFPScoreFusion(nn.Module):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("CMFPScoreFusion (expts/05, SURVEY.md section 8f row N3) is not built yet")
+class IndividualFuturePrediction(_UnimodalPrediction):
+    """Individual modality future predictor - reference models/future_prediction.py:189-225 (expts/00_*)."""
+
+    def __init__(self, model_cfg, num_classes, strict: bool = False, max_batch: int = 64):
+        super().__init__()
+        assert not cfg_get(cfg_get(model_cfg, "common"), "fusion_cls")  # reference :194
+        self._init_common(model_cfg, num_classes, strict, max_batch)
+        self._init_classifiers(model_cfg)   # registration order of the reference: classifiers, then predictors (:196-198)
+        self._init_future_predictor(model_cfg)
+
+    def forward(self, z: Dict[str, Tensor]) -> Dict[str, Dict[str, Tensor]]:
+        out, _ = self._unimodal_outputs(z)
+        return out
+
+
+class CMFPScoreFusion(_UnimodalPrediction):
+    """Late (score) fusion with MATT - reference models/future_prediction.py:294-351 (expts/05_MATT_ek100_train.txt)."""
+
+    def __init__(self, model_cfg, num_classes, strict: bool = False, max_batch: int = 64):
+        super().__init__()
+        common = cfg_get(model_cfg, "common")
+        assert not cfg_get(common, "fusion_cls")  # reference :298
+        if not cfg_get(common, "modality_cls"):
+            logging.getLogger(__name__).warning("Enforcing modality classification for CMFPScoreFusion.")
+        self._init_common(model_cfg, num_classes, strict, max_batch)
+        if self.fp_output_len != 1:
+            raise NotImplementedError("CMFPScoreFusion broadcasts one attention row over the future logits: fp_output_len must be 1")
+        self.mapping = nn.ModuleDict()  # reference :47-54
+        for mod, dim in self.modality_dims.items():
+            self.mapping[mod] = instantiate(cfg_get(model_cfg, "mapping"), in_features=dim, out_features=self.latent_dim)
+        self.fuser = instantiate(cfg_get(model_cfg, "fuser"))
+        self._init_future_predictor(model_cfg)
+        self._init_classifiers(model_cfg)
+
+    @staticmethod
+    def ordered_feature_list(x_d: Dict[str, Tensor], feats_order):
+        return [x_d[m] for m in feats_order]
+
+    def forward(self, z: Dict[str, Tensor]) -> Dict[str, Dict[str, Tensor]]:
+        feats_order = [mod for mod in self.modal_feature_order if mod in z]  # reference :308
+        out, bufs = self._unimodal_outputs(z)
+        first = z[feats_order[0]]
+        B, T = first.shape[0], first.shape[1]
+        # [first frame | predictions] (:327-330) is exactly the native past_futures buffer; map it to the common width
+        mapped = {}
+        for mod in feats_order:
+            self.mapping[mod].strict = bool(self.strict)
+            mapped[mod] = self.mapping[mod](bufs[mod][0])
+        self.fuser.strict = bool(self.strict)
+        scores = self.fuser.attn_logits(mapped, lambda d: [d[m] for m in feats_order])  # (B*(T+1), M), pre-softmax
+        attn = torch.empty(scores.shape[0], len(feats_order), device=scores.device, dtype=torch.float32)
+        for k, (cls, c) in enumerate(self.num_classes.items()):  # :341-350, softmax fused with the weighted sum
+            per_mod = [bufs[m][1][k] for m in feats_order]  # (B, T+1, ld) each
+            fused = torch.empty_like(per_mod[0])
+            _capi.score_fusion(scores, [t.view(-1, t.shape[-1]) for t in per_mod], c, attn=attn,
+                               out=fused.view(-1, fused.shape[-1]))
+            out[f'{PAST_LOGITS_PREFIX}logits/{cls}'] = {'all-fused': fused[:, :T, :c]}
+            out[f'logits/{cls}'] = {'all-fused': fused[:, T:, :c]}
+        self.last_modality_attns = attn.view(B, T + 1, len(feats_order))  # not a reference output; kept for inspection
+        return out

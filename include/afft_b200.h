@@ -60,7 +60,10 @@ AFFT_API const char* afft_last_error(void);
 /* Stateless operators (one per library call the reference makes on the path)                  */
 /* ------------------------------------------------------------------------------------------ */
 
-enum { AFFT_ACT_NONE = 0, AFFT_ACT_GELU_ERF = 1, AFFT_ACT_GELU_TANH = 2 };
+/* AFFT_ACT_RELU: nn.ReLU (models/feature_mapping.py:81-88 NonLinear, models/fusion.py:41,44 MATT).
+ * AFFT_ACT_GATE: out = residual * sigmoid(A . W^T + bias) - ContextGating's cat + glu (models/feature_mapping.py:21-33);
+ *                the residual operand is required and multiplies instead of adding. */
+enum { AFFT_ACT_NONE = 0, AFFT_ACT_GELU_ERF = 1, AFFT_ACT_GELU_TANH = 2, AFFT_ACT_RELU = 3, AFFT_ACT_GATE = 4 };
 
 /*
  * C = epilogue(A . W^T): replaces torch.nn.Linear / transformers Conv1D
@@ -152,6 +155,14 @@ typedef struct afft_attention_desc {
 
 AFFT_API int afft_attention(const afft_attention_desc* d, void* stream);
 
+/* Score fusion: p = softmax(attn_logits[r, :n_mod]); out[r, :C] = sum_i p[i] * logits[i][r, :C].
+ * Replaces MATT's softmax (models/fusion.py:57) and the weighted sum of the per-modality logits in
+ * CMFPScoreFusion.forward (models/future_prediction.py:341-350).  attn [rows, n_mod] may be NULL; with out == NULL
+ * only the softmax is computed (MATT.forward's return value) and logits / C are ignored.
+ * n_mod <= 8; the logits / out pitches are multiples of 4 floats and >= ceil4(C), pointers 16-byte aligned. */
+AFFT_API int afft_score_fusion(const float* attn_logits, int64_t ld_a, int32_t n_mod, const float* const* logits,
+                               int64_t ld_l, int32_t rows, int32_t C, float* attn, float* out, int64_t ld_o, void* stream);
+
 /* Logit post-processing (the step right after the path): softmax over the action logits,
  * verb/noun marginalisation and top-K ranking - replaces challenge.py:196-210 (scipy softmax + two matmuls with the
  * 0/1 class_mappings matrices) and the argsort ranking of common/utils.py:19-42.  verb_of/noun_of [A] int32 give the
@@ -188,7 +199,10 @@ enum {
   AFFT_FUSER_SA = 0,       /* models.fusion.ModalTokenCMFuser        (fusion.py:273-365) */
   AFFT_FUSER_SA_NOTOKEN = 1, /* models.fusion.CMFuser                (fusion.py:61-118)  */
   AFFT_FUSER_TSA = 2,      /* models.fusion.TemporalCMFuser          (fusion.py:121-215) */
-  AFFT_FUSER_CA = 3        /* models.fusion.TemporalCrossAttentFuser (fusion.py:218-270) */
+  AFFT_FUSER_CA = 3,       /* models.fusion.TemporalCrossAttentFuser (fusion.py:218-270) */
+  AFFT_FUSER_NONE = 4      /* no fuser: one modality of width `dim` goes straight to dim_encoder -> GPT-2 -> dim_decoder ->
+                              classifier (IndividualFuturePrediction / CMFPScoreFusion, future_prediction.py:200-225,
+                              315-327); n_mod must be 1, mod_dim[0] == dim, dim a multiple of 8 */
 };
 
 typedef struct afft_config {

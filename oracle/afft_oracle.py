@@ -24,6 +24,10 @@ BaseModel.future_predictor in eval mode:
     models/future_prediction.py:387-415  BaseFuturePredictor      _gpt2() (output_len == 1)
     models/future_prediction.py:155-182  prepare_output           forward()
     models/future_prediction.py:144-153  apply_classifier         forward()
+    models/feature_mapping.py:21-48,91-107 GatedLinear / NonLinear _mapping_layer()
+    models/fusion.py:35-58               MATT                     _matt()
+    models/future_prediction.py:189-225  IndividualFuturePrediction _forward_individual()
+    models/future_prediction.py:294-351  CMFPScoreFusion          _forward_scorefusion()
 
 GPT-2 itself is third-party: transformers (pinned 4.18.0 in the reference's environment.yml:166; 5.5.0 in
 this image), class GPT2Model called with inputs_embeds / position_ids=arange(T) / past_key_values=None
@@ -297,21 +301,118 @@ def _gpt2(x, w: _W, n_layer, n_head, output_len=1):
 
 
 # ------------------------------------------------------------------------------------------------
+# feature mapping variants (models/feature_mapping.py) and MATT (models/fusion.py:35-58)
+# ------------------------------------------------------------------------------------------------
+def _mapping_layer(x, w: _W, mcfg):
+    """One modality's mapping nn.Sequential; ``w`` is rooted at ``mapping.<mod>.mapping.``.
+    Linear (feature_mapping.py:54-78): [Linear(no bias) | Identity if in == out and sparse_mapping] [+ LN 1e-6]
+    NonLinear (:91-107): Linear(bias), relu | gelu | none [+ LN]
+    GatedLinear (:36-51): Linear(bias), ContextGating x * sigmoid(fc(x)) (:21-33; cat + glu over dim 1) [+ LN]"""
+    kind = mcfg["_target_"].rsplit(".", 1)[-1] if mcfg is not None else "Linear"
+    use_ln = bool(mcfg.get("use_layernorm", kind != "Linear")) if mcfg is not None else False
+    if kind == "Linear":
+        mw = w("0.weight", optional=True)
+        y = x if mw is None else _linear(x, mw)
+        ln_idx = 1
+    elif kind == "NonLinear":
+        y = _linear(x, w("0.weight"), w("0.bias"))
+        act = mcfg.get("activation", "relu")
+        if act == "relu":
+            y = torch.clamp(y, min=0)
+        elif act == "gelu":
+            y = _gelu_erf(y)
+        elif act != "none":
+            raise ValueError(act)
+        ln_idx = 2
+    elif kind == "GatedLinear":
+        y = _linear(x, w("0.weight"), w("0.bias"))
+        gate = _linear(y, w("1.fc.weight"), w("1.fc.bias"))
+        y = y * (1.0 / (1.0 + torch.exp(-gate)))
+        ln_idx = 2
+    else:
+        raise ValueError(kind)
+    if use_ln:
+        y = _ln(y, w(f"{ln_idx}.weight"), w(f"{ln_idx}.bias"), 1e-6)
+    return y
+
+
+def _matt(flist: List[torch.Tensor], w: _W):
+    """MATT.forward (fusion.py:49-58): concat over channels, Linear-ReLU-Linear-ReLU-Linear, softmax over modalities
+    (Dropout layers at indices 2 and 5 are identities in eval mode)."""
+    x = torch.cat(flist, dim=2)
+    x = torch.clamp(_linear(x, w("matt.0.weight"), w("matt.0.bias")), min=0)
+    x = torch.clamp(_linear(x, w("matt.3.weight"), w("matt.3.bias")), min=0)
+    return _softmax(_linear(x, w("matt.6.weight"), w("matt.6.bias")))
+
+
+def _predict_unimodal(z, w: _W, cfg, m):
+    """dim_encoder[m] -> (shared or per-modality) GPT-2 -> dim_decoder[m]  (future_prediction.py:203-214)."""
+    enc = w(f"dim_encoder.{m}.weight", optional=True)
+    dec = w(f"dim_decoder.{m}.weight", optional=True)
+    gw = w.sub("future_predictor.gpt_model.") if cfg["common"]["share_predictors"] else \
+        w.sub(f"future_predictor.{m}.gpt_model.")
+    g = _gpt2(z if enc is None else _linear(z, enc), gw, cfg["common"]["fp_layers"], cfg["common"]["fp_heads"],
+              cfg["common"].get("fp_output_len", 1))
+    return g if dec is None else _linear(g, dec)
+
+
+def _unimodal_outputs(w: _W, cfg, num_classes, feats):
+    """The part IndividualFuturePrediction and CMFPScoreFusion share: per-modality prediction, prepare_output
+    (:155-182) and the per-modality classifiers (:144-153)."""
+    z_hat = {m: _predict_unimodal(z, w, cfg, m) for m, z in feats.items()}
+    T = next(iter(feats.values())).shape[1]
+    out = {"orig_past": dict(feats), "future": {m: zh[:, T - 1:] for m, zh in z_hat.items()}, "all-fused": {},
+           "past_futures": {m: torch.cat([feats[m][:, :1], z_hat[m][:, :T - 1]], dim=1) for m in z_hat}}
+    for prefix, src in (("past_", out["past_futures"]), ("", out["future"])):
+        for c in num_classes:
+            out[f"{prefix}logits/{c}"] = {m: _linear(x, w(f"classifiers.{c}.{m}.1.weight"), w(f"classifiers.{c}.{m}.1.bias"))
+                                          for m, x in src.items()}
+    return out, z_hat
+
+
+def _forward_individual(w: _W, cfg, num_classes, feats):
+    out, _ = _unimodal_outputs(w, cfg, num_classes, feats)  # future_prediction.py:200-225
+    return out
+
+
+def _forward_scorefusion(w: _W, cfg, num_classes, feats):
+    """CMFPScoreFusion.forward (future_prediction.py:307-351): per-modality logits weighted by MATT's softmax over
+    the mapped [first frame | predictions] sequence."""
+    order = [m for m in cfg["modal_feature_order"] if m in feats]
+    out, z_hat = _unimodal_outputs(w, cfg, num_classes, feats)
+    mapped = [_mapping_layer(torch.cat([feats[m][:, :1], z_hat[m]], dim=1), w.sub(f"mapping.{m}.mapping."), cfg.get("mapping"))
+              for m in order]  # :327-333
+    attn = _matt(mapped, w.sub("fuser."))  # (B, T + 1, M)
+    for c in num_classes:  # :341-350
+        past, fut = out[f"past_logits/{c}"], out[f"logits/{c}"]
+        out[f"past_logits/{c}"] = {"all-fused": sum(attn[:, :-1, i].unsqueeze(-1) * past[m] for i, m in enumerate(order))}
+        out[f"logits/{c}"] = {"all-fused": sum(attn[:, -1:, i].unsqueeze(-1) * fut[m] for i, m in enumerate(order))}
+    out["modality_attns"] = attn  # not a reference output key; exposed for the parity tests
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # the path
 # ------------------------------------------------------------------------------------------------
 def forward(state_dict: Dict[str, torch.Tensor], cfg: Dict, num_classes: Dict[str, int],
             feats: Dict[str, torch.Tensor], dtype=torch.float32) -> Dict:
-    """CMFPEarly.forward on {mod: (B, T, C_mod)} features; returns the reference's dict-of-dict outputs."""
+    """CMFPEarly.forward (or IndividualFuturePrediction / CMFPScoreFusion, by cfg["CMFP"]["_target_"]) on
+    {mod: (B, T, C_mod)} features; returns the reference's dict-of-dict outputs."""
     w = _W(state_dict, PREFIX, dtype)
     feats = {m: f.reshape(f.shape[0], f.shape[1], -1).to(dtype) for m, f in feats.items()}
+    head = cfg.get("CMFP", {}).get("_target_", "CMFPEarly").rsplit(".", 1)[-1]
+    if head == "IndividualFuturePrediction":
+        return _forward_individual(w, cfg, num_classes, feats)
+    if head == "CMFPScoreFusion":
+        return _forward_scorefusion(w, cfg, num_classes, feats)
     order = [m for m in cfg["modal_feature_order"] if m in feats]  # future_prediction.py:258
     D = cfg["common"]["in_features"]
 
-    # feature mapping: bias-free Linear, Identity when the width already matches  (feature_mapping.py:59-63)
+    # feature mapping (future_prediction.py:133-142): by default a bias-free Linear, Identity when the width
+    # already matches (feature_mapping.py:59-63)
     mapped = {}
     for m, x in feats.items():
-        mw = w(f"mapping.{m}.mapping.0.weight", optional=True)
-        mapped[m] = x if mw is None else _linear(x, mw)
+        mapped[m] = _mapping_layer(x, w.sub(f"mapping.{m}.mapping."), cfg.get("mapping"))
         assert mapped[m].shape[-1] == D
     flist = [mapped[m] for m in order]
 

@@ -38,6 +38,26 @@ CASES = [
     ("egtea_sa_rollout3_b3", "egtea_sa_rollout3", 3, 123, "randn"),
 ]
 
+# head / mapping variants.  Their outputs are keyed per modality, so the fixtures
+# store every leaf as "<outer>|<inner>" (flatten_generic) instead of the fixed "all-fused" layout above.
+CASES_N3 = [
+    ("ek100_individual_b2", "ek100_individual", 2, 123, "randn"),
+    ("ek100_matt_b2", "ek100_matt", 2, 123, "randn"),
+    ("ek100_sa_gatedlinear_b2", "ek100_sa_gatedlinear", 2, 123, "randn"),
+    ("ek100_sa_nonlinear_b2", "ek100_sa_nonlinear", 2, 123, "randn"),
+    ("ek100_sa_linear_ln_b2", "ek100_sa_linear_ln", 2, 123, "randn"),
+]
+
+
+def flatten_generic(out):
+    flat = {}
+    for k, inner in out.items():
+        if k in ("attentions", "modality_attns"):
+            continue
+        for kk, t in inner.items():
+            flat[f"{k}|{kk}"] = t
+    return flat
+
 
 def flatten_outputs(out):
     flat = {}
@@ -109,6 +129,49 @@ def main():
             with open(os.path.join(HERE, f"param_names_{cfg_name}.json"), "w") as f:
                 json.dump({n: list(p.shape) for n, p in model.named_parameters()}, f, indent=0)
 
+    for case, cfg_name, B, seed, family in CASES_N3:
+        if only and case not in only:
+            continue
+        cfg, T, ncls, _ = configs.named_config(cfg_name)
+        model = ref_shim.build_reference_model(cfg, ncls)
+        sd = synthetic.synthetic_state_dict(model, seed=0)
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not unexpected, unexpected
+        assert all(("attn.bias" in m or "masked_bias" in m) for m in missing), missing
+        feats6 = synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=seed, family=family, six_d=True)
+        feats = {m: t.reshape(B, T, -1) for m, t in feats6.items()}
+        ref32 = flatten_generic(ref_shim.reference_forward(model, feats6))
+        model64 = model.double()
+        ref64 = flatten_generic(ref_shim.reference_forward(model64, {m: t.double() for m, t in feats6.items()}))
+        model.float()
+        sd_full = {k: v for k, v in model.state_dict().items()}
+        o64 = flatten_generic(afft_oracle.forward(sd_full, cfg, ncls, feats, dtype=torch.float64))
+        o32 = flatten_generic(afft_oracle.forward(sd_full, cfg, ncls, feats, dtype=torch.float32))
+        rec, save = {}, {}
+        for k in ref64:
+            d64 = (o64[k].double() - ref64[k].double()).abs().max().item()
+            d32 = (o32[k].double() - ref32[k].double()).abs().max().item()
+            rec[k] = {"oracle64_vs_ref64": d64, "oracle32_vs_ref32": d32,
+                      "ref32_vs_ref64": (ref32[k].double() - ref64[k].double()).abs().max().item(),
+                      "scale": ref64[k].abs().max().item()}
+            assert d64 < 1e-11, (case, k, d64)
+            assert d32 < 5e-5, (case, k, d32)
+            if k.startswith("orig_past"):
+                continue  # the inputs themselves (individual heads) or covered by past_futures
+            if k.startswith("past_logits"):
+                save[k] = ref32[k][:1].numpy()  # clip 0 only: keeps the fixtures small
+            else:
+                save[k] = ref32[k].numpy()
+            if k.startswith("logits/"):
+                save["logits64|" + k] = ref64[k].numpy()
+                save["top5|" + k] = afft_oracle.top5(ref32[k][:, 0]).numpy()
+        pin[case] = rec
+        print(case, {k: (round(v["oracle64_vs_ref64"], 18), round(v["oracle32_vs_ref32"], 9)) for k, v in rec.items()},
+              flush=True)
+        np.savez_compressed(os.path.join(HERE, case + ".npz"), **save)
+        with open(os.path.join(HERE, f"param_names_{cfg_name}.json"), "w") as f:
+            json.dump({n: list(p.shape) for n, p in model.named_parameters()}, f, indent=0)
+
     pin_path = os.path.join(HERE, "oracle_pin.json")
     if only and os.path.exists(pin_path):
         with open(pin_path) as f:
@@ -118,7 +181,7 @@ def main():
     with open(pin_path, "w") as f:
         json.dump({"generated_with": {"torch": torch.__version__, "transformers": __import__("transformers").__version__,
                                       "reference": ref_shim.REFERENCE_ROOT},
-                   "cases": {c: list(x) for c, *x in CASES}, "pin": pin}, f, indent=1)
+                   "cases": {c: list(x) for c, *x in CASES + CASES_N3}, "pin": pin}, f, indent=1)
     print("wrote fixtures to", HERE)
 
 

@@ -84,6 +84,65 @@ def test_golden_parity(case, strict, golden_dir, golden_cases):
     assert model.future_predictor.last_launch_count() > 20  # native kernels, not a fallback
 
 
+CASES_N3 = ["ek100_individual_b2", "ek100_matt_b2", "ek100_sa_gatedlinear_b2", "ek100_sa_nonlinear_b2",
+            "ek100_sa_linear_ln_b2"]
+
+
+@pytest.mark.parametrize("strict", [False, True])
+@pytest.mark.parametrize("case", CASES_N3)
+def test_golden_parity_head_and_mapping_variants(case, strict, golden_dir, golden_cases):
+    """IndividualFuturePrediction, CMFPScoreFusion + MATT, GatedLinear / NonLinear / layer-normed
+    Linear mappings against the reference module's outputs (every leaf stored as "<outer>|<inner>")."""
+    cfg_name, B, seed, family = golden_cases[case]
+    cfg, T, ncls, _ = configs.named_config(cfg_name)
+    model = _model(cfg_name, strict)
+    feats = synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=seed, family=family, six_d=True)
+    out = _run(model, feats)
+    gold = np.load(os.path.join(golden_dir, case + ".npz"))
+    tol = TOL[strict]
+    checked = 0
+    for key in gold.files:
+        if key.startswith(("logits64|", "top5|")):
+            continue
+        outer, inner = key.split("|")
+        mine = out[outer][inner]
+        if outer.startswith("past_logits"):
+            mine = mine[:1]
+        a = mine.float().cpu().numpy()
+        assert a.shape == gold[key].shape, key
+        assert not np.isnan(a).any(), key
+        d = np.abs(a - gold[key]).max()
+        assert d < (tol["logits"] if "logits" in outer else tol["feat"]), (key, d)
+        if strict and outer.startswith("logits/"):
+            t5 = out[outer][inner][:, 0].topk(5, dim=-1).indices.cpu().numpy()
+            assert (t5 == gold["top5|" + key]).all(), f"ordered top-5 must be identical in strict mode ({key})"
+        checked += 1
+    assert checked >= 5
+    if "individual" in case or "matt" in case:  # the inputs themselves are the 'orig_past' of these heads
+        for m, t in feats.items():
+            assert torch.equal(out["orig_past"][m].cpu(), t.reshape(B, T, -1))
+    assert model.future_predictor.last_launch_count() > 20
+
+
+def test_score_fusion_operator():
+    """afft_score_fusion against its definition (softmax over modalities, weighted sum of the logits)."""
+    g = torch.Generator().manual_seed(3)
+    rows, M, C = 37, 4, 3806
+    ld = (C + 3) // 4 * 4
+    scores = (torch.randn(rows, 4, generator=g) * 3).cuda()
+    logits = [torch.randn(rows, ld, generator=g).cuda() for _ in range(M)]
+    attn = torch.empty(rows, M, device="cuda")
+    out = torch.empty(rows, ld, device="cuda")
+    _capi.score_fusion(scores, logits, C, attn=attn, out=out)
+    p = torch.softmax(scores.double(), dim=-1)
+    ref = sum(p[:, i:i + 1] * logits[i].double() for i in range(M))
+    assert (attn.double() - p).abs().max().item() < 1e-6
+    assert (out[:, :C].double() - ref[:, :C]).abs().max().item() < 1e-5
+    only = torch.empty(rows, M, device="cuda")
+    _capi.score_fusion(scores, attn=only)
+    assert torch.equal(only, attn)
+
+
 @pytest.mark.parametrize("strict", [False, True])
 def test_against_oracle_fresh_inputs(strict):
     """Same seeded inputs through the CUDA path and the CPU oracle (not a stored fixture)."""

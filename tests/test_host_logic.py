@@ -11,7 +11,10 @@ from afft_b200.models import BaseModel
 from afft_b200.models import future_prediction as fp
 
 
-@pytest.mark.parametrize("name", configs.CONFIG_NAMES)
+N3_CONFIGS = ["ek100_individual", "ek100_matt", "ek100_sa_gatedlinear", "ek100_sa_nonlinear", "ek100_sa_linear_ln"]
+
+
+@pytest.mark.parametrize("name", configs.CONFIG_NAMES + N3_CONFIGS)
 def test_state_dict_contract_matches_reference(name, golden_dir):
     """Same parameter names and shapes as the reference module (train.py:55-103 init_model contract);
     tests/golden/param_names_*.json was written from the reference's named_parameters()."""
@@ -120,10 +123,17 @@ def test_error_behaviour():
     bad["common"]["fp_output_len"] = 0
     with pytest.raises(ValueError):
         BaseModel(bad, ncls, {})
-    bad = configs.named_config("egtea_sa")[0]
-    bad["mapping"]["_target_"] = "models.feature_mapping.GatedLinear"
+    bad = configs.named_config("ek100_matt")[0]
+    bad["common"]["fp_output_len"] = 2  # one attention row cannot weight several future steps
     with pytest.raises(NotImplementedError):
-        BaseModel(bad, ncls, {})
+        BaseModel(bad, {"action": 3806}, {})
+    bad = configs.named_config("ek100_individual")[0]
+    bad["common"]["fusion_cls"] = True  # reference future_prediction.py:194
+    with pytest.raises(AssertionError):
+        BaseModel(bad, {"action": 3806}, {})
+    gated = BaseModel(configs.named_config("ek100_sa_gatedlinear")[0], {"action": 3806}, {})
+    with pytest.raises(_capi.AfftError):  # ablation mappings run as library kernels too: no CPU path
+        gated.eval()({m: torch.zeros(1, 10, d, 1, 1, 1) for m, d in (("rgb", 1024), ("objects", 352), ("flow", 1024))})
 
 
 def test_instantiate_accepts_attribute_configs():

@@ -101,6 +101,28 @@ def test_gemm_strict_bf16x3(dev, M, N, K, bn):
     assert ((oh.float() + ol.float())[:, :N] - ref).abs().max().item() < 2e-4
 
 
+def test_gemm_relu_gate_and_skinny_n(dev):
+    """ReLU and ContextGating (residual * sigmoid) epilogues of the ablation mappings / MATT, and MATT's N = 4 output."""
+    g = torch.Generator().manual_seed(11)
+    M, N, K = 333, 1024, 352
+    a = _randn(g, dev, M, K).bfloat16()
+    w = _randn(g, dev, N, K, scale=0.05).bfloat16()
+    bias, u = _randn(g, dev, N), _randn(g, dev, M, N)
+    ref0 = _mm(a, w) + bias
+    out = torch.zeros(M, N, device=dev)
+    capi.gemm(a, w, bias=bias, act=capi.ACT_RELU, out_f32=out)
+    assert (out - torch.relu(ref0)).abs().max().item() < 1e-4
+    capi.gemm(a, w, bias=bias, act=capi.ACT_GATE, res=u, out_f32=out)
+    assert (out - u * torch.sigmoid(ref0)).abs().max().item() < 1e-4
+    with pytest.raises(capi.AfftError):
+        capi.gemm(a, w, bias=bias, act=capi.ACT_GATE, out_f32=out)  # the gated operand is required
+    w4 = _randn(g, dev, 4, K, scale=0.05).bfloat16()
+    b4 = _randn(g, dev, 4)
+    out4 = torch.zeros(M, 4, device=dev)
+    capi.gemm(a, w4, bias=b4, out_f32=out4)
+    assert (out4 - (_mm(a, w4) + b4)).abs().max().item() < 1e-4
+
+
 def test_gemm_rejects_bad_arguments(dev):
     a = torch.zeros(128, 64, device=dev, dtype=torch.bfloat16)
     w = torch.zeros(128, 64, device=dev, dtype=torch.bfloat16)

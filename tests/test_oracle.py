@@ -56,6 +56,36 @@ def test_oracle_matches_golden(case, golden_dir, golden_cases):
         assert np.abs(o64["logits/action"]["all-fused"].numpy() - gold["logits64"]).max() < TOL_F64
 
 
+CASES_N3 = ["ek100_individual_b2", "ek100_matt_b2", "ek100_sa_gatedlinear_b2", "ek100_sa_nonlinear_b2",
+            "ek100_sa_linear_ln_b2"]
+
+
+@pytest.mark.parametrize("case", CASES_N3)
+def test_oracle_matches_golden_head_and_mapping_variants(case, golden_dir, golden_cases):
+    """SURVEY 8f row N3 (IndividualFuturePrediction, CMFPScoreFusion + MATT, GatedLinear / NonLinear / layer-normed
+    mappings): fixtures hold every output leaf of the reference module as "<outer>|<inner>"."""
+    cfg_name, B, seed, family = golden_cases[case]
+    cfg, T, ncls, _ = configs.named_config(cfg_name)
+    sd = _weights(cfg_name)
+    feats = synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=seed, family=family)
+    gold = np.load(os.path.join(golden_dir, case + ".npz"))
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    out = afft_oracle.forward(sd, cfg, ncls, feats, dtype=torch.float32)
+    checked = 0
+    for key in gold.files:
+        if key.startswith(("logits64|", "top5|")):
+            continue
+        outer, inner = key.split("|")
+        mine = out[outer][inner]
+        if outer.startswith("past_logits"):
+            mine = mine[:1]
+        assert np.abs(mine.numpy() - gold[key]).max() < TOL_F32, key
+        if outer.startswith("logits/"):
+            assert (afft_oracle.top5(out[outer][inner][:, 0]).numpy() == gold["top5|" + key]).all()
+        checked += 1
+    assert checked >= 5
+
+
 def test_oracle_output_contract():
     """Keys and shapes of CMFPEarly.forward (reference models/future_prediction.py:282-291)."""
     cfg, T, ncls, _ = configs.named_config("egtea_sa")
