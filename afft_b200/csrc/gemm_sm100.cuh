@@ -121,6 +121,20 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return fmaf(-x, r, x);
 }
 
+__device__ __forceinline__ float gelu_erf_bf16out(float x) {
+  // erf-GELU for results that are rounded to bf16 straight away (FC1 of the fuser MLP in bf16 mode).
+  // Phi(x) = 0.5 (1 + erf(x / sqrt 2)) = sigmoid(2 g(x)) with g = atanh(erf(x / sqrt 2)), an odd function; g(x) / x is
+  // fitted by c0 + c1 x^2 + c2 x^4 (minimax on x Phi(x) over |x| <= 9: max |error| 2.6e-5, i.e. <= 1/4 of a bf16
+  // half-ulp wherever |x Phi(x)| >= 0.05, and the saturated limits are exact).  8 issue slots instead of 15.
+  const float l2e2 = 2.0f * 1.4426950408889634f;
+  const float x2 = fminf(x * x, 81.0f);  // the fit (and w > 0) holds for |x| <= 9; beyond that Phi is 0 or 1 in fp32
+  float w = fmaf(l2e2 * -0.0003515187397213507f, x2, l2e2 * 0.03700565900935642f);
+  w = fmaf(w, x2, l2e2 * 0.7975078687760178f);
+  const float e = mufu_ex2(x * w);
+  const float r = mufu_rcp(1.0f + e);
+  return fmaf(-x, r, x);
+}
+
 // --------------------------------------------------------------------------------------------
 // Epilogue variants.  The combinations the forward path uses are compiled with their flags as
 // constants (the 8-row unrolled epilogue of the all-runtime version is ~60 KB of SASS and thrashes
@@ -160,10 +174,17 @@ __device__ __forceinline__ float4 epilogue_math(const GemmEpilogue& ep, float4 x
   x.w += bias4.w;
   const int act = F::act(ep);
   if (act == ACT_GELU_ERF) {
-    x.x = gelu_erf(x.x);
-    x.y = gelu_erf(x.y);
-    x.z = gelu_erf(x.z);
-    x.w = gelu_erf(x.w);
+    if (!F::kGeneric && SPLIT == 1 && !F::f32(ep)) {  // result only ever stored as bf16
+      x.x = gelu_erf_bf16out(x.x);
+      x.y = gelu_erf_bf16out(x.y);
+      x.z = gelu_erf_bf16out(x.z);
+      x.w = gelu_erf_bf16out(x.w);
+    } else {
+      x.x = gelu_erf(x.x);
+      x.y = gelu_erf(x.y);
+      x.z = gelu_erf(x.z);
+      x.w = gelu_erf(x.w);
+    }
   } else if (act == ACT_GELU_TANH) {
     x.x = gelu_tanh(x.x);
     x.y = gelu_tanh(x.y);
@@ -218,6 +239,27 @@ __device__ __forceinline__ void epilogue_row_ptrs(const GemmEpilogue& ep, int ro
     if (F::res(ep)) P.res[i] = ep.res + ((ep.res_mod > 0) ? static_cast<long long>(r % ep.res_mod) : orow) * ep.ld_res;
     if (F::bf16(ep)) P.hi[i] = ep.out_hi + orow * ep.ld_bf16;
     if (F::bf16(ep) && F::lo(ep)) P.lo[i] = ep.out_lo + orow * ep.ld_bf16;
+  }
+}
+
+// Residual tiles are read once, straight from DRAM (the stream is far larger than L2), and the epilogue of a tile is a
+// short dependent chain per slab (TMEM load -> transpose -> residual load -> store): at K <= 2048 that chain, not the
+// tensor pipe, set the tile rate (ncu: 51 % tensor-active on the K = 1024 projection).  So the lines of the whole
+// 32-row x (BLOCK_N / 2)-column residual block this warp will add are requested into L2 while the warp still waits
+// for the accumulator.  Lane (sub_row, chunk) covers row chunk * 4 + sub_row: 4 x 128 B.
+template <int EPI, int SPLIT, int BLOCK_N>
+__device__ __forceinline__ void epilogue_prefetch_residual(const GemmEpilogue& ep, const EpiRowPtrs& P, int chunk, int n_tile0,
+                                                           int egrp, int N) {
+  using F = EpiFlags<EPI, SPLIT>;
+  if (EPI < 0 || !F::res(ep)) return;
+  const float* p = P.res[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i)
+    if (chunk == i) p = P.res[i];
+#pragma unroll
+  for (int s = 0; s < BLOCK_N / 32 / (kNumEpilogueWarps / 4); ++s) {
+    const int col = n_tile0 + (egrp + s * (kNumEpilogueWarps / 4)) * 32;
+    if (col + 32 <= N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + col));
   }
 }
 
@@ -457,15 +499,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       const bool rows_full = (row0 + 32 <= M);
       EpiRowPtrs rp;
       epilogue_row_ptrs<EPI, SPLIT>(ep, row0, sub_row, rp);
+      if (rows_full) epilogue_prefetch_residual<EPI, SPLIT, BLOCK_N>(ep, rp, chunk, n_idx * BLOCK_N, egrp, N);
       ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+      // Software pipeline: the TMEM load of slab c + 2 is in flight while slab c is transposed, transformed and stored.
+      constexpr int kCStep = kNumEpilogueWarps / 4;
+      uint32_t v[32];
+      int c = egrp;
+      bool have = n_idx * BLOCK_N + c * 32 < N;  // warp-uniform
+      constexpr bool kPipe = EPI >= 0;  // the all-runtime epilogue has no registers to spare for the overlap
+      if (have && kPipe) ptx::tmem_ld_32x32(t_row + c * 32, v);
 #pragma unroll 1
-      for (int c = egrp; c < BLOCK_N / 32; c += kNumEpilogueWarps / 4) {
+      while (have) {
         const int n0 = n_idx * BLOCK_N + c * 32;
-        if (n0 >= N) break;  // warp-uniform
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(t_row + c * 32, v);
+        if (!kPipe) ptx::tmem_ld_32x32(t_row + c * 32, v);
         ptx::tmem_ld_wait();
         // own row (= lane) -> staging, 16-B chunk j at position j ^ (lane & 7): conflict-free
 #pragma unroll
@@ -475,6 +523,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                        "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
                        : "memory");
         }
+        const int cn = c + kCStep;
+        have = cn < BLOCK_N / 32 && n_idx * BLOCK_N + cn * 32 < N;
+        if (have && kPipe) ptx::tmem_ld_32x32(t_row + cn * 32, v);
         __syncwarp();
         const int col = n0 + chunk * 4;
         if (rows_full && n0 + 32 <= N) {
@@ -485,6 +536,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           epilogue_slab_edge<EPI, SPLIT>(ep, stage, sub_row, chunk, row0, col, M, N);
         }
         __syncwarp();  // staging tile is rewritten by the next slab
+        c = cn;
       }
       ptx::tcgen05_fence_before();
       __syncwarp();
@@ -675,15 +727,21 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
       const bool rows_full = (row0 + 32 <= M);
       EpiRowPtrs rp;
       epilogue_row_ptrs<EPI, SPLIT>(ep, row0, sub_row, rp);
+      if (rows_full) epilogue_prefetch_residual<EPI, SPLIT, BLOCK_N>(ep, rp, chunk, n_idx * BLOCK_N, egrp, N);
       ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+      // Software pipeline: the TMEM load of slab c + 2 is in flight while slab c is transposed, transformed and stored.
+      constexpr int kCStep = kNumEpilogueWarps / 4;
+      uint32_t v[32];
+      int c = egrp;
+      bool have = n_idx * BLOCK_N + c * 32 < N;  // warp-uniform
+      constexpr bool kPipe = EPI >= 0;  // the all-runtime epilogue has no registers to spare for the overlap
+      if (have && kPipe) ptx::tmem_ld_32x32(t_row + c * 32, v);
 #pragma unroll 1
-      for (int c = egrp; c < BLOCK_N / 32; c += kNumEpilogueWarps / 4) {
+      while (have) {
         const int n0 = n_idx * BLOCK_N + c * 32;
-        if (n0 >= N) break;
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(t_row + c * 32, v);
+        if (!kPipe) ptx::tmem_ld_32x32(t_row + c * 32, v);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -692,6 +750,9 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
                        "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
                        : "memory");
         }
+        const int cn = c + kCStep;
+        have = cn < BLOCK_N / 32 && n_idx * BLOCK_N + cn * 32 < N;
+        if (have && kPipe) ptx::tmem_ld_32x32(t_row + cn * 32, v);
         __syncwarp();
         const int col = n0 + chunk * 4;
         if (row0 < M) {
@@ -704,6 +765,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
           }
         }
         __syncwarp();
+        c = cn;
       }
       ptx::tcgen05_fence_before();
       __syncwarp();
