@@ -19,7 +19,7 @@ AFFT_OK = 0
 AFFT_MAX_MODS = 8
 AFFT_MAX_CLS = 4
 AFFT_NAME_LEN = 32
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH, ACT_RELU, ACT_GATE = 0, 1, 2, 3, 4
 FUSER_SA, FUSER_SA_NOTOKEN, FUSER_TSA, FUSER_CA, FUSER_NONE = 0, 1, 2, 3, 4
@@ -108,7 +108,7 @@ EXPORTED_SYMBOLS = [
     "afft_abi_version", "afft_last_error", "afft_gemm", "afft_convert_bf16", "afft_layernorm", "afft_attention",
     "afft_create", "afft_destroy", "afft_handle_error", "afft_workspace_bytes", "afft_weight_bytes",
     "afft_set_weight", "afft_missing_weights", "afft_forward", "afft_last_launch_count",
-    "afft_profile_enable", "afft_profile_read", "afft_marginalize_topk", "afft_score_fusion",
+    "afft_profile_enable", "afft_profile_read", "afft_set_max_ksplit", "afft_marginalize_topk", "afft_score_fusion",
     "afft_transpose_bf16", "afft_layernorm_bwd", "afft_gelu_fwd", "afft_gelu_bwd", "afft_colsum", "afft_attention_bwd",
 ]
 
@@ -162,6 +162,8 @@ def lib() -> C.CDLL:
     for _n in ("afft_transpose_bf16", "afft_layernorm_bwd", "afft_gelu_fwd", "afft_gelu_bwd", "afft_colsum", "afft_attention_bwd"):
         getattr(l, _n).restype = C.c_int
     l.afft_profile_enable.argtypes = [C.c_void_p, C.c_int32]
+    l.afft_set_max_ksplit.argtypes = [C.c_void_p, C.c_int32]
+    l.afft_set_max_ksplit.restype = C.c_int
     l.afft_profile_read.argtypes = [C.c_void_p, C.POINTER(Profile)]
     for name in ("afft_gemm", "afft_convert_bf16", "afft_layernorm", "afft_attention", "afft_create",
                  "afft_set_weight", "afft_missing_weights", "afft_forward", "afft_last_launch_count",

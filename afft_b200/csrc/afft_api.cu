@@ -35,7 +35,7 @@ static int cuda_fail(const char* what, cudaError_t e) {
   return fail(AFFT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-extern "C" int afft_abi_version(void) { return 3; }
+extern "C" int afft_abi_version(void) { return 4; }
 extern "C" const char* afft_last_error(void) { return g_err.c_str(); }
 
 static int device_sm_count(int* out) {
@@ -61,7 +61,7 @@ static int device_sm_count(int* out) {
 // ================================================================================================
 // stateless operators
 // ================================================================================================
-static int run_gemm(const afft_gemm_desc& d, int num_sms, cudaStream_t stream) {
+static int run_gemm(const afft_gemm_desc& d, int num_sms, cudaStream_t stream, const SplitKScratch* sk = nullptr) {
   GemmOperands g;
   g.a = static_cast<const bf16*>(d.a_hi);
   g.a_lo = static_cast<const bf16*>(d.a_lo);
@@ -91,7 +91,7 @@ static int run_gemm(const afft_gemm_desc& d, int num_sms, cudaStream_t stream) {
   if (ep.act < ACT_NONE || ep.act > ACT_GATE) return fail(AFFT_ERR_INVALID, "gemm: unknown activation");
   if (ep.act == ACT_GATE && ep.res == nullptr) return fail(AFFT_ERR_INVALID, "gemm: AFFT_ACT_GATE needs the gated operand in res");
   std::string err;
-  if (!launch_gemm(g, ep, d.strict != 0, d.force_block_n, num_sms, stream, &err)) return fail(AFFT_ERR_CUDA, err);
+  if (!launch_gemm(g, ep, d.strict != 0, d.force_block_n, num_sms, stream, &err, sk)) return fail(AFFT_ERR_CUDA, err);
   return AFFT_OK;
 }
 
@@ -498,6 +498,7 @@ struct afft_handle {
   // workspace
   char* ws = nullptr;
   size_t ws_bytes = 0;
+  SplitKScratch splitk{nullptr, 0, nullptr, 0, 16};  // partial tiles + band counters of the split-K GEMM path
   int n_slots = 0;  // tokens per (b, t) in the fuser stream (CA: 1)
   float* h = nullptr;
   PairBuf y, att, f;
@@ -705,6 +706,8 @@ extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
   want_pair(h->f2, R2 * 4 * G);
   want(&h->qkv2, R2 * 3 * G * (strict ? 4 : 2));
   want_pair(h->pfb, RP * D);
+  want(reinterpret_cast<void**>(&h->splitk.partials), kSplitKPartialFloats * 4);
+  want(reinterpret_cast<void**>(&h->splitk.counters), kSplitKCounters * 4);
   if (OL > 1) {
     h->qkv_layer.assign(c.gpt_layers, nullptr);
     h->qkv_new.assign(c.gpt_layers, nullptr);
@@ -730,6 +733,15 @@ extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
   for (auto& r : reqs) {
     *r.dst = h->ws + off;
     off += r.bytes;
+  }
+  h->splitk.partial_floats = kSplitKPartialFloats;
+  h->splitk.n_counters = kSplitKCounters;
+  e = cudaMemset(h->splitk.counters, 0, kSplitKCounters * 4);  // once: the kernels leave the counters at zero
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cudaFree(h->ws);
+    delete h;
+    return cuda_fail("cudaMemset(split-K counters)", e);
   }
   *out = h;
   return AFFT_OK;
@@ -903,7 +915,7 @@ struct Fwd {
     d.row_stride = row_stride;
     d.row_off = row_off;
     const int pi = prof_begin(AFFT_CAT_GEMM, d.M, d.N, d.K);
-    check(run_gemm(d, h->num_sms, stream));
+    check(run_gemm(d, h->num_sms, stream, &h->splitk));
     prof_end(pi);
   }
 
@@ -1340,6 +1352,13 @@ extern "C" int afft_forward(afft_handle* h, int32_t B, const afft_io* io, void* 
   for (int b0 = 0; b0 < B && F.ok(); b0 += chunk) run_fuser(F, *io, b0, std::min(chunk, B - b0));
   if (F.ok()) run_predictor(F, *io, B);
   return F.rc;
+}
+
+extern "C" int afft_set_max_ksplit(afft_handle* h, int32_t max_split) {
+  if (h == nullptr) return fail(AFFT_ERR_INVALID, "set_max_ksplit: null handle");
+  if (max_split < 1 || max_split > 64) return hfail(h, AFFT_ERR_INVALID, "set_max_ksplit: value must be in [1, 64]");
+  h->splitk.max_split = max_split;
+  return AFFT_OK;
 }
 
 extern "C" int afft_profile_enable(afft_handle* h, int32_t enable) {

@@ -25,6 +25,33 @@ struct GemmOperands {
   int M, N, K;
 };
 
+// Scratch of the split-K path (owned by a handle; nullptr = split-K off, e.g. the stateless afft_gemm entry).
+struct SplitKScratch {
+  float* partials;        // partial_floats fp32
+  size_t partial_floats;
+  unsigned* counters;     // n_counters, zeroed once at allocation (the kernel leaves them zero)
+  int n_counters;
+  int max_split;          // <= 1: off
+};
+constexpr size_t kSplitKPartialFloats = static_cast<size_t>(160) * kBlockM * 256;  // one 128 x 256 tile per CTA, 160 >= SMs
+constexpr int kSplitKCounters = 160 * kNumEpilogueWarps;
+
+// Number of K splits for a problem of `tiles` output tiles on `slots` CTAs (or CTA pairs): only when at most half of
+// the slots would be busy, every split gets >= 2 K blocks, and the scratch holds one partial tile per CTA.
+inline int pick_ksplit(int tiles, int slots, int num_kb, int ctas_per_tile, size_t tile_floats, const SplitKScratch* sk) {
+  static const int env = [] { const char* v = getenv("AFFT_GEMM_KSPLIT"); return v == nullptr ? 16 : atoi(v); }();
+  if (sk == nullptr || sk->partials == nullptr || sk->counters == nullptr || env <= 1 || sk->max_split <= 1) return 1;
+  if (tiles * 2 > slots) return 1;
+  int s = slots / tiles;
+  if (s > num_kb / 2) s = num_kb / 2;
+  if (s > env) s = env;
+  if (s > sk->max_split) s = sk->max_split;
+  while (s > 1 && (s - 1) * ((num_kb + s - 1) / s) >= num_kb) --s;  // no empty split
+  while (s > 1 && (static_cast<size_t>(tiles) * s * ctas_per_tile * tile_floats > sk->partial_floats)) --s;
+  if (tiles * ctas_per_tile * kNumEpilogueWarps > sk->n_counters) return 1;
+  return s < 1 ? 1 : s;
+}
+
 inline PFN_cuTensorMapEncodeTiled_v12000 get_tensormap_encoder(std::string* err) {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
@@ -94,7 +121,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 template <int BLOCK_N, int SPLIT, int EPI>
 inline cudaError_t launch_gemm_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal,
                                        const CUtensorMap& tbl, const GemmEpilogue& ep, int M, int N, int K,
-                                       int num_sms, const GemmSched& sched, cudaStream_t stream) {
+                                       int num_sms, GemmSched sched, const SplitKScratch* sk, cudaStream_t stream) {
   using T = GemmTraits<BLOCK_N, SPLIT>;
   auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT, EPI>;
   static bool attr_set[64] = {false};  // per variant and device; benign race (idempotent)
@@ -107,14 +134,18 @@ inline cudaError_t launch_gemm_variant(const CUtensorMap& ta, const CUtensorMap&
     attr_set[dev] = true;
   }
   const int num_tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
-  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  sched.ksplit = pick_ksplit(num_tiles, num_sms, (K + kBlockK - 1) / kBlockK, 1, static_cast<size_t>(kBlockM) * BLOCK_N, sk);
+  sched.partials = sk ? sk->partials : nullptr;
+  sched.counters = sk ? sk->counters : nullptr;
+  const int num_units = num_tiles * sched.ksplit;
+  const int grid = num_units < num_sms ? num_units : num_sms;
   return launch_pdl(kern, dim3(grid), dim3(kGemmThreads), T::kSmemBytes, stream, ta, tb, tal, tbl, ep, M, N, K, sched);
 }
 
 template <int SPLIT, int EPI>
 inline cudaError_t launch_gemm_2cta_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal,
                                             const CUtensorMap& tbl, const GemmEpilogue& ep, int M, int N, int K,
-                                            int num_sms, const GemmSched& sched, cudaStream_t stream) {
+                                            int num_sms, GemmSched sched, const SplitKScratch* sk, cudaStream_t stream) {
   using T = Gemm2Traits<SPLIT>;
   auto kern = gemm_bf16_tcgen05_2cta_kernel<SPLIT, EPI>;
   static bool attr_set[64] = {false};
@@ -128,7 +159,10 @@ inline cudaError_t launch_gemm_2cta_variant(const CUtensorMap& ta, const CUtenso
   }
   const int num_tiles = ((M + 255) / 256) * ((N + 255) / 256);
   int clusters = num_sms / 2;
-  if (num_tiles < clusters) clusters = num_tiles;
+  sched.ksplit = pick_ksplit(num_tiles, clusters, (K + kBlockK - 1) / kBlockK, 2, static_cast<size_t>(kBlockM) * 256, sk);
+  sched.partials = sk ? sk->partials : nullptr;
+  sched.counters = sk ? sk->counters : nullptr;
+  if (num_tiles * sched.ksplit < clusters) clusters = num_tiles * sched.ksplit;
   // __cluster_dims__(2) is compiled into the kernel
   return launch_pdl(kern, dim3(2 * clusters), dim3(kGemmThreads), T::kSmemBytes, stream, ta, tb, tal, tbl, ep, M, N, K, sched);
 }
@@ -159,6 +193,9 @@ inline const GemmSched& default_sched() {
     g.n_fastest = (o != nullptr && o[0] == 'm') ? 0 : 1;
     g.policy_a = policy_from_env("AFFT_GEMM_HINT_A", ptx::kEvictFirst);   // activations: streamed once
     g.policy_b = policy_from_env("AFFT_GEMM_HINT_B", ptx::kEvictNormal);  // weights: hot for the whole launch
+    g.ksplit = 1;
+    g.partials = nullptr;
+    g.counters = nullptr;
     return g;
   }();
   return s;
@@ -166,7 +203,7 @@ inline const GemmSched& default_sched() {
 
 // Returns false and fills *err on failure.  force_block_n: 0 = auto.
 inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, bool strict, int force_block_n,
-                        int num_sms, cudaStream_t stream, std::string* err) {
+                        int num_sms, cudaStream_t stream, std::string* err, const SplitKScratch* sk = nullptr) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) {
     if (err) *err = "gemm: empty problem";
     return false;
@@ -205,8 +242,8 @@ inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, bool stri
   const bool lo_ok = (ep.out_hi == nullptr) || ((ep.out_lo != nullptr) == strict);  // specialised kernels tie lo to SPLIT
   cudaError_t e = cudaErrorInvalidValue;
 #define AFFT_LAUNCH(BN, SP, EP)                                                                                       \
-  e = (BN == 512) ? launch_gemm_2cta_variant<SP, EP>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, default_sched(), stream) \
-                  : launch_gemm_variant<(BN == 512 ? 256 : BN), SP, EP>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, default_sched(), stream)
+  e = (BN == 512) ? launch_gemm_2cta_variant<SP, EP>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, default_sched(), sk, stream) \
+                  : launch_gemm_variant<(BN == 512 ? 256 : BN), SP, EP>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, default_sched(), sk, stream)
 #define AFFT_DISPATCH_EPI(BN, SP)                                                            \
   do {                                                                                       \
     if (!lo_ok || ep.act > ACT_GELU_TANH) { AFFT_LAUNCH(BN, SP, EPI_GENERIC); break; }                               \

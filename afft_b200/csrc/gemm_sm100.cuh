@@ -57,9 +57,19 @@ struct GemmEpilogue {
 
 // Tile order and L2 policy.  n_fastest: consecutive tiles share the A (activation) row block and sweep the
 // N tiles of the (small, L2-resident) weight, so every activation tile is fetched from DRAM once.
+//
+// Split-K (skinny problems: fewer tiles than SMs, e.g. the GPT-2 projections at the reference's eval batch of 32,
+// or any GEMM at batch 1): a work unit is (tile, split); split s accumulates K blocks [s * kb_per, (s+1) * kb_per)
+// into TMEM and its epilogue warps store the raw fp32 partial tile to `partials` (unit-major, tile-local layout,
+// so the scratch is bounded by one tile per CTA).  Each epilogue warp then bumps the counter of its (tile, warp)
+// band; the warp that arrives last sums the `ksplit` partials of its band IN SPLIT ORDER (bit-reproducible
+// whatever the arrival order) and runs the normal epilogue on the sum.  Counters reset themselves.
 struct GemmSched {
   int n_fastest;
   unsigned long long policy_a, policy_b;
+  int ksplit;           // 1 = off
+  float* partials;      // >= grid CTAs * 128 * BLOCK_N floats
+  unsigned* counters;   // >= tiles * (CTAs per tile) * kNumEpilogueWarps, zero before the first launch
 };
 
 template <int BLOCK_N, int SPLIT>
@@ -352,14 +362,132 @@ __device__ __noinline__ void epilogue_slab_edge(const GemmEpilogue& ep, uint32_t
 }
 
 // --------------------------------------------------------------------------------------------
+// Split-K helpers (see GemmSched).  `band` = this warp's 32 rows x BLOCK_N columns of the CTA's 128-row half tile;
+// the warp owns slabs c = egrp, egrp + 2, ... of it, in the partial buffer as in the accumulator.
+// --------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__device__ __forceinline__ void splitk_store_partial(float* cta_partial, uint32_t stage, int quad, int sub_row, int chunk, int c) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = i * 4 + sub_row;
+    const float4 x = lds128(stage + static_cast<uint32_t>(rl) * 128u + static_cast<uint32_t>((chunk ^ (rl & 7)) * 16));
+    __stcg(reinterpret_cast<float4*>(cta_partial + static_cast<size_t>(quad * 32 + rl) * BLOCK_N + c * 32 + chunk * 4), x);
+  }
+}
+
+// Sum of the ksplit partials of one slab, in split order, written back into the warp's staging tile in exactly the
+// layout the TMEM transposition produces (each lane later re-reads the positions it wrote itself).
+template <int BLOCK_N>
+__device__ __forceinline__ void splitk_sum_to_stage(const float* tile_partial0, size_t split_stride, int ksplit, uint32_t stage,
+                                                    int quad, int sub_row, int chunk, int c) {
+  float4 x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int sp = 0; sp < ksplit; ++sp) {
+    const float* p = tile_partial0 + sp * split_stride;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rl = i * 4 + sub_row;
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(p + static_cast<size_t>(quad * 32 + rl) * BLOCK_N + c * 32 + chunk * 4));
+      x[i].x += v.x;
+      x[i].y += v.y;
+      x[i].z += v.z;
+      x[i].w += v.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = i * 4 + sub_row;
+    const uint32_t addr = stage + static_cast<uint32_t>(rl) * 128u + static_cast<uint32_t>((chunk ^ (rl & 7)) * 16);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x[i].x), "f"(x[i].y), "f"(x[i].z), "f"(x[i].w) : "memory");
+  }
+}
+
+// The epilogue of one work unit for one warp (both kernels).  Pass 0 drains the warp's slabs from TMEM (software
+// pipelined: the TMEM load of the next slab is in flight while the current one is transposed, transformed and
+// stored) and either finishes them (ksplit == 1) or stores them as split-K partials; `release_tmem()` then hands the
+// accumulator back to the MMA warp.  With split-K the warp that arrives last on the band counter runs pass 1: same
+// slab loop, but the staging tile is filled with the in-order sum of the partials instead of from TMEM.
+template <int EPI, int SPLIT, int BLOCK_N, typename ReleaseFn>
+__device__ __forceinline__ void epilogue_unit(const GemmEpilogue& ep, int ksplit, uint32_t stage, uint32_t t_row, int quad, int egrp,
+                                              int lane, int row0, int n_tile0, int M, int N, float* cta_partial,
+                                              const float* tile_partial0, size_t split_stride, unsigned* counter,
+                                              ReleaseFn release_tmem) {
+  constexpr int kCStep = kNumEpilogueWarps / 4;
+  constexpr bool kPipe = EPI >= 0;  // the all-runtime epilogue has no registers to spare for the overlap
+  const int sub_row = lane >> 3;    // row within a group of 4
+  const int chunk = lane & 7;       // 16-byte chunk = 4 fp32 columns
+  const bool rows_full = (row0 + 32 <= M);
+  EpiRowPtrs rp;
+  epilogue_row_ptrs<EPI, SPLIT>(ep, row0, sub_row, rp);
+  if (rows_full && ksplit == 1) epilogue_prefetch_residual<EPI, SPLIT, BLOCK_N>(ep, rp, chunk, n_tile0, egrp, N);
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    uint32_t v[32];
+    int c = egrp;
+    bool have = n_tile0 + c * 32 < N;  // warp-uniform
+    if (pass == 0 && have && kPipe) ptx::tmem_ld_32x32(t_row + c * 32, v);
+#pragma unroll 1
+    while (have) {
+      const int n0 = n_tile0 + c * 32;
+      const int cn = c + kCStep;
+      have = cn < BLOCK_N / 32 && n_tile0 + cn * 32 < N;
+      if (pass == 0) {
+        if (!kPipe) ptx::tmem_ld_32x32(t_row + c * 32, v);
+        ptx::tmem_ld_wait();
+        // own row (= lane) -> staging, 16-B chunk j at position j ^ (lane & 7): conflict-free
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = stage + static_cast<uint32_t>(lane) * 128u + static_cast<uint32_t>((j ^ (lane & 7)) * 16);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * j]), "r"(v[4 * j + 1]),
+                       "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                       : "memory");
+        }
+        if (have && kPipe) ptx::tmem_ld_32x32(t_row + cn * 32, v);
+      } else {
+        splitk_sum_to_stage<BLOCK_N>(tile_partial0, split_stride, ksplit, stage, quad, sub_row, chunk, c);
+      }
+      __syncwarp();
+      const int col = n0 + chunk * 4;
+      if (pass == 0 && ksplit > 1) {
+        splitk_store_partial<BLOCK_N>(cta_partial, stage, quad, sub_row, chunk, c);
+      } else if (row0 < M) {
+        if (rows_full && n0 + 32 <= N) {
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+          epilogue_slab_full<EPI, SPLIT>(ep, stage, sub_row, chunk, col, rp, bias4);
+        } else {
+          epilogue_slab_edge<EPI, SPLIT>(ep, stage, sub_row, chunk, row0, col, M, N);
+        }
+      }
+      __syncwarp();  // staging tile is rewritten by the next slab
+      c = cn;
+    }
+    if (pass == 1) break;
+    ptx::tcgen05_fence_before();
+    __syncwarp();
+    release_tmem();
+    if (ksplit == 1) break;
+    __threadfence();  // this lane's partial stores are visible device-wide before the band counter moves
+    __syncwarp();
+    unsigned old = 0;
+    if (lane == 0) old = atomicAdd(counter, 1u);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old != static_cast<unsigned>(ksplit - 1)) break;  // another split's warp will finish this band
+    __threadfence();
+    if (lane == 0) *counter = 0u;  // ready for the next launch (stream-ordered)
+  }
+}
+
+// --------------------------------------------------------------------------------------------
 // The kernel
 // --------------------------------------------------------------------------------------------
 template <int BLOCK_N, int SPLIT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                          const __grid_constant__ CUtensorMap tm_a_lo,
-                         const __grid_constant__ CUtensorMap tm_b_lo, const GemmEpilogue ep, const int M,
-                         const int N, const int K, const GemmSched sched) {
+                         const __grid_constant__ CUtensorMap tm_b_lo, const __grid_constant__ GemmEpilogue ep, const int M,
+                         const int N, const int K, const __grid_constant__ GemmSched sched) {
   using T = GemmTraits<BLOCK_N, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_raw_u32 = ptx::smem_u32(smem_raw);
@@ -381,6 +509,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + kBlockK - 1) / kBlockK;
+  const int ksplit = sched.ksplit;  // work unit = (tile, split); ksplit == 1: unit = tile
+  const int num_units = num_tiles * ksplit;
+  const int kb_per = (num_kb + ksplit - 1) / ksplit;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_a);
@@ -412,10 +543,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     // ======================= TMA producer =======================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int tile = unit / ksplit, split = unit - tile * ksplit;
         const int m_idx = sched.n_fastest ? tile / num_n : tile % num_m;
         const int n_idx = sched.n_fastest ? tile % num_n : tile / num_m;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = split * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * T::kStageBytes;
           const uint32_t b_dst = a_dst + T::kABytes;
@@ -441,11 +574,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, BLOCK_N);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int split = unit % ksplit;
+        const int kb0 = split * kb_per, kb1 = min(num_kb, kb0 + kb_per);
         ptx::mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this buffer
         ptx::tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tcgen05_fence_after();
           const uint32_t a_src = smem_base + stage * T::kStageBytes;
@@ -454,7 +589,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             ptx::umma_bf16_ss(d_tmem, ptx::make_smem_desc_sw128(a_src + k * (kUmmaK * 2)),
                               ptx::make_smem_desc_sw128(b_src + k * (kUmmaK * 2)), idesc,
-                              (kb | k) != 0 ? 1u : 0u);
+                              ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           if (SPLIT == 3) {
             const uint32_t a_lo_src = b_src + T::kBBytes;
@@ -488,59 +623,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     // leaves as fully coalesced 16-byte accesses: each warp instruction covers 4 rows x 128 B.
     const int quad = warp & 3;
     const int egrp = (warp - 4) >> 2;
-    const int sub_row = lane >> 3;  // row within a group of 4
-    const int chunk = lane & 7;     // 16-byte chunk = 4 fp32 columns
     const uint32_t stage = staging_base + static_cast<uint32_t>(warp - 4) * 4096u;
+    constexpr size_t kTileFloats = static_cast<size_t>(kBlockM) * BLOCK_N;
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int tile = unit / ksplit;
       const int m_idx = sched.n_fastest ? tile / num_n : tile % num_m;
       const int n_idx = sched.n_fastest ? tile % num_n : tile / num_m;
       const int row0 = m_idx * kBlockM + quad * 32;
-      const bool rows_full = (row0 + 32 <= M);
-      EpiRowPtrs rp;
-      epilogue_row_ptrs<EPI, SPLIT>(ep, row0, sub_row, rp);
-      if (rows_full) epilogue_prefetch_residual<EPI, SPLIT, BLOCK_N>(ep, rp, chunk, n_idx * BLOCK_N, egrp, N);
       ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
-      // Software pipeline: the TMEM load of slab c + 2 is in flight while slab c is transposed, transformed and stored.
-      constexpr int kCStep = kNumEpilogueWarps / 4;
-      uint32_t v[32];
-      int c = egrp;
-      bool have = n_idx * BLOCK_N + c * 32 < N;  // warp-uniform
-      constexpr bool kPipe = EPI >= 0;  // the all-runtime epilogue has no registers to spare for the overlap
-      if (have && kPipe) ptx::tmem_ld_32x32(t_row + c * 32, v);
-#pragma unroll 1
-      while (have) {
-        const int n0 = n_idx * BLOCK_N + c * 32;
-        if (!kPipe) ptx::tmem_ld_32x32(t_row + c * 32, v);
-        ptx::tmem_ld_wait();
-        // own row (= lane) -> staging, 16-B chunk j at position j ^ (lane & 7): conflict-free
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t addr = stage + static_cast<uint32_t>(lane) * 128u + static_cast<uint32_t>((j ^ (lane & 7)) * 16);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * j]), "r"(v[4 * j + 1]),
-                       "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
-                       : "memory");
-        }
-        const int cn = c + kCStep;
-        have = cn < BLOCK_N / 32 && n_idx * BLOCK_N + cn * 32 < N;
-        if (have && kPipe) ptx::tmem_ld_32x32(t_row + cn * 32, v);
-        __syncwarp();
-        const int col = n0 + chunk * 4;
-        if (rows_full && n0 + 32 <= N) {
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ep.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-          epilogue_slab_full<EPI, SPLIT>(ep, stage, sub_row, chunk, col, rp, bias4);
-        } else {
-          epilogue_slab_edge<EPI, SPLIT>(ep, stage, sub_row, chunk, row0, col, M, N);
-        }
-        __syncwarp();  // staging tile is rewritten by the next slab
-        c = cn;
-      }
-      ptx::tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(acc));
+      const uint32_t empty_addr = tmem_empty_bar(acc);
+      epilogue_unit<EPI, SPLIT, BLOCK_N>(ep, ksplit, stage, t_row, quad, egrp, lane, row0, n_idx * BLOCK_N, M, N,
+                                         sched.partials + static_cast<size_t>(unit) * kTileFloats,
+                                         sched.partials + static_cast<size_t>(tile) * ksplit * kTileFloats, kTileFloats,
+                                         sched.counters + tile * kNumEpilogueWarps + (warp - 4),
+                                         [&] { if (lane == 0) ptx::mbar_arrive(empty_addr); });
       acc ^= 1u;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -584,8 +683,8 @@ template <int SPLIT, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                               const __grid_constant__ CUtensorMap tm_a_lo,
-                              const __grid_constant__ CUtensorMap tm_b_lo, const GemmEpilogue ep, const int M,
-                              const int N, const int K, const GemmSched sched) {
+                              const __grid_constant__ CUtensorMap tm_b_lo, const __grid_constant__ GemmEpilogue ep, const int M,
+                              const int N, const int K, const __grid_constant__ GemmSched sched) {
   using T = Gemm2Traits<SPLIT>;
   constexpr int BLOCK_N = 256;
   extern __shared__ uint8_t smem_raw[];
@@ -610,6 +709,9 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
   const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + kBlockK - 1) / kBlockK;
+  const int ksplit = sched.ksplit;  // work unit = (tile, split), see GemmSched
+  const int num_units = num_tiles * ksplit;
+  const int kb_per = (num_kb + ksplit - 1) / ksplit;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_a);
@@ -641,12 +743,14 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
     // ======================= TMA producer (both CTAs) =======================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+        const int tile = unit / ksplit, split = unit - tile * ksplit;
         const int m_idx = sched.n_fastest ? tile / num_n : tile % num_m;
         const int n_idx = sched.n_fastest ? tile % num_n : tile / num_m;
         const int a_row = m_idx * 256 + static_cast<int>(rank) * 128;
         const int b_row = n_idx * BLOCK_N + static_cast<int>(rank) * 128;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = split * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * T::kStageBytes;
           const uint32_t b_dst = a_dst + T::kABytes;
@@ -673,11 +777,13 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(256, BLOCK_N);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+        const int split = unit % ksplit;
+        const int kb0 = split * kb_per, kb1 = min(num_kb, kb0 + kb_per);
         ptx::mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
         ptx::tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tcgen05_fence_after();
           const uint32_t a_src = smem_base + stage * T::kStageBytes;
@@ -685,7 +791,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             ptx::umma_bf16_ss_2cta(d_tmem, ptx::make_smem_desc_sw128(a_src + k * (kUmmaK * 2)),
-                                   ptx::make_smem_desc_sw128(b_src + k * (kUmmaK * 2)), idesc, (kb | k) != 0 ? 1u : 0u);
+                                   ptx::make_smem_desc_sw128(b_src + k * (kUmmaK * 2)), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           if (SPLIT == 3) {
             const uint32_t a_lo_src = b_src + T::kBBytes;
@@ -716,60 +822,23 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
     // ======================= epilogue (both CTAs, own 128 rows) =======================
     const int quad = warp & 3;
     const int egrp = (warp - 4) >> 2;
-    const int sub_row = lane >> 3;
-    const int chunk = lane & 7;
     const uint32_t stage = staging_base + static_cast<uint32_t>(warp - 4) * 4096u;
+    constexpr size_t kHalfTile = static_cast<size_t>(kBlockM) * BLOCK_N;  // one CTA's 128 x 256 accumulator
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+      const int tile = unit / ksplit;
       const int m_idx = sched.n_fastest ? tile / num_n : tile % num_m;
       const int n_idx = sched.n_fastest ? tile % num_n : tile / num_m;
       const int row0 = m_idx * 256 + static_cast<int>(rank) * 128 + quad * 32;
-      const bool rows_full = (row0 + 32 <= M);
-      EpiRowPtrs rp;
-      epilogue_row_ptrs<EPI, SPLIT>(ep, row0, sub_row, rp);
-      if (rows_full) epilogue_prefetch_residual<EPI, SPLIT, BLOCK_N>(ep, rp, chunk, n_idx * BLOCK_N, egrp, N);
       ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
-      // Software pipeline: the TMEM load of slab c + 2 is in flight while slab c is transposed, transformed and stored.
-      constexpr int kCStep = kNumEpilogueWarps / 4;
-      uint32_t v[32];
-      int c = egrp;
-      bool have = n_idx * BLOCK_N + c * 32 < N;  // warp-uniform
-      constexpr bool kPipe = EPI >= 0;  // the all-runtime epilogue has no registers to spare for the overlap
-      if (have && kPipe) ptx::tmem_ld_32x32(t_row + c * 32, v);
-#pragma unroll 1
-      while (have) {
-        const int n0 = n_idx * BLOCK_N + c * 32;
-        if (!kPipe) ptx::tmem_ld_32x32(t_row + c * 32, v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t addr = stage + static_cast<uint32_t>(lane) * 128u + static_cast<uint32_t>((j ^ (lane & 7)) * 16);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * j]), "r"(v[4 * j + 1]),
-                       "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
-                       : "memory");
-        }
-        const int cn = c + kCStep;
-        have = cn < BLOCK_N / 32 && n_idx * BLOCK_N + cn * 32 < N;
-        if (have && kPipe) ptx::tmem_ld_32x32(t_row + cn * 32, v);
-        __syncwarp();
-        const int col = n0 + chunk * 4;
-        if (row0 < M) {
-          if (rows_full && n0 + 32 <= N) {
-            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ep.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-            epilogue_slab_full<EPI, SPLIT>(ep, stage, sub_row, chunk, col, rp, bias4);
-          } else {
-            epilogue_slab_edge<EPI, SPLIT>(ep, stage, sub_row, chunk, row0, col, M, N);
-          }
-        }
-        __syncwarp();
-        c = cn;
-      }
-      ptx::tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(tmem_empty_bar(acc), 0));
+      const uint32_t empty_leader = ptx::mapa(tmem_empty_bar(acc), 0);
+      epilogue_unit<EPI, SPLIT, BLOCK_N>(ep, ksplit, stage, t_row, quad, egrp, lane, row0, n_idx * BLOCK_N, M, N,
+                                         sched.partials + (static_cast<size_t>(unit) * 2 + rank) * kHalfTile,
+                                         sched.partials + (static_cast<size_t>(tile) * ksplit * 2 + rank) * kHalfTile, 2 * kHalfTile,
+                                         sched.counters + (tile * 2 + rank) * kNumEpilogueWarps + (warp - 4),
+                                         [&] { if (lane == 0) ptx::mbar_arrive_cluster(empty_leader); });
       acc ^= 1u;
       if (acc == 0) acc_phase ^= 1u;
     }

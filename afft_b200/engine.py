@@ -52,6 +52,7 @@ class Engine:
         h = C.c_void_p()
         _capi.check(self.lib.afft_create(C.byref(cfg), C.byref(h)))
         self.handle = h
+        self.max_ksplit = 16  # library default
         self._versions: Optional[tuple] = None
 
     def close(self):
@@ -146,6 +147,11 @@ class Engine:
         p = _capi.Profile()
         _capi.check(self.lib.afft_profile_read(self.handle, C.byref(p)), self.handle)
         return [(r.cat, r.M, r.N, r.K, r.ms) for r in p.recs[:p.n]]
+
+    def set_max_ksplit(self, max_split: int):
+        """Upper bound on the K splits of skinny GEMMs (1 = off); see ``afft_set_max_ksplit``."""
+        _capi.check(self.lib.afft_set_max_ksplit(self.handle, int(max_split)), self.handle)
+        self.max_ksplit = int(max_split)
 
     def launch_count(self) -> int:
         return int(self.lib.afft_last_launch_count(self.handle))

@@ -196,6 +196,9 @@ class CMFPEarly(nn.Module):
         self.strict = strict
         self.max_batch = max_batch
         self.return_attentions = True
+        # upper bound on the K splits of skinny GEMMs (small batches); 1 = off, which makes a clip's result bitwise
+        # independent of the batch size it is computed in (see afft_set_max_ksplit)
+        self.max_ksplit = 16
         self._engines: Dict[tuple, Engine] = {}
 
     # ---- reference helpers kept for API parity ----
@@ -232,6 +235,8 @@ class CMFPEarly(nn.Module):
                          cls_dims=list(self.num_classes.values()), strict=bool(self.strict),
                          max_batch=max(B, self.max_batch), device=device, fp_output_len=self.fp_output_len)
             self._engines[key] = eng
+        if eng.max_ksplit != self.max_ksplit:
+            eng.set_max_ksplit(self.max_ksplit)
         return eng
 
     def forward(self, feats: Dict[str, Tensor]) -> Dict[str, Dict[str, Tensor]]:

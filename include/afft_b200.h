@@ -278,6 +278,11 @@ typedef struct afft_profile {
   afft_profile_rec recs[AFFT_MAX_PROFILE_RECS];
 } afft_profile;
 AFFT_API int afft_profile_enable(afft_handle* h, int32_t enable);
+/* Upper bound on the number of K splits a GEMM of this handle may use (split-K runs when a GEMM has too few output
+ * tiles to occupy the GPU: small batches).  1 switches split-K off; the default is 16.  Results are bit-reproducible
+ * for a fixed value (partials are summed in split order), and differ between values only by fp32 summation order.
+ * There is no reference counterpart (PyTorch picks its cuBLAS algorithm internally). */
+AFFT_API int afft_set_max_ksplit(afft_handle* h, int32_t max_split);
 AFFT_API int afft_profile_read(afft_handle* h, afft_profile* out);
 
 #ifdef __cplusplus

@@ -174,6 +174,9 @@ def test_properties_at_baseline_batch():
     cfg_name = "ek100_sa_tsn"
     cfg, T, ncls, bs = configs.named_config(cfg_name)
     model = _model(cfg_name, False)
+    # bitwise independence of the batch size needs a fixed summation order: split-K off (it is on by default and is
+    # covered by test_splitk_small_batches below)
+    model.future_predictor.max_ksplit = 1
     for B in (bs, 256):
         feats = synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=77)
         out = _run(model, feats)
@@ -203,6 +206,47 @@ def test_properties_at_baseline_batch():
         out2 = _run(model, f2)
         assert torch.equal(out2["past_logits/action"]["all-fused"][:, :T - 1], pl[:, :T - 1])
         assert not torch.equal(out2["logits/action"]["all-fused"], lg)
+    model.future_predictor.max_ksplit = 16
+
+
+@pytest.mark.parametrize("strict", [False, True])
+def test_splitk_small_batches(strict):
+    """Small batches run their GEMMs split along K (few output tiles -> the K loop is spread over the SMs).
+    The result is bit-reproducible run to run (partials are summed in split order), equals the unsplit result up
+    to fp32 summation order, keeps clips independent at a fixed batch size, and matches the oracle."""
+    from oracle import afft_oracle
+    cfg_name = "ek100_sa_tsn"
+    cfg, T, ncls, _ = configs.named_config(cfg_name)
+    model = _model(cfg_name, strict)
+    head = model.future_predictor
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    tol = TOL[strict]
+    keys = ("logits/action", "past_logits/action", "orig_past", "past_futures")
+    for B in (1, 3, 8, 32):
+        feats = synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=900 + B)
+        head.max_ksplit = 16
+        a = _run(model, feats)
+        b = _run(model, feats)
+        for k in keys:
+            assert torch.equal(a[k]["all-fused"], b[k]["all-fused"]), (B, k)  # deterministic reduction
+        if B > 1:
+            perm = torch.randperm(B, generator=torch.Generator().manual_seed(B))
+            p = _run(model, {m: f[perm] for m, f in feats.items()})
+            assert torch.equal(p["logits/action"]["all-fused"], a["logits/action"]["all-fused"][perm.cuda()])
+        head.max_ksplit = 1
+        u = _run(model, feats)
+        head.max_ksplit = 16
+        for k in keys:
+            d = (a[k]["all-fused"] - u[k]["all-fused"]).abs().max().item()
+            assert d < (2e-5 if strict else tol["logits"]), (B, k, d)
+        if B <= 3:
+            ref = afft_oracle.forward(sd, cfg, ncls, feats, dtype=torch.float32)
+            for k in keys:
+                d = (a[k]["all-fused"].cpu() - ref[k]["all-fused"]).abs().max().item()
+                assert d < (tol["logits"] if "logits" in k else tol["feat"]), (B, k, d)
+            if strict:
+                assert torch.equal(a["logits/action"]["all-fused"][:, 0].topk(5).indices.cpu(),
+                                   afft_oracle.top5(ref["logits/action"]["all-fused"][:, 0]))
 
 
 def test_edge_batches_and_regrowth():
@@ -211,6 +255,7 @@ def test_edge_batches_and_regrowth():
     m = BaseModel(cfg, ncls, {}, max_batch=4)
     m.load_state_dict(synthetic.synthetic_state_dict(m, seed=0))
     m = m.to("cuda:0").eval()
+    m.future_predictor.max_ksplit = 1  # the B = 1 vs B = 9 comparison below is bitwise
     feats = synthetic.synthetic_features(cfg["modal_dims"], 9, T, seed=5)
     full = _run(m, feats)["logits/action"]["all-fused"]  # B=9 > max_batch=4: the engine is rebuilt larger
     one = _run(m, {k: v[:1] for k, v in feats.items()})["logits/action"]["all-fused"]  # B=1
@@ -231,6 +276,7 @@ def test_fuser_chunking_is_equivalent(monkeypatch):
         monkeypatch.setenv("AFFT_FUSER_CHUNK", chunk)
         m = BaseModel(cfg, ncls, {})
         m.load_state_dict(synthetic.synthetic_state_dict(m, seed=0))
+        m.future_predictor.max_ksplit = 1  # chunking changes the GEMM heights, hence the split-K factor; compare bitwise
         outs.append(_run(m.to("cuda:0").eval(), feats))
     for k in ("logits/action", "past_logits/action", "orig_past", "past_futures"):
         assert torch.equal(outs[0][k]["all-fused"], outs[1][k]["all-fused"]), k

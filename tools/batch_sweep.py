@@ -54,7 +54,8 @@ def timeit(fn, iters):
 
 
 rows = []
-for B in (1, 8, 32, 64, 128, 256, 512, 1024):
+for B, ks in [(b, k) for b in (1, 8, 32, 64, 128, 256, 512, 1024) for k in ((1, 16) if b <= 128 else (16,))]:
+    eng.set_max_ksplit(ks)  # 1 = split-K off (for comparison); 16 = library default
     iters = 50 if B <= 128 else 20
     ms_plain = timeit(lambda: eng.forward_into(io, B), iters)
     g = torch.cuda.CUDAGraph()
@@ -66,7 +67,7 @@ for B in (1, 8, 32, 64, 128, 256, 512, 1024):
     with torch.cuda.graph(g):
         eng.forward_into(io, B)
     ms_graph = timeit(g.replay, iters)
-    rec = {"config": name, "B": B, "ms_plain": round(ms_plain, 4), "ms_graph": round(ms_graph, 4),
+    rec = {"config": name, "B": B, "max_ksplit": ks, "ms_plain": round(ms_plain, 4), "ms_graph": round(ms_graph, 4),
            "clips_per_s_plain": round(B / ms_plain * 1e3, 1), "clips_per_s_graph": round(B / ms_graph * 1e3, 1),
            "tflops_graph": round(B * flops / ms_graph / 1e9, 1), "launches": eng.launch_count()}
     rows.append(rec)
