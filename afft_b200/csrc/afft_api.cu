@@ -498,7 +498,7 @@ struct afft_handle {
   // workspace
   char* ws = nullptr;
   size_t ws_bytes = 0;
-  SplitKScratch splitk{nullptr, 0, nullptr, 0, 16};  // partial tiles + band counters of the split-K GEMM path
+  SplitKScratch splitk{nullptr, 0, nullptr, 0, 4};  // partial tiles + band counters of the split-K GEMM path
   int n_slots = 0;  // tokens per (b, t) in the fuser stream (CA: 1)
   float* h = nullptr;
   PairBuf y, att, f;

@@ -52,7 +52,7 @@ class Engine:
         h = C.c_void_p()
         _capi.check(self.lib.afft_create(C.byref(cfg), C.byref(h)))
         self.handle = h
-        self.max_ksplit = 16  # library default
+        self.max_ksplit = 4  # library default
         self._versions: Optional[tuple] = None
 
     def close(self):

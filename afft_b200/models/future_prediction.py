@@ -198,7 +198,7 @@ class CMFPEarly(nn.Module):
         self.return_attentions = True
         # upper bound on the K splits of skinny GEMMs (small batches); 1 = off, which makes a clip's result bitwise
         # independent of the batch size it is computed in (see afft_set_max_ksplit)
-        self.max_ksplit = 16
+        self.max_ksplit = 4
         self._engines: Dict[tuple, Engine] = {}
 
     # ---- reference helpers kept for API parity ----

@@ -279,7 +279,8 @@ typedef struct afft_profile {
 } afft_profile;
 AFFT_API int afft_profile_enable(afft_handle* h, int32_t enable);
 /* Upper bound on the number of K splits a GEMM of this handle may use (split-K runs when a GEMM has too few output
- * tiles to occupy the GPU: small batches).  1 switches split-K off; the default is 16.  Results are bit-reproducible
+ * tiles to occupy the GPU: small batches).  1 switches split-K off; the default is 4 (the last-arriving CTA reduces all
+ * partials of its tile, so deeper splits cost more in the reduction than they save in the K loop - measured).  Results are bit-reproducible
  * for a fixed value (partials are summed in split order), and differ between values only by fp32 summation order.
  * There is no reference counterpart (PyTorch picks its cuBLAS algorithm internally). */
 AFFT_API int afft_set_max_ksplit(afft_handle* h, int32_t max_split);

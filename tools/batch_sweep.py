@@ -54,8 +54,8 @@ def timeit(fn, iters):
 
 
 rows = []
-for B, ks in [(b, k) for b in (1, 8, 32, 64, 128, 256, 512, 1024) for k in ((1, 16) if b <= 128 else (16,))]:
-    eng.set_max_ksplit(ks)  # 1 = split-K off (for comparison); 16 = library default
+for B, ks in [(b, k) for b in (1, 8, 32, 64, 128, 256, 512, 1024) for k in ((1, 4) if b <= 128 else (4,))]:
+    eng.set_max_ksplit(ks)  # 1 = split-K off (for comparison); 4 = library default
     iters = 50 if B <= 128 else 20
     ms_plain = timeit(lambda: eng.forward_into(io, B), iters)
     g = torch.cuda.CUDAGraph()
