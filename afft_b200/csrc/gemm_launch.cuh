@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 #include <string>
@@ -36,20 +37,34 @@ struct SplitKScratch {
 constexpr size_t kSplitKPartialFloats = static_cast<size_t>(160) * kBlockM * 256;  // one 128 x 256 tile per CTA, 160 >= SMs
 constexpr int kSplitKCounters = 160 * kNumEpilogueWarps;
 
-// Number of K splits for a problem of `tiles` output tiles on `slots` CTAs (or CTA pairs): only when at most half of
-// the slots would be busy, every split gets >= 2 K blocks, and the scratch holds one partial tile per CTA.
+// Number of K splits for a problem of `tiles` output tiles on `slots` persistent CTAs (or CTA pairs).  Cost model in
+// units of one K block of main-loop time: a CTA runs ceil(tiles * S / slots) units back to back, each
+// ceil(num_kb / S) K blocks plus a fixed pipeline fill / drain / epilogue (~6 K blocks, measured from the per-kernel
+// floor of ~13 us at K = 1024); the last-arriving CTA of a tile re-reads S partial tiles (~1 K block each).  The
+// smallest cost wins, ties go to fewer splits; S = 1 unless splitting saves at least 10 %.
 inline int pick_ksplit(int tiles, int slots, int num_kb, int ctas_per_tile, size_t tile_floats, const SplitKScratch* sk) {
-  static const int env = [] { const char* v = getenv("AFFT_GEMM_KSPLIT"); return v == nullptr ? 16 : atoi(v); }();
+  static const int env = [] { const char* v = getenv("AFFT_GEMM_KSPLIT"); return v == nullptr ? 64 : atoi(v); }();
   if (sk == nullptr || sk->partials == nullptr || sk->counters == nullptr || env <= 1 || sk->max_split <= 1) return 1;
-  if (tiles * 2 > slots) return 1;
-  int s = slots / tiles;
-  if (s > num_kb / 2) s = num_kb / 2;
-  if (s > env) s = env;
-  if (s > sk->max_split) s = sk->max_split;
-  while (s > 1 && (s - 1) * ((num_kb + s - 1) / s) >= num_kb) --s;  // no empty split
-  while (s > 1 && (static_cast<size_t>(tiles) * s * ctas_per_tile * tile_floats > sk->partial_floats)) --s;
   if (tiles * ctas_per_tile * kNumEpilogueWarps > sk->n_counters) return 1;
-  return s < 1 ? 1 : s;
+  const double kFixed = 6.0, kReduce = 1.0;
+  auto cost = [&](int s) {
+    const int waves = (tiles * s + slots - 1) / slots;
+    return waves * ((num_kb + s - 1) / s + kFixed) + (s > 1 ? kReduce * s : 0.0);
+  };
+  const double c1 = cost(1);
+  int best = 1;
+  double best_cost = c1;
+  const int smax = std::min(std::min(env, sk->max_split), num_kb / 2);
+  for (int s = 2; s <= smax; ++s) {
+    if ((s - 1) * ((num_kb + s - 1) / s) >= num_kb) continue;  // would leave an empty split
+    if (static_cast<size_t>(tiles) * s * ctas_per_tile * tile_floats > sk->partial_floats) break;
+    const double c = cost(s);
+    if (c < best_cost - 1e-9) {
+      best_cost = c;
+      best = s;
+    }
+  }
+  return (best > 1 && best_cost <= 0.9 * c1) ? best : 1;
 }
 
 inline PFN_cuTensorMapEncodeTiled_v12000 get_tensormap_encoder(std::string* err) {

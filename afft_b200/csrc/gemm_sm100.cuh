@@ -254,18 +254,21 @@ __device__ __forceinline__ void epilogue_row_ptrs(const GemmEpilogue& ep, int ro
 
 // Residual tiles are read once, straight from DRAM (the stream is far larger than L2), and the epilogue of a tile is a
 // short dependent chain per slab (TMEM load -> transpose -> residual load -> store): at K <= 2048 that chain, not the
-// tensor pipe, set the tile rate (ncu: 51 % tensor-active on the K = 1024 projection).  So the lines of the whole
-// 32-row x (BLOCK_N / 2)-column residual block this warp will add are requested into L2 while the warp still waits
-// for the accumulator.  Lane (sub_row, chunk) covers row chunk * 4 + sub_row: 4 x 128 B.
+// tensor pipe, sets the tile rate (ncu: 50 % tensor-active on the K = 1024 projection, the epilogue warps stalled on
+// the residual's long scoreboard).  So the lines of the 32-row x (BLOCK_N / 2)-column residual block this warp will
+// add are requested into L2 ONE TILE AHEAD (a prefetch issued when the warp reaches the tile comes too late: the
+// accumulator is already waiting).  Lane (sub_row, chunk) covers row chunk * 4 + sub_row: 4 x 128 B.
 template <int EPI, int SPLIT, int BLOCK_N>
-__device__ __forceinline__ void epilogue_prefetch_residual(const GemmEpilogue& ep, const EpiRowPtrs& P, int chunk, int n_tile0,
-                                                           int egrp, int N) {
+__device__ __forceinline__ void epilogue_prefetch_residual(const GemmEpilogue& ep, int row0, int n_tile0, int egrp, int lane,
+                                                           int M, int N) {
   using F = EpiFlags<EPI, SPLIT>;
   if (EPI < 0 || !F::res(ep)) return;
-  const float* p = P.res[0];
-#pragma unroll
-  for (int i = 1; i < 8; ++i)
-    if (chunk == i) p = P.res[i];
+  if (row0 + 32 > M) return;
+  const int r = row0 + (lane & 7) * 4 + (lane >> 3);
+  long long rrow = r;
+  if (ep.res_mod > 0) rrow = r % ep.res_mod;
+  else if (ep.row_group > 0) rrow = static_cast<long long>(r / ep.row_group) * ep.row_stride + (r % ep.row_group) + ep.row_off;
+  const float* p = ep.res + rrow * ep.ld_res;
 #pragma unroll
   for (int s = 0; s < BLOCK_N / 32 / (kNumEpilogueWarps / 4); ++s) {
     const int col = n_tile0 + (egrp + s * (kNumEpilogueWarps / 4)) * 32;
@@ -412,7 +415,7 @@ template <int EPI, int SPLIT, int BLOCK_N, typename ReleaseFn>
 __device__ __forceinline__ void epilogue_unit(const GemmEpilogue& ep, int ksplit, uint32_t stage, uint32_t t_row, int quad, int egrp,
                                               int lane, int row0, int n_tile0, int M, int N, float* cta_partial,
                                               const float* tile_partial0, size_t split_stride, unsigned* counter,
-                                              ReleaseFn release_tmem) {
+                                              int next_row0, int next_n_tile0, ReleaseFn release_tmem) {
   constexpr int kCStep = kNumEpilogueWarps / 4;
   constexpr bool kPipe = EPI >= 0;  // the all-runtime epilogue has no registers to spare for the overlap
   const int sub_row = lane >> 3;    // row within a group of 4
@@ -420,7 +423,7 @@ __device__ __forceinline__ void epilogue_unit(const GemmEpilogue& ep, int ksplit
   const bool rows_full = (row0 + 32 <= M);
   EpiRowPtrs rp;
   epilogue_row_ptrs<EPI, SPLIT>(ep, row0, sub_row, rp);
-  if (rows_full && ksplit == 1) epilogue_prefetch_residual<EPI, SPLIT, BLOCK_N>(ep, rp, chunk, n_tile0, egrp, N);
+  if (ksplit == 1 && next_row0 >= 0) epilogue_prefetch_residual<EPI, SPLIT, BLOCK_N>(ep, next_row0, next_n_tile0, egrp, lane, M, N);
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
     uint32_t v[32];
@@ -631,6 +634,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       const int m_idx = sched.n_fastest ? tile / num_n : tile % num_m;
       const int n_idx = sched.n_fastest ? tile % num_n : tile / num_m;
       const int row0 = m_idx * kBlockM + quad * 32;
+      // residual of the NEXT unit of this CTA -> L2 (and of this one, for the CTA's first unit)
+      if (unit == static_cast<int>(blockIdx.x) && ksplit == 1)
+        epilogue_prefetch_residual<EPI, SPLIT, BLOCK_N>(ep, row0, n_idx * BLOCK_N, egrp, lane, M, N);
+      int next_row0 = -1, next_n0 = 0;
+      if (unit + static_cast<int>(gridDim.x) < num_units) {
+        const int nt = (unit + static_cast<int>(gridDim.x)) / ksplit;
+        next_row0 = (sched.n_fastest ? nt / num_n : nt % num_m) * kBlockM + quad * 32;
+        next_n0 = (sched.n_fastest ? nt % num_n : nt / num_m) * BLOCK_N;
+      }
       ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
@@ -638,7 +650,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       epilogue_unit<EPI, SPLIT, BLOCK_N>(ep, ksplit, stage, t_row, quad, egrp, lane, row0, n_idx * BLOCK_N, M, N,
                                          sched.partials + static_cast<size_t>(unit) * kTileFloats,
                                          sched.partials + static_cast<size_t>(tile) * ksplit * kTileFloats, kTileFloats,
-                                         sched.counters + tile * kNumEpilogueWarps + (warp - 4),
+                                         sched.counters + tile * kNumEpilogueWarps + (warp - 4), next_row0, next_n0,
                                          [&] { if (lane == 0) ptx::mbar_arrive(empty_addr); });
       acc ^= 1u;
       if (acc == 0) acc_phase ^= 1u;
@@ -830,6 +842,15 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
       const int m_idx = sched.n_fastest ? tile / num_n : tile % num_m;
       const int n_idx = sched.n_fastest ? tile % num_n : tile / num_m;
       const int row0 = m_idx * 256 + static_cast<int>(rank) * 128 + quad * 32;
+      // residual of the NEXT unit of this CTA pair -> L2 (and of this one, for the pair's first unit)
+      if (unit == cluster_id && ksplit == 1)
+        epilogue_prefetch_residual<EPI, SPLIT, BLOCK_N>(ep, row0, n_idx * BLOCK_N, egrp, lane, M, N);
+      int next_row0 = -1, next_n0 = 0;
+      if (unit + num_clusters < num_units) {
+        const int nt = (unit + num_clusters) / ksplit;
+        next_row0 = (sched.n_fastest ? nt / num_n : nt % num_m) * 256 + static_cast<int>(rank) * 128 + quad * 32;
+        next_n0 = (sched.n_fastest ? nt % num_n : nt / num_m) * BLOCK_N;
+      }
       ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
@@ -837,7 +858,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
       epilogue_unit<EPI, SPLIT, BLOCK_N>(ep, ksplit, stage, t_row, quad, egrp, lane, row0, n_idx * BLOCK_N, M, N,
                                          sched.partials + (static_cast<size_t>(unit) * 2 + rank) * kHalfTile,
                                          sched.partials + (static_cast<size_t>(tile) * ksplit * 2 + rank) * kHalfTile, 2 * kHalfTile,
-                                         sched.counters + (tile * 2 + rank) * kNumEpilogueWarps + (warp - 4),
+                                         sched.counters + (tile * 2 + rank) * kNumEpilogueWarps + (warp - 4), next_row0, next_n0,
                                          [&] { if (lane == 0) ptx::mbar_arrive_cluster(empty_leader); });
       acc ^= 1u;
       if (acc == 0) acc_phase ^= 1u;

@@ -30,6 +30,7 @@ struct Modality {
   bool orig_fps = false;
   const float* rows = nullptr;
   int64_t n_rows = 0;
+  bool rows_on_device = false;
   std::unordered_map<std::string, VideoIndex> videos;
 };
 
@@ -100,6 +101,10 @@ extern "C" int afft_store_set_rows(afft_feature_store* s, int32_t mod, const voi
   if ((reinterpret_cast<uintptr_t>(rows) & 15u) != 0) return sfail(s, AFFT_ERR_INVALID, "store_set_rows: the row table must be 16-byte aligned");
   s->mods[mod].rows = static_cast<const float*>(rows);
   s->mods[mod].n_rows = n_rows;
+  // where the table lives decides the gather's grid (no device needed to build a plan-only store: errors are ignored)
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, rows) == cudaSuccess) s->mods[mod].rows_on_device = (attr.type == cudaMemoryTypeDevice);
+  (void)cudaGetLastError();
   return AFFT_OK;
 }
 
@@ -278,7 +283,11 @@ extern "C" int afft_store_gather(afft_feature_store* s, int32_t B, int32_t T, co
     a.width4[m] = s->mods[m].width / 4;
   }
   const long long total = static_cast<long long>(a.n_mod) * a.rows_per_mod;
-  const int ctas = static_cast<int>(std::min<long long>((total + 7) / 8, 148LL * 8));
+  // HBM tables: fill the GPU.  Pinned host tables: PCIe needs ~100 KB in flight (50 GB/s x 2 us); 32 CTAs x 8 rows x
+  // >= 1.4 KB is ten times that, and a small grid leaves the SMs to the forward pass running on the other stream.
+  bool all_device = true;
+  for (int m = 0; m < a.n_mod; ++m) all_device = all_device && s->mods[m].rows_on_device;
+  const int ctas = static_cast<int>(std::min<long long>((total + 7) / 8, all_device ? 148LL * 4 : 32LL));
   gather_rows_kernel<<<ctas, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return sfail(s, AFFT_ERR_CUDA, std::string("gather launch failed: ") + cudaGetErrorString(e));
