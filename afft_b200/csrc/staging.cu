@@ -226,8 +226,14 @@ extern "C" int afft_store_plan(afft_feature_store* s, int32_t B, const char* con
 
 // ------------------------------------------------------------------------------------------------
 // Device gather.  One warp per output row (clip b, step t) of one modality; lanes stride the row in 16-byte
-// vectors.  Source rows are 1.4 - 4 KB contiguous, so reads from pinned host memory are full PCIe bursts; -1 rows are
-// written as zeros (reader_fns.py:95).  Bound: PCIe (pinned store) or HBM (device store): bytes = 2 * B * T * C * 4.
+// vectors, all loads of a row in flight before the first store.  Source rows are 1.4 - 4 KB contiguous, so reads from
+// pinned host memory are full PCIe bursts; -1 rows are written as zeros (reader_fns.py:95).
+// Bound: PCIe (pinned store) or HBM (device store); algorithmic bytes = 2 * B * T * C * 4.
+// CTAs are SHORT-LIVED on purpose (8 rows each, no grid-stride loop): the gather runs on a side stream next to the
+// forward pass, whose persistent GEMM CTAs fill every SM's register file; a long-lived gather CTA would hold an SM
+// and make the next GEMM wait for its straggler (measured: +0.65 ms per 6.3 ms step with a 32-CTA looping grid).
+// Short CTAs slip into kernel tails and next to the LayerNorm / attention kernels; run the forward on a
+// higher-priority stream so the block scheduler prefers it whenever both have CTAs pending.
 // ------------------------------------------------------------------------------------------------
 struct GatherArgs {
   const float* rows[AFFT_MAX_MODS];
@@ -239,31 +245,28 @@ struct GatherArgs {
 };
 
 __global__ void __launch_bounds__(256) gather_rows_kernel(const GatherArgs a) {
-  const int warps_per_cta = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const long long total = static_cast<long long>(a.n_mod) * a.rows_per_mod;
-  for (long long r = static_cast<long long>(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); r < total;
-       r += static_cast<long long>(gridDim.x) * warps_per_cta) {
-    const int m = static_cast<int>(r / a.rows_per_mod);
-    const int o = static_cast<int>(r - static_cast<long long>(m) * a.rows_per_mod);
-    const int src = __ldg(a.idx + r);
-    const int w4 = a.width4[m];
-    float4* dst = reinterpret_cast<float4*>(a.out[m]) + static_cast<long long>(o) * w4;
-    if (src < 0) {
-      for (int c = lane; c < w4; c += 32) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {
-      const float4* sp = reinterpret_cast<const float4*>(a.rows[m]) + static_cast<long long>(src) * w4;
-      // all loads of the row in flight before the first store (PCIe latency ~ 1 us per request)
-      float4 v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (lane + 32 * i < w4) v[i] = __ldcs(sp + lane + 32 * i);
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (lane + 32 * i < w4) dst[lane + 32 * i] = v[i];
-      for (int c = lane + 256; c < w4; c += 32) dst[c] = __ldcs(sp + c);  // rows wider than 1024 floats
-    }
+  const long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= total) return;
+  const int m = static_cast<int>(r / a.rows_per_mod);
+  const int o = static_cast<int>(r - static_cast<long long>(m) * a.rows_per_mod);
+  const int src = __ldg(a.idx + r);
+  const int w4 = a.width4[m];
+  float4* dst = reinterpret_cast<float4*>(a.out[m]) + static_cast<long long>(o) * w4;
+  if (src < 0) {
+    for (int c = lane; c < w4; c += 32) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
   }
+  const float4* sp = reinterpret_cast<const float4*>(a.rows[m]) + static_cast<long long>(src) * w4;
+  float4 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (lane + 32 * i < w4) v[i] = __ldcs(sp + lane + 32 * i);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (lane + 32 * i < w4) dst[lane + 32 * i] = v[i];
+  for (int c = lane + 256; c < w4; c += 32) dst[c] = __ldcs(sp + c);  // rows wider than 1024 floats
 }
 
 extern "C" int afft_store_gather(afft_feature_store* s, int32_t B, int32_t T, const int32_t* row_idx_dev, void* const* out_dev,
@@ -283,11 +286,7 @@ extern "C" int afft_store_gather(afft_feature_store* s, int32_t B, int32_t T, co
     a.width4[m] = s->mods[m].width / 4;
   }
   const long long total = static_cast<long long>(a.n_mod) * a.rows_per_mod;
-  // HBM tables: fill the GPU.  Pinned host tables: PCIe needs ~100 KB in flight (50 GB/s x 2 us); 32 CTAs x 8 rows x
-  // >= 1.4 KB is ten times that, and a small grid leaves the SMs to the forward pass running on the other stream.
-  bool all_device = true;
-  for (int m = 0; m < a.n_mod; ++m) all_device = all_device && s->mods[m].rows_on_device;
-  const int ctas = static_cast<int>(std::min<long long>((total + 7) / 8, all_device ? 148LL * 4 : 32LL));
+  const int ctas = static_cast<int>((total + 7) / 8);
   gather_rows_kernel<<<ctas, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return sfail(s, AFFT_ERR_CUDA, std::string("gather launch failed: ") + cudaGetErrorString(e));
