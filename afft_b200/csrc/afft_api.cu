@@ -252,7 +252,7 @@ static int launch_attention_mma(const AttentionArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return cuda_fail("attention_mma smem attribute", e);
     configured[dev] = true;
   }
-  cudaError_t e = launch_pdl(kern, dim3(a.n_seq * a.H), dim3(128), smem, stream, a);
+  cudaError_t e = launch_pdl(kern, dim3(a.n_seq * a.H), dim3(128), AttnMmaSmem<HD, LP>::bytes_for(a.L), stream, a);
   if (e != cudaSuccess) return cuda_fail("attention_mma launch", e);
   return AFFT_OK;
 }

@@ -546,7 +546,11 @@ struct AttnMmaSmem {
   static constexpr int kTileBytes = kLP * kRowBytes;
   static constexpr int kSStride = LP + 1;         // fp32 scores [LP][LP + 1]
   static constexpr int kPRowBytes = LP * 2 + 16;  // bf16 probabilities [LP][LP] + pad
-  static constexpr int kBytes = 3 * kTileBytes + kLP * kSStride * 4 + kLP * kPRowBytes;
+  static constexpr int kBytes = 3 * kTileBytes + kLP * kSStride * 4 + kLP * kPRowBytes;  // upper bound (L = LP)
+  // Only the L real rows of Q, K and V are staged (ldmatrix row addresses are clamped to row L - 1: the duplicated
+  // rows only feed scores / probabilities that are masked or zero), which is what lets 3 CTAs share an SM for the
+  // GPT-2 shape (L = 18, head_dim 512: 61.5 KB instead of 104 KB).
+  static constexpr int bytes_for(int L) { return 3 * L * kRowBytes + kLP * kSStride * 4 + kLP * kPRowBytes; }
 };
 
 template <int HD, int LP>
@@ -555,24 +559,25 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs 
   constexpr int MT = LP / 16;  // 16-row tiles
   extern __shared__ uint4 smem_attn[];
   uint8_t* base = reinterpret_cast<uint8_t*>(smem_attn);
+  const int L = a.L;
+  const int tile_bytes = L * S::kRowBytes;  // L real rows per operand
   const uint32_t sq = static_cast<uint32_t>(__cvta_generic_to_shared(base));
-  const uint32_t sk = sq + S::kTileBytes, sv = sk + S::kTileBytes;
-  float* ss = reinterpret_cast<float*>(base + 3 * S::kTileBytes);
-  uint8_t* sp_ptr = base + 3 * S::kTileBytes + S::kLP * S::kSStride * 4;
-  const uint32_t sp = sv + S::kTileBytes + S::kLP * S::kSStride * 4;
+  const uint32_t sk = sq + tile_bytes, sv = sk + tile_bytes;
+  float* ss = reinterpret_cast<float*>(base + 3 * tile_bytes);
+  uint8_t* sp_ptr = base + 3 * tile_bytes + S::kLP * S::kSStride * 4;
+  const uint32_t sp = sv + tile_bytes + S::kLP * S::kSStride * 4;
 
   ptx::griddep_launch();
   ptx::griddep_wait();
   const int seq = blockIdx.x / a.H, h = blockIdx.x % a.H;
-  const int L = a.L;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const __nv_bfloat16* qg = reinterpret_cast<const __nv_bfloat16*>(a.q) + static_cast<long long>(seq) * L * a.ldq + h * HD;
   const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(a.k) + static_cast<long long>(seq) * L * a.ldk + h * HD;
   const __nv_bfloat16* vg = reinterpret_cast<const __nv_bfloat16*>(a.v) + static_cast<long long>(seq) * L * a.ldv + h * HD;
 
-  // ---- stage rows < L of Q, K, V with cp.async (every 16-byte copy in flight at once) ----
-  // Pad rows of Q and K only produce scores that are never read; pad rows of V meet zero probabilities but must
-  // be finite (0 * NaN), so they are zero-filled.
+  // ---- stage the L rows of Q, K, V with cp.async (every 16-byte copy in flight at once) ----
+  // Tile rows >= L are never stored: the ldmatrix addresses below clamp to row L - 1.  Duplicated Q / K rows only
+  // produce scores that are masked or never read; duplicated V rows meet zero probabilities and are finite.
   constexpr int kVecPerRow = HD / 8;             // 16-byte vectors per row
   constexpr int kRowsPerPass = 128 / kVecPerRow;  // rows covered by the CTA per pass (2 for HD 512, 4 for 256)
   {
@@ -584,19 +589,14 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs 
     uint32_t dst = sq + r0 * S::kRowBytes + c * 16;
     for (int r = r0; r < L; r += kRowsPerPass) {
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(qp) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + S::kTileBytes), "l"(kp) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 2 * S::kTileBytes), "l"(vp) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + tile_bytes), "l"(kp) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 2 * tile_bytes), "l"(vp) : "memory");
       qp += kRowsPerPass * a.ldq;
       kp += kRowsPerPass * a.ldk;
       vp += kRowsPerPass * a.ldv;
       dst += kRowsPerPass * S::kRowBytes;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    for (int r = L + r0; r < S::kLP; r += kRowsPerPass) {
-      *reinterpret_cast<uint4*>(base + r * S::kRowBytes + c * 16) = make_uint4(0u, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(base + S::kTileBytes + r * S::kRowBytes + c * 16) = make_uint4(0u, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(base + 2 * S::kTileBytes + r * S::kRowBytes + c * 16) = make_uint4(0u, 0u, 0u, 0u);
-    }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
@@ -608,8 +608,8 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs 
     const bool skip = (nb * 16 >= L) || (mt * 16 >= L) || (a.mask == 1 && nb * 16 > mt * 16 + 15);
     if (skip) continue;
     float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    const uint32_t a_addr = sq + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * S::kRowBytes + (lane >> 4) * 16;
-    const uint32_t b_addr = sk + (nb * 16 + (lane & 7) + (lane >> 4) * 8) * S::kRowBytes + ((lane >> 3) & 1) * 16;
+    const uint32_t a_addr = sq + min(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, L - 1) * S::kRowBytes + (lane >> 4) * 16;
+    const uint32_t b_addr = sk + min(nb * 16 + (lane & 7) + (lane >> 4) * 8, L - 1) * S::kRowBytes + ((lane >> 3) & 1) * 16;
 #pragma unroll 4
     for (int ks = 0; ks < HD / 16; ++ks) {
       uint32_t af[4], bf[4];
@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs 
       for (int ks = 0; ks < MT; ++ks) {
         if (ks < ksteps) {
           uint32_t vf[4];
-          ldmatrix_x4_trans(sv + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * S::kRowBytes + (n0 + (lane >> 4) * 8) * 2, vf);
+          ldmatrix_x4_trans(sv + min(ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, L - 1) * S::kRowBytes + (n0 + (lane >> 4) * 8) * 2, vf);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             uint32_t pa[4];
@@ -698,9 +698,10 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs 
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
+          // output rows < L only: the Q region holds L rows and the K / V regions behind it are still being read
           uint8_t* o0 = base + (mt * 16 + g8) * S::kRowBytes + (n0 + nt * 8 + t4 * 2) * 2;
-          *reinterpret_cast<uint32_t*>(o0) = pack_bf16x2(acc[mt][nt][0], acc[mt][nt][1]);
-          *reinterpret_cast<uint32_t*>(o0 + 8 * S::kRowBytes) = pack_bf16x2(acc[mt][nt][2], acc[mt][nt][3]);
+          if (mt * 16 + g8 < L) *reinterpret_cast<uint32_t*>(o0) = pack_bf16x2(acc[mt][nt][0], acc[mt][nt][1]);
+          if (mt * 16 + g8 + 8 < L) *reinterpret_cast<uint32_t*>(o0 + 8 * S::kRowBytes) = pack_bf16x2(acc[mt][nt][2], acc[mt][nt][3]);
         }
     }
   }

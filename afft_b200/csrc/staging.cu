@@ -229,11 +229,12 @@ extern "C" int afft_store_plan(afft_feature_store* s, int32_t B, const char* con
 // vectors, all loads of a row in flight before the first store.  Source rows are 1.4 - 4 KB contiguous, so reads from
 // pinned host memory are full PCIe bursts; -1 rows are written as zeros (reader_fns.py:95).
 // Bound: PCIe (pinned store) or HBM (device store); algorithmic bytes = 2 * B * T * C * 4.
-// CTAs are SHORT-LIVED on purpose (8 rows each, no grid-stride loop): the gather runs on a side stream next to the
-// forward pass, whose persistent GEMM CTAs fill every SM's register file; a long-lived gather CTA would hold an SM
-// and make the next GEMM wait for its straggler (measured: +0.65 ms per 6.3 ms step with a 32-CTA looping grid).
-// Short CTAs slip into kernel tails and next to the LayerNorm / attention kernels; run the forward on a
-// higher-priority stream so the block scheduler prefers it whenever both have CTAs pending.
+// Grid: the gather runs on a side stream next to the forward pass, whose persistent GEMM CTAs fill every SM's
+// register file, so gather CTAs only get SMs at kernel boundaries.  HBM tables: one short CTA per 8 rows (the whole
+// gather is ~0.1 ms of SM time).  Pinned tables: the transfer lasts ~1.2 ms per 256 clips at PCIe speed whatever
+// the grid; 32 looping CTAs keep ~1 MB in flight (PCIe needs ~100 KB) and hold 32 SMs for that long, which costs the
+// concurrent GEMMs ~0.6 ms per 6.3 ms step (measured).  Short CTAs on a low-priority stream were measured too: they
+// starve behind the back-to-back forward kernels and the transfer ends up serialised after the step (+1.0 ms).
 // ------------------------------------------------------------------------------------------------
 struct GatherArgs {
   const float* rows[AFFT_MAX_MODS];
@@ -245,28 +246,30 @@ struct GatherArgs {
 };
 
 __global__ void __launch_bounds__(256) gather_rows_kernel(const GatherArgs a) {
+  const int warps_per_cta = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const long long total = static_cast<long long>(a.n_mod) * a.rows_per_mod;
-  const long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= total) return;
-  const int m = static_cast<int>(r / a.rows_per_mod);
-  const int o = static_cast<int>(r - static_cast<long long>(m) * a.rows_per_mod);
-  const int src = __ldg(a.idx + r);
-  const int w4 = a.width4[m];
-  float4* dst = reinterpret_cast<float4*>(a.out[m]) + static_cast<long long>(o) * w4;
-  if (src < 0) {
-    for (int c = lane; c < w4; c += 32) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    return;
+  for (long long r = static_cast<long long>(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); r < total;
+       r += static_cast<long long>(gridDim.x) * warps_per_cta) {
+    const int m = static_cast<int>(r / a.rows_per_mod);
+    const int o = static_cast<int>(r - static_cast<long long>(m) * a.rows_per_mod);
+    const int src = __ldg(a.idx + r);
+    const int w4 = a.width4[m];
+    float4* dst = reinterpret_cast<float4*>(a.out[m]) + static_cast<long long>(o) * w4;
+    if (src < 0) {
+      for (int c = lane; c < w4; c += 32) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    const float4* sp = reinterpret_cast<const float4*>(a.rows[m]) + static_cast<long long>(src) * w4;
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (lane + 32 * i < w4) v[i] = __ldcs(sp + lane + 32 * i);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (lane + 32 * i < w4) dst[lane + 32 * i] = v[i];
+    for (int c = lane + 256; c < w4; c += 32) dst[c] = __ldcs(sp + c);  // rows wider than 1024 floats
   }
-  const float4* sp = reinterpret_cast<const float4*>(a.rows[m]) + static_cast<long long>(src) * w4;
-  float4 v[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (lane + 32 * i < w4) v[i] = __ldcs(sp + lane + 32 * i);
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (lane + 32 * i < w4) dst[lane + 32 * i] = v[i];
-  for (int c = lane + 256; c < w4; c += 32) dst[c] = __ldcs(sp + c);  // rows wider than 1024 floats
 }
 
 extern "C" int afft_store_gather(afft_feature_store* s, int32_t B, int32_t T, const int32_t* row_idx_dev, void* const* out_dev,
@@ -286,7 +289,9 @@ extern "C" int afft_store_gather(afft_feature_store* s, int32_t B, int32_t T, co
     a.width4[m] = s->mods[m].width / 4;
   }
   const long long total = static_cast<long long>(a.n_mod) * a.rows_per_mod;
-  const int ctas = static_cast<int>((total + 7) / 8);
+  bool all_device = true;
+  for (int m = 0; m < a.n_mod; ++m) all_device = all_device && s->mods[m].rows_on_device;
+  const int ctas = static_cast<int>(all_device ? (total + 7) / 8 : std::min<long long>((total + 7) / 8, 32LL));
   gather_rows_kernel<<<ctas, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return sfail(s, AFFT_ERR_CUDA, std::string("gather launch failed: ") + cudaGetErrorString(e));

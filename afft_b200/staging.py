@@ -150,8 +150,7 @@ class FeatureStager:
     (default: a private staging stream), and returns ``(feature_dict, event, slot)``; make the consuming stream wait on
     the event (``torch.cuda.current_stream().wait_event(event)``) before the forward and call ``done(slot)`` after
     enqueuing it, so that the slot's buffers are not refilled before the forward has read them.  ``depth`` batches may
-    be in flight.  Run the forward on a high-priority stream (``torch.cuda.Stream(priority=-1)``): the gather's CTAs
-    are short-lived and then only fill SM time the forward leaves idle."""
+    be in flight."""
 
     def __init__(self, store: FeatureStore, T: int, max_batch: int, device="cuda:0", depth: int = 2, fps: float = 30.0,
                  frame_rate: Optional[float] = 4.0, strategy: str = "last_clip"):

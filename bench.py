@@ -152,7 +152,7 @@ def cpu_forward_timer(cfg, T, ncls, batch, steps, warmup, budget_s=240.0):
 
 
 
-def staged_e2e(args, cfg, T, B, model, dev, main_stream, sampler, n_gpus, rank, C):
+def staged_e2e(args, cfg, T, B, model, dev, main_stream, sampler, n_gpus, rank, C, location="pinned"):
     """The same metric measured from CLIP DESCRIPTORS: (video, start_sec, end_sec) -> native plan (host integers) ->
     gather kernel reading the pinned host row tables over PCIe -> BaseModel -> logits to the host.  Replaces the
     reference's LMDB reader + collate + .to(device) (datasets/reader_fns.py:65-138, test.py:81)."""
@@ -167,7 +167,8 @@ def staged_e2e(args, cfg, T, B, model, dev, main_stream, sampler, n_gpus, rank, 
         n = n_frames if m != "audio" else int(n_frames / 30.0 * 50.0) + 2
         frames = np.arange(1, n + 1, dtype=np.int32)
         frames = frames[(frames % 11) != 0]  # every 11th frame absent: the closest-earlier-frame fallback runs
-        store.set_modality(m, {v: (frames, torch.randn(len(frames), width, generator=g).numpy()) for v in names}, "pinned")
+        store.set_modality(m, {v: (frames, torch.randn(len(frames), width, generator=g).numpy()) for v in names},
+                           "pinned" if location == "pinned" else str(dev))
     rng = np.random.default_rng(rank)
     batches = []
     for _ in range(4):
@@ -176,28 +177,24 @@ def staged_e2e(args, cfg, T, B, model, dev, main_stream, sampler, n_gpus, rank, 
         batches.append((vids, en - T / 4.0, en))
     stager = staging.FeatureStager(store, T, max_batch=B, device=dev, depth=2, fps=30.0, frame_rate=4.0)
     host_outs = [torch.empty(B, C).pin_memory() for _ in range(2)]
-    compute = torch.cuda.Stream(dev, priority=-1)  # the forward outranks the gather's CTAs in the block scheduler
 
     def loop(n):
-        compute.wait_stream(main_stream)
         nxt = stager.stage(*batches[0])
         done = [None, None]
-        with torch.cuda.stream(compute):
-            for i in range(n):
-                feats, ev, slot = nxt
-                compute.wait_event(ev)
-                if i + 1 < n:
-                    nxt = stager.stage(*batches[(i + 1) % len(batches)])  # plan + gather of the next batch overlap this forward
-                with torch.no_grad():
-                    o, _ = model(dict(feats), **KW)
-                stager.done(slot, compute)
-                host_outs[i % 2].copy_(o["logits/action"]["all-fused"][:, 0, :], non_blocking=True)
-                done[i % 2] = torch.cuda.Event()
-                done[i % 2].record(compute)
-                if i > 0:
-                    done[(i - 1) % 2].synchronize()
-            done[(n - 1) % 2].synchronize()
-        main_stream.wait_stream(compute)
+        for i in range(n):
+            feats, ev, slot = nxt
+            main_stream.wait_event(ev)
+            if i + 1 < n:
+                nxt = stager.stage(*batches[(i + 1) % len(batches)])  # plan + gather of the next batch overlap this forward
+            with torch.no_grad():
+                o, _ = model(dict(feats), **KW)
+            stager.done(slot)
+            host_outs[i % 2].copy_(o["logits/action"]["all-fused"][:, 0, :], non_blocking=True)
+            done[i % 2] = torch.cuda.Event()
+            done[i % 2].record(main_stream)
+            if i > 0:
+                done[(i - 1) % 2].synchronize()
+        done[(n - 1) % 2].synchronize()
 
     loop(max(2, args.warmup))
     adist.barrier()
@@ -211,8 +208,10 @@ def staged_e2e(args, cfg, T, B, model, dev, main_stream, sampler, n_gpus, rank, 
     ms = adist.max_over_ranks(e0.elapsed_time(e1), dev)
     table_bytes = sum(t.numel() * 4 for t in store.rows.values())
     return {"value": round(n_gpus * B * args.steps / (ms / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms / args.steps, 4),
-            "plan_bytes_h2d_per_step": len(dims) * B * T * 4, "feature_bytes_read_over_pcie_per_step": sum(dims.values()) * B * T * 4,
-            "d2h_bytes_per_step": B * C * 4, "store": f"pinned host row tables, {table_bytes / 1e6:.0f} MB, {n_videos} videos",
+            "plan_bytes_h2d_per_step": len(dims) * B * T * 4,
+            "feature_bytes_read_over_pcie_per_step": sum(dims.values()) * B * T * 4 if location == "pinned" else 0,
+            "d2h_bytes_per_step": B * C * 4,
+            "store": f"{'pinned host' if location == 'pinned' else 'HBM-resident'} row tables, {table_bytes / 1e6:.0f} MB, {n_videos} videos",
             "api": "afft_b200.staging.FeatureStager.stage (afft_store_plan + afft_store_gather) -> BaseModel.__call__"}
 
 def run_reference(args):
@@ -384,7 +383,8 @@ def run_afft(args):
     # ---- e2e from clip descriptors (row N4): native plan + device gather from a pinned host feature store ----
     staged = None
     if not args.no_staged:
-        staged = staged_e2e(args, cfg, T, B, model, dev, main_stream, sampler, n_gpus, rank, C)
+        staged = {"pinned_store": staged_e2e(args, cfg, T, B, model, dev, main_stream, sampler, n_gpus, rank, C, "pinned"),
+                  "hbm_store": staged_e2e(args, cfg, T, B, model, dev, main_stream, sampler, n_gpus, rank, C, "hbm")}
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): per-launch CUDA events, separate pass ----
     eng.profile_enable(True)
