@@ -278,9 +278,16 @@ __device__ __forceinline__ void epilogue_prefetch_residual(const GemmEpilogue& e
 
 // One 32-row x 32-column slab, interior case: every row < M and every column < N, so no predicates.
 // Lane (sub_row, chunk) handles rows sub_row + 4 i (i < 8), columns col .. col + 3.
+//
+// Residual operand: `r` may arrive PRELOADED (issued one slab earlier by this function, see next_col), so that the
+// HBM / L2 latency of the residual overlaps the stores of the previous slab and the TMEM wait / transposition of this
+// one instead of sitting between the shared-memory read and the add.  All residual loads of a slab are issued
+// before any of its stores (the residual may alias the output: in-place stream); loads of the NEXT slab touch other
+// columns, so they may be issued ahead of this slab's stores.
 template <int EPI, int SPLIT>
 __device__ __forceinline__ void epilogue_slab_full(const GemmEpilogue& ep, uint32_t stage, int sub_row, int chunk, int col,
-                                                   const EpiRowPtrs& P, const float4& bias4) {
+                                                   const EpiRowPtrs& P, const float4& bias4, float4 (&r)[8], bool preloaded,
+                                                   int next_col) {
   using F = EpiFlags<EPI, SPLIT>;
   float4 x[8];
 #pragma unroll
@@ -289,10 +296,10 @@ __device__ __forceinline__ void epilogue_slab_full(const GemmEpilogue& ep, uint3
     x[i] = lds128(stage + static_cast<uint32_t>(rl) * 128u + static_cast<uint32_t>((chunk ^ (rl & 7)) * 16));
   }
   if (F::res(ep)) {
-    // all residual loads are issued before any store: the residual may alias the output (in-place stream)
-    float4 r[8];
+    if (!preloaded) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] = *reinterpret_cast<const float4*>(P.res[i] + col);
+      for (int i = 0; i < 8; ++i) r[i] = *reinterpret_cast<const float4*>(P.res[i] + col);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       x[i] = epilogue_math<EPI, SPLIT>(ep, x[i], bias4);
@@ -300,6 +307,10 @@ __device__ __forceinline__ void epilogue_slab_full(const GemmEpilogue& ep, uint3
       x[i].y = epilogue_combine<EPI, SPLIT>(ep, x[i].y, r[i].y);
       x[i].z = epilogue_combine<EPI, SPLIT>(ep, x[i].z, r[i].z);
       x[i].w = epilogue_combine<EPI, SPLIT>(ep, x[i].w, r[i].w);
+    }
+    if (next_col >= 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = *reinterpret_cast<const float4*>(P.res[i] + next_col);
     }
   } else {
 #pragma unroll
@@ -424,12 +435,21 @@ __device__ __forceinline__ void epilogue_unit(const GemmEpilogue& ep, int ksplit
   EpiRowPtrs rp;
   epilogue_row_ptrs<EPI, SPLIT>(ep, row0, sub_row, rp);
   if (ksplit == 1 && next_row0 >= 0) epilogue_prefetch_residual<EPI, SPLIT, BLOCK_N>(ep, next_row0, next_n_tile0, egrp, lane, M, N);
+  using F = EpiFlags<EPI, SPLIT>;
+  constexpr bool kResAhead = EPI >= 0 && (EPI & 4) != 0;  // compiled-in residual variants: load one slab ahead
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
     uint32_t v[32];
+    float4 r[8];
+    bool r_loaded = false;
     int c = egrp;
     bool have = n_tile0 + c * 32 < N;  // warp-uniform
     if (pass == 0 && have && kPipe) ptx::tmem_ld_32x32(t_row + c * 32, v);
+    if (kResAhead && pass == 0 && ksplit == 1 && have && rows_full && n_tile0 + c * 32 + 32 <= N) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = *reinterpret_cast<const float4*>(rp.res[i] + n_tile0 + c * 32 + chunk * 4);
+      r_loaded = true;
+    }
 #pragma unroll 1
     while (have) {
       const int n0 = n_tile0 + c * 32;
@@ -458,7 +478,11 @@ __device__ __forceinline__ void epilogue_unit(const GemmEpilogue& ep, int ksplit
         if (rows_full && n0 + 32 <= N) {
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ep.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-          epilogue_slab_full<EPI, SPLIT>(ep, stage, sub_row, chunk, col, rp, bias4);
+          // the next slab's residual is requested now if that slab is an interior one too
+          const bool next_full = kResAhead && r_loaded && have && n_tile0 + cn * 32 + 32 <= N;
+          epilogue_slab_full<EPI, SPLIT>(ep, stage, sub_row, chunk, col, rp, bias4, r, r_loaded,
+                                         next_full ? n_tile0 + cn * 32 + chunk * 4 : -1);
+          r_loaded = next_full;
         } else {
           epilogue_slab_edge<EPI, SPLIT>(ep, stage, sub_row, chunk, row0, col, M, N);
         }
