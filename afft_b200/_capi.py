@@ -13,7 +13,8 @@ import torch
 
 _LIB_NAME = "libafft_b200.so"
 _LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib")
-LIB_PATH = os.path.join(_LIB_DIR, _LIB_NAME)
+# AFFT_B200_LIB selects another build of the library (A/B timing of kernel variants); default: the in-tree build
+LIB_PATH = os.environ.get("AFFT_B200_LIB") or os.path.join(_LIB_DIR, _LIB_NAME)
 
 AFFT_OK = 0
 AFFT_MAX_MODS = 8

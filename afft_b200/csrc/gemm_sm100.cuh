@@ -252,17 +252,20 @@ __device__ __forceinline__ void epilogue_row_ptrs(const GemmEpilogue& ep, int ro
   }
 }
 
-// Residual tiles are read once, straight from DRAM (the stream is far larger than L2), and the epilogue of a tile is a
-// short dependent chain per slab (TMEM load -> transpose -> residual load -> store): at K <= 2048 that chain, not the
-// tensor pipe, sets the tile rate (ncu: 50 % tensor-active on the K = 1024 projection, the epilogue warps stalled on
-// the residual's long scoreboard).  So the lines of the 32-row x (BLOCK_N / 2)-column residual block this warp will
-// add are requested into L2 ONE TILE AHEAD (a prefetch issued when the warp reaches the tile comes too late: the
-// accumulator is already waiting).  Lane (sub_row, chunk) covers row chunk * 4 + sub_row: 4 x 128 B.
+// Optional L2 prefetch of the residual block of the NEXT tile (AFFT_RES_PREFETCH, off).  Together with the TMEM-load
+// software pipeline (AFFT_TMEM_PIPE, off) and the one-slab-ahead residual load (AFFT_RES_AHEAD, off) it was built on
+// the hypothesis that the residual GEMMs (50 % tensor-active at K = 1024) are bound by the epilogue's dependent
+// chain.  A/B builds timed on the same box say otherwise: none of the three helps.  The limiter is the L2 -> SM
+// operand feed the epilogue's residual reads share with the TMA loads; the switches stay for
+// re-testing once the main loop's feed changes.  Lane (sub_row, chunk) covers row chunk * 4 + sub_row: 4 x 128 B.
 template <int EPI, int SPLIT, int BLOCK_N>
 __device__ __forceinline__ void epilogue_prefetch_residual(const GemmEpilogue& ep, int row0, int n_tile0, int egrp, int lane,
                                                            int M, int N) {
   using F = EpiFlags<EPI, SPLIT>;
-  if (EPI < 0 || !F::res(ep)) return;
+#ifndef AFFT_RES_PREFETCH
+#define AFFT_RES_PREFETCH 0  // A/B on one box (tools/gemm_time.py): no gain (60.7 us off vs 61.9 us on, K = 1024 projection)
+#endif
+  if (!AFFT_RES_PREFETCH || EPI < 0 || !F::res(ep)) return;
   if (row0 + 32 > M) return;
   const int r = row0 + (lane & 7) * 4 + (lane >> 3);
   long long rrow = r;
@@ -428,7 +431,10 @@ __device__ __forceinline__ void epilogue_unit(const GemmEpilogue& ep, int ksplit
                                               const float* tile_partial0, size_t split_stride, unsigned* counter,
                                               int next_row0, int next_n_tile0, ReleaseFn release_tmem) {
   constexpr int kCStep = kNumEpilogueWarps / 4;
-  constexpr bool kPipe = EPI >= 0;  // the all-runtime epilogue has no registers to spare for the overlap
+#ifndef AFFT_TMEM_PIPE
+#define AFFT_TMEM_PIPE 0  // A/B on one box: no gain (59.1 us off vs 61.9 us on; FC1 160.4 vs 162.1 us)
+#endif
+  constexpr bool kPipe = AFFT_TMEM_PIPE && EPI >= 0;  // the all-runtime epilogue has no registers to spare for the overlap
   const int sub_row = lane >> 3;    // row within a group of 4
   const int chunk = lane & 7;       // 16-byte chunk = 4 fp32 columns
   const bool rows_full = (row0 + 32 <= M);
@@ -436,7 +442,10 @@ __device__ __forceinline__ void epilogue_unit(const GemmEpilogue& ep, int ksplit
   epilogue_row_ptrs<EPI, SPLIT>(ep, row0, sub_row, rp);
   if (ksplit == 1 && next_row0 >= 0) epilogue_prefetch_residual<EPI, SPLIT, BLOCK_N>(ep, next_row0, next_n_tile0, egrp, lane, M, N);
   using F = EpiFlags<EPI, SPLIT>;
-  constexpr bool kResAhead = EPI >= 0 && (EPI & 4) != 0;  // compiled-in residual variants: load one slab ahead
+#ifndef AFFT_RES_AHEAD
+#define AFFT_RES_AHEAD 0  // measured (A/B on one box): 61.6 us without vs 67.4 us with, on the K = 1024 projection
+#endif
+  constexpr bool kResAhead = AFFT_RES_AHEAD && EPI >= 0 && (EPI & 4) != 0;  // compiled-in residual variants: load one slab ahead
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
     uint32_t v[32];
