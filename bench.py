@@ -32,6 +32,26 @@ UNIT = "clips/s"
 KW = dict(mixup_fn=None, target=None, target_subclips=None, target_subclips_ignore_index=None)
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line to fd 1 when
+    NCCL_DEBUG=VERSION), so everything but the result is sent to stderr: fd 1 is pointed at fd 2 for the whole run and
+    the result goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -230,7 +250,7 @@ def run_reference(args):
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, cfg, T, batch, how, ncls=None):
@@ -467,7 +487,7 @@ def run_afft(args):
         v, cores, desc, _, _ = cpu_forward_timer(cfg, T, ncls, args.cpu_batch or eval_bs, 3, 1, budget_s=60.0)
         line["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     adist.shutdown()
 
 
@@ -578,7 +598,7 @@ def run_train(args):
         "clocks": sampler.summary(),
     }
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     adist.shutdown()
 
 
@@ -598,6 +618,7 @@ def main():
     ap.add_argument("--no-staged", action="store_true", help="skip the clip-descriptor (feature store) e2e measurement")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.mode == "train":
         run_train(args)
     elif args.impl == "reference":
