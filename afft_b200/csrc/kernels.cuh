@@ -587,17 +587,23 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs 
     const __nv_bfloat16* kp = kg + static_cast<long long>(r0) * a.ldk + c * 8;
     const __nv_bfloat16* vp = vg + static_cast<long long>(r0) * a.ldv + c * 8;
     uint32_t dst = sq + r0 * S::kRowBytes + c * 16;
+    // two groups: Q and K first (scores and softmax run while V is still in flight), then V
     for (int r = r0; r < L; r += kRowsPerPass) {
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(qp) : "memory");
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + tile_bytes), "l"(kp) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 2 * tile_bytes), "l"(vp) : "memory");
       qp += kRowsPerPass * a.ldq;
       kp += kRowsPerPass * a.ldk;
+      dst += kRowsPerPass * S::kRowBytes;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    dst = sv + r0 * S::kRowBytes + c * 16;
+    for (int r = r0; r < L; r += kRowsPerPass) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(vp) : "memory");
       vp += kRowsPerPass * a.ldv;
       dst += kRowsPerPass * S::kRowBytes;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // Q and K have landed
   }
   __syncthreads();
 
@@ -668,6 +674,8 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs 
   __syncthreads();
 
   // ---- O = P V: warp -> HD / 4 output dims; output tile staged in the (now free) Q region ----
+  asm volatile("cp.async.wait_group 0;" ::: "memory");  // V has landed (the barrier above published the probabilities;
+  __syncthreads();                                       //  this one publishes every thread's share of V)
   {
     const int ksteps = (L + 15) / 16;
 #pragma unroll 1
@@ -742,13 +750,19 @@ __global__ void __launch_bounds__(256) attention_tokens_mma_kernel(const Attenti
   const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(a.k) + row0 * a.ldk + h * HD + lane * 8;
   const __nv_bfloat16* vg = reinterpret_cast<const __nv_bfloat16*>(a.v) + row0 * a.ldv + h * HD + lane * 8;
   {
+    // two groups: Q and K first (the scores and the softmax run while V is still in flight), then V
     uint32_t dst = sq + lane * 16;
     for (int r = 0; r < nrows; ++r) {
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(qg) : "memory");
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + TILE), "l"(kg) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 2 * TILE), "l"(vg) : "memory");
       qg += a.ldq;
       kg += a.ldk;
+      dst += RB;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    dst = sv + lane * 16;
+    for (int r = 0; r < nrows; ++r) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(vg) : "memory");
       vg += a.ldv;
       dst += RB;
     }
@@ -760,7 +774,7 @@ __global__ void __launch_bounds__(256) attention_tokens_mma_kernel(const Attenti
       *reinterpret_cast<uint4*>(wbase + TILE + r * RB + lane * 16) = make_uint4(0u, 0u, 0u, 0u);
       *reinterpret_cast<uint4*>(wbase + 2 * TILE + r * RB + lane * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // Q and K have landed
   }
   __syncwarp();
 
@@ -821,7 +835,8 @@ __global__ void __launch_bounds__(256) attention_tokens_mma_kernel(const Attenti
   pa[1] = pack_bf16x2(p[1][0], p[1][1]);
   pa[2] = pack_bf16x2(p[0][2], p[0][3]);
   pa[3] = pack_bf16x2(p[1][2], p[1][3]);
-  __syncwarp();  // every lane is done reading Q before the region is reused for the output tile
+  asm volatile("cp.async.wait_group 0;" ::: "memory");  // V has landed
+  __syncwarp();  // ... for every lane; and every lane is done reading Q before the region is reused for the output tile
 #pragma unroll 4
   for (int np = 0; np < HD / 16; ++np) {
     uint32_t vf[4];
