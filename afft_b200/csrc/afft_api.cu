@@ -128,15 +128,19 @@ extern "C" int afft_convert_bf16(const float* src, int64_t lds, int32_t rows, in
 static int run_layernorm(const LayerNormArgs& a, cudaStream_t stream) {
   if (a.x == nullptr || a.rows <= 0) return fail(AFFT_ERR_INVALID, "layernorm: bad argument");
   if (a.dim % 128 != 0) return fail(AFFT_ERR_INVALID, "layernorm: dim must be a multiple of 128");
-  const int blocks = (a.rows + 7) / 8;  // 8 warps (rows) per 256-thread block
+  // one warp per row; CTA size is a tuning knob (AFFT_LN_THREADS = 64 / 128 / 256)
+  static const int ln_threads = [] { const char* v = getenv("AFFT_LN_THREADS"); const int t = v ? atoi(v) : 256;
+                                     return (t == 64 || t == 128 || t == 256) ? t : 256; }();
+  const int rows_per_block = ln_threads / 32;
+  const int blocks = (a.rows + rows_per_block - 1) / rows_per_block;
   const bool avg = a.n_avg > 1;
   const bool fast = !avg && a.gamma != nullptr && a.beta != nullptr && a.y_hi != nullptr && a.y_f32 == nullptr &&
                     a.y_lo == nullptr && a.aux_mod == 0;
 #define AFFT_LN(NV)                                                                                          \
   case NV:                                                                                                   \
-    if (fast) launch_pdl(layernorm_kernel<NV, false, true>, dim3(blocks), dim3(256), 0, stream, a);          \
-    else if (avg) launch_pdl(layernorm_kernel<NV, true, false>, dim3(blocks), dim3(256), 0, stream, a);      \
-    else launch_pdl(layernorm_kernel<NV, false, false>, dim3(blocks), dim3(256), 0, stream, a);              \
+    if (fast) launch_pdl(layernorm_kernel<NV, false, true>, dim3(blocks), dim3(ln_threads), 0, stream, a);   \
+    else if (avg) launch_pdl(layernorm_kernel<NV, true, false>, dim3(blocks), dim3(ln_threads), 0, stream, a); \
+    else launch_pdl(layernorm_kernel<NV, false, false>, dim3(blocks), dim3(ln_threads), 0, stream, a);       \
     break;
   switch (a.dim / 128) {
     AFFT_LN(2)

@@ -54,3 +54,12 @@ probs = torch.empty(n_seq, H, L, L, device=dev)
 t = timeit(lambda: capi.attention(qkv, n_seq, L, H, hd, mask=2, T=10, out_hi=out, probs=probs, p_outer=H * L * L, p_inner=1))
 byts = qkv.numel() * 2 + out.numel() * 2 + probs.numel() * 4
 print(f"{name} T-SA block-causal attention n_seq={n_seq} L=50 H=4 hd=256: {t:.1f} us, {byts / t / 1e3:.0f} GB/s")
+
+# LayerNorm (bf16 output, affine): fuser shape and GPT-2 shape
+for rows, dim in ((B * 90, 1024), (B * 18, 2048)):
+    x = torch.randn(rows, dim, generator=g).to(dev)
+    gam, bet = torch.ones(dim, device=dev), torch.zeros(dim, device=dev)
+    y = torch.empty(rows, dim, device=dev, dtype=torch.bfloat16)
+    t = timeit(lambda: capi.layernorm(x, gam, bet, 1e-5, y_hi=y))
+    print(f"{name} LayerNorm rows={rows} dim={dim} (AFFT_LN_THREADS={os.environ.get('AFFT_LN_THREADS', '256')}): {t:.1f} us, "
+          f"{rows * dim * 6 / t / 1e3:.0f} GB/s")
