@@ -111,7 +111,7 @@ static int run_convert(const float* src, long long lds, int rows, int cols, bf16
     convert_transpose_f32_bf16_kernel<<<grid, block, 0, stream>>>(src, lds, rows, cols, hi, lo, ldd);
   } else {
     const long long total = static_cast<long long>(rows) * cols;
-    int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    int blocks = static_cast<int>(std::min<long long>((total / 8 + 255) / 256 + 1, 148 * 16));
     convert_f32_bf16_kernel<<<blocks, 256, 0, stream>>>(src, lds, rows, cols, hi, lo, ldd);
   }
   cudaError_t e = cudaGetLastError();

@@ -49,6 +49,28 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
 __global__ void convert_f32_bf16_kernel(const float* __restrict__ src, long long lds, int rows, int cols,
                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                         long long ldd) {
+  // fast path: 8 elements per thread (two 16-byte loads, one 16-byte store per output) when rows are 8-element
+  // multiples and every pitch / base is 16-byte aligned - weights (per training step) and most activations
+  const bool vec = (cols % 8 == 0) && (lds % 4 == 0) && (ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(hi) & 15u) == 0) && (lo == nullptr || (reinterpret_cast<uintptr_t>(lo) & 15u) == 0);
+  if (vec) {
+    const int c8 = cols / 8;
+    const long long total8 = static_cast<long long>(rows) * c8;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const long long r = i / c8;
+      const int c = static_cast<int>(i - r * c8) * 8;
+      const float4 v0 = *reinterpret_cast<const float4*>(src + r * lds + c);
+      const float4 v1 = *reinterpret_cast<const float4*>(src + r * lds + c + 4);
+      const uint4 h = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+      *reinterpret_cast<uint4*>(hi + r * ldd + c) = h;
+      if (lo != nullptr)
+        *reinterpret_cast<uint4*>(lo + r * ldd + c) =
+            make_uint4(pack_bf16x2(bf16_residual(v0.x), bf16_residual(v0.y)), pack_bf16x2(bf16_residual(v0.z), bf16_residual(v0.w)),
+                       pack_bf16x2(bf16_residual(v1.x), bf16_residual(v1.y)), pack_bf16x2(bf16_residual(v1.z), bf16_residual(v1.w)));
+    }
+    return;
+  }
   const long long total = static_cast<long long>(rows) * cols;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {

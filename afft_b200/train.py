@@ -85,13 +85,15 @@ class LinearFn(torch.autograd.Function):
             bias_p[:N] = bias.detach()
             bias = bias_p[:N]
         _capi.gemm(xb, w_fwd[:, :xb.shape[1]], bias=bias, out_f32=y[:, :N])
-        ctx.save_for_backward(xb, weight)
+        # the bf16 operand is kept for dgrad (its transpose is the dgrad operand): transposing 2-byte elements reads
+        # half of what a second conversion of the fp32 weight would
+        ctx.save_for_backward(xb, weight, w_fwd)
         ctx.conv1d, ctx.has_bias = conv1d, bias is not None
         return y[:, :N]
 
     @staticmethod
     def backward(ctx, dy):
-        xb, weight = ctx.saved_tensors
+        xb, weight, w_fwd = ctx.saved_tensors
         dy = dy.contiguous()
         M, N = dy.shape
         K = xb.shape[1]
@@ -99,7 +101,7 @@ class LinearFn(torch.autograd.Function):
         dyb = to_bf16(dy)
         if ctx.needs_input_grad[0]:
             # dgrad: dx [M, K] = dy [M, N] . W;  B operand [K, N] with N contiguous
-            w_dg = to_bf16(weight) if ctx.conv1d else to_bf16_t(weight)
+            w_dg = bf16_t(w_fwd[:, :K])  # [K, pad8(N)]: W for nn.Linear, W^T^T = W [K, N] for Conv1D
             dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
             _capi.gemm(dyb, w_dg[:, :N], out_f32=dx)
         if ctx.needs_input_grad[1]:
