@@ -510,7 +510,22 @@ def run_train(args):
     C = list(ncls.values())[0]
     torch.manual_seed(0)
     model = BaseModel(cfg, ncls, {}).to(dev).train()
-    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if world > 1 else model
+    # N > 1: either DistributedDataParallel (eager, bucketed all-reduce overlapped with backward; --no-graph) or - the
+    # default - the whole step in one CUDA graph with ONE NCCL all-reduce of a flat gradient buffer between backward
+    # and the optimizer (captured with the rest; not overlapped, but the step is no longer launch-bound)
+    flat_graph = world > 1 and not args.no_graph
+    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if (world > 1 and not flat_graph) else model
+    flat = None
+    if flat_graph:
+        import torch.distributed as tdist
+        params = [p for p in model.parameters() if p.requires_grad]
+        for p in params:
+            tdist.broadcast(p.data, src=0)  # what DDP's constructor does
+        flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+        off = 0
+        for p in params:
+            p.grad = flat[off:off + p.numel()].view_as(p)  # autograd accumulates in place into these views
+            off += p.numel()
     # expts/01 :48-52; fused=True: one multi-tensor kernel pass over (p, grad, momentum) instead of ~5 foreach passes
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, nesterov=True, weight_decay=1e-6, fused=True)
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
@@ -518,13 +533,21 @@ def run_train(args):
     target = torch.randint(0, C, (B, 1), device=dev, generator=g)
     target_sub = torch.randint(0, C, (B, T), device=dev, generator=g)
 
-    def step(i):
-        opt.zero_grad(set_to_none=True)
-        out, _ = ddp(dict(sets[i % 2]), **KW)
+    def fwd_bwd_opt(feats):
+        if flat is not None:
+            flat.zero_()
+        else:
+            opt.zero_grad(set_to_none=True)
+        out, _ = ddp(feats, **KW)
         loss = atrain.reference_losses(out, target, target_sub)["total"]
         loss.backward()  # DDP: bucketed NCCL all-reduce overlapped with the remaining backward
+        if flat is not None:
+            tdist.all_reduce(flat, op=tdist.ReduceOp.AVG)  # 1.55 GB over NVLink / NVSwitch
         opt.step()
         return loss
+
+    def step(i):
+        return fwd_bwd_opt(dict(sets[i % 2]))
 
     for i in range(max(3, args.warmup)):
         step(i)
@@ -533,7 +556,7 @@ def run_train(args):
     # One GPU: the whole step (forward, backward, SGD) is captured into ONE CUDA graph - at 16 clips per GPU the step is
     # ~1900 launches of small kernels and Python-launch-bound.  (With DDP the NCCL bucket hooks stay eager.)
     graphed = False
-    if world == 1 and not args.no_graph:
+    if not args.no_graph:
         try:
             static = {m: torch.empty_like(t) for m, t in sets[0].items()}
             eager_step = step
@@ -543,18 +566,14 @@ def run_train(args):
                 for i in range(3):  # warm-up on the capture pool's side stream (PyTorch whole-network capture recipe)
                     for m in static:
                         static[m].copy_(sets[i % 2][m])
-                    opt.zero_grad(set_to_none=True)
-                    out, _ = model(dict(static), **KW)
-                    atrain.reference_losses(out, target, target_sub)["total"].backward()
-                    opt.step()
+                    fwd_bwd_opt(dict(static))
             torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            opt.zero_grad(set_to_none=True)
+            if flat is None:
+                opt.zero_grad(set_to_none=True)
             with torch.cuda.graph(graph):
-                out, _ = model(dict(static), **KW)
-                static_loss = atrain.reference_losses(out, target, target_sub)["total"]
-                static_loss.backward()
-                opt.step()
+                static_loss = fwd_bwd_opt(dict(static))
 
             def step(i):  # noqa: F811
                 for m in static:
@@ -591,7 +610,10 @@ def run_train(args):
         "dtype": "bf16", "data": "synthetic", "mode": "train",
         "config": {"workload": "ek100_sa_swin training step (expts/01_SA-Fuser_ek100_train.txt: T=16, 4 modalities, SGD-nesterov)",
                    "clips_per_gpu_per_step": B, "T": T, "params": n_params, "grad_allreduce_bytes": 4 * n_params if world > 1 else 0,
-                   "allreduce": "torch DDP bucketed NCCL all-reduce overlapped with backward" if world > 1 else "none (1 GPU)",
+                   "allreduce": ("one NCCL all-reduce (AVG) of the flat fp32 gradient buffer, captured in the step's CUDA graph"
+                                 if (world > 1 and flat is not None and graphed) else
+                                 "one NCCL all-reduce of the flat gradient buffer (eager)" if (world > 1 and flat is not None) else
+                                 "torch DDP bucketed NCCL all-reduce overlapped with backward" if world > 1 else "none (1 GPU)"),
                    "gemm_gflop_per_clip_fwd_bwd": round(flops_per_clip / 1e9, 2), "final_loss": round(float(loss), 4)},
         "achieved_tflops": round(value * flops_per_clip / 1e12, 1),
         "cuda_graph": graphed,
