@@ -621,6 +621,17 @@ def run_train(args):
     }
     if rank == 0:
         emit(line)
+    if graphed and world > 1:
+        # Tearing the NCCL communicator down while a graph with captured collectives is alive hung at exit (observed
+        # once, N = 2): release the graph, meet the other ranks, and leave without destroy_process_group.
+        torch.cuda.synchronize()
+        adist.barrier()
+        try:
+            graph.reset()
+        except Exception:  # noqa: BLE001
+            pass
+        sys.stderr.flush()
+        os._exit(0)
     adist.shutdown()
 
 
