@@ -614,7 +614,7 @@ def run_train(args):
                                  if (world > 1 and flat is not None and graphed) else
                                  "one NCCL all-reduce of the flat gradient buffer (eager)" if (world > 1 and flat is not None) else
                                  "torch DDP bucketed NCCL all-reduce overlapped with backward" if world > 1 else "none (1 GPU)"),
-                   "gemm_gflop_per_clip_fwd_bwd": round(flops_per_clip / 1e9, 2), "final_loss": round(float(loss), 4)},
+                   "gemm_gflop_per_clip_fwd_bwd": round(flops_per_clip / 1e9, 2), "final_loss": round(float(loss.detach()), 4)},
         "achieved_tflops": round(value * flops_per_clip / 1e12, 1),
         "cuda_graph": graphed,
         "clocks": sampler.summary(),

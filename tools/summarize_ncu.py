@@ -76,5 +76,23 @@ def metrics(path):
     print(f"total {sum(a[1] for a in agg.values()):.1f} us over {sum(a[0] for a in agg.values())} launches")
 
 
+def traffic(path):
+    """JSON for profiles/r01_gemm_traffic.json (read by bench.py): DRAM bytes per GEMM launch of one forward."""
+    import json
+    per = OrderedDict()
+    for r in rows(path):
+        d = per.setdefault(int(r["ID"]), {"kernel": r["Kernel Name"]})
+        d[r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
+        d[r["Metric Name"] + "#unit"] = r["Metric Unit"]
+    g = [d for d in per.values() if "gemm_bf16" in d["kernel"]]
+    rd = sum(d["dram__bytes_read.sum"] for d in g)
+    wr = sum(d["dram__bytes_write.sum"] for d in g)
+    t = sum(d["gpu__time_duration.sum"] / (1e3 if d["gpu__time_duration.sum#unit"].startswith("n") else 1.0) for d in g)
+    print(json.dumps({"what": "per-launch DRAM traffic of the GEMM launches of one forward (headline config, B=256), ncu --metrics "
+                              "dram__bytes_read.sum,dram__bytes_write.sum (cold cache per launch)",
+                      "launches": len(g), "dram_read_bytes_total": rd, "dram_write_bytes_total": wr,
+                      "traffic_bytes_per_launch_avg": (rd + wr) / max(1, len(g)), "time_us_total": t}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "metrics": metrics}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "metrics": metrics, "traffic": traffic}[sys.argv[1]](sys.argv[2])
