@@ -390,14 +390,20 @@ def run_afft(args):
         return checksum
 
     e2e_loop(max(2, args.warmup))
-    adist.barrier()
-    with sampler:
-        e0.record()
-        e2e_loop(args.steps)
-        e1.record()
-        torch.cuda.synchronize()
-    adist.barrier()
-    e2e_ms = adist.max_over_ranks(e0.elapsed_time(e1), dev)
+    # Three timed passes of K steps each; the MEDIAN pass is reported and all three are listed.  The host <-> device
+    # copies share PCIe and host memory with whatever else runs on the box: single passes were seen 25 % off
+    # (8.5 instead of 6.4 ms per step) with the device-resident `value` of the same run unchanged.
+    e2e_passes = []
+    for _ in range(3):
+        adist.barrier()
+        with sampler:
+            e0.record()
+            e2e_loop(args.steps)
+            e1.record()
+            torch.cuda.synchronize()
+        adist.barrier()
+        e2e_passes.append(adist.max_over_ranks(e0.elapsed_time(e1), dev))
+    e2e_ms = sorted(e2e_passes)[1]
     e2e_value = n_gpus * B * args.steps / (e2e_ms / 1e3)
 
     # ---- e2e from clip descriptors (row N4): native plan + device gather from a pinned host feature store ----
@@ -445,6 +451,7 @@ def run_afft(args):
         "config": workload_config(args, cfg, T, B, "afft_forward (C ABI), " + ("strict bf16x3" if args.strict else "bf16 operands / fp32 accumulate")),
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(e2e_ms / args.steps, 4),
+                "passes_ms_per_step": [round(p / args.steps, 4) for p in e2e_passes], "reported": "median of 3 passes of K steps",
                 "api": "afft_b200.models.BaseModel.__call__ (test.py:72-86 pattern), pinned host inputs, double-buffered H2D, logits of batch i-1 read on the host while batch i computes"},
         "e2e_from_clip_descriptors": staged,
         "gpu_launches": launches_per_fwd * args.steps,

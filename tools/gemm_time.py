@@ -17,8 +17,10 @@ g = torch.Generator().manual_seed(0)
 a = torch.randn(M, K, generator=g).to(dev).bfloat16()
 w = (torch.randn(N, K, generator=g) * 0.05).to(dev).bfloat16()
 bias = torch.randn(N, generator=g).to(dev)
-out_b = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
-out_f = torch.zeros(M, N, device=dev)
+Np = (N + 7) // 8 * 8  # 16-byte row pitches for the epilogue's vector accesses
+out_b = torch.zeros(M, Np, device=dev, dtype=torch.bfloat16)[:, :N]
+out_f = torch.zeros(M, Np, device=dev)[:, :N]
+bias = torch.cat([bias, torch.zeros(Np - N, device=dev)])[:N]
 kw = {}
 if epi == "gelu":
     kw.update(bias=bias, act=capi.ACT_GELU_ERF, out_hi=out_b)
