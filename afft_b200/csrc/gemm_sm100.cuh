@@ -420,11 +420,12 @@ __device__ __forceinline__ void splitk_sum_to_stage(const float* tile_partial0, 
   }
 }
 
-// The epilogue of one work unit for one warp (both kernels).  Pass 0 drains the warp's slabs from TMEM (software
-// pipelined: the TMEM load of the next slab is in flight while the current one is transposed, transformed and
-// stored) and either finishes them (ksplit == 1) or stores them as split-K partials; `release_tmem()` then hands the
-// accumulator back to the MMA warp.  With split-K the warp that arrives last on the band counter runs pass 1: same
-// slab loop, but the staging tile is filled with the in-order sum of the partials instead of from TMEM.
+// The epilogue of one work unit for one warp (both kernels).  Pass 0 drains the warp's slabs from TMEM (optionally
+// software pipelined, AFFT_TMEM_PIPE: the TMEM load of the next slab in flight while the current one is
+// transposed, transformed and stored) and either finishes them (ksplit == 1) or stores them as split-K partials;
+// `release_tmem()` then hands the accumulator back to the MMA warp.  With split-K the warp that arrives last on
+// the band counter runs pass 1: same slab loop, but the staging tile is filled with the in-order sum of the
+// partials instead of from TMEM.
 template <int EPI, int SPLIT, int BLOCK_N, typename ReleaseFn>
 __device__ __forceinline__ void epilogue_unit(const GemmEpilogue& ep, int ksplit, uint32_t stage, uint32_t t_row, int quad, int egrp,
                                               int lane, int row0, int n_tile0, int M, int N, float* cta_partial,
