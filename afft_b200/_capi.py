@@ -109,7 +109,7 @@ EXPORTED_SYMBOLS = [
     "afft_abi_version", "afft_last_error", "afft_gemm", "afft_convert_bf16", "afft_layernorm", "afft_attention",
     "afft_create", "afft_destroy", "afft_handle_error", "afft_workspace_bytes", "afft_weight_bytes",
     "afft_set_weight", "afft_missing_weights", "afft_forward", "afft_last_launch_count",
-    "afft_profile_enable", "afft_profile_read", "afft_set_max_ksplit", "afft_marginalize_topk", "afft_score_fusion",
+    "afft_profile_enable", "afft_profile_read", "afft_set_max_ksplit", "afft_plan_ksplit", "afft_marginalize_topk", "afft_score_fusion",
     "afft_transpose_bf16", "afft_layernorm_bwd", "afft_gelu_fwd", "afft_gelu_bwd", "afft_colsum", "afft_attention_bwd",
 ]
 
@@ -165,6 +165,8 @@ def lib() -> C.CDLL:
     l.afft_profile_enable.argtypes = [C.c_void_p, C.c_int32]
     l.afft_set_max_ksplit.argtypes = [C.c_void_p, C.c_int32]
     l.afft_set_max_ksplit.restype = C.c_int
+    l.afft_plan_ksplit.argtypes = [C.c_int32] * 5
+    l.afft_plan_ksplit.restype = C.c_int
     l.afft_profile_read.argtypes = [C.c_void_p, C.POINTER(Profile)]
     for name in ("afft_gemm", "afft_convert_bf16", "afft_layernorm", "afft_attention", "afft_create",
                  "afft_set_weight", "afft_missing_weights", "afft_forward", "afft_last_launch_count",

@@ -1365,6 +1365,14 @@ extern "C" int afft_set_max_ksplit(afft_handle* h, int32_t max_split) {
   return AFFT_OK;
 }
 
+extern "C" int afft_plan_ksplit(int32_t tiles, int32_t slots, int32_t num_kb, int32_t ctas_per_tile, int32_t max_split) {
+  if (tiles < 1 || slots < 1 || num_kb < 1 || ctas_per_tile < 1) return 1;
+  static float dummy_partials;
+  static unsigned dummy_counters;
+  SplitKScratch sk{&dummy_partials, kSplitKPartialFloats, &dummy_counters, kSplitKCounters, max_split};  // never dereferenced
+  return pick_ksplit(tiles, slots, num_kb, ctas_per_tile, static_cast<size_t>(kBlockM) * (ctas_per_tile == 2 ? 256 : 128), &sk);
+}
+
 extern "C" int afft_profile_enable(afft_handle* h, int32_t enable) {
   if (h == nullptr) return fail(AFFT_ERR_INVALID, "profile_enable: null handle");
   if (enable && h->ev.empty()) {

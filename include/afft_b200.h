@@ -284,6 +284,9 @@ AFFT_API int afft_profile_enable(afft_handle* h, int32_t enable);
  * for a fixed value (partials are summed in split order), and differ between values only by fp32 summation order.
  * There is no reference counterpart (PyTorch picks its cuBLAS algorithm internally). */
 AFFT_API int afft_set_max_ksplit(afft_handle* h, int32_t max_split);
+/* The split factor the scheduler would choose for a GEMM of `tiles` output tiles and `num_kb` 64-wide K blocks on
+ * `slots` persistent CTAs (or CTA pairs) with the given cap - host arithmetic only (exposed for tests and tuning). */
+AFFT_API int afft_plan_ksplit(int32_t tiles, int32_t slots, int32_t num_kb, int32_t ctas_per_tile, int32_t max_split);
 AFFT_API int afft_profile_read(afft_handle* h, afft_profile* out);
 
 #ifdef __cplusplus

@@ -156,3 +156,29 @@ def test_synthetic_weights_are_deterministic():
     f1 = synthetic.synthetic_features(cfg["modal_dims"], 2, T, seed=9)
     f2 = synthetic.synthetic_features(cfg["modal_dims"], 2, T, seed=9)
     assert all(torch.equal(f1[k], f2[k]) for k in f1)
+
+
+def test_splitk_plan_cost_model():
+    """afft_plan_ksplit (host arithmetic of the split-K scheduler): no split when the tiles fill the GPU,
+    a split when few tiles carry a long K loop, never an empty split, never beyond the cap."""
+    from afft_b200 import _capi
+    lib = _capi.lib()
+    plan = lambda tiles, slots, kb, ctas=1, cap=4: lib.afft_plan_ksplit(tiles, slots, kb, ctas, cap)  # noqa: E731
+    # headline batch (B = 256): every GEMM has >= 1 wave of tiles -> unsplit (bitwise identical to the unsplit build)
+    for tiles, kb in ((360, 16), (360, 64), (1080, 16), (1440, 16), (144, 32), (144, 128), (285, 16), (72, 32)):
+        assert plan(tiles, 74, kb, ctas=2) == 1, (tiles, kb)
+    # batch 1: 8 tiles with K = 4096 (64 K blocks) on 148 CTAs -> split to the cap; cap 1 switches it off
+    assert plan(8, 148, 64) == 4
+    assert plan(8, 148, 64, cap=1) == 1
+    assert plan(8, 148, 64, cap=16) >= 4
+    # batch 32, GPT-2 mlp c_proj: 80 tiles, K = 8192: 3 splits (2 waves of 43 K blocks instead of 1 of 128)
+    assert plan(80, 148, 128) == 3
+    # full single wave: nothing to gain
+    assert plan(144, 148, 64) == 1
+    # a split never leaves a K range empty and never exceeds num_kb / 2
+    for kb in range(1, 40):
+        for tiles in (1, 3, 8, 24):
+            s = plan(tiles, 148, kb, cap=16)
+            assert 1 <= s <= max(1, kb // 2)
+            per = -(-kb // s)
+            assert (s - 1) * per < kb

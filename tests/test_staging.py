@@ -182,3 +182,22 @@ def test_staged_batch_drives_the_model():
     with torch.no_grad():
         out2, _ = model({m: torch.from_numpy(ref[m]).reshape(B, T, dims[m], 1, 1, 1).cuda() for m in dims}, **kw)
     assert torch.equal(out["logits/action"]["all-fused"], out2["logits/action"]["all-fused"])
+
+
+def test_plan_shards_over_ranks_like_the_forward(golden):
+    """Multi-GPU: clips are independent units; each rank plans (and gathers) its contiguous shard.  The per-rank plans
+    concatenate to the single-process plan (no collective on the data path)."""
+    from afft_b200 import dist as adist
+    z, stores = golden
+    store, dims = _native_store(stores, "host")
+    rng = np.random.default_rng(11)
+    vids = rng.choice(["P01_101", "P02_07", "P03_123"], size=37).tolist()
+    en = np.array([rng.uniform(5.0, 10.0) for _ in vids])
+    st = en - 4.5
+    full = store.plan(vids, st, en, FPS, 18, REQ_FPS)
+    for world in (2, 3, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = adist.shard_bounds(len(vids), r, world)
+            parts.append(store.plan(vids[lo:hi], st[lo:hi], en[lo:hi], FPS, 18, REQ_FPS))
+        assert torch.equal(torch.cat(parts, dim=1), full)
