@@ -994,8 +994,8 @@ struct Fwd {
 
   void assemble(const AssembleArgs& a) {
     if (!ok()) return;
-    const long long total = static_cast<long long>(a.B) * a.T * a.n_slots * (a.dim / 4);
-    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    const long long rows = static_cast<long long>(a.B) * a.T * a.n_slots;
+    const int blocks = static_cast<int>(std::min<long long>(rows, 148 * 16));
     const int pi = prof_begin(AFFT_CAT_OTHER);
     assemble_tokens_kernel<<<blocks, 256, 0, stream>>>(a);
     cudaError_t e = cudaGetLastError();

@@ -241,36 +241,42 @@ struct AssembleArgs {
 };
 
 __global__ void __launch_bounds__(256) assemble_tokens_kernel(const AssembleArgs a) {
+  // One CTA per token row (grid-stride over rows), threads across the row's 16-byte vectors: the (b, t, slot)
+  // decomposition is three 32-bit divisions per ROW (the first version did 64-bit divisions per element and ran at
+  // 2 TB/s).
   const int d4 = a.dim / 4;
-  const long long total = static_cast<long long>(a.B) * a.T * a.n_slots * d4;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c4 = static_cast<int>(i % d4);
-    long long r = i / d4;
-    const int s = static_cast<int>(r % a.n_slots);
-    r /= a.n_slots;
-    const int t = static_cast<int>(r % a.T);
-    const int b = static_cast<int>(r / a.T);
-    float4 v;
+  const int rows = a.B * a.T * a.n_slots;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int s = r % a.n_slots;
+    const int bt = r / a.n_slots;
+    const int t = bt % a.T;
+    const int b = bt / a.T;
+    const float4* src;
     if (a.is_token[s]) {
-      v = __ldg(reinterpret_cast<const float4*>(a.token + static_cast<long long>(t % a.tok_mod) * a.dim) + c4);
+      src = reinterpret_cast<const float4*>(a.token + static_cast<long long>(t % a.tok_mod) * a.dim);
     } else if (a.src[s] != nullptr) {
-      v = __ldg(reinterpret_cast<const float4*>(a.src[s] + (static_cast<long long>(b) * a.T + t) * a.dim) + c4);
+      src = reinterpret_cast<const float4*>(a.src[s] + static_cast<long long>(bt) * a.dim);
     } else {
-      continue;
+      continue;  // slot written by a projection GEMM
     }
-    if (a.pos_emb != nullptr) {
-      const float4 p = __ldg(reinterpret_cast<const float4*>(a.pos_emb + static_cast<long long>(t) * a.dim) + c4);
-      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
-    }
-    if (a.mod_emb != nullptr) {
-      const float4 p = __ldg(reinterpret_cast<const float4*>(a.mod_emb + static_cast<long long>(s) * a.dim) + c4);
-      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
-    }
+    const float4* pe = a.pos_emb != nullptr ? reinterpret_cast<const float4*>(a.pos_emb + static_cast<long long>(t) * a.dim) : nullptr;
+    const float4* me = a.mod_emb != nullptr ? reinterpret_cast<const float4*>(a.mod_emb + static_cast<long long>(s) * a.dim) : nullptr;
     const long long orow = static_cast<long long>(b) * a.n_slots * a.T +
                            (a.layout == 0 ? static_cast<long long>(t) * a.n_slots + s
                                           : static_cast<long long>(s) * a.T + t);
-    reinterpret_cast<float4*>(a.h + orow * a.dim)[c4] = v;
+    float4* dst = reinterpret_cast<float4*>(a.h + orow * a.dim);
+    for (int c4 = threadIdx.x; c4 < d4; c4 += blockDim.x) {
+      float4 v = __ldg(src + c4);
+      if (pe != nullptr) {
+        const float4 p = __ldg(pe + c4);
+        v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+      }
+      if (me != nullptr) {
+        const float4 p = __ldg(me + c4);
+        v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+      }
+      dst[c4] = v;
+    }
   }
 }
 
