@@ -201,3 +201,37 @@ def test_plan_shards_over_ranks_like_the_forward(golden):
             lo, hi = adist.shard_bounds(len(vids), r, world)
             parts.append(store.plan(vids[lo:hi], st[lo:hi], en[lo:hi], FPS, 18, REQ_FPS))
         assert torch.equal(torch.cat(parts, dim=1), full)
+
+
+def test_native_frame_ids_match_oracle_over_rates_and_windows(golden):
+    """The window / subsampling / padding / original-fps arithmetic at other frame rates than the 30 -> 4 fps of the
+    shipped configs (float64 floor / int / round-half-even edge cases): frame ids bit-identical to the oracle."""
+    _, stores = golden
+    store, _ = _native_store(stores, "host")
+    rng = np.random.default_rng(2024)
+    vids = rng.choice(["P01_101", "P02_07", "P03_123"], size=64).tolist()
+    n_checked = 0
+    for fps in (30.0, 29.97, 25.0, 50.0, 59.94005994005994, 24.0):
+        for frame_rate in (4.0, 2.5, 5.0, 7.5, None):
+            for T, strat in ((18, "last_clip"), (10, "center_clip"), (16, "first_clip"), (1, "last_clip")):
+                en = rng.uniform(0.5, 60.0, size=64)
+                st = en - rng.choice([T / 4.0, 0.37, 3.0, 11.1], size=64) + rng.choice([0.0, 1e-9, -1e-9, 0.004], size=64)
+                # frame-boundary end points: k / fps and its float neighbours
+                en[:8] = [k / fps for k in (1, 2, 7, 30, 31, 135, 299, 1200)]
+                en[8:16] = np.nextafter(en[:8], 0.0)
+                en[16:24] = np.nextafter(en[:8], 1e9)
+                keep = []
+                for i in range(64):
+                    try:
+                        ids = [feats_oracle.clip_frame_ids(vids[i], float(st[i]), float(en[i]), fps, T, frame_rate, strat,
+                                                            orig_fps_index=(m == "audio")) for m in MODS]
+                    except (AssertionError, ValueError):
+                        continue  # empty window / no frame id >= 1: the native planner refuses those (covered elsewhere)
+                    keep.append((i, ids))
+                sel = [i for i, _ in keep]
+                _, fids = store.plan([vids[i] for i in sel], st[sel], en[sel], fps, T, frame_rate, strat, want_frame_ids=True)
+                for bi, (i, ids) in enumerate(keep):
+                    for mi in range(len(MODS)):
+                        assert np.array_equal(fids[mi, bi].numpy(), ids[mi]), (fps, frame_rate, T, strat, vids[i], st[i], en[i], MODS[mi])
+                        n_checked += 1
+    assert n_checked > 20000
