@@ -243,9 +243,9 @@ static int launch_attention_tokens_mma(const AttentionArgs& a, cudaStream_t stre
   return AFFT_OK;
 }
 
-template <int HD, int LP>
+template <int HD, int LP, int NW = 4>
 static int launch_attention_mma(const AttentionArgs& a, cudaStream_t stream) {
-  auto kern = attention_mma_kernel<HD, LP>;
+  auto kern = attention_mma_kernel<HD, LP, NW>;
   constexpr int smem = AttnMmaSmem<HD, LP>::kBytes;
   static bool configured[64] = {false};
   int dev = 0;
@@ -256,7 +256,7 @@ static int launch_attention_mma(const AttentionArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return cuda_fail("attention_mma smem attribute", e);
     configured[dev] = true;
   }
-  cudaError_t e = launch_pdl(kern, dim3(a.n_seq * a.H), dim3(128), AttnMmaSmem<HD, LP>::bytes_for(a.L), stream, a);
+  cudaError_t e = launch_pdl(kern, dim3(a.n_seq * a.H), dim3(NW * 32), AttnMmaSmem<HD, LP>::bytes_for(a.L), stream, a);
   if (e != cudaSuccess) return cuda_fail("attention_mma launch", e);
   return AFFT_OK;
 }
@@ -287,7 +287,7 @@ static int run_attention(const AttentionArgs& a, int head_dim, bool in_f32, cuda
       if (head_dim == 256) return launch_attention_mma<256, 32>(a, stream);
       if (head_dim == 512) return launch_attention_mma<512, 32>(a, stream);
     } else if (head_dim == 256) {  // T-SA-Fuser: up to 64 tokens, block-causal
-      return launch_attention_mma<256, 64>(a, stream);
+      return launch_attention_mma<256, 64, 8>(a, stream);
     }
   }
   if (head_dim == 256) return in_f32 ? launch_attention<float, 256>(a, stream) : launch_attention<bf16, 256>(a, stream);

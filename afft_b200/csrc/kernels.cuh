@@ -581,8 +581,10 @@ struct AttnMmaSmem {
   static constexpr int bytes_for(int L) { return 3 * L * kRowBytes + kLP * kSStride * 4 + kLP * kPRowBytes; }
 };
 
-template <int HD, int LP>
-__global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs a) {
+// NW warps per CTA: 4 for sequences up to 32 tokens, 8 for the 50-token T-SA-Fuser sequences (16 score blocks and
+// 64 softmax rows per CTA: twice the warps halve the CTA's serial compute between its load and its store).
+template <int HD, int LP, int NW = 4>
+__global__ void __launch_bounds__(NW * 32) attention_mma_kernel(const AttentionArgs a) {
   using S = AttnMmaSmem<HD, LP>;
   constexpr int MT = LP / 16;  // 16-row tiles
   extern __shared__ uint4 smem_attn[];
@@ -607,7 +609,7 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs 
   // Tile rows >= L are never stored: the ldmatrix addresses below clamp to row L - 1.  Duplicated Q / K rows only
   // produce scores that are masked or never read; duplicated V rows meet zero probabilities and are finite.
   constexpr int kVecPerRow = HD / 8;             // 16-byte vectors per row
-  constexpr int kRowsPerPass = 128 / kVecPerRow;  // rows covered by the CTA per pass (2 for HD 512, 4 for 256)
+  constexpr int kRowsPerPass = NW * 32 / kVecPerRow;  // rows covered by the CTA per pass
   {
     const int c = tid % kVecPerRow;
     const int r0 = tid / kVecPerRow;
@@ -637,7 +639,7 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs 
 
   const int g8 = lane >> 2, t4 = lane & 3;
   // ---- S = Q K^T: 16 x 16 blocks (query tile mt, key tile nb) over the full head_dim, dealt round-robin to warps ----
-  for (int blk = warp; blk < MT * MT; blk += 4) {
+  for (int blk = warp; blk < MT * MT; blk += NW) {
     const int mt = blk / MT, nb = blk % MT;
     const bool skip = (nb * 16 >= L) || (mt * 16 >= L) || (a.mask == 1 && nb * 16 > mt * 16 + 15);
     if (skip) continue;
@@ -664,7 +666,7 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs 
   __syncthreads();
 
   // ---- softmax rows (fp32), P -> bf16.  mask 1: j <= i; mask 2: (j % T) <= (i % T); mask 0: none ----
-  for (int i = warp; i < S::kLP; i += 4) {
+  for (int i = warp; i < S::kLP; i += NW) {
     float p[LP / 32];
 #pragma unroll
     for (int c = 0; c < LP / 32; ++c) p[c] = 0.f;
@@ -701,14 +703,14 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs 
   }
   __syncthreads();
 
-  // ---- O = P V: warp -> HD / 4 output dims; output tile staged in the (now free) Q region ----
+  // ---- O = P V: warp -> HD / NW output dims; output tile staged in the (now free) Q region ----
   asm volatile("cp.async.wait_group 0;" ::: "memory");  // V has landed (the barrier above published the probabilities;
   __syncthreads();                                       //  this one publishes every thread's share of V)
   {
     const int ksteps = (L + 15) / 16;
 #pragma unroll 1
-    for (int np = 0; np < HD / 4 / 16; ++np) {
-      const int n0 = warp * (HD / 4) + np * 16;
+    for (int np = 0; np < HD / NW / 16; ++np) {
+      const int n0 = warp * (HD / NW) + np * 16;
       float acc[MT][2][4];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
@@ -742,7 +744,7 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttentionArgs 
     }
   }
   __syncthreads();
-  for (int i = tid; i < L * kVecPerRow; i += 128) {
+  for (int i = tid; i < L * kVecPerRow; i += NW * 32) {
     const int r = i / kVecPerRow, c = i % kVecPerRow;
     *reinterpret_cast<uint4*>(a.out_hi + (static_cast<long long>(seq) * L + r) * a.ldo + h * HD + c * 8) =
         *reinterpret_cast<const uint4*>(base + r * S::kRowBytes + c * 16);
