@@ -126,6 +126,32 @@ class FeatureStore:
             store.set_modality(mod, vids, location)
         return store
 
+    @classmethod
+    def from_lmdb(cls, modal_dims: Mapping[str, int], lmdb_paths: Mapping[str, str],
+                  orig_fps_mods: Optional[Iterable[str]] = None, location: str = "pinned") -> "FeatureStore":
+        """Ingest the RULSTM feature LMDBs the reference reads (``EpicRULSTMFeatsReader(lmdb_path=...)``,
+        reader_fns.py:41-53): one environment per modality, opened read-only without locking like the reference does.
+        ``orig_fps_mods`` defaults to the reference's rule: 'audio' or 'poses' in the LMDB path (reader_fns.py:131).
+        Needs the ``lmdb`` package (part of the reference's environment.yml); the whole store is read once."""
+        try:
+            import lmdb
+        except ImportError as e:  # pragma: no cover - depends on the environment
+            raise _capi.AfftError("FeatureStore.from_lmdb needs the `lmdb` package (reference environment.yml); "
+                                  "use from_key_value() with any (key, value) iterable otherwise") from e
+        if orig_fps_mods is None:
+            orig_fps_mods = [m for m, pth in lmdb_paths.items() if "audio" in str(pth) or "poses" in str(pth)]
+        envs, its = [], {}
+        for m, pth in lmdb_paths.items():
+            env = lmdb.open(str(pth), readonly=True, lock=False)
+            envs.append(env)
+            txn = env.begin()
+            its[m] = txn.cursor()
+        try:
+            return cls.from_key_value(modal_dims, its, orig_fps_mods=orig_fps_mods, location=location)
+        finally:
+            for env in envs:
+                env.close()
+
     def plan(self, video_names: Sequence[str], start_sec: Sequence[float], end_sec: Sequence[float], fps: float, T: int,
              frame_rate: Optional[float], strategy: str = "last_clip", out: Optional[torch.Tensor] = None,
              want_frame_ids: bool = False):

@@ -235,3 +235,47 @@ def test_native_frame_ids_match_oracle_over_rates_and_windows(golden):
                         assert np.array_equal(fids[mi, bi].numpy(), ids[mi]), (fps, frame_rate, T, strat, vids[i], st[i], en[i], MODS[mi])
                         n_checked += 1
     assert n_checked > 20000
+
+
+def test_from_lmdb_uses_the_reference_open_mode_and_path_rule(golden, monkeypatch):
+    """FeatureStore.from_lmdb against a stand-in `lmdb` module (the package is not in this image): environments are
+    opened readonly / lock=False like reader_fns.py:52, and 'audio' in the path selects the original-fps index."""
+    import sys
+    import types
+    _, stores = golden
+    opened = []
+
+    class Txn:
+        def __init__(self, d):
+            self.d = d
+
+        def cursor(self):
+            return iter((k.encode(), v.tobytes()) for k, v in self.d.items())
+
+    class Env:
+        def __init__(self, d):
+            self.d, self.closed = d, False
+
+        def begin(self):
+            return Txn(self.d)
+
+        def close(self):
+            self.closed = True
+
+    def fake_open(path, readonly=False, lock=True):
+        assert readonly and not lock
+        env = Env(stores[path.split("/")[-1].split("_")[0]])
+        opened.append(env)
+        return env
+
+    fake = types.ModuleType("lmdb")
+    fake.open = fake_open
+    monkeypatch.setitem(sys.modules, "lmdb", fake)
+    dims = {m: len(next(iter(d.values()))) for m, d in stores.items()}
+    store = staging.FeatureStore.from_lmdb(dims, {m: f"/data/{m}_lmdb" for m in MODS}, location="host")
+    assert store.orig_fps_mods == ("audio",) and all(e.closed for e in opened) and len(opened) == len(MODS)
+    ref_store, _ = _native_store(stores, "host")
+    args = (["P01_101", "P02_07"], [3.0, 10.0], [7.5, 14.5], FPS, 18, REQ_FPS)
+    assert torch.equal(store.plan(*args), ref_store.plan(*args))
+    for m in MODS:
+        assert torch.equal(store.rows[m], ref_store.rows[m])
