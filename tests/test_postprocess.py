@@ -61,3 +61,34 @@ def test_mapping_validation():
     bad = torch.zeros(4, 3)
     with pytest.raises(ValueError):
         VerbNounMarginalizer(bad, bad, "cpu")
+
+
+@pytest.mark.gpu
+def test_metrics_from_kernel_topk_equal_score_matrix_metrics(golden_dir):
+    """End of the evaluation chain (test.py:95-97, challenge.py:94-106): the top-5 indices the kernel returns give
+    the same top-1 / top-5 / MT5R numbers as the reference's argsort over the full score matrices."""
+    from afft_b200 import metrics
+    from afft_b200.postprocess import VerbNounMarginalizer
+    z, V, N = _fixture(golden_dir)
+    m = VerbNounMarginalizer(V, N, "cuda:0")
+    g = torch.Generator().manual_seed(11)
+    logits = torch.randn(512, 3806, generator=g)
+    act = torch.randint(0, 3806, (512,), generator=g)
+    logits[torch.arange(512)[::2], act[::2]] += 4.0  # half of the clips are (nearly) right
+    out = m(logits.cuda(), k=5)
+    tk = out["topk"].cpu().numpy()
+    verb_lab = torch.from_numpy(z["verb_of"].astype(np.int64))[act].numpy()
+    noun_lab = torch.from_numpy(z["noun_of"].astype(np.int64))[act].numpy()
+
+    def ref_metrics(scores, labels):  # common/utils.py:19-56 restated with a stable descending sort
+        rank = np.argsort(-scores, axis=1, kind="stable")[:, :5]
+        hit = rank == labels.reshape(-1, 1)
+        t1, t5 = hit[:, :1].any(1).mean(), hit.any(1).mean()
+        mt5r = np.mean([hit[labels == c].any(1).mean() for c in np.unique(labels)])
+        return t1 * 100, t5 * 100, mt5r * 100
+
+    got = metrics.epic_metrics(tk[:, 1], tk[:, 2], tk[:, 0], verb_lab, noun_lab, act.numpy())
+    for p, scores, lab in (("v", out["verb"].cpu().numpy(), verb_lab), ("n", out["noun"].cpu().numpy(), noun_lab),
+                           ("a", logits.numpy(), act.numpy())):
+        t1, t5, mt = ref_metrics(scores, lab)
+        assert abs(got[f"{p}top1"] - t1) < 1e-9 and abs(got[f"{p}top5"] - t5) < 1e-9 and abs(got[f"{p}mt5r"] - mt) < 1e-9, p
