@@ -20,9 +20,29 @@ AFFT_OK = 0
 AFFT_MAX_MODS = 8
 AFFT_MAX_CLS = 4
 AFFT_NAME_LEN = 32
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH, ACT_RELU, ACT_GATE = 0, 1, 2, 3, 4
+PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2
+DT_BF16, DT_F32, DT_FP16 = 0, 1, 2
+# precision names of the Python API -> AFFT_PREC_* (include/afft_b200.h)
+PRECISIONS = {"bf16": PREC_BF16, "strict": PREC_BF16X3, "fp16": PREC_FP16}
+
+
+def resolve_precision(strict=False, precision=None) -> str:
+    """The one precision name ('bf16' | 'fp16' | 'strict') behind the (strict=, precision=) constructor arguments."""
+    if precision is None:
+        return "strict" if strict else "bf16"
+    if precision not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+    if strict and precision != "strict":
+        raise ValueError("strict=True contradicts precision=%r" % (precision,))
+    return precision
+
+
+def operand_dtype(precision: str):
+    """torch dtype of the 16-bit GEMM operands of a precision."""
+    return torch.float16 if precision == "fp16" else torch.bfloat16
 FUSER_SA, FUSER_SA_NOTOKEN, FUSER_TSA, FUSER_CA, FUSER_NONE = 0, 1, 2, 3, 4
 
 
@@ -34,7 +54,7 @@ class GemmDesc(C.Structure):
     _fields_ = [
         ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("lda", C.c_int64),
         ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("ldw", C.c_int64),
-        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("strict", C.c_int32),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("precision", C.c_int32),
         ("bias", C.c_void_p), ("res", C.c_void_p), ("ld_res", C.c_int64),
         ("res_mod", C.c_int32), ("act", C.c_int32),
         ("out_f32", C.c_void_p), ("ld_f32", C.c_int64),
@@ -53,6 +73,7 @@ class LayerNormDesc(C.Structure):
         ("y_f32", C.c_void_p), ("y_hi", C.c_void_p), ("y_lo", C.c_void_p), ("ldy", C.c_int64),
         ("aux_mod", C.c_int32), ("aux_stride", C.c_int32), ("aux_rem", C.c_int32),
         ("aux_f32", C.c_void_p), ("aux_hi", C.c_void_p), ("aux_lo", C.c_void_p), ("ld_aux", C.c_int64),
+        ("out_fp16", C.c_int32),
     ]
 
 
@@ -60,7 +81,7 @@ class AttentionDesc(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
         ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64),
-        ("in_f32", C.c_int32),
+        ("in_dtype", C.c_int32),
         ("n_seq", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("head_dim", C.c_int32),
         ("scale", C.c_float), ("mask", C.c_int32), ("T", C.c_int32),
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldo", C.c_int64),
@@ -80,7 +101,7 @@ class Config(C.Structure):
         ("n_cls", C.c_int32),
         ("cls_name", (C.c_char * AFFT_NAME_LEN) * AFFT_MAX_CLS),
         ("cls_dim", C.c_int32 * AFFT_MAX_CLS),
-        ("strict", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32), ("fp_output_len", C.c_int32),
+        ("precision", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32), ("fp_output_len", C.c_int32),
     ]
 
 
@@ -106,7 +127,7 @@ class Profile(C.Structure):
 
 # every symbol include/afft_b200.h declares
 EXPORTED_SYMBOLS = [
-    "afft_abi_version", "afft_last_error", "afft_gemm", "afft_convert_bf16", "afft_layernorm", "afft_attention",
+    "afft_abi_version", "afft_last_error", "afft_gemm", "afft_convert_bf16", "afft_convert_operand", "afft_layernorm", "afft_attention",
     "afft_create", "afft_destroy", "afft_handle_error", "afft_workspace_bytes", "afft_weight_bytes",
     "afft_set_weight", "afft_missing_weights", "afft_forward", "afft_last_launch_count",
     "afft_profile_enable", "afft_profile_read", "afft_set_max_ksplit", "afft_plan_ksplit", "afft_marginalize_topk", "afft_score_fusion",
@@ -131,6 +152,9 @@ def lib() -> C.CDLL:
     l.afft_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     l.afft_convert_bf16.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_int32, C.c_void_p]
+    l.afft_convert_operand.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_int32, C.c_int32, C.c_void_p]
+    l.afft_convert_operand.restype = C.c_int
     l.afft_layernorm.argtypes = [C.POINTER(LayerNormDesc), C.c_void_p]
     l.afft_attention.argtypes = [C.POINTER(AttentionDesc), C.c_void_p]
     l.afft_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
@@ -217,7 +241,7 @@ def gemm(a, w, *, a_lo=None, w_lo=None, bias=None, res=None, res_mod=0, act=ACT_
     d.a_hi, d.a_lo, d.lda = ptr(a), ptr(a_lo), a.stride(0)
     d.w_hi, d.w_lo, d.ldw = ptr(w), ptr(w_lo), w.stride(0)
     d.M, d.N, d.K = (M if M is not None else a.shape[0]), w.shape[0], w.shape[1]
-    d.strict = 1 if a_lo is not None else 0
+    d.precision = PREC_BF16X3 if a_lo is not None else (PREC_FP16 if a.dtype == torch.float16 else PREC_BF16)
     d.bias = ptr(bias)
     d.res, d.ld_res, d.res_mod = ptr(res), (res.stride(0) if res is not None else 0), res_mod
     d.act = act
@@ -242,6 +266,7 @@ def layernorm(x, gamma, beta, eps, *, rows=None, ldx=None, y_f32=None, y_hi=None
     d.aux_mod, d.aux_stride = aux[0], aux[1]
     d.aux_rem = aux[2] if len(aux) > 2 else 0
     d.aux_f32, d.aux_hi, d.aux_lo = ptr(aux_f32), ptr(aux_hi), ptr(aux_lo)
+    d.out_fp16 = int(any(t is not None and t.dtype == torch.float16 for t in (y_hi, aux_hi)))
     fa = next((t for t in (aux_f32, aux_hi, aux_lo) if t is not None), None)
     d.ld_aux = fa.stride(0) if fa is not None else 0
     check(lib().afft_layernorm(C.byref(d), current_stream_ptr(x.device)))
@@ -256,7 +281,7 @@ def attention(qkv, n_seq, L, H, head_dim, *, mask=0, T=1, out_hi, out_lo=None, p
     base = qkv.data_ptr()
     d.q, d.k, d.v = base, base + D * es, base + 2 * D * es
     d.ldq = d.ldk = d.ldv = qkv.stride(0)
-    d.in_f32 = 1 if qkv.dtype == torch.float32 else 0
+    d.in_dtype = {torch.float32: DT_F32, torch.float16: DT_FP16}.get(qkv.dtype, DT_BF16)
     d.n_seq, d.L, d.H, d.head_dim = n_seq, L, H, head_dim
     d.scale = scale if scale is not None else head_dim ** -0.5
     d.mask, d.T = mask, T

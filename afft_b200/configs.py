@@ -128,6 +128,18 @@ def named_config(name: str):
         # Linear mapping with use_layernorm=true, sparse_mapping=false (feature_mapping.py:58-67)
         "ek100_sa_linear_ln": (lambda: _with_mapping(model_cfg(ek3, depth=2, fp_layers=2), "linear", use_layernorm=True,
                                                      sparse_mapping=False), 10, {"action": 3806}, 16),
+        # options of the fusers no shipped experiment switches on but the constructors accept:
+        # three classifier heads (future_prediction.py:97-122,144-153 with num_classes = {action, verb, noun})
+        "ek100_sa_3head": (lambda: model_cfg(ek3, depth=2, fp_layers=2), 10, {"action": 3806, "verb": 97, "noun": 300}, 16),
+        # SA-Fuser with modality embedding and a frame-level modality token (fusion.py:300-317,338-353)
+        "ek100_sa_modenc_flt": (lambda: model_cfg(ek3, depth=2, fp_layers=2, fuser_kwargs=dict(
+            modal_encoding=True, frame_level_token=True, temporal_sequence_length=10)), 10, {"action": 3806}, 16),
+        # SA-Fuser with cross_attn=True: a token does not attend to itself (fusion.py:330-335)
+        "ek100_sa_cross_attn": (lambda: model_cfg(ek3, depth=2, fp_layers=2, fuser_kwargs=dict(cross_attn=True)),
+                                10, {"action": 3806}, 16),
+        # T-SA-Fuser without frame-level token: per-timestep mean over the modalities (fusion.py:211-214)
+        "ek100_tsa_mean": (lambda: model_cfg(ek4, fuser="T-SA-Fuser", depth=2, fp_layers=2, fuser_kwargs=dict(
+            modal_encoding=True, frame_level_token=False, temporal_sequence_length=None)), 10, {"action": 3806}, 16),
     }
     if name not in table:
         raise KeyError(f"unknown config {name}; have {sorted(table)}")

@@ -35,7 +35,7 @@ static int cuda_fail(const char* what, cudaError_t e) {
   return fail(AFFT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-extern "C" int afft_abi_version(void) { return 4; }
+extern "C" int afft_abi_version(void) { return 5; }
 extern "C" const char* afft_last_error(void) { return g_err.c_str(); }
 
 static int device_sm_count(int* out) {
@@ -61,7 +61,8 @@ static int device_sm_count(int* out) {
 // ================================================================================================
 // stateless operators
 // ================================================================================================
-static int run_gemm(const afft_gemm_desc& d, int num_sms, cudaStream_t stream, const SplitKScratch* sk = nullptr) {
+static int run_gemm(const afft_gemm_desc& d, int num_sms, cudaStream_t stream, const SplitKScratch* sk = nullptr,
+                    unsigned long long* t_end = nullptr) {
   GemmOperands g;
   g.a = static_cast<const bf16*>(d.a_hi);
   g.a_lo = static_cast<const bf16*>(d.a_lo);
@@ -91,7 +92,11 @@ static int run_gemm(const afft_gemm_desc& d, int num_sms, cudaStream_t stream, c
   if (ep.act < ACT_NONE || ep.act > ACT_GATE) return fail(AFFT_ERR_INVALID, "gemm: unknown activation");
   if (ep.act == ACT_GATE && ep.res == nullptr) return fail(AFFT_ERR_INVALID, "gemm: AFFT_ACT_GATE needs the gated operand in res");
   std::string err;
-  if (!launch_gemm(g, ep, d.strict != 0, d.force_block_n, num_sms, stream, &err, sk)) return fail(AFFT_ERR_CUDA, err);
+  if (d.precision < AFFT_PREC_BF16 || d.precision > AFFT_PREC_FP16) return fail(AFFT_ERR_INVALID, "gemm: unknown precision");
+  if (d.precision == AFFT_PREC_FP16 && (ep.out_lo != nullptr || g.a_lo != nullptr || g.w_lo != nullptr))
+    return fail(AFFT_ERR_INVALID, "gemm: AFFT_PREC_FP16 takes no lo operands / outputs");
+  const int mode = d.precision == AFFT_PREC_BF16X3 ? MODE_BF16X3 : (d.precision == AFFT_PREC_FP16 ? MODE_FP16 : MODE_BF16);
+  if (!launch_gemm(g, ep, mode, d.force_block_n, num_sms, stream, &err, sk, t_end)) return fail(AFFT_ERR_CUDA, err);
   return AFFT_OK;
 }
 
@@ -104,15 +109,16 @@ extern "C" int afft_gemm(const afft_gemm_desc* d, void* stream) {
 }
 
 static int run_convert(const float* src, long long lds, int rows, int cols, bf16* hi, bf16* lo, long long ldd,
-                       int transpose, cudaStream_t stream) {
+                       int transpose, cudaStream_t stream, int fp16 = 0, unsigned long long* t_end = nullptr) {
   if (src == nullptr || hi == nullptr || rows <= 0 || cols <= 0) return fail(AFFT_ERR_INVALID, "convert: bad argument");
+  if (fp16 && lo != nullptr) return fail(AFFT_ERR_INVALID, "convert: fp16 operands have no lo part");
   if (transpose) {
     dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-    convert_transpose_f32_bf16_kernel<<<grid, block, 0, stream>>>(src, lds, rows, cols, hi, lo, ldd);
+    convert_transpose_f32_bf16_kernel<<<grid, block, 0, stream>>>(src, lds, rows, cols, hi, lo, ldd, fp16);
   } else {
     const long long total = static_cast<long long>(rows) * cols;
     int blocks = static_cast<int>(std::min<long long>((total / 8 + 255) / 256 + 1, 148 * 16));
-    convert_f32_bf16_kernel<<<blocks, 256, 0, stream>>>(src, lds, rows, cols, hi, lo, ldd);
+    convert_f32_bf16_kernel<<<blocks, 256, 0, stream>>>(src, lds, rows, cols, hi, lo, ldd, fp16, t_end);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail("convert launch", e);
@@ -123,6 +129,14 @@ extern "C" int afft_convert_bf16(const float* src, int64_t lds, int32_t rows, in
                                  int64_t ldd, int32_t transpose, void* stream) {
   return run_convert(src, lds, rows, cols, static_cast<bf16*>(hi), static_cast<bf16*>(lo), ldd, transpose,
                      static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int afft_convert_operand(const float* src, int64_t lds, int32_t rows, int32_t cols, void* hi, void* lo,
+                                    int64_t ldd, int32_t transpose, int32_t precision, void* stream) {
+  if (precision < AFFT_PREC_BF16 || precision > AFFT_PREC_FP16) return fail(AFFT_ERR_INVALID, "convert: unknown precision");
+  if (precision == AFFT_PREC_BF16X3 && lo == nullptr) return fail(AFFT_ERR_INVALID, "convert: AFFT_PREC_BF16X3 needs the lo output");
+  return run_convert(src, lds, rows, cols, static_cast<bf16*>(hi), static_cast<bf16*>(lo), ldd, transpose,
+                     static_cast<cudaStream_t>(stream), precision == AFFT_PREC_FP16 ? 1 : 0);
 }
 
 static int run_layernorm(const LayerNormArgs& a, cudaStream_t stream) {
@@ -182,6 +196,9 @@ extern "C" int afft_layernorm(const afft_layernorm_desc* d, void* stream) {
   a.aux_hi = static_cast<bf16*>(d->aux_hi);
   a.aux_lo = static_cast<bf16*>(d->aux_lo);
   a.ld_aux = d->ld_aux;
+  a.out_fp16 = d->out_fp16 != 0;
+  a.t_end = nullptr;
+  if (a.out_fp16 && (a.y_lo != nullptr || a.aux_lo != nullptr)) return fail(AFFT_ERR_INVALID, "layernorm: fp16 outputs have no lo part");
   return run_layernorm(a, static_cast<cudaStream_t>(stream));
 }
 
@@ -224,9 +241,9 @@ static int launch_attention_tokens(const AttentionArgs& a, cudaStream_t stream) 
   return AFFT_OK;
 }
 
-template <int L>
+template <int L, bool FP16>
 static int launch_attention_tokens_mma(const AttentionArgs& a, cudaStream_t stream) {
-  auto kern = attention_tokens_mma_kernel<L>;
+  auto kern = attention_tokens_mma_kernel<L, FP16>;
   const int smem = a.H * 3 * 16 * (256 * 2 + 16);
   static int configured[64] = {0};
   int dev = 0;
@@ -243,9 +260,9 @@ static int launch_attention_tokens_mma(const AttentionArgs& a, cudaStream_t stre
   return AFFT_OK;
 }
 
-template <int HD, int LP, int NW = 4>
+template <int HD, int LP, int NW, bool FP16>
 static int launch_attention_mma(const AttentionArgs& a, cudaStream_t stream) {
-  auto kern = attention_mma_kernel<HD, LP, NW>;
+  auto kern = attention_mma_kernel<HD, LP, NW, FP16>;
   constexpr int smem = AttnMmaSmem<HD, LP>::kBytes;
   static bool configured[64] = {false};
   int dev = 0;
@@ -261,37 +278,50 @@ static int launch_attention_mma(const AttentionArgs& a, cudaStream_t stream) {
   return AFFT_OK;
 }
 
-static int run_attention(const AttentionArgs& a, int head_dim, bool in_f32, cudaStream_t stream) {
+template <bool FP16>
+static int run_attention_mma_tokens(const AttentionArgs& a, cudaStream_t stream) {
+  switch (a.L) {
+    case 2: return launch_attention_tokens_mma<2, FP16>(a, stream);
+    case 3: return launch_attention_tokens_mma<3, FP16>(a, stream);
+    case 4: return launch_attention_tokens_mma<4, FP16>(a, stream);
+    case 5: return launch_attention_tokens_mma<5, FP16>(a, stream);
+    default: return launch_attention_tokens_mma<6, FP16>(a, stream);
+  }
+}
+
+// in_dtype: AFFT_DT_BF16 / AFFT_DT_F32 / AFFT_DT_FP16
+static int run_attention(const AttentionArgs& a, int head_dim, int in_dtype, cudaStream_t stream) {
   if (a.q == nullptr || a.k == nullptr || a.v == nullptr || a.out_hi == nullptr)
     return fail(AFFT_ERR_INVALID, "attention: null pointer");
   if (a.L < 1 || a.L > 64) return fail(AFFT_ERR_INVALID, "attention: sequence length must be in [1, 64]");
   if (a.n_seq <= 0 || a.H <= 0) return fail(AFFT_ERR_INVALID, "attention: empty problem");
+  if (in_dtype < AFFT_DT_BF16 || in_dtype > AFFT_DT_FP16) return fail(AFFT_ERR_INVALID, "attention: unknown input dtype");
+  const bool in_f32 = in_dtype == AFFT_DT_F32, fp16 = in_dtype == AFFT_DT_FP16;
+  if (fp16 && a.out_lo != nullptr) return fail(AFFT_ERR_INVALID, "attention: fp16 outputs have no lo part");
   static const int use_mma = [] { const char* v = getenv("AFFT_ATTN_MMA"); return v == nullptr ? 1 : atoi(v); }();
-  // few modality tokens per timestep (SA-Fuser): tensor-core kernel for bf16 inputs, register-resident
+  // few modality tokens per timestep (SA-Fuser): tensor-core kernel for 16-bit inputs, register-resident
   // warp-per-(timestep, head) kernel for fp32 inputs (strict mode)
   if (head_dim == 256 && a.L >= 2 && a.L <= 6 && (a.mask == 0 || a.mask == 3)) {
-    if (use_mma && !in_f32 && a.out_lo == nullptr && a.H <= 8) {
-      switch (a.L) {
-        case 2: return launch_attention_tokens_mma<2>(a, stream);
-        case 3: return launch_attention_tokens_mma<3>(a, stream);
-        case 4: return launch_attention_tokens_mma<4>(a, stream);
-        case 5: return launch_attention_tokens_mma<5>(a, stream);
-        default: return launch_attention_tokens_mma<6>(a, stream);
-      }
-    }
-    return in_f32 ? launch_attention_tokens<float>(a, stream) : launch_attention_tokens<bf16>(a, stream);
+    if (use_mma && !in_f32 && a.out_lo == nullptr && a.H <= 8)
+      return fp16 ? run_attention_mma_tokens<true>(a, stream) : run_attention_mma_tokens<false>(a, stream);
+    return in_f32 ? launch_attention_tokens<float>(a, stream)
+                  : (fp16 ? launch_attention_tokens<__half>(a, stream) : launch_attention_tokens<bf16>(a, stream));
   }
-  // short sequences with bf16 inputs (GPT-2 predictor, CA-Fuser): tensor-core (mma.sync) kernel
+  // short sequences with 16-bit inputs (GPT-2 predictor, CA-Fuser): tensor-core (mma.sync) kernel
   if (use_mma && !in_f32 && a.out_lo == nullptr && a.L > 6 && a.mask >= 0 && a.mask <= 2) {
     if (a.L <= 32) {
-      if (head_dim == 256) return launch_attention_mma<256, 32>(a, stream);
-      if (head_dim == 512) return launch_attention_mma<512, 32>(a, stream);
+      if (head_dim == 256) return fp16 ? launch_attention_mma<256, 32, 4, true>(a, stream) : launch_attention_mma<256, 32, 4, false>(a, stream);
+      if (head_dim == 512) return fp16 ? launch_attention_mma<512, 32, 4, true>(a, stream) : launch_attention_mma<512, 32, 4, false>(a, stream);
     } else if (head_dim == 256) {  // T-SA-Fuser: up to 64 tokens, block-causal
-      return launch_attention_mma<256, 64, 8>(a, stream);
+      return fp16 ? launch_attention_mma<256, 64, 8, true>(a, stream) : launch_attention_mma<256, 64, 8, false>(a, stream);
     }
   }
-  if (head_dim == 256) return in_f32 ? launch_attention<float, 256>(a, stream) : launch_attention<bf16, 256>(a, stream);
-  if (head_dim == 512) return in_f32 ? launch_attention<float, 512>(a, stream) : launch_attention<bf16, 512>(a, stream);
+  if (head_dim == 256)
+    return in_f32 ? launch_attention<float, 256>(a, stream)
+                  : (fp16 ? launch_attention<__half, 256>(a, stream) : launch_attention<bf16, 256>(a, stream));
+  if (head_dim == 512)
+    return in_f32 ? launch_attention<float, 512>(a, stream)
+                  : (fp16 ? launch_attention<__half, 512>(a, stream) : launch_attention<bf16, 512>(a, stream));
   return fail(AFFT_ERR_INVALID, "attention: head_dim must be 256 or 512");
 }
 
@@ -317,7 +347,8 @@ extern "C" int afft_attention(const afft_attention_desc* d, void* stream) {
   a.p_outer = d->p_outer;
   a.p_inner_stride = d->p_inner_stride;
   a.p_inner = d->p_inner > 0 ? d->p_inner : 1;
-  return run_attention(a, d->head_dim, d->in_f32 != 0, static_cast<cudaStream_t>(stream));
+  a.t_end = nullptr;
+  return run_attention(a, d->head_dim, d->in_dtype, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int afft_marginalize_topk(const float* logits, int64_t ld, int32_t B, int32_t A, const int32_t* verb_of,
@@ -523,9 +554,10 @@ struct afft_handle {
   PairBuf yn, attn_n, fn;         // [B, G], [B, G], [B, 4G]
   int launches = 0;
   int fuser_chunk = 0;
-  // optional per-launch event timing
+  // optional per-launch timing: slot 0 = start mark, slot 1 + i = latest exit time of launch i (device %globaltimer)
   bool profile = false;
-  std::vector<cudaEvent_t> ev;  // 2 per record
+  unsigned long long* prof_slots = nullptr;
+  cudaStream_t prof_stream = nullptr;
   afft_profile prof;
 };
 
@@ -628,6 +660,7 @@ extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
   *out = nullptr;
   const afft_config& c = *cfg;
   if (c.fuser_kind < 0 || c.fuser_kind > AFFT_FUSER_NONE) return fail(AFFT_ERR_INVALID, "create: unknown fuser_kind");
+  if (c.precision < AFFT_PREC_BF16 || c.precision > AFFT_PREC_FP16) return fail(AFFT_ERR_INVALID, "create: unknown precision");
   const bool no_fuser = c.fuser_kind == AFFT_FUSER_NONE;
   if (c.n_mod < 1 || c.n_mod > AFFT_MAX_MODS - 1) return fail(AFFT_ERR_INVALID, "create: n_mod out of range");
   if (c.n_cls < 1 || c.n_cls > AFFT_MAX_CLS) return fail(AFFT_ERR_INVALID, "create: n_cls out of range");
@@ -675,7 +708,7 @@ extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
   if (const char* env = getenv("AFFT_FUSER_CHUNK")) h->fuser_chunk = atoi(env);
 
   // ---- workspace ----
-  const bool strict = c.strict != 0;
+  const bool strict = c.precision == AFFT_PREC_BF16X3;
   const size_t B = c.max_batch, T = c.T, D = c.dim, G = c.gpt_dim;
   const size_t OL = c.fp_output_len;
   const size_t R2 = B * T, R1 = R2 * h->n_slots, RP = B * (T + OL);
@@ -760,7 +793,7 @@ extern "C" void afft_destroy(afft_handle* h) {
     if (kv.second.f32) cudaFree(kv.second.f32);
   }
   if (h->ws) cudaFree(h->ws);
-  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  if (h->prof_slots) cudaFree(h->prof_slots);
   delete h;
 }
 
@@ -793,7 +826,8 @@ extern "C" int afft_set_weight(afft_handle* h, const char* name, const float* sr
   cudaError_t e = cudaSetDevice(h->cfg.device);
   if (e != cudaSuccess) return hfail(h, AFFT_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
   Tensor& t = h->w[name];
-  const bool strict = h->cfg.strict != 0;
+  const bool strict = h->cfg.precision == AFFT_PREC_BF16X3;
+  const int fp16 = h->cfg.precision == AFFT_PREC_FP16 ? 1 : 0;
   if (ex.pack == Pack::F32) {
     if (t.f32 == nullptr) {
       e = cudaMalloc(reinterpret_cast<void**>(&t.f32), align_up(numel * 4, 256));
@@ -822,8 +856,8 @@ extern "C" int afft_set_weight(afft_handle* h, const char* name, const float* sr
   t.rows = N;
   t.cols = K;
   int rc = (ex.pack == Pack::Gemm)
-               ? run_convert(src, K, static_cast<int>(N), static_cast<int>(K), t.hi, t.lo, K, 0, stream)
-               : run_convert(src, N, static_cast<int>(K), static_cast<int>(N), t.hi, t.lo, K, 1, stream);
+               ? run_convert(src, K, static_cast<int>(N), static_cast<int>(K), t.hi, t.lo, K, 0, stream, fp16)
+               : run_convert(src, N, static_cast<int>(K), static_cast<int>(N), t.hi, t.lo, K, 1, stream, fp16);
   if (rc != AFFT_OK) h->err = g_err;
   return rc;
 }
@@ -854,7 +888,8 @@ namespace {
 struct Fwd {
   afft_handle* h;
   cudaStream_t stream;
-  bool strict;
+  bool strict;  // AFFT_PREC_BF16X3
+  bool fp16;    // AFFT_PREC_FP16
   int rc = AFFT_OK;
 
   const Tensor* W(const std::string& n) {
@@ -873,16 +908,12 @@ struct Fwd {
     }
     if (r == AFFT_OK) ++h->launches;
   }
-  // event pair around one launch when profiling is on
-  int prof_begin(int cat, int M = 0, int N = 0, int K = 0) {
-    if (!h->profile || h->prof.n >= AFFT_MAX_PROFILE_RECS) return -1;
+  // profiling slot of the next launch (nullptr when profiling is off): the kernel itself records its exit time
+  unsigned long long* prof_slot(int cat, int M = 0, int N = 0, int K = 0) {
+    if (!h->profile || h->prof.n >= AFFT_MAX_PROFILE_RECS) return nullptr;
     const int i = h->prof.n++;
     h->prof.recs[i] = {cat, M, N, K, 0.f};
-    cudaEventRecord(h->ev[2 * i], stream);
-    return i;
-  }
-  void prof_end(int i) {
-    if (i >= 0) cudaEventRecord(h->ev[2 * i + 1], stream);
+    return h->prof_slots + 1 + i;
   }
 
   // out = epilogue(A . W^T)
@@ -902,7 +933,7 @@ struct Fwd {
     d.M = M;
     d.N = static_cast<int>(w->rows);
     d.K = static_cast<int>(w->cols);
-    d.strict = strict ? 1 : 0;
+    d.precision = h->cfg.precision;
     d.bias = bias;
     d.res = res;
     d.ld_res = ld_res;
@@ -918,9 +949,7 @@ struct Fwd {
     d.row_group = row_group;
     d.row_stride = row_stride;
     d.row_off = row_off;
-    const int pi = prof_begin(AFFT_CAT_GEMM, d.M, d.N, d.K);
-    check(run_gemm(d, h->num_sms, stream, &h->splitk));
-    prof_end(pi);
+    check(run_gemm(d, h->num_sms, stream, &h->splitk, prof_slot(AFFT_CAT_GEMM, d.M, d.N, d.K)));
   }
 
   void layernorm(const float* x, long long ldx, int rows, int dim, const std::string& name, float eps, const PairBuf* yb,
@@ -951,9 +980,9 @@ struct Fwd {
     a.aux_hi = aux_b ? aux_b->hi : nullptr;
     a.aux_lo = aux_b ? aux_b->lo : nullptr;
     a.ld_aux = ld_aux;
-    const int pi = prof_begin(AFFT_CAT_LAYERNORM);
+    a.out_fp16 = fp16 ? 1 : 0;
+    a.t_end = prof_slot(AFFT_CAT_LAYERNORM);
     check(run_layernorm(a, stream));
-    prof_end(pi);
   }
 
   // q/k/v live in one buffer of row pitch ld (elements) at column offsets qo/ko/vo
@@ -980,36 +1009,30 @@ struct Fwd {
     a.p_outer = p_outer;
     a.p_inner_stride = p_inner_stride;
     a.p_inner = p_inner > 0 ? p_inner : 1;
-    const int pi = prof_begin(AFFT_CAT_ATTENTION);
-    check(run_attention(a, hd, strict, stream));
-    prof_end(pi);
+    a.t_end = prof_slot(AFFT_CAT_ATTENTION);
+    check(run_attention(a, hd, strict ? AFFT_DT_F32 : (fp16 ? AFFT_DT_FP16 : AFFT_DT_BF16), stream));
   }
 
   void convert(const float* src, long long lds, int rows, int cols, const PairBuf& dst, long long ldd) {
     if (!ok()) return;
-    const int pi = prof_begin(AFFT_CAT_OTHER);
-    check(run_convert(src, lds, rows, cols, dst.hi, dst.lo, ldd, 0, stream));
-    prof_end(pi);
+    check(run_convert(src, lds, rows, cols, dst.hi, dst.lo, ldd, 0, stream, fp16 ? 1 : 0, prof_slot(AFFT_CAT_OTHER)));
   }
 
-  void assemble(const AssembleArgs& a) {
+  void assemble(AssembleArgs a) {
     if (!ok()) return;
     const long long rows = static_cast<long long>(a.B) * a.T * a.n_slots;
     const int blocks = static_cast<int>(std::min<long long>(rows, 148 * 16));
-    const int pi = prof_begin(AFFT_CAT_OTHER);
+    a.t_end = prof_slot(AFFT_CAT_OTHER);
     assemble_tokens_kernel<<<blocks, 256, 0, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     check(e == cudaSuccess ? AFFT_OK : cuda_fail("assemble launch", e));
-    prof_end(pi);
   }
 
   void add_row_vector(float* out, const float* in, const float* vec, int rows, int dim) {
     if (!ok()) return;
-    const int pi = prof_begin(AFFT_CAT_OTHER);
-    add_row_vector_kernel<<<(rows * dim + 255) / 256, 256, 0, stream>>>(out, in, vec, rows, dim);
+    add_row_vector_kernel<<<(rows * dim + 255) / 256, 256, 0, stream>>>(out, in, vec, rows, dim, prof_slot(AFFT_CAT_OTHER));
     cudaError_t e = cudaGetLastError();
     check(e == cudaSuccess ? AFFT_OK : cuda_fail("add_row_vector launch", e));
-    prof_end(pi);
   }
 
   void decode_attention(const void* cache, const void* fresh, long long ld, int B, int T, int H, int hd, int n_new,
@@ -1027,27 +1050,26 @@ struct Fwd {
     a.scale = 1.0f / sqrtf(static_cast<float>(hd));
     a.out_hi = out.hi;
     a.out_lo = out.lo;
+    a.t_end = prof_slot(AFFT_CAT_ATTENTION);
     const int blocks = (B * H + 3) / 4;
-    const int pi = prof_begin(AFFT_CAT_ATTENTION);
     if (hd == 512) {
       if (strict) attention_decode_kernel<float, 512><<<blocks, 128, 0, stream>>>(a);
+      else if (fp16) attention_decode_kernel<__half, 512><<<blocks, 128, 0, stream>>>(a);
       else attention_decode_kernel<bf16, 512><<<blocks, 128, 0, stream>>>(a);
     } else {
       if (strict) attention_decode_kernel<float, 256><<<blocks, 128, 0, stream>>>(a);
+      else if (fp16) attention_decode_kernel<__half, 256><<<blocks, 128, 0, stream>>>(a);
       else attention_decode_kernel<bf16, 256><<<blocks, 128, 0, stream>>>(a);
     }
     cudaError_t e = cudaGetLastError();
     check(e == cudaSuccess ? AFFT_OK : cuda_fail("decode attention launch", e));
-    prof_end(pi);
   }
 
   void embed_table(float* table, const float* pos, const float* mod, int T, int dim) {
     if (!ok()) return;
-    const int pi = prof_begin(AFFT_CAT_OTHER);
-    embed_table_kernel<<<(T * dim + 255) / 256, 256, 0, stream>>>(table, pos, mod, T, dim);
+    embed_table_kernel<<<(T * dim + 255) / 256, 256, 0, stream>>>(table, pos, mod, T, dim, prof_slot(AFFT_CAT_OTHER));
     cudaError_t e = cudaGetLastError();
     check(e == cudaSuccess ? AFFT_OK : cuda_fail("embed_table launch", e));
-    prof_end(pi);
   }
 };
 
@@ -1349,9 +1371,16 @@ extern "C" int afft_forward(afft_handle* h, int32_t B, const afft_io* io, void* 
   Fwd F;
   F.h = h;
   F.stream = static_cast<cudaStream_t>(stream_);
-  F.strict = c.strict != 0;
+  F.strict = c.precision == AFFT_PREC_BF16X3;
+  F.fp16 = c.precision == AFFT_PREC_FP16;
   h->launches = 0;
   h->prof.n = 0;
+  if (h->profile) {  // clear the slots and record the start mark (stream-ordered ahead of the first kernel)
+    h->prof_stream = F.stream;
+    e = cudaMemsetAsync(h->prof_slots, 0, (AFFT_MAX_PROFILE_RECS + 1) * sizeof(unsigned long long), F.stream);
+    if (e != cudaSuccess) return hfail(h, AFFT_ERR_CUDA, std::string("profile reset: ") + cudaGetErrorString(e));
+    prof_mark_kernel<<<1, 32, 0, F.stream>>>(h->prof_slots);
+  }
   const int chunk = (h->fuser_chunk > 0) ? h->fuser_chunk : B;
   for (int b0 = 0; b0 < B && F.ok(); b0 += chunk) run_fuser(F, *io, b0, std::min(chunk, B - b0));
   if (F.ok()) run_predictor(F, *io, B);
@@ -1375,14 +1404,10 @@ extern "C" int afft_plan_ksplit(int32_t tiles, int32_t slots, int32_t num_kb, in
 
 extern "C" int afft_profile_enable(afft_handle* h, int32_t enable) {
   if (h == nullptr) return fail(AFFT_ERR_INVALID, "profile_enable: null handle");
-  if (enable && h->ev.empty()) {
+  if (enable && h->prof_slots == nullptr) {
     cudaError_t e = cudaSetDevice(h->cfg.device);
-    if (e != cudaSuccess) return hfail(h, AFFT_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
-    h->ev.resize(2 * AFFT_MAX_PROFILE_RECS);
-    for (auto& ev : h->ev) {
-      e = cudaEventCreate(&ev);
-      if (e != cudaSuccess) return hfail(h, AFFT_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e));
-    }
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->prof_slots), (AFFT_MAX_PROFILE_RECS + 1) * sizeof(unsigned long long));
+    if (e != cudaSuccess) return hfail(h, AFFT_ERR_CUDA, std::string("profile_enable: ") + cudaGetErrorString(e));
   }
   h->profile = enable != 0;
   h->prof.n = 0;
@@ -1391,10 +1416,18 @@ extern "C" int afft_profile_enable(afft_handle* h, int32_t enable) {
 
 extern "C" int afft_profile_read(afft_handle* h, afft_profile* out) {
   if (h == nullptr || out == nullptr) return fail(AFFT_ERR_INVALID, "profile_read: null argument");
-  for (int i = 0; i < h->prof.n; ++i) {
-    cudaError_t e = cudaEventSynchronize(h->ev[2 * i + 1]);
-    if (e == cudaSuccess) e = cudaEventElapsedTime(&h->prof.recs[i].ms, h->ev[2 * i], h->ev[2 * i + 1]);
+  if (h->prof.n > 0) {
+    static thread_local unsigned long long host[AFFT_MAX_PROFILE_RECS + 1];
+    cudaError_t e = cudaStreamSynchronize(h->prof_stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(host, h->prof_slots, (h->prof.n + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return hfail(h, AFFT_ERR_CUDA, std::string("profile_read: ") + cudaGetErrorString(e));
+    unsigned long long prev = host[0];
+    for (int i = 0; i < h->prof.n; ++i) {  // launch i owns (end of launch i - 1, end of launch i]
+      const unsigned long long t = host[1 + i] > prev ? host[1 + i] : prev;
+      h->prof.recs[i].ms = static_cast<float>(static_cast<double>(t - prev) * 1e-6);
+      prev = t;
+    }
   }
   *out = h->prof;
   return AFFT_OK;

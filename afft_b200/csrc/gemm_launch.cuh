@@ -90,7 +90,7 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_tensormap_encoder(std::string* err)
 // bf16 matrix [rows, cols] with row pitch ld (elements) -> 2-D tiled map, box = 64 x box_rows,
 // SWIZZLE_128B, out-of-bounds elements read as zero.
 inline bool make_tmap_bf16(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld,
-                           int box_rows, std::string* err) {
+                           int box_rows, std::string* err, bool fp16 = false) {
   auto enc = get_tensormap_encoder(err);
   if (enc == nullptr) return false;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (ld * 2) % 16 != 0) {
@@ -101,7 +101,7 @@ inline bool make_tmap_bf16(CUtensorMap* out, const void* ptr, long long rows, lo
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estride[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box,
+  CUresult r = enc(out, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box,
                    estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -133,12 +133,12 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
-template <int BLOCK_N, int SPLIT, int EPI>
+template <int BLOCK_N, int MODE, int EPI>
 inline cudaError_t launch_gemm_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal,
                                        const CUtensorMap& tbl, const GemmEpilogue& ep, int M, int N, int K,
                                        int num_sms, GemmSched sched, const SplitKScratch* sk, cudaStream_t stream) {
-  using T = GemmTraits<BLOCK_N, SPLIT>;
-  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT, EPI>;
+  using T = GemmTraits<BLOCK_N, MODE>;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, MODE, EPI>;
   static bool attr_set[64] = {false};  // per variant and device; benign race (idempotent)
   int dev = 0;
   cudaGetDevice(&dev);
@@ -157,12 +157,12 @@ inline cudaError_t launch_gemm_variant(const CUtensorMap& ta, const CUtensorMap&
   return launch_pdl(kern, dim3(grid), dim3(kGemmThreads), T::kSmemBytes, stream, ta, tb, tal, tbl, ep, M, N, K, sched);
 }
 
-template <int SPLIT, int EPI>
+template <int MODE, int EPI>
 inline cudaError_t launch_gemm_2cta_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal,
                                             const CUtensorMap& tbl, const GemmEpilogue& ep, int M, int N, int K,
                                             int num_sms, GemmSched sched, const SplitKScratch* sk, cudaStream_t stream) {
-  using T = Gemm2Traits<SPLIT>;
-  auto kern = gemm_bf16_tcgen05_2cta_kernel<SPLIT, EPI>;
+  using T = Gemm2Traits<MODE>;
+  auto kern = gemm_bf16_tcgen05_2cta_kernel<MODE, EPI>;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -211,14 +211,21 @@ inline const GemmSched& default_sched() {
     g.ksplit = 1;
     g.partials = nullptr;
     g.counters = nullptr;
+    g.t_end = nullptr;
     return g;
   }();
   return s;
 }
 
-// Returns false and fills *err on failure.  force_block_n: 0 = auto.
-inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, bool strict, int force_block_n,
-                        int num_sms, cudaStream_t stream, std::string* err, const SplitKScratch* sk = nullptr) {
+// Returns false and fills *err on failure.  mode: MODE_BF16 / MODE_FP16 / MODE_BF16X3.  force_block_n: 0 = auto.
+inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, int mode, int force_block_n,
+                        int num_sms, cudaStream_t stream, std::string* err, const SplitKScratch* sk = nullptr,
+                        unsigned long long* t_end = nullptr) {
+  if (mode != MODE_BF16 && mode != MODE_FP16 && mode != MODE_BF16X3) {
+    if (err) *err = "gemm: unknown precision mode";
+    return false;
+  }
+  const bool strict = (mode == MODE_BF16X3), fp16 = (mode == MODE_FP16);
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) {
     if (err) *err = "gemm: empty problem";
     return false;
@@ -243,8 +250,8 @@ inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, bool stri
   if (force_block_n == 512) bn = 256;
   const int b_box_rows = use_2cta ? 128 : bn;  // each CTA of a pair loads half of the 256-row weight tile
   CUtensorMap ta, tb, tal, tbl;
-  if (!make_tmap_bf16(&ta, g.a, g.M, g.K, g.lda, kBlockM, err)) return false;
-  if (!make_tmap_bf16(&tb, g.w, g.N, g.K, g.ldw, b_box_rows, err)) return false;
+  if (!make_tmap_bf16(&ta, g.a, g.M, g.K, g.lda, kBlockM, err, fp16)) return false;
+  if (!make_tmap_bf16(&tb, g.w, g.N, g.K, g.ldw, b_box_rows, err, fp16)) return false;
   if (strict) {
     if (!make_tmap_bf16(&tal, g.a_lo, g.M, g.K, g.lda, kBlockM, err)) return false;
     if (!make_tmap_bf16(&tbl, g.w_lo, g.N, g.K, g.ldw, b_box_rows, err)) return false;
@@ -254,11 +261,13 @@ inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, bool stri
   }
   // epilogue variant: the combinations the forward path uses are compiled with constant flags
   const int code = epi_code(ep.act, ep.res != nullptr, ep.out_f32 != nullptr, ep.out_hi != nullptr);
-  const bool lo_ok = (ep.out_hi == nullptr) || ((ep.out_lo != nullptr) == strict);  // specialised kernels tie lo to SPLIT
+  const bool lo_ok = (ep.out_hi == nullptr) || ((ep.out_lo != nullptr) == strict);  // specialised kernels tie lo to MODE
   cudaError_t e = cudaErrorInvalidValue;
+  GemmSched sched0 = default_sched();
+  sched0.t_end = t_end;
 #define AFFT_LAUNCH(BN, SP, EP)                                                                                       \
-  e = (BN == 512) ? launch_gemm_2cta_variant<SP, EP>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, default_sched(), sk, stream) \
-                  : launch_gemm_variant<(BN == 512 ? 256 : BN), SP, EP>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, default_sched(), sk, stream)
+  e = (BN == 512) ? launch_gemm_2cta_variant<SP, EP>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, sched0, sk, stream) \
+                  : launch_gemm_variant<(BN == 512 ? 256 : BN), SP, EP>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, sched0, sk, stream)
 #define AFFT_DISPATCH_EPI(BN, SP)                                                            \
   do {                                                                                       \
     if (!lo_ok || ep.act > ACT_GELU_TANH) { AFFT_LAUNCH(BN, SP, EPI_GENERIC); break; }                               \
@@ -273,9 +282,11 @@ inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, bool stri
     }                                                                                        \
   } while (0)
   if (strict) {
-    if (use_2cta) AFFT_DISPATCH_EPI(512, 3); else if (bn == 256) AFFT_DISPATCH_EPI(256, 3); else AFFT_DISPATCH_EPI(128, 3);
+    if (use_2cta) AFFT_DISPATCH_EPI(512, MODE_BF16X3); else if (bn == 256) AFFT_DISPATCH_EPI(256, MODE_BF16X3); else AFFT_DISPATCH_EPI(128, MODE_BF16X3);
+  } else if (fp16) {
+    if (use_2cta) AFFT_DISPATCH_EPI(512, MODE_FP16); else if (bn == 256) AFFT_DISPATCH_EPI(256, MODE_FP16); else AFFT_DISPATCH_EPI(128, MODE_FP16);
   } else {
-    if (use_2cta) AFFT_DISPATCH_EPI(512, 1); else if (bn == 256) AFFT_DISPATCH_EPI(256, 1); else AFFT_DISPATCH_EPI(128, 1);
+    if (use_2cta) AFFT_DISPATCH_EPI(512, MODE_BF16); else if (bn == 256) AFFT_DISPATCH_EPI(256, MODE_BF16); else AFFT_DISPATCH_EPI(128, MODE_BF16);
   }
 #undef AFFT_DISPATCH_EPI
 #undef AFFT_LAUNCH

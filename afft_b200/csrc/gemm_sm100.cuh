@@ -18,12 +18,18 @@
 //                               residual / casts -> coalesced 16-B global accesses.  Two warps per 32-lane
 //                               TMEM quadrant (= 32 output rows), interleaved over 32-column slabs.
 //
-// SPLIT == 3 is the "strict" mode: both operands are given as bf16 hi/lo
-// pairs (x = hi + lo to ~16 mantissa bits) and the kernel accumulates hi.hi + hi.lo + lo.hi into
-// the same TMEM tile, i.e. three tensor-core passes per K slab for ~fp32-grade products.
+// MODE selects the operand arithmetic:
+//   MODE_BF16   (1)  bf16 operands, one tensor-core pass
+//   MODE_FP16   (2)  fp16 operands, one pass at the same tensor rate: 11 significand bits instead of 8, i.e. 8x less
+//                    operand rounding than bf16 (the mode that keeps the reference's top-5 at speed); the host side
+//                    saturates on conversion, accumulation / residual / LayerNorm / softmax stay fp32
+//   MODE_BF16X3 (3)  "strict" (SURVEY.md Appendix D): both operands are bf16 hi/lo pairs (x = hi + lo to ~16
+//                    mantissa bits) and the kernel accumulates hi.hi + hi.lo + lo.hi into the same TMEM tile,
+//                    i.e. three tensor-core passes per K slab for ~fp32-grade products.
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "ptx_sm100.cuh"
 
@@ -35,6 +41,7 @@ constexpr int kUmmaK = 16;
 constexpr int kNumEpilogueWarps = 8;   // two per TMEM lane quadrant
 constexpr int kGemmThreads = 128 + 32 * kNumEpilogueWarps;
 
+enum : int { MODE_BF16 = 1, MODE_FP16 = 2, MODE_BF16X3 = 3 };
 enum : int { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_GELU_TANH = 2, ACT_RELU = 3, ACT_GATE = 4 };
 
 // Everything the epilogue may do with an accumulator tile.  Pointers may be null (= skip).
@@ -70,17 +77,18 @@ struct GemmSched {
   int ksplit;           // 1 = off
   float* partials;      // >= grid CTAs * 128 * BLOCK_N floats
   unsigned* counters;   // >= tiles * (CTAs per tile) * kNumEpilogueWarps, zero before the first launch
+  unsigned long long* t_end;  // profiling slot (ptx::prof_mark_end) or nullptr
 };
 
-template <int BLOCK_N, int SPLIT>
+template <int BLOCK_N, int MODE>
 struct GemmTraits {
   static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N must be 128 or 256");
-  static_assert(SPLIT == 1 || SPLIT == 3, "SPLIT must be 1 (bf16) or 3 (bf16x3)");
-  static constexpr int kPairs = (SPLIT == 3) ? 2 : 1;
+  static_assert(MODE >= 1 && MODE <= 3, "MODE must be MODE_BF16, MODE_FP16 or MODE_BF16X3");
+  static constexpr int kPairs = (MODE == MODE_BF16X3) ? 2 : 1;
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
   static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr uint32_t kStageBytes = kPairs * (kABytes + kBBytes);
-  static constexpr int kStages = (SPLIT == 3) ? (BLOCK_N == 256 ? 2 : 3) : (BLOCK_N == 256 ? 4 : 6);
+  static constexpr int kStages = (MODE == MODE_BF16X3) ? (BLOCK_N == 256 ? 2 : 3) : (BLOCK_N == 256 ? 4 : 6);
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
   static constexpr uint32_t kBarrierBytes = 256;
   // per epilogue warp: one 32 x 32 fp32 transposition tile (4 KB, 16-B chunks XOR-swizzled by row)
@@ -145,12 +153,27 @@ __device__ __forceinline__ float gelu_erf_bf16out(float x) {
   return fmaf(-x, r, x);
 }
 
+__device__ __forceinline__ float gelu_erf_fp16out(float x) {
+  // Same construction as gelu_erf_bf16out with two more terms for results rounded to fp16: g(x) / x = c0 + c1 x^2 +
+  // c2 x^4 + c3 x^6 + c4 x^8, minimax on x Phi(x) over |x| <= 9: max |error| 3.2e-6 (below the fp16 half-ulp for
+  // |x Phi(x)| >= 0.014 and 75x below the rounding of O(1) values); 10 issue slots.
+  const float l2e2 = 2.0f * 1.4426950408889634f;
+  const float x2 = fminf(x * x, 81.0f);
+  float w = fmaf(l2e2 * 1.13808805438112e-06f, x2, l2e2 * -3.09436089875207e-05f);
+  w = fmaf(w, x2, l2e2 * -0.0001227816512535698f);
+  w = fmaf(w, x2, l2e2 * 0.03646477196229458f);
+  w = fmaf(w, x2, l2e2 * 0.7978301352938109f);
+  const float e = mufu_ex2(x * w);
+  const float r = mufu_rcp(1.0f + e);
+  return fmaf(-x, r, x);
+}
+
 // --------------------------------------------------------------------------------------------
 // Epilogue variants.  The combinations the forward path uses are compiled with their flags as
 // constants (the 8-row unrolled epilogue of the all-runtime version is ~60 KB of SASS and thrashes
 // the instruction cache - ncu: stall_no_inst dominated); EPI_GENERIC keeps every flag at run time
 // for the stateless afft_gemm() entry point.
-//   bit 0-1 activation, bit 2 residual, bit 3 fp32 output, bit 4 bf16 output (+ lo when SPLIT == 3)
+//   bit 0-1 activation, bit 2 residual, bit 3 fp32 output, bit 4 bf16 output (+ lo when MODE == MODE_BF16X3)
 // ACT_RELU / ACT_GATE (ablation mappings, MATT) exist in the generic variant only.
 // --------------------------------------------------------------------------------------------
 constexpr int EPI_GENERIC = -1;
@@ -158,37 +181,52 @@ constexpr int epi_code(int act, bool res, bool f32, bool bf16) {
   return act | (res ? 4 : 0) | (f32 ? 8 : 0) | (bf16 ? 16 : 0);
 }
 
-template <int EPI, int SPLIT>
+template <int EPI, int MODE>
 struct EpiFlags {
   static constexpr bool kGeneric = EPI < 0;
   __device__ static __forceinline__ int act(const GemmEpilogue& ep) { return kGeneric ? ep.act : (EPI & 3); }
   __device__ static __forceinline__ bool res(const GemmEpilogue& ep) { return kGeneric ? ep.res != nullptr : (EPI & 4) != 0; }
   __device__ static __forceinline__ bool f32(const GemmEpilogue& ep) { return kGeneric ? ep.out_f32 != nullptr : (EPI & 8) != 0; }
   __device__ static __forceinline__ bool bf16(const GemmEpilogue& ep) { return kGeneric ? ep.out_hi != nullptr : (EPI & 16) != 0; }
-  __device__ static __forceinline__ bool lo(const GemmEpilogue& ep) { return kGeneric ? ep.out_lo != nullptr : (SPLIT == 3); }
+  __device__ static __forceinline__ bool lo(const GemmEpilogue& ep) { return kGeneric ? ep.out_lo != nullptr : (MODE == MODE_BF16X3); }
 };
 
 __device__ __forceinline__ uint32_t pack2_bf16_rn(float a, float b) {  // a -> low half
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// 16-bit operand packing of the epilogue: bf16 (round to nearest even), or fp16 saturated to the finite range
+__device__ __forceinline__ uint32_t pack2_f16_sat(float a, float b) {  // a -> low half; one F2FP.SATFINITE instruction
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+template <int MODE>
+__device__ __forceinline__ uint32_t pack2_operand(float a, float b) {
+  return MODE == MODE_FP16 ? pack2_f16_sat(a, b) : pack2_bf16_rn(a, b);
+}
 __device__ __forceinline__ float bf16_lo_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16_hi_f32(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
 
-template <int EPI, int SPLIT>
+template <int EPI, int MODE>
 __device__ __forceinline__ float4 epilogue_math(const GemmEpilogue& ep, float4 x, const float4& bias4) {
-  using F = EpiFlags<EPI, SPLIT>;
+  using F = EpiFlags<EPI, MODE>;
   x.x += bias4.x;
   x.y += bias4.y;
   x.z += bias4.z;
   x.w += bias4.w;
   const int act = F::act(ep);
   if (act == ACT_GELU_ERF) {
-    if (!F::kGeneric && SPLIT == 1 && !F::f32(ep)) {  // result only ever stored as bf16
+    if (!F::kGeneric && MODE == MODE_BF16 && !F::f32(ep)) {  // result only ever stored as bf16
       x.x = gelu_erf_bf16out(x.x);
       x.y = gelu_erf_bf16out(x.y);
       x.z = gelu_erf_bf16out(x.z);
       x.w = gelu_erf_bf16out(x.w);
+    } else if (!F::kGeneric && MODE == MODE_FP16 && !F::f32(ep)) {  // result only ever stored as fp16
+      x.x = gelu_erf_fp16out(x.x);
+      x.y = gelu_erf_fp16out(x.y);
+      x.z = gelu_erf_fp16out(x.z);
+      x.w = gelu_erf_fp16out(x.w);
     } else {
       x.x = gelu_erf(x.x);
       x.y = gelu_erf(x.y);
@@ -215,9 +253,9 @@ __device__ __forceinline__ float4 epilogue_math(const GemmEpilogue& ep, float4 x
 }
 
 // residual combine: + for the residual stream, * for ACT_GATE (the "residual" is the gated value)
-template <int EPI, int SPLIT>
+template <int EPI, int MODE>
 __device__ __forceinline__ float epilogue_combine(const GemmEpilogue& ep, float x, float r) {
-  if (EpiFlags<EPI, SPLIT>::kGeneric && ep.act == ACT_GATE) return x * r;
+  if (EpiFlags<EPI, MODE>::kGeneric && ep.act == ACT_GATE) return x * r;
   return x + r;
 }
 
@@ -236,9 +274,9 @@ struct EpiRowPtrs {
   __nv_bfloat16* lo[8];
 };
 
-template <int EPI, int SPLIT>
+template <int EPI, int MODE>
 __device__ __forceinline__ void epilogue_row_ptrs(const GemmEpilogue& ep, int row0, int sub_row, EpiRowPtrs& P) {
-  using F = EpiFlags<EPI, SPLIT>;
+  using F = EpiFlags<EPI, MODE>;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = row0 + i * 4 + sub_row;
@@ -258,10 +296,10 @@ __device__ __forceinline__ void epilogue_row_ptrs(const GemmEpilogue& ep, int ro
 // chain.  A/B builds timed on the same box say otherwise: none of the three helps.  The limiter is the L2 -> SM
 // operand feed the epilogue's residual reads share with the TMA loads; the switches stay for
 // re-testing once the main loop's feed changes.  Lane (sub_row, chunk) covers row chunk * 4 + sub_row: 4 x 128 B.
-template <int EPI, int SPLIT, int BLOCK_N>
+template <int EPI, int MODE, int BLOCK_N>
 __device__ __forceinline__ void epilogue_prefetch_residual(const GemmEpilogue& ep, int row0, int n_tile0, int egrp, int lane,
                                                            int M, int N) {
-  using F = EpiFlags<EPI, SPLIT>;
+  using F = EpiFlags<EPI, MODE>;
 #ifndef AFFT_RES_PREFETCH
 #define AFFT_RES_PREFETCH 0  // A/B on one box (tools/gemm_time.py): no gain (60.7 us off vs 61.9 us on, K = 1024 projection)
 #endif
@@ -287,11 +325,11 @@ __device__ __forceinline__ void epilogue_prefetch_residual(const GemmEpilogue& e
 // one instead of sitting between the shared-memory read and the add.  All residual loads of a slab are issued
 // before any of its stores (the residual may alias the output: in-place stream); loads of the NEXT slab touch other
 // columns, so they may be issued ahead of this slab's stores.
-template <int EPI, int SPLIT>
+template <int EPI, int MODE>
 __device__ __forceinline__ void epilogue_slab_full(const GemmEpilogue& ep, uint32_t stage, int sub_row, int chunk, int col,
                                                    const EpiRowPtrs& P, const float4& bias4, float4 (&r)[8], bool preloaded,
                                                    int next_col) {
-  using F = EpiFlags<EPI, SPLIT>;
+  using F = EpiFlags<EPI, MODE>;
   float4 x[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -305,11 +343,11 @@ __device__ __forceinline__ void epilogue_slab_full(const GemmEpilogue& ep, uint3
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      x[i] = epilogue_math<EPI, SPLIT>(ep, x[i], bias4);
-      x[i].x = epilogue_combine<EPI, SPLIT>(ep, x[i].x, r[i].x);
-      x[i].y = epilogue_combine<EPI, SPLIT>(ep, x[i].y, r[i].y);
-      x[i].z = epilogue_combine<EPI, SPLIT>(ep, x[i].z, r[i].z);
-      x[i].w = epilogue_combine<EPI, SPLIT>(ep, x[i].w, r[i].w);
+      x[i] = epilogue_math<EPI, MODE>(ep, x[i], bias4);
+      x[i].x = epilogue_combine<EPI, MODE>(ep, x[i].x, r[i].x);
+      x[i].y = epilogue_combine<EPI, MODE>(ep, x[i].y, r[i].y);
+      x[i].z = epilogue_combine<EPI, MODE>(ep, x[i].z, r[i].z);
+      x[i].w = epilogue_combine<EPI, MODE>(ep, x[i].w, r[i].w);
     }
     if (next_col >= 0) {
 #pragma unroll
@@ -317,7 +355,7 @@ __device__ __forceinline__ void epilogue_slab_full(const GemmEpilogue& ep, uint3
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = epilogue_math<EPI, SPLIT>(ep, x[i], bias4);
+    for (int i = 0; i < 8; ++i) x[i] = epilogue_math<EPI, MODE>(ep, x[i], bias4);
   }
   if (F::f32(ep)) {
 #pragma unroll
@@ -326,7 +364,7 @@ __device__ __forceinline__ void epilogue_slab_full(const GemmEpilogue& ep, uint3
   if (F::bf16(ep)) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const uint32_t h01 = pack2_bf16_rn(x[i].x, x[i].y), h23 = pack2_bf16_rn(x[i].z, x[i].w);
+      const uint32_t h01 = pack2_operand<MODE>(x[i].x, x[i].y), h23 = pack2_operand<MODE>(x[i].z, x[i].w);
       *reinterpret_cast<uint2*>(P.hi[i] + col) = make_uint2(h01, h23);
       if (F::lo(ep)) {
         const uint32_t l01 = pack2_bf16_rn(x[i].x - bf16_lo_f32(h01), x[i].y - bf16_hi_f32(h01));
@@ -339,10 +377,10 @@ __device__ __forceinline__ void epilogue_slab_full(const GemmEpilogue& ep, uint3
 
 // Edge slab (partial rows and/or columns): element-wise predicates; kept out of line so the interior path
 // stays small in the instruction cache.
-template <int EPI, int SPLIT>
+template <int EPI, int MODE>
 __device__ __noinline__ void epilogue_slab_edge(const GemmEpilogue& ep, uint32_t stage, int sub_row, int chunk, int row0,
                                                 int col, int M, int N) {
-  using F = EpiFlags<EPI, SPLIT>;
+  using F = EpiFlags<EPI, MODE>;
   if (col >= N) return;
   float bias[4] = {0.f, 0.f, 0.f, 0.f};
   if (ep.bias != nullptr) {
@@ -360,19 +398,23 @@ __device__ __noinline__ void epilogue_slab_edge(const GemmEpilogue& ep, uint32_t
     if (ep.row_group > 0)
       orow = static_cast<long long>(row / ep.row_group) * ep.row_stride + (row % ep.row_group) + ep.row_off;
     float4 x4 = lds128(stage + static_cast<uint32_t>(rl) * 128u + static_cast<uint32_t>((chunk ^ (rl & 7)) * 16));
-    x4 = epilogue_math<EPI, SPLIT>(ep, x4, bias4);
+    x4 = epilogue_math<EPI, MODE>(ep, x4, bias4);
     float x[4] = {x4.x, x4.y, x4.z, x4.w};
     const long long rrow = (ep.res_mod > 0) ? static_cast<long long>(row % ep.res_mod) : orow;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       if (col + e >= N) break;
       float v = x[e];
-      if (F::res(ep)) v = epilogue_combine<EPI, SPLIT>(ep, v, ep.res[rrow * ep.ld_res + col + e]);
+      if (F::res(ep)) v = epilogue_combine<EPI, MODE>(ep, v, ep.res[rrow * ep.ld_res + col + e]);
       if (F::f32(ep)) ep.out_f32[orow * ep.ld_f32 + col + e] = v;
       if (F::bf16(ep)) {
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        ep.out_hi[orow * ep.ld_bf16 + col + e] = h;
-        if (F::lo(ep)) ep.out_lo[orow * ep.ld_bf16 + col + e] = __float2bfloat16_rn(v - __bfloat162float(h));
+        if (MODE == MODE_FP16) {
+          reinterpret_cast<__half*>(ep.out_hi)[orow * ep.ld_bf16 + col + e] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+        } else {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v);
+          ep.out_hi[orow * ep.ld_bf16 + col + e] = h;
+          if (F::lo(ep)) ep.out_lo[orow * ep.ld_bf16 + col + e] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
       }
     }
   }
@@ -426,7 +468,7 @@ __device__ __forceinline__ void splitk_sum_to_stage(const float* tile_partial0, 
 // `release_tmem()` then hands the accumulator back to the MMA warp.  With split-K the warp that arrives last on
 // the band counter runs pass 1: same slab loop, but the staging tile is filled with the in-order sum of the
 // partials instead of from TMEM.
-template <int EPI, int SPLIT, int BLOCK_N, typename ReleaseFn>
+template <int EPI, int MODE, int BLOCK_N, typename ReleaseFn>
 __device__ __forceinline__ void epilogue_unit(const GemmEpilogue& ep, int ksplit, uint32_t stage, uint32_t t_row, int quad, int egrp,
                                               int lane, int row0, int n_tile0, int M, int N, float* cta_partial,
                                               const float* tile_partial0, size_t split_stride, unsigned* counter,
@@ -440,9 +482,9 @@ __device__ __forceinline__ void epilogue_unit(const GemmEpilogue& ep, int ksplit
   const int chunk = lane & 7;       // 16-byte chunk = 4 fp32 columns
   const bool rows_full = (row0 + 32 <= M);
   EpiRowPtrs rp;
-  epilogue_row_ptrs<EPI, SPLIT>(ep, row0, sub_row, rp);
-  if (ksplit == 1 && next_row0 >= 0) epilogue_prefetch_residual<EPI, SPLIT, BLOCK_N>(ep, next_row0, next_n_tile0, egrp, lane, M, N);
-  using F = EpiFlags<EPI, SPLIT>;
+  epilogue_row_ptrs<EPI, MODE>(ep, row0, sub_row, rp);
+  if (ksplit == 1 && next_row0 >= 0) epilogue_prefetch_residual<EPI, MODE, BLOCK_N>(ep, next_row0, next_n_tile0, egrp, lane, M, N);
+  using F = EpiFlags<EPI, MODE>;
 #ifndef AFFT_RES_AHEAD
 #define AFFT_RES_AHEAD 0  // measured (A/B on one box): 61.6 us without vs 67.4 us with, on the K = 1024 projection
 #endif
@@ -490,11 +532,11 @@ __device__ __forceinline__ void epilogue_unit(const GemmEpilogue& ep, int ksplit
           if (ep.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
           // the next slab's residual is requested now if that slab is an interior one too
           const bool next_full = kResAhead && r_loaded && have && n_tile0 + cn * 32 + 32 <= N;
-          epilogue_slab_full<EPI, SPLIT>(ep, stage, sub_row, chunk, col, rp, bias4, r, r_loaded,
+          epilogue_slab_full<EPI, MODE>(ep, stage, sub_row, chunk, col, rp, bias4, r, r_loaded,
                                          next_full ? n_tile0 + cn * 32 + chunk * 4 : -1);
           r_loaded = next_full;
         } else {
-          epilogue_slab_edge<EPI, SPLIT>(ep, stage, sub_row, chunk, row0, col, M, N);
+          epilogue_slab_edge<EPI, MODE>(ep, stage, sub_row, chunk, row0, col, M, N);
         }
       }
       __syncwarp();  // staging tile is rewritten by the next slab
@@ -519,13 +561,13 @@ __device__ __forceinline__ void epilogue_unit(const GemmEpilogue& ep, int ksplit
 // --------------------------------------------------------------------------------------------
 // The kernel
 // --------------------------------------------------------------------------------------------
-template <int BLOCK_N, int SPLIT, int EPI>
+template <int BLOCK_N, int MODE, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                          const __grid_constant__ CUtensorMap tm_a_lo,
                          const __grid_constant__ CUtensorMap tm_b_lo, const __grid_constant__ GemmEpilogue ep, const int M,
                          const int N, const int K, const __grid_constant__ GemmSched sched) {
-  using T = GemmTraits<BLOCK_N, SPLIT>;
+  using T = GemmTraits<BLOCK_N, MODE>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_raw_u32 = ptx::smem_u32(smem_raw);
   const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;  // SWIZZLE_128B tiles: 1024-B aligned
@@ -553,7 +595,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_a);
     ptx::prefetch_tensormap(&tm_b);
-    if (SPLIT == 3) {
+    if (MODE == MODE_BF16X3) {
       ptx::prefetch_tensormap(&tm_a_lo);
       ptx::prefetch_tensormap(&tm_b_lo);
     }
@@ -593,7 +635,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           ptx::mbar_arrive_expect_tx(fb, T::kStageBytes);
           ptx::tma_load_2d(a_dst, &tm_a, fb, kb * kBlockK, m_idx * kBlockM, sched.policy_a);
           ptx::tma_load_2d(b_dst, &tm_b, fb, kb * kBlockK, n_idx * BLOCK_N, sched.policy_b);
-          if (SPLIT == 3) {
+          if (MODE == MODE_BF16X3) {
             const uint32_t a_lo_dst = b_dst + T::kBBytes;
             const uint32_t b_lo_dst = a_lo_dst + T::kABytes;
             ptx::tma_load_2d(a_lo_dst, &tm_a_lo, fb, kb * kBlockK, m_idx * kBlockM, sched.policy_a);
@@ -609,7 +651,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, BLOCK_N);
+      constexpr uint32_t idesc = ptx::make_idesc_f16_f32(kBlockM, BLOCK_N, MODE == MODE_FP16);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         const int split = unit % ksplit;
@@ -628,7 +670,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                               ptx::make_smem_desc_sw128(b_src + k * (kUmmaK * 2)), idesc,
                               ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
-          if (SPLIT == 3) {
+          if (MODE == MODE_BF16X3) {
             const uint32_t a_lo_src = b_src + T::kBBytes;
             const uint32_t b_lo_src = a_lo_src + T::kABytes;
 #pragma unroll
@@ -670,7 +712,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       const int row0 = m_idx * kBlockM + quad * 32;
       // residual of the NEXT unit of this CTA -> L2 (and of this one, for the CTA's first unit)
       if (unit == static_cast<int>(blockIdx.x) && ksplit == 1)
-        epilogue_prefetch_residual<EPI, SPLIT, BLOCK_N>(ep, row0, n_idx * BLOCK_N, egrp, lane, M, N);
+        epilogue_prefetch_residual<EPI, MODE, BLOCK_N>(ep, row0, n_idx * BLOCK_N, egrp, lane, M, N);
       int next_row0 = -1, next_n0 = 0;
       if (unit + static_cast<int>(gridDim.x) < num_units) {
         const int nt = (unit + static_cast<int>(gridDim.x)) / ksplit;
@@ -681,7 +723,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
       const uint32_t empty_addr = tmem_empty_bar(acc);
-      epilogue_unit<EPI, SPLIT, BLOCK_N>(ep, ksplit, stage, t_row, quad, egrp, lane, row0, n_idx * BLOCK_N, M, N,
+      epilogue_unit<EPI, MODE, BLOCK_N>(ep, ksplit, stage, t_row, quad, egrp, lane, row0, n_idx * BLOCK_N, M, N,
                                          sched.partials + static_cast<size_t>(unit) * kTileFloats,
                                          sched.partials + static_cast<size_t>(tile) * ksplit * kTileFloats, kTileFloats,
                                          sched.counters + tile * kNumEpilogueWarps + (warp - 4), next_row0, next_n0,
@@ -697,6 +739,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc<T::kTmemCols>(tmem_base);
   }
+  if (warp == 0) ptx::prof_mark_end(sched.t_end);
 }
 
 
@@ -711,13 +754,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 //   - each CTA's epilogue warps drain their own 128 x 256 TMEM accumulator and arrive (remotely for the peer)
 //     on the leader's tmem-empty barrier
 // --------------------------------------------------------------------------------------------
-template <int SPLIT>
+template <int MODE>
 struct Gemm2Traits {
-  static constexpr int kPairs = (SPLIT == 3) ? 2 : 1;
+  static constexpr int kPairs = (MODE == MODE_BF16X3) ? 2 : 1;
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;       // 128 rows of A
   static constexpr uint32_t kBBytes = 128 * kBlockK * 2;           // this CTA's half of the 256-row B tile
   static constexpr uint32_t kStageBytes = kPairs * (kABytes + kBBytes);
-  static constexpr int kStages = (SPLIT == 3) ? 3 : 6;
+  static constexpr int kStages = (MODE == MODE_BF16X3) ? 3 : 6;
   static constexpr uint32_t kTmemCols = 512;                       // 2 accumulators x 256 columns
   static constexpr uint32_t kBarrierBytes = 256;
   static constexpr uint32_t kStagingBytes = kNumEpilogueWarps * 4096;
@@ -725,13 +768,13 @@ struct Gemm2Traits {
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
-template <int SPLIT, int EPI>
+template <int MODE, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                               const __grid_constant__ CUtensorMap tm_a_lo,
                               const __grid_constant__ CUtensorMap tm_b_lo, const __grid_constant__ GemmEpilogue ep, const int M,
                               const int N, const int K, const __grid_constant__ GemmSched sched) {
-  using T = Gemm2Traits<SPLIT>;
+  using T = Gemm2Traits<MODE>;
   constexpr int BLOCK_N = 256;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_raw_u32 = ptx::smem_u32(smem_raw);
@@ -762,7 +805,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_a);
     ptx::prefetch_tensormap(&tm_b);
-    if (SPLIT == 3) {
+    if (MODE == MODE_BF16X3) {
       ptx::prefetch_tensormap(&tm_a_lo);
       ptx::prefetch_tensormap(&tm_b_lo);
     }
@@ -805,7 +848,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
           else ptx::mbar_arrive_cluster(fb_leader);
           ptx::tma_load_2d_2cta(a_dst, &tm_a, fb_leader, kb * kBlockK, a_row, sched.policy_a);
           ptx::tma_load_2d_2cta(b_dst, &tm_b, fb_leader, kb * kBlockK, b_row, sched.policy_b);
-          if (SPLIT == 3) {
+          if (MODE == MODE_BF16X3) {
             const uint32_t a_lo_dst = b_dst + T::kBBytes;
             const uint32_t b_lo_dst = a_lo_dst + T::kABytes;
             ptx::tma_load_2d_2cta(a_lo_dst, &tm_a_lo, fb_leader, kb * kBlockK, a_row, sched.policy_a);
@@ -821,7 +864,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
   } else if (warp == 1) {
     // ======================= MMA issuer (leader CTA only) =======================
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(256, BLOCK_N);
+      constexpr uint32_t idesc = ptx::make_idesc_f16_f32(256, BLOCK_N, MODE == MODE_FP16);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
         const int split = unit % ksplit;
@@ -839,7 +882,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
             ptx::umma_bf16_ss_2cta(d_tmem, ptx::make_smem_desc_sw128(a_src + k * (kUmmaK * 2)),
                                    ptx::make_smem_desc_sw128(b_src + k * (kUmmaK * 2)), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
-          if (SPLIT == 3) {
+          if (MODE == MODE_BF16X3) {
             const uint32_t a_lo_src = b_src + T::kBBytes;
             const uint32_t b_lo_src = a_lo_src + T::kABytes;
 #pragma unroll
@@ -878,7 +921,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
       const int row0 = m_idx * 256 + static_cast<int>(rank) * 128 + quad * 32;
       // residual of the NEXT unit of this CTA pair -> L2 (and of this one, for the pair's first unit)
       if (unit == cluster_id && ksplit == 1)
-        epilogue_prefetch_residual<EPI, SPLIT, BLOCK_N>(ep, row0, n_idx * BLOCK_N, egrp, lane, M, N);
+        epilogue_prefetch_residual<EPI, MODE, BLOCK_N>(ep, row0, n_idx * BLOCK_N, egrp, lane, M, N);
       int next_row0 = -1, next_n0 = 0;
       if (unit + num_clusters < num_units) {
         const int nt = (unit + num_clusters) / ksplit;
@@ -889,7 +932,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
       const uint32_t empty_leader = ptx::mapa(tmem_empty_bar(acc), 0);
-      epilogue_unit<EPI, SPLIT, BLOCK_N>(ep, ksplit, stage, t_row, quad, egrp, lane, row0, n_idx * BLOCK_N, M, N,
+      epilogue_unit<EPI, MODE, BLOCK_N>(ep, ksplit, stage, t_row, quad, egrp, lane, row0, n_idx * BLOCK_N, M, N,
                                          sched.partials + (static_cast<size_t>(unit) * 2 + rank) * kHalfTile,
                                          sched.partials + (static_cast<size_t>(tile) * ksplit * 2 + rank) * kHalfTile, 2 * kHalfTile,
                                          sched.counters + (tile * 2 + rank) * kNumEpilogueWarps + (warp - 4), next_row0, next_n0,
@@ -905,6 +948,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc_2cta<T::kTmemCols>(tmem_base);
   }
+  if (warp == 0) ptx::prof_mark_end(sched.t_end);
 }
 
 }  // namespace afft

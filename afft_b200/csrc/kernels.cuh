@@ -4,8 +4,11 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <type_traits>
 
 #include "ptx_sm100.cuh"
 
@@ -29,6 +32,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {  // a -> low
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// fp16 operand pair, saturated to the finite range (MODE_FP16: activations that feed the next GEMM)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {  // a -> low half; one F2FP.SATFINITE instruction
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// the 16-bit GEMM operand format of this launch: bf16, or fp16 when `fp16` (warp-uniform)
+__device__ __forceinline__ uint32_t pack_op16x2(float a, float b, bool fp16) {
+  return fp16 ? pack_f16x2_sat(a, b) : pack_bf16x2(a, b);
+}
+__device__ __forceinline__ void unpack_f16x8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
 // residual part of the hi/lo split: bf16(a - float(bf16(a)))
 __device__ __forceinline__ float bf16_residual(float a) {
   return a - __bfloat162float(__float2bfloat16_rn(a));
@@ -48,7 +70,7 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
 // ------------------------------------------------------------------------------------------------
 __global__ void convert_f32_bf16_kernel(const float* __restrict__ src, long long lds, int rows, int cols,
                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                        long long ldd) {
+                                        long long ldd, int fp16, unsigned long long* t_end = nullptr) {
   // fast path: 8 elements per thread (two 16-byte loads, one 16-byte store per output) when rows are 8-element
   // multiples and every pitch / base is 16-byte aligned - weights (per training step) and most activations
   const bool vec = (cols % 8 == 0) && (lds % 4 == 0) && (ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) &&
@@ -62,13 +84,15 @@ __global__ void convert_f32_bf16_kernel(const float* __restrict__ src, long long
       const int c = static_cast<int>(i - r * c8) * 8;
       const float4 v0 = *reinterpret_cast<const float4*>(src + r * lds + c);
       const float4 v1 = *reinterpret_cast<const float4*>(src + r * lds + c + 4);
-      const uint4 h = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+      const uint4 h = make_uint4(pack_op16x2(v0.x, v0.y, fp16), pack_op16x2(v0.z, v0.w, fp16), pack_op16x2(v1.x, v1.y, fp16),
+                                 pack_op16x2(v1.z, v1.w, fp16));
       *reinterpret_cast<uint4*>(hi + r * ldd + c) = h;
       if (lo != nullptr)
         *reinterpret_cast<uint4*>(lo + r * ldd + c) =
             make_uint4(pack_bf16x2(bf16_residual(v0.x), bf16_residual(v0.y)), pack_bf16x2(bf16_residual(v0.z), bf16_residual(v0.w)),
                        pack_bf16x2(bf16_residual(v1.x), bf16_residual(v1.y)), pack_bf16x2(bf16_residual(v1.z), bf16_residual(v1.w)));
     }
+    ptx::prof_mark_end(t_end);
     return;
   }
   const long long total = static_cast<long long>(rows) * cols;
@@ -76,16 +100,21 @@ __global__ void convert_f32_bf16_kernel(const float* __restrict__ src, long long
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
     const float v = src[r * lds + c];
+    if (fp16) {
+      reinterpret_cast<__half*>(hi)[r * ldd + c] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+      continue;
+    }
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     hi[r * ldd + c] = h;
     if (lo != nullptr) lo[r * ldd + c] = __float2bfloat16_rn(v - __bfloat162float(h));
   }
+  ptx::prof_mark_end(t_end);
 }
 
 // dst[c, r] = src[r, c]   (src [rows, cols] pitch lds; dst [cols, rows] pitch ldd)
 __global__ void convert_transpose_f32_bf16_kernel(const float* __restrict__ src, long long lds, int rows,
                                                   int cols, __nv_bfloat16* __restrict__ hi,
-                                                  __nv_bfloat16* __restrict__ lo, long long ldd) {
+                                                  __nv_bfloat16* __restrict__ lo, long long ldd, int fp16) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -97,6 +126,10 @@ __global__ void convert_transpose_f32_bf16_kernel(const float* __restrict__ src,
     const int c = c0 + j, r = r0 + threadIdx.x;
     if (c < cols && r < rows) {
       const float v = tile[threadIdx.x][j];
+      if (fp16) {
+        reinterpret_cast<__half*>(hi)[c * ldd + r] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+        continue;
+      }
       const __nv_bfloat16 h = __float2bfloat16_rn(v);
       hi[c * ldd + r] = h;
       if (lo != nullptr) lo[c * ldd + r] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -130,10 +163,12 @@ struct LayerNormArgs {
   __nv_bfloat16* aux_hi;
   __nv_bfloat16* aux_lo;
   long long ld_aux;
+  int out_fp16;  // y_hi / aux_hi are fp16 (MODE_FP16) instead of bf16
+  unsigned long long* t_end;  // profiling slot or nullptr
 };
 
 __device__ __forceinline__ void ln_store(const LayerNormArgs& a, int row, bool aux, long long arow, int c4, const float4& y) {
-  const uint2 hi = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+  const uint2 hi = make_uint2(pack_op16x2(y.x, y.y, a.out_fp16), pack_op16x2(y.z, y.w, a.out_fp16));
   if (a.y_f32 != nullptr) reinterpret_cast<float4*>(a.y_f32 + row * a.ldy)[c4] = y;
   if (a.y_hi != nullptr) reinterpret_cast<uint2*>(a.y_hi + row * a.ldy)[c4] = hi;
   if (a.y_lo != nullptr)
@@ -200,7 +235,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs a) {
       y.z = fmaf((v[i].z - mean) * rstd, g.z, b.z);
       y.w = fmaf((v[i].w - mean) * rstd, g.w, b.w);
       if (FAST) {
-        reinterpret_cast<uint2*>(a.y_hi + warp * a.ldy)[c4] = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+        reinterpret_cast<uint2*>(a.y_hi + warp * a.ldy)[c4] =
+            make_uint2(pack_op16x2(y.x, y.y, a.out_fp16), pack_op16x2(y.z, y.w, a.out_fp16));
       } else if (AVG) {
         float4& t = acc[AVG ? i : 0];
         t.x += y.x; t.y += y.y; t.z += y.z; t.w += y.w;
@@ -218,6 +254,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs a) {
       ln_store(a, warp, aux, arow, lane + 32 * i, y);
     }
   }
+  ptx::prof_mark_end(a.t_end);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -238,6 +275,7 @@ struct AssembleArgs {
   int tok_mod;
   const float* pos_emb;  // [>=T, dim] or nullptr
   const float* mod_emb;  // [n_slots, dim] or nullptr
+  unsigned long long* t_end;  // profiling slot or nullptr
 };
 
 __global__ void __launch_bounds__(256) assemble_tokens_kernel(const AssembleArgs a) {
@@ -278,18 +316,20 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const AssembleArgs
       dst[c4] = v;
     }
   }
+  ptx::prof_mark_end(a.t_end);
 }
 
 // table[t, :] = pos_emb[t, :] + (mod_emb ? mod_emb[:] : 0)   for t < T - the additive term a projected
 // modality receives through the GEMM residual input (T-SA-Fuser / CA-Fuser embeddings).
 __global__ void embed_table_kernel(float* __restrict__ table, const float* __restrict__ pos_emb,
-                                   const float* __restrict__ mod_emb, int T, int dim) {
+                                   const float* __restrict__ mod_emb, int T, int dim, unsigned long long* t_end = nullptr) {
   const int total = T * dim;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     float v = (pos_emb != nullptr) ? pos_emb[i] : 0.f;
     if (mod_emb != nullptr) v += mod_emb[i % dim];
     table[i] = v;
   }
+  ptx::prof_mark_end(t_end);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -318,6 +358,7 @@ struct AttentionArgs {
   float* probs;
   long long p_outer, p_inner_stride;
   int p_inner;
+  unsigned long long* t_end;  // profiling slot or nullptr
 };
 
 template <typename TIn, int HD>
@@ -336,7 +377,8 @@ __device__ __forceinline__ void load_row_regs(const TIn* row, int lane, float (&
     const uint4 u = *reinterpret_cast<const uint4*>(row + c * A::kChunkElems + lane * A::kVecElems);
     if constexpr (sizeof(TIn) == 2) {
       float t[8];
-      unpack_bf16x8(u, t);
+      if constexpr (std::is_same<TIn, __half>::value) unpack_f16x8(u, t);
+      else unpack_bf16x8(u, t);
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[c * 8 + e] = t[e];
     } else {
@@ -423,8 +465,9 @@ __global__ void __launch_bounds__(256) attention_small_kernel(const AttentionArg
       const int d0 = c * A::kChunkElems + lane * VE;
       if constexpr (VE == 8) {
         const float* oo = &o[c * 8];
-        uint4 hv = make_uint4(pack_bf16x2(oo[0], oo[1]), pack_bf16x2(oo[2], oo[3]), pack_bf16x2(oo[4], oo[5]),
-                              pack_bf16x2(oo[6], oo[7]));
+        constexpr bool kF16 = std::is_same<TIn, __half>::value;  // 16-bit inputs: the output keeps their format
+        uint4 hv = make_uint4(pack_op16x2(oo[0], oo[1], kF16), pack_op16x2(oo[2], oo[3], kF16), pack_op16x2(oo[4], oo[5], kF16),
+                              pack_op16x2(oo[6], oo[7], kF16));
         *reinterpret_cast<uint4*>(a.out_hi + orow + d0) = hv;
         if (a.out_lo != nullptr) {
           uint4 lv = make_uint4(pack_bf16x2(bf16_residual(oo[0]), bf16_residual(oo[1])),
@@ -445,6 +488,7 @@ __global__ void __launch_bounds__(256) attention_small_kernel(const AttentionArg
       }
     }
   }
+  ptx::prof_mark_end(a.t_end);
 }
 
 
@@ -464,8 +508,9 @@ __device__ __forceinline__ void store_row_regs(__nv_bfloat16* out_hi, __nv_bfloa
     const int d0 = c * A::kChunkElems + lane * VE;
     if constexpr (VE == 8) {
       const float* oo = &o[c * 8];
-      *reinterpret_cast<uint4*>(out_hi + off + d0) = make_uint4(pack_bf16x2(oo[0], oo[1]), pack_bf16x2(oo[2], oo[3]),
-                                                                 pack_bf16x2(oo[4], oo[5]), pack_bf16x2(oo[6], oo[7]));
+      constexpr bool kF16 = std::is_same<TIn, __half>::value;  // 16-bit inputs: the output keeps their format
+      *reinterpret_cast<uint4*>(out_hi + off + d0) = make_uint4(pack_op16x2(oo[0], oo[1], kF16), pack_op16x2(oo[2], oo[3], kF16),
+                                                                 pack_op16x2(oo[4], oo[5], kF16), pack_op16x2(oo[6], oo[7], kF16));
       if (out_lo != nullptr)
         *reinterpret_cast<uint4*>(out_lo + off + d0) =
             make_uint4(pack_bf16x2(bf16_residual(oo[0]), bf16_residual(oo[1])), pack_bf16x2(bf16_residual(oo[2]), bf16_residual(oo[3])),
@@ -537,6 +582,7 @@ __global__ void __launch_bounds__(128) attention_tokens_kernel(const AttentionAr
     if (pr != nullptr && lane < L) pr[i * L + lane] = mine;
     store_row_regs<TIn, HD>(a.out_hi, a.out_lo, (static_cast<long long>(seq) * L + i) * a.ldo + h * HD, lane, o);
   }
+  ptx::prof_mark_end(a.t_end);
 }
 
 
@@ -567,6 +613,19 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// operand format of the warp-level attention kernels: bf16 (MODE_BF16) or fp16 (MODE_FP16)
+template <bool FP16>
+__device__ __forceinline__ void mma_op16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (FP16) mma_f16_16816(d, a, b0, b1);
+  else mma_bf16_16816(d, a, b0, b1);
+}
+
 template <int HD, int LP>
 struct AttnMmaSmem {
   static constexpr int kLP = LP;                  // padded sequence length (LP / 16 m16 tiles): 32 or 64
@@ -583,7 +642,7 @@ struct AttnMmaSmem {
 
 // NW warps per CTA: 4 for sequences up to 32 tokens, 8 for the 50-token T-SA-Fuser sequences (16 score blocks and
 // 64 softmax rows per CTA: twice the warps halve the CTA's serial compute between its load and its store).
-template <int HD, int LP, int NW = 4>
+template <int HD, int LP, int NW = 4, bool FP16 = false>
 __global__ void __launch_bounds__(NW * 32) attention_mma_kernel(const AttentionArgs a) {
   using S = AttnMmaSmem<HD, LP>;
   constexpr int MT = LP / 16;  // 16-row tiles
@@ -651,8 +710,8 @@ __global__ void __launch_bounds__(NW * 32) attention_mma_kernel(const AttentionA
       uint32_t af[4], bf[4];
       ldmatrix_x4(a_addr + ks * 32, af);
       ldmatrix_x4(b_addr + ks * 32, bf);
-      mma_bf16_16816(acc[0], af, bf[0], bf[1]);
-      mma_bf16_16816(acc[1], af, bf[2], bf[3]);
+      mma_op16_16816<FP16>(acc[0], af, bf[0], bf[1]);
+      mma_op16_16816<FP16>(acc[1], af, bf[2], bf[3]);
     }
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
@@ -699,7 +758,10 @@ __global__ void __launch_bounds__(NW * 32) attention_mma_kernel(const AttentionA
     }
 #pragma unroll
     for (int c = 0; c < LP / 32; ++c)
-      reinterpret_cast<__nv_bfloat16*>(sp_ptr + i * S::kPRowBytes)[lane + 32 * c] = __float2bfloat16_rn(p[c]);
+    {
+      if constexpr (FP16) reinterpret_cast<__half*>(sp_ptr + i * S::kPRowBytes)[lane + 32 * c] = __float2half_rn(p[c]);
+      else reinterpret_cast<__nv_bfloat16*>(sp_ptr + i * S::kPRowBytes)[lane + 32 * c] = __float2bfloat16_rn(p[c]);
+    }
   }
   __syncthreads();
 
@@ -727,8 +789,8 @@ __global__ void __launch_bounds__(NW * 32) attention_mma_kernel(const AttentionA
           for (int mt = 0; mt < MT; ++mt) {
             uint32_t pa[4];
             ldmatrix_x4(sp + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * S::kPRowBytes + ks * 32 + (lane >> 4) * 16, pa);
-            mma_bf16_16816(acc[mt][0], pa, vf[0], vf[1]);
-            mma_bf16_16816(acc[mt][1], pa, vf[2], vf[3]);
+            mma_op16_16816<FP16>(acc[mt][0], pa, vf[0], vf[1]);
+            mma_op16_16816<FP16>(acc[mt][1], pa, vf[2], vf[3]);
           }
         }
       }
@@ -738,8 +800,8 @@ __global__ void __launch_bounds__(NW * 32) attention_mma_kernel(const AttentionA
         for (int nt = 0; nt < 2; ++nt) {
           // output rows < L only: the Q region holds L rows and the K / V regions behind it are still being read
           uint8_t* o0 = base + (mt * 16 + g8) * S::kRowBytes + (n0 + nt * 8 + t4 * 2) * 2;
-          if (mt * 16 + g8 < L) *reinterpret_cast<uint32_t*>(o0) = pack_bf16x2(acc[mt][nt][0], acc[mt][nt][1]);
-          if (mt * 16 + g8 + 8 < L) *reinterpret_cast<uint32_t*>(o0 + 8 * S::kRowBytes) = pack_bf16x2(acc[mt][nt][2], acc[mt][nt][3]);
+          if (mt * 16 + g8 < L) *reinterpret_cast<uint32_t*>(o0) = pack_op16x2(acc[mt][nt][0], acc[mt][nt][1], FP16);
+          if (mt * 16 + g8 + 8 < L) *reinterpret_cast<uint32_t*>(o0 + 8 * S::kRowBytes) = pack_op16x2(acc[mt][nt][2], acc[mt][nt][3], FP16);
         }
     }
   }
@@ -749,6 +811,7 @@ __global__ void __launch_bounds__(NW * 32) attention_mma_kernel(const AttentionA
     *reinterpret_cast<uint4*>(a.out_hi + (static_cast<long long>(seq) * L + r) * a.ldo + h * HD + c * 8) =
         *reinterpret_cast<const uint4*>(base + r * S::kRowBytes + c * 16);
   }
+  ptx::prof_mark_end(a.t_end);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -758,7 +821,7 @@ __global__ void __launch_bounds__(NW * 32) attention_mma_kernel(const AttentionA
 // m16n8k16), block-diagonal mask (a token only sees the tokens of its own timestep), softmax on the accumulator
 // fragments, P.V with one k-step per 8 output dims.  Rows are staged per warp with cp.async; no block barrier.
 // ------------------------------------------------------------------------------------------------
-template <int L>
+template <int L, bool FP16 = false>
 __global__ void __launch_bounds__(256) attention_tokens_mma_kernel(const AttentionArgs a) {
   constexpr int HD = 256;
   constexpr int G = 16 / L;
@@ -818,8 +881,8 @@ __global__ void __launch_bounds__(256) attention_tokens_mma_kernel(const Attenti
       uint32_t af[4], bf[4];
       ldmatrix_x4(a_addr + ks * 32, af);
       ldmatrix_x4(b_addr + ks * 32, bf);
-      mma_bf16_16816(acc[0], af, bf[0], bf[1]);
-      mma_bf16_16816(acc[1], af, bf[2], bf[3]);
+      mma_op16_16816<FP16>(acc[0], af, bf[0], bf[1]);
+      mma_op16_16816<FP16>(acc[1], af, bf[2], bf[3]);
     }
   }
   // softmax on the fragments: this thread holds rows g8 and g8 + 8, columns nt * 8 + 2 * t4 + {0, 1}
@@ -861,10 +924,10 @@ __global__ void __launch_bounds__(256) attention_tokens_mma_kernel(const Attenti
     }
   }
   uint32_t pa[4];
-  pa[0] = pack_bf16x2(p[0][0], p[0][1]);
-  pa[1] = pack_bf16x2(p[1][0], p[1][1]);
-  pa[2] = pack_bf16x2(p[0][2], p[0][3]);
-  pa[3] = pack_bf16x2(p[1][2], p[1][3]);
+  pa[0] = pack_op16x2(p[0][0], p[0][1], FP16);
+  pa[1] = pack_op16x2(p[1][0], p[1][1], FP16);
+  pa[2] = pack_op16x2(p[0][2], p[0][3], FP16);
+  pa[3] = pack_op16x2(p[1][2], p[1][3], FP16);
   asm volatile("cp.async.wait_group 0;" ::: "memory");  // V has landed
   __syncwarp();  // ... for every lane; and every lane is done reading Q before the region is reused for the output tile
 #pragma unroll 4
@@ -872,13 +935,13 @@ __global__ void __launch_bounds__(256) attention_tokens_mma_kernel(const Attenti
     uint32_t vf[4];
     ldmatrix_x4_trans(sv + ((lane & 7) + ((lane >> 3) & 1) * 8) * RB + (np * 16 + (lane >> 4) * 8) * 2, vf);
     float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    mma_bf16_16816(o[0], pa, vf[0], vf[1]);
-    mma_bf16_16816(o[1], pa, vf[2], vf[3]);
+    mma_op16_16816<FP16>(o[0], pa, vf[0], vf[1]);
+    mma_op16_16816<FP16>(o[1], pa, vf[2], vf[3]);
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
       uint8_t* o0 = wbase + g8 * RB + (np * 16 + nt * 8 + t4 * 2) * 2;
-      *reinterpret_cast<uint32_t*>(o0) = pack_bf16x2(o[nt][0], o[nt][1]);
-      *reinterpret_cast<uint32_t*>(o0 + 8 * RB) = pack_bf16x2(o[nt][2], o[nt][3]);
+      *reinterpret_cast<uint32_t*>(o0) = pack_op16x2(o[nt][0], o[nt][1], FP16);
+      *reinterpret_cast<uint32_t*>(o0 + 8 * RB) = pack_op16x2(o[nt][2], o[nt][3], FP16);
     }
   }
   __syncwarp();
@@ -887,6 +950,7 @@ __global__ void __launch_bounds__(256) attention_tokens_mma_kernel(const Attenti
     *reinterpret_cast<uint4*>(og) = *reinterpret_cast<const uint4*>(wbase + r * RB + lane * 16);
     og += a.ldo;
   }
+  ptx::prof_mark_end(a.t_end);
 }
 
 
@@ -997,10 +1061,14 @@ __global__ void __launch_bounds__(256) marginalize_topk_kernel(const Marginalize
 // the cached keys/values of the T prompt positions plus the positions generated so far (online softmax).
 // ------------------------------------------------------------------------------------------------
 __global__ void add_row_vector_kernel(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ vec,
-                                      int rows, int dim) {
+                                      int rows, int dim, unsigned long long* t_end = nullptr) {
   const int total = rows * dim;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) out[i] = in[i] + vec[i % dim];
+  ptx::prof_mark_end(t_end);
 }
+
+// first kernel of a profiled forward: the reference point of launch 0's interval
+__global__ void prof_mark_kernel(unsigned long long* slot) { ptx::prof_mark_end(slot); }
 
 struct DecodeAttnArgs {
   const void* cache;   // [B * T, ld] rows (b, t): q | k | v of the prompt positions
@@ -1010,6 +1078,7 @@ struct DecodeAttnArgs {
   float scale;
   __nv_bfloat16* out_hi;  // [B, H * HD]
   __nv_bfloat16* out_lo;
+  unsigned long long* t_end;  // profiling slot or nullptr
 };
 
 template <typename TIn, int HD>
@@ -1050,6 +1119,7 @@ __global__ void __launch_bounds__(128) attention_decode_kernel(const DecodeAttnA
 #pragma unroll
   for (int e = 0; e < PL; ++e) o[e] *= inv;
   store_row_regs<TIn, HD>(a.out_hi, a.out_lo, static_cast<long long>(b) * D + h * HD, lane, o);
+  ptx::prof_mark_end(a.t_end);
 }
 
 // ------------------------------------------------------------------------------------------------

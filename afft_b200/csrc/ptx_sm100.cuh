@@ -16,6 +16,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// In-kernel profiling (afft_profile_enable): every kernel of the forward takes an optional pointer to a 64-bit slot and
+// records the latest %globaltimer value any of its warps saw on exit.  The host attributes to launch i the interval
+// (end of launch i-1, end of launch i]: the slices add up to the step exactly and, unlike CUDA events recorded between
+// launches, the marks do not break the programmatic-dependent-launch overlap of consecutive kernels.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void prof_mark_end(unsigned long long* slot) {  // call as the last statement of a warp
+  if (slot != nullptr && (threadIdx.x & 31) == 0) atomicMax(slot, globaltimer_ns());
+}
+
 __device__ __forceinline__ uint32_t lane_id() {
   uint32_t l;
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
@@ -266,11 +279,11 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor for kind::f16 with bf16 A/B (both K-major), fp32 accumulator, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(uint32_t m, uint32_t n) {
-  return (1u << 4)             // c_format = F32
-         | (1u << 7)           // a_format = BF16
-         | (1u << 10)          // b_format = BF16
+// Instruction descriptor for kind::f16 with bf16 or fp16 A/B (both K-major), fp32 accumulator, M x N tile.
+__host__ __device__ constexpr uint32_t make_idesc_f16_f32(uint32_t m, uint32_t n, bool fp16) {
+  return (1u << 4)                      // c_format = F32
+         | ((fp16 ? 0u : 1u) << 7)      // a_format: 0 = F16, 1 = BF16
+         | ((fp16 ? 0u : 1u) << 10)     // b_format
          | (0u << 15)          // a_major = K
          | (0u << 16)          // b_major = K
          | ((n >> 3) << 17)    // n_dim

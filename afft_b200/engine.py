@@ -21,7 +21,7 @@ class Engine:
     def __init__(self, *, fuser_kind: int, T: int, mod_names: List[str], mod_dims: List[int], dim: int,
                  fuser_depth: int, fuser_heads: int, modal_encoding: bool, frame_level_token: bool, cross_attn: bool,
                  norm_elementwise: bool, gpt_dim: int, gpt_layers: int, gpt_heads: int, cls_names: List[str],
-                 cls_dims: List[int], strict: bool, max_batch: int, device: torch.device, fp_output_len: int = 1):
+                 cls_dims: List[int], precision: str, max_batch: int, device: torch.device, fp_output_len: int = 1):
         if device.type != "cuda":
             raise _capi.AfftError("afft_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
         self.lib = _capi.lib()
@@ -45,7 +45,8 @@ class Engine:
         for i, (n, d) in enumerate(zip(cls_names, cls_dims)):
             cfg.cls_name[i].value = n.encode()
             cfg.cls_dim[i] = d
-        cfg.strict, cfg.max_batch = int(strict), max_batch
+        self.precision = precision
+        cfg.precision, cfg.max_batch = _capi.PRECISIONS[precision], max_batch
         cfg.fp_output_len = fp_output_len
         cfg.device = device.index if device.index is not None else torch.cuda.current_device()
         self.cfg = cfg

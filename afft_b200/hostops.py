@@ -2,7 +2,8 @@
 ``afft_forward`` call (GatedLinear / NonLinear / layer-normed mappings, MATT).
 
 Every arithmetic step is a library kernel (afft_convert_bf16, afft_gemm, afft_layernorm); PyTorch only owns the
-buffers.  Weights are packed to bf16 (hi/lo pairs in strict mode) once per parameter version.
+buffers.  Weights are packed to the precision's 16-bit operand format (bf16; hi/lo bf16 pairs in strict mode; fp16)
+once per parameter version.
 """
 from __future__ import annotations
 
@@ -19,41 +20,42 @@ class WeightCache:
     def __init__(self):
         self._packed: Dict[int, Tuple[tuple, torch.Tensor, Optional[torch.Tensor]]] = {}
 
-    def get(self, weight: torch.Tensor, strict: bool):
-        key = (weight.data_ptr(), weight._version, strict, str(weight.device))
+    def get(self, weight: torch.Tensor, precision: str):
+        key = (weight.data_ptr(), weight._version, precision, str(weight.device))
         hit = self._packed.get(id(weight))
         if hit is not None and hit[0] == key:
             return hit[1], hit[2]
         w = weight.detach()
         if w.dtype != torch.float32 or not w.is_contiguous():
             w = w.float().contiguous()
-        hi, lo = to_bf16(w, strict)
+        hi, lo = to_operand(w, precision)
         self._packed[id(weight)] = (key, hi, lo)
         return hi, lo
 
 
-def to_bf16(x: torch.Tensor, strict: bool):
-    """fp32 [R, K] -> bf16 hi (and lo = bf16(x - hi) in strict mode) through afft_convert_bf16."""
+def to_operand(x: torch.Tensor, precision: str):
+    """fp32 [R, K] -> the precision's GEMM operand through afft_convert_operand: bf16 hi (and lo = bf16(x - hi) in strict
+    mode), or saturated fp16."""
     if not x.is_cuda:
         raise _capi.AfftError("afft_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
     R, K = x.shape
     if K % 8 != 0:
         raise _capi.AfftError(f"feature width {K} must be a multiple of 8 (16-byte bf16 row pitch for TMA)")
-    hi = torch.empty(R, K, device=x.device, dtype=torch.bfloat16)
-    lo = torch.empty_like(hi) if strict else None
-    _capi.check(_capi.lib().afft_convert_bf16(x.data_ptr(), x.stride(0), R, K, hi.data_ptr(), _capi.ptr(lo), K, 0,
-                                              _capi.current_stream_ptr(x.device)))
+    hi = torch.empty(R, K, device=x.device, dtype=_capi.operand_dtype(precision))
+    lo = torch.empty_like(hi) if precision == "strict" else None
+    _capi.check(_capi.lib().afft_convert_operand(x.data_ptr(), x.stride(0), R, K, hi.data_ptr(), _capi.ptr(lo), K, 0,
+                                                 _capi.PRECISIONS[precision], _capi.current_stream_ptr(x.device)))
     return hi, lo
 
 
-def dense(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], cache: WeightCache, *, strict: bool,
+def dense(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], cache: WeightCache, *, precision: str,
           act: int = _capi.ACT_NONE, res: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """epilogue(x . weight^T + bias) for fp32 x [R, K] -> fp32 [R, N] (pitch padded to 4 floats)."""
     x = x.contiguous()
     R = x.shape[0]
     N = weight.shape[0]
-    a_hi, a_lo = to_bf16(x, strict)
-    w_hi, w_lo = cache.get(weight, strict)
+    a_hi, a_lo = to_operand(x, precision)
+    w_hi, w_lo = cache.get(weight, precision)
     if out is None:
         Np = (N + 3) // 4 * 4
         out = torch.empty(R, Np, device=x.device, dtype=torch.float32)[:, :N]

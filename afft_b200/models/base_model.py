@@ -24,7 +24,7 @@ PAST_LOGITS_PREFIX = 'past_'
 class BaseModel(nn.Module):
     def __init__(self, model_cfg, num_classes: Dict[str, int],
                  class_mappings: Dict[Tuple[str, str], torch.FloatTensor], strict: bool = False,
-                 max_batch: int = 64):
+                 max_batch: int = 64, precision: str = None):
         super().__init__()
         self.backbone = nn.ModuleDict()
         for mod, backbone_conf in cfg_items(cfg_get(cfg_get(model_cfg, "common"), "backbones")):
@@ -33,7 +33,7 @@ class BaseModel(nn.Module):
                 raise NotImplementedError("only torch.nn.Identity backbones (pre-extracted features) are supported")
             self.backbone[mod] = bb
         self.future_predictor = instantiate(cfg_get(model_cfg, "CMFP"), model_cfg=model_cfg, num_classes=num_classes,
-                                            strict=strict, max_batch=max_batch)
+                                            strict=strict, max_batch=max_batch, precision=precision)
         for (src, dst), mapping in class_mappings.items():  # reference base_model.py:27-29
             self.register_buffer(f'{CLS_MAP_PREFIX}{src}_{dst}', mapping)
 

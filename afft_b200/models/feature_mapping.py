@@ -36,7 +36,7 @@ class _Mapping(nn.Module):
             c = self.__dict__["_wcache"] = hostops.WeightCache()
         return c
 
-    strict = False  # set by the owning head (bf16x3 GEMMs)
+    precision = "bf16"  # set by the owning head ('bf16' | 'fp16' | 'strict')
 
 
 class Linear(_Mapping):
@@ -60,7 +60,7 @@ class Linear(_Mapping):
     def forward(self, x):
         x2, lead = self._prepare(x)
         lin = self.mapping[0]
-        y = x2 if isinstance(lin, nn.Identity) else hostops.dense(x2, lin.weight, None, self._cache(), strict=self.strict)
+        y = x2 if isinstance(lin, nn.Identity) else hostops.dense(x2, lin.weight, None, self._cache(), precision=self.precision)
         return self._finish(y, lead)
 
     def __str__(self):
@@ -91,8 +91,8 @@ class GatedLinear(_Mapping):
     def forward(self, x):
         x2, lead = self._prepare(x)
         lin, cg = self.mapping[0], self.mapping[1]
-        u = hostops.dense(x2, lin.weight, lin.bias, self._cache(), strict=self.strict)
-        y = hostops.dense(u, cg.fc.weight, cg.fc.bias, self._cache(), strict=self.strict, act=_capi.ACT_GATE, res=u)
+        u = hostops.dense(x2, lin.weight, lin.bias, self._cache(), precision=self.precision)
+        y = hostops.dense(u, cg.fc.weight, cg.fc.bias, self._cache(), precision=self.precision, act=_capi.ACT_GATE, res=u)
         return self._finish(y, lead)
 
     def __str__(self):
@@ -118,7 +118,7 @@ class NonLinear(_Mapping):
     def forward(self, x):
         x2, lead = self._prepare(x)
         lin = self.mapping[0]
-        y = hostops.dense(x2, lin.weight, lin.bias, self._cache(), strict=self.strict, act=_ACTS[self.activation][1])
+        y = hostops.dense(x2, lin.weight, lin.bias, self._cache(), precision=self.precision, act=_ACTS[self.activation][1])
         return self._finish(y, lead)
 
     def __str__(self):

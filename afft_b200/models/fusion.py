@@ -164,7 +164,7 @@ class MATT(nn.Module):
                                   nn.Linear(int(in_size / 4), int(in_size / 8)), nn.ReLU(), nn.Dropout(drop_rate),
                                   nn.Linear(int(in_size / 8), num_modality))
         self.num_modality = num_modality
-        self.strict = False
+        self.precision = "bf16"
         self.__dict__["_wcache"] = hostops.WeightCache()
 
     def attn_logits(self, modal_feats, ordered_feature_list):
@@ -176,7 +176,7 @@ class MATT(nn.Module):
         cache = self.__dict__["_wcache"]
         for idx, act in ((0, _capi.ACT_RELU), (3, _capi.ACT_RELU), (6, _capi.ACT_NONE)):
             lin = self.matt[idx]
-            x = hostops.dense(x, lin.weight, lin.bias, cache, strict=self.strict, act=act)
+            x = hostops.dense(x, lin.weight, lin.bias, cache, precision=self.precision, act=act)
         return x
 
     def forward(self, modal_feats, ordered_feature_list):

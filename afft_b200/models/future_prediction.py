@@ -151,12 +151,14 @@ class BaseFuturePredictor(nn.Module):
 class CMFPEarly(nn.Module):
     """Early-fusion cross-modal future predictor - reference models/future_prediction.py:19-186,228-291.
 
-    strict=False: bf16 tensor-core operands, fp32 accumulation/residual/LayerNorm/softmax.
-    strict=True : error-compensated bf16x3 GEMMs (hi.hi + hi.lo + lo.hi), fp32 activations between kernels;
-                  this is the mode whose top-5 indices are required to be identical to the fp32 reference.
+    precision (include/afft_b200.h AFFT_PREC_*; accumulation / residual stream / LayerNorm / softmax are fp32 in all):
+      "bf16"   bf16 tensor-core operands (the default).
+      "fp16"   fp16 operands at the same tensor rate, 8x less operand rounding (saturating conversions).
+      "strict" error-compensated bf16x3 GEMMs (hi.hi + hi.lo + lo.hi), fp32 activations between kernels; the mode
+               whose top-5 indices are required to be identical to the fp32 reference (``strict=True`` selects it).
     """
 
-    def __init__(self, model_cfg, num_classes, strict: bool = False, max_batch: int = 64):
+    def __init__(self, model_cfg, num_classes, strict: bool = False, max_batch: int = 64, precision: str = None):
         super().__init__()
         logger = logging.getLogger(__name__)
         common = cfg_get(model_cfg, "common")
@@ -193,13 +195,21 @@ class CMFPEarly(nn.Module):
             self.classifiers[cls_type] = nn.ModuleDict(
                 {'all-fused': nn.Sequential(nn.Dropout(dropout), nn.Linear(self.latent_dim, cls_dim))})
 
-        self.strict = strict
+        self.precision = _capi.resolve_precision(strict, precision)
         self.max_batch = max_batch
         self.return_attentions = True
         # upper bound on the K splits of skinny GEMMs (small batches); 1 = off, which makes a clip's result bitwise
         # independent of the batch size it is computed in (see afft_set_max_ksplit)
         self.max_ksplit = 4
         self._engines: Dict[tuple, Engine] = {}
+
+    @property
+    def strict(self) -> bool:
+        return self.precision == "strict"
+
+    @strict.setter
+    def strict(self, on: bool):
+        self.precision = "strict" if on else "bf16"
 
     # ---- reference helpers kept for API parity ----
     @staticmethod
@@ -217,7 +227,7 @@ class CMFPEarly(nn.Module):
             {n: p for n, p in self.named_parameters()}
 
     def _engine(self, feats_order, T: int, B: int, device: torch.device) -> Engine:
-        key = (tuple(feats_order), T, str(device), bool(self.strict), self.fp_output_len)
+        key = (tuple(feats_order), T, str(device), self.precision, self.fp_output_len)
         eng = self._engines.get(key)
         if eng is not None and B > eng.max_batch:
             eng.close()
@@ -232,7 +242,7 @@ class CMFPEarly(nn.Module):
                          frame_level_token=bool(f.frame_level_token), cross_attn=bool(f.cross_attn),
                          norm_elementwise=bool(f.norm_elementwise), gpt_dim=gpt.n_embd, gpt_layers=gpt.n_layer,
                          gpt_heads=gpt.n_head, cls_names=list(self.num_classes.keys()),
-                         cls_dims=list(self.num_classes.values()), strict=bool(self.strict),
+                         cls_dims=list(self.num_classes.values()), precision=self.precision,
                          max_batch=max(B, self.max_batch), device=device, fp_output_len=self.fp_output_len)
             self._engines[key] = eng
         if eng.max_ksplit != self.max_ksplit:
@@ -263,7 +273,7 @@ class CMFPEarly(nn.Module):
         for m in feats_order:
             x = feats[m].to(torch.float32).contiguous()
             if not self._fused_mapping(m):  # ablation mapping: library kernels ahead of the fused call
-                self.mapping[m].strict = bool(self.strict)
+                self.mapping[m].precision = self.precision
                 x = self.mapping[m](x).contiguous()
             xs.append(x)
         z, pf, logits, attn = eng.forward(xs, want_attn=self.return_attentions)
@@ -295,7 +305,15 @@ class _UnimodalPrediction(nn.Module):
     classifier on the modality's own width.  One native handle per modality (AFFT_FUSER_NONE) runs
     dim_encoder -> GPT-2 -> dim_decoder -> prepare_output -> classifier."""
 
-    def _init_common(self, model_cfg, num_classes, strict, max_batch):
+    @property
+    def strict(self) -> bool:
+        return self.precision == "strict"
+
+    @strict.setter
+    def strict(self, on: bool):
+        self.precision = "strict" if on else "bf16"
+
+    def _init_common(self, model_cfg, num_classes, strict, max_batch, precision=None):
         common = cfg_get(model_cfg, "common")
         modal_dims = cfg_get(model_cfg, "modal_dims")
         assert isinstance(modal_dims, Mapping), 'cfg.model.modal_dims must be a Dict!'
@@ -308,7 +326,7 @@ class _UnimodalPrediction(nn.Module):
         self.common_classifier = bool(cfg_get(common, "share_classifiers"))
         self.fp_output_len = int(cfg_get(common, "fp_output_len", 1))
         self.modal_feature_order = list(cfg_get(model_cfg, "modal_feature_order"))
-        self.strict, self.max_batch = strict, max_batch
+        self.precision, self.max_batch = _capi.resolve_precision(strict, precision), max_batch
         self._engines: Dict[tuple, Engine] = {}
 
     def _init_future_predictor(self, model_cfg):  # reference :78-95
@@ -354,7 +372,7 @@ class _UnimodalPrediction(nn.Module):
         if x.device.type != "cuda":
             raise _capi.AfftError("afft_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
         B, T, d = x.shape
-        key = (mod, T, str(x.device), bool(self.strict), self.fp_output_len)
+        key = (mod, T, str(x.device), self.precision, self.fp_output_len)
         eng = self._engines.get(key)
         if eng is not None and B > eng.max_batch:
             eng.close()
@@ -365,7 +383,7 @@ class _UnimodalPrediction(nn.Module):
                          fuser_heads=1, modal_encoding=False, frame_level_token=False, cross_attn=False,
                          norm_elementwise=True, gpt_dim=gpt.n_embd, gpt_layers=gpt.n_layer, gpt_heads=gpt.n_head,
                          cls_names=list(self.num_classes.keys()), cls_dims=list(self.num_classes.values()),
-                         strict=bool(self.strict), max_batch=max(B, self.max_batch), device=x.device,
+                         precision=self.precision, max_batch=max(B, self.max_batch), device=x.device,
                          fp_output_len=self.fp_output_len)
             self._engines[key] = eng
         eng.sync_weights(self._weights_for(mod))
@@ -397,10 +415,10 @@ class _UnimodalPrediction(nn.Module):
 class IndividualFuturePrediction(_UnimodalPrediction):
     """Individual modality future predictor - reference models/future_prediction.py:189-225 (expts/00_*)."""
 
-    def __init__(self, model_cfg, num_classes, strict: bool = False, max_batch: int = 64):
+    def __init__(self, model_cfg, num_classes, strict: bool = False, max_batch: int = 64, precision: str = None):
         super().__init__()
         assert not cfg_get(cfg_get(model_cfg, "common"), "fusion_cls")  # reference :194
-        self._init_common(model_cfg, num_classes, strict, max_batch)
+        self._init_common(model_cfg, num_classes, strict, max_batch, precision)
         self._init_classifiers(model_cfg)   # registration order of the reference: classifiers, then predictors (:196-198)
         self._init_future_predictor(model_cfg)
 
@@ -412,13 +430,13 @@ class IndividualFuturePrediction(_UnimodalPrediction):
 class CMFPScoreFusion(_UnimodalPrediction):
     """Late (score) fusion with MATT - reference models/future_prediction.py:294-351 (expts/05_MATT_ek100_train.txt)."""
 
-    def __init__(self, model_cfg, num_classes, strict: bool = False, max_batch: int = 64):
+    def __init__(self, model_cfg, num_classes, strict: bool = False, max_batch: int = 64, precision: str = None):
         super().__init__()
         common = cfg_get(model_cfg, "common")
         assert not cfg_get(common, "fusion_cls")  # reference :298
         if not cfg_get(common, "modality_cls"):
             logging.getLogger(__name__).warning("Enforcing modality classification for CMFPScoreFusion.")
-        self._init_common(model_cfg, num_classes, strict, max_batch)
+        self._init_common(model_cfg, num_classes, strict, max_batch, precision)
         if self.fp_output_len != 1:
             raise NotImplementedError("CMFPScoreFusion broadcasts one attention row over the future logits: fp_output_len must be 1")
         self.mapping = nn.ModuleDict()  # reference :47-54
@@ -440,9 +458,9 @@ class CMFPScoreFusion(_UnimodalPrediction):
         # [first frame | predictions] (:327-330) is exactly the native past_futures buffer; map it to the common width
         mapped = {}
         for mod in feats_order:
-            self.mapping[mod].strict = bool(self.strict)
+            self.mapping[mod].precision = self.precision
             mapped[mod] = self.mapping[mod](bufs[mod][0])
-        self.fuser.strict = bool(self.strict)
+        self.fuser.precision = self.precision
         scores = self.fuser.attn_logits(mapped, lambda d: [d[m] for m in feats_order])  # (B*(T+1), M), pre-softmax
         attn = torch.empty(scores.shape[0], len(feats_order), device=scores.device, dtype=torch.float32)
         for k, (cls, c) in enumerate(self.num_classes.items()):  # :341-350, softmax fused with the weighted sum

@@ -134,9 +134,21 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm (oracle port) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_forward_timer(cfg, T, ncls, batch, steps, warmup, budget_s=240.0):
-    """Times oracle.forward (the CPU restatement of the reference path, pinned to the reference module) on all
-    host cores.  Returns (clips/s, cores, description)."""
+def _cpu_name():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_forward_timer(cfg, T, ncls, batch, steps, warmup, budget_s=240.0, chunk=0):
+    """Times oracle.forward (the CPU restatement of the reference path, pinned to the reference module; issued as the
+    ATen library calls the module makes) on all host cores.  One step = `batch` clips, processed in chunks of `chunk`
+    clips (0: the whole batch at once).  Returns (clips/s, cores, description, steps, seconds)."""
     from afft_b200.models import BaseModel
     from oracle import afft_oracle  # bench.py's cpu_baseline / --impl reference legs may execute the oracle
     cores = os.cpu_count() or 1
@@ -146,30 +158,38 @@ def cpu_forward_timer(cfg, T, ncls, batch, steps, warmup, budget_s=240.0):
     model = BaseModel(cfg, ncls, {})  # random-init weights of the architecture (CPU tensors; no native call)
     sd = {k: v.detach() for k, v in model.state_dict().items()}
     feats = synthetic.synthetic_features(cfg["modal_dims"], batch, T, seed=1000)
+    chunk = chunk if 0 < chunk < batch else batch
+
+    def one_step():
+        for b0 in range(0, batch, chunk):
+            afft_oracle.forward(sd, cfg, ncls, {m: f[b0:b0 + chunk] for m, f in feats.items()})
+
     with torch.no_grad():
         t0 = time.perf_counter()
-        afft_oracle.forward(sd, cfg, ncls, feats)
+        one_step()
         first = time.perf_counter() - t0
         if first * (steps + warmup) > budget_s:  # keep the whole run bounded
             steps = max(1, int(budget_s / first) - warmup)
         for _ in range(max(0, warmup - 1)):
-            afft_oracle.forward(sd, cfg, ncls, feats)
+            one_step()
         t0 = time.perf_counter()
         for _ in range(steps):
-            afft_oracle.forward(sd, cfg, ncls, feats)
+            one_step()
         dt = time.perf_counter() - t0
-    cpu_name = "unknown"
-    try:
-        with open("/proc/cpuinfo") as f:
-            for line in f:
-                if line.startswith("model name"):
-                    cpu_name = line.split(":", 1)[1].strip()
-                    break
-    except OSError:
-        pass
-    desc = f"{steps} forwards of {batch} clips, fp32 torch CPU ops, {cores} threads on {cpu_name}"
+    desc = (f"{steps} steps of {batch} clips" + (f" in chunks of {chunk}" if chunk != batch else "") +
+            f", fp32 torch CPU ops (oracle port issuing the reference module's ATen calls), {cores} threads on {_cpu_name()}")
     return batch * steps / dt, cores, desc, steps, dt
 
+
+def cpu_best_of(cfg, T, ncls, batches=(8, 32, 128), budget_s=45.0):
+    """cpu_baseline: best clips/s over the batch sizes SURVEY section 8d names (1 warm-up + up to 3 timed forwards each)."""
+    best, table = None, {}
+    for b in batches:
+        v, cores, desc, _, _ = cpu_forward_timer(cfg, T, ncls, b, 3, 1, budget_s=budget_s / len(batches))
+        table[str(b)] = round(v, 2)
+        if best is None or v > best[0]:
+            best = (v, cores, desc, b)
+    return best, table
 
 
 def staged_e2e(args, cfg, T, B, model, dev, main_stream, sampler, n_gpus, rank, C, location="pinned"):
@@ -235,18 +255,28 @@ def staged_e2e(args, cfg, T, B, model, dev, main_stream, sampler, n_gpus, rank, 
             "api": "afft_b200.staging.FeatureStager.stage (afft_store_plan + afft_store_gather) -> BaseModel.__call__"}
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path (the oracle port - /root/reference does not
+    exist on the GPU box - issuing the ATen calls the reference module makes; within 4 % of the module's own speed in
+    the build container) on all host cores, on the GPU arm's config: one step = the same B clips per step, processed in
+    chunks of the CPU's best batch size (the reference's eval batch is 32; expts/01_SA-Fuser_ek100_val_TSN.txt:6)."""
     rank, _, world = adist.env_world()
     if rank != 0:
         return
     cfg, T, ncls, eval_bs = configs.named_config(args.config)
-    batch = args.cpu_batch or eval_bs
-    value, cores, desc, steps, dt = cpu_forward_timer(cfg, T, ncls, batch, args.steps, args.warmup)
+    B = args.batch
+    chunk = args.cpu_batch
+    chunk_table = None
+    if not chunk:  # pick the CPU's best chunk with one short probe each
+        best, chunk_table = cpu_best_of(cfg, T, ncls, batches=(eval_bs, 128), budget_s=20.0)
+        chunk = best[3]
+    value, cores, desc, steps, dt = cpu_forward_timer(cfg, T, ncls, B, args.steps, args.warmup, budget_s=200.0, chunk=chunk)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": round(1e3 * dt / steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, cfg, T, batch, "reference algorithm on host CPU"),
-        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "config": workload_config(args, cfg, T, B, "reference algorithm on host CPU"),
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                         "chunk_clips": chunk, "chunk_probe_clips_per_s": chunk_table},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -260,16 +290,168 @@ def workload_config(args, cfg, T, batch, how, ncls=None):
             "gemm_gflop_per_clip": round(configs.gemm_flops_per_clip(cfg, T, ncls or configs.named_config(args.config)[2]) / 1e9, 3),
             "weights": "random init (torch.manual_seed(0))", "parallelism": f"dp{args.gpus} (clips sharded, no collective)",
             "path": how,
-            "l2": "no explicit flush: per-step working set (772 MB bf16 weights + >1 GB activations) exceeds the 126 MB L2; "
+            "l2": "no explicit flush: per-step working set (772 MB 16-bit weights + >1 GB activations) exceeds the 126 MB L2; "
                   "4 input buffer sets are rotated"}
 
 
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+PREC_DESC = {"bf16": "bf16 operands / fp32 accumulate", "fp16": "fp16 operands / fp32 accumulate",
+             "strict": "strict bf16x3 (hi.hi + hi.lo + lo.hi) / fp32 accumulate"}
+
+
+class DeviceRun:
+    """One precision mode of the model on this rank: engine, persistent io structs, the lowest-overhead step."""
+
+    def __init__(self, cfg, T, ncls, B, precision, dev, dev_sets, order):
+        from afft_b200 import _capi
+        from afft_b200.models import BaseModel
+        torch.manual_seed(0)
+        self.model = BaseModel(cfg, ncls, {}, precision=precision, max_batch=B).to(dev).eval()
+        self.head = self.model.future_predictor
+        with torch.no_grad():
+            self.model(dict(dev_sets[0]), **KW)  # builds the engine, packs the weights
+        torch.cuda.synchronize()
+        self.eng = eng = next(iter(self.head._engines.values()))
+        self.launches_per_fwd = eng.launch_count()
+        D = cfg["common_dim"]
+        self.C = C = list(ncls.values())[0]
+        ldc = (C + 3) // 4 * 4
+        n_tok, H1 = eng.n_slots, eng.fuser_heads
+        if eng.fuser_kind == _capi.FUSER_TSA:
+            attn_buf = torch.empty(B, eng.fuser_depth, H1, n_tok * T, n_tok * T, device=dev)
+        elif eng.fuser_kind == _capi.FUSER_CA:
+            attn_buf = None
+        else:
+            attn_buf = torch.empty(B, eng.fuser_depth, T, H1, n_tok, n_tok, device=dev)
+        self.bufs = dict(orig=torch.empty(B, T, D, device=dev), pf=torch.empty(B, T + eng.fp_output_len, D, device=dev),
+                         logits=torch.empty(B, T + eng.fp_output_len, ldc, device=dev), attn=attn_buf)
+        self.ios = []
+        for sset in dev_sets:
+            io = _capi.IO()
+            for i, m in enumerate(order):
+                io.feat[i] = sset[m].data_ptr()
+            io.orig_past, io.past_futures = self.bufs["orig"].data_ptr(), self.bufs["pf"].data_ptr()
+            io.logits[0], io.ld_logits[0] = self.bufs["logits"].data_ptr(), ldc
+            io.fuser_attn = attn_buf.data_ptr() if attn_buf is not None else None
+            self.ios.append(io)
+        self.B = B
+
+    def step(self, i):
+        self.eng.forward_into(self.ios[i % len(self.ios)], self.B)
+
+    def timed(self, steps, warmup, dev, sampler=None):
+        """K steps between a barrier + synchronize on both sides, CUDA events, max over ranks -> total ms."""
+        for i in range(warmup):
+            self.step(i)
+        torch.cuda.synchronize()
+        adist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx = sampler if sampler is not None else _Null()
+        with ctx:
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(steps):
+                self.step(i)
+            e1.record()
+            torch.cuda.synchronize()
+        adist.barrier()
+        return adist.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    def profile(self, psteps=5):
+        """Per-launch device time slices of `psteps` forwards (in-kernel exit timestamps; see afft_profile_enable)."""
+        self.eng.profile_enable(True)
+        agg = {0: [0.0, 0], 1: [0.0, 0], 2: [0.0, 0], 3: [0.0, 0]}
+        by_shape, gemm_flops, last = {}, 0.0, None
+        for i in range(psteps):
+            self.step(i)
+            torch.cuda.synchronize()
+            last = self.eng.profile_read()
+            for cat, M, N, K, ms in last:
+                agg[cat][0] += ms
+                agg[cat][1] += 1
+                if cat == 0:
+                    gemm_flops += 2.0 * M * N * K
+                    sh = by_shape.setdefault((M, N, K), [0.0, 0])
+                    sh[0] += ms
+                    sh[1] += 1
+        self.eng.profile_enable(False)
+        return agg, by_shape, gemm_flops, last
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def parity_block(runs, cfg, T, ncls, dev, n_clips=1024, chunk=128):
+    """>= 1024 seeded clips (seed 123) through every precision mode and through the fp32 CPU oracle:
+    max |dlogit| and ordered top-5 identity, stratified by the oracle's 5th-6th logit gap (afft_b200/parity.py)."""
+    from afft_b200 import parity
+    from oracle import afft_oracle  # checker
+    any_run = next(iter(runs.values()))
+    sd = {k: v.detach().cpu() for k, v in any_run.model.state_dict().items()}
+    feats = synthetic.synthetic_features(cfg["modal_dims"], n_clips, T, seed=123)
+    torch.set_num_threads(os.cpu_count() or 1)
+    afft_oracle.ATEN_OPS = True
+    t0 = time.perf_counter()
+    refs = []
+    with torch.no_grad():
+        for b0 in range(0, n_clips, chunk):
+            r = afft_oracle.forward(sd, cfg, ncls, {m: f[b0:b0 + chunk] for m, f in feats.items()}, dtype=torch.float32)
+            refs.append(r["logits/action"]["all-fused"][:, 0])
+    ref = torch.cat(refs)
+    oracle_s = time.perf_counter() - t0
+    out = {"clips": n_clips, "reference": "oracle/afft_oracle.py fp32 on the host CPU (pinned to the reference module, tests/golden)",
+           "inputs": "synthetic randn features, seed 123; weights torch.manual_seed(0) random init",
+           "oracle_seconds": round(oracle_s, 1), "modes": {}}
+    for prec, run in runs.items():
+        got = []
+        for b0 in range(0, n_clips, run.B):
+            with torch.no_grad():
+                o, _ = run.model({m: f[b0:b0 + run.B].reshape(-1, T, f.shape[-1], 1, 1, 1).to(dev) for m, f in feats.items()}, **KW)
+            got.append(o["logits/action"]["all-fused"][:, 0].float().cpu())
+        out["modes"][prec] = parity.top5_stats(torch.cat(got), ref)
+    return out
+
+
+def gpu_baseline_block(B, T, dev, steps=10):
+    """Stock eager PyTorch on the same GPU (tools/stock_torch_gpu.py: the library calls the reference module makes -
+    F.linear / F.layer_norm / F.gelu / softmax attention; shares no code with afft_b200 or oracle/)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import stock_torch_gpu as st
+    W = st.make_weights(dev)
+    feats = [torch.randn(B, T, d, device=dev) for d in (1024, 352, 1024, 1024)]
+    res = {"what": "stock eager PyTorch (F.linear / F.layer_norm / F.gelu / softmax attention), same GPU, same batch; "
+                   "tools/stock_torch_gpu.py", "unit": UNIT, "steps": steps}
+    old = torch.backends.cuda.matmul.allow_tf32
+    for mode in ("tf32", "bf16_autocast"):
+        torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
+        ctx = torch.autocast("cuda", dtype=torch.bfloat16) if mode == "bf16_autocast" else torch.autocast("cuda", enabled=False)
+        with torch.no_grad(), ctx:
+            for _ in range(3):
+                st.forward(W, feats, T=T)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                st.forward(W, feats, T=T)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        res[mode] = {"ms_per_step": round(ms, 3), "value": round(B / ms * 1e3, 1)}
+    torch.backends.cuda.matmul.allow_tf32 = old
+    del W, feats
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_afft(args):
     from afft_b200 import _capi
-    from afft_b200.models import BaseModel
 
     rank, local_rank, world = adist.init()
     if world != args.gpus and rank == 0:
@@ -285,10 +467,6 @@ def run_afft(args):
     B = args.batch
     peaks = load_peaks()
     flops_per_clip = configs.gemm_flops_per_clip(cfg, T, ncls)
-
-    torch.manual_seed(0)
-    model = BaseModel(cfg, ncls, {}, strict=args.strict, max_batch=B).to(dev).eval()
-    head = model.future_predictor
     order = [m for m in cfg["modal_feature_order"] if m in cfg["modal_dims"]]
 
     # ---- device-resident inputs: NBUF rotating sets ----
@@ -296,56 +474,21 @@ def run_afft(args):
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     dev_sets = [{m: torch.randn(B, T, cfg["modal_dims"][m], 1, 1, 1, device=dev, generator=g) for m in order}
                 for _ in range(NBUF)]
-    with torch.no_grad():
-        out, _ = model(dict(dev_sets[0]), **KW)  # builds the engine, packs the weights
-    torch.cuda.synchronize()
-    eng = next(iter(head._engines.values()))
-    launches_per_fwd = eng.launch_count()
+    run = DeviceRun(cfg, T, ncls, B, args.precision, dev, dev_sets, order)
+    model, head, eng, C = run.model, run.head, run.eng, run.C
 
-    # persistent output buffers + io structs for the lowest-overhead call (C ABI with raw pointers)
-    D = cfg["common_dim"]
-    C = list(ncls.values())[0]
-    ldc = (C + 3) // 4 * 4
-    n_tok, H1 = eng.n_slots, eng.fuser_heads
-    if eng.fuser_kind == _capi.FUSER_TSA:
-        attn_buf = torch.empty(B, eng.fuser_depth, H1, n_tok * T, n_tok * T, device=dev)
-    elif eng.fuser_kind == _capi.FUSER_CA:
-        attn_buf = None
-    else:
-        attn_buf = torch.empty(B, eng.fuser_depth, T, H1, n_tok, n_tok, device=dev)
-    bufs = dict(orig=torch.empty(B, T, D, device=dev), pf=torch.empty(B, T + eng.fp_output_len, D, device=dev),
-                logits=torch.empty(B, T + eng.fp_output_len, ldc, device=dev), attn=attn_buf)
-    ios = []
-    for s in dev_sets:
-        io = _capi.IO()
-        for i, m in enumerate(order):
-            io.feat[i] = s[m].data_ptr()
-        io.orig_past, io.past_futures = bufs["orig"].data_ptr(), bufs["pf"].data_ptr()
-        io.logits[0], io.ld_logits[0] = bufs["logits"].data_ptr(), ldc
-        io.fuser_attn = bufs["attn"].data_ptr() if bufs["attn"] is not None else None
-        ios.append(io)
-
-    def step(i):
-        eng.forward_into(ios[i % NBUF], B)
-
-    # ---- value: device-resident inputs, CUDA events, max over ranks ----
-    for i in range(args.warmup):
-        step(i)
-    torch.cuda.synchronize()
-    adist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- value: device-resident inputs, exactly K steps, CUDA events, max over ranks ----
     sampler = ClockSampler(local_rank)
-    with sampler:
-        torch.cuda.synchronize()
-        e0.record()
-        for i in range(args.steps):
-            step(i)
-        e1.record()
-        torch.cuda.synchronize()
-    adist.barrier()
-    ms_total = adist.max_over_ranks(e0.elapsed_time(e1), dev)
+    ms_total = run.timed(args.steps, args.warmup, dev, sampler)
     ms_per_step = ms_total / args.steps
     value = n_gpus * B * args.steps / (ms_total / 1e3)
+
+    # ---- sustained: the same loop repeated for >= 2 s (the power cap settles after ~1 s of dense tensor work) ----
+    sus_steps = max(args.steps, int(args.sustain_s * 1e3 / ms_per_step) + 1)
+    sus_sampler = ClockSampler(local_rank)
+    sus_ms = run.timed(sus_steps, 0, dev, sus_sampler)
+    sustained = {"value": round(n_gpus * B * sus_steps / (sus_ms / 1e3), 1), "unit": UNIT, "steps": sus_steps,
+                 "seconds": round(sus_ms / 1e3, 3), "ms_per_step": round(sus_ms / sus_steps, 4), "clocks": sus_sampler.summary()}
 
     # ---- e2e: public API, pinned host inputs, H2D + forward + D2H of the consumed logits every step ----
     host_sets = [{m: torch.randn(B, T, cfg["modal_dims"][m], 1, 1, 1).pin_memory() for m in order} for _ in range(2)]
@@ -394,13 +537,13 @@ def run_afft(args):
     # copies share PCIe and host memory with whatever else runs on the box: single passes were seen 25 % off
     # (8.5 instead of 6.4 ms per step) with the device-resident `value` of the same run unchanged.
     e2e_passes = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
         adist.barrier()
-        with sampler:
-            e0.record()
-            e2e_loop(args.steps)
-            e1.record()
-            torch.cuda.synchronize()
+        e0.record()
+        e2e_loop(args.steps)
+        e1.record()
+        torch.cuda.synchronize()
         adist.barrier()
         e2e_passes.append(adist.max_over_ranks(e0.elapsed_time(e1), dev))
     e2e_ms = sorted(e2e_passes)[1]
@@ -409,64 +552,60 @@ def run_afft(args):
     # ---- e2e from clip descriptors (row N4): native plan + device gather from a pinned host feature store ----
     staged = None
     if not args.no_staged:
-        staged = {"pinned_store": staged_e2e(args, cfg, T, B, model, dev, main_stream, sampler, n_gpus, rank, C, "pinned"),
-                  "hbm_store": staged_e2e(args, cfg, T, B, model, dev, main_stream, sampler, n_gpus, rank, C, "hbm")}
+        st_sampler = ClockSampler(local_rank)
+        staged = {"pinned_store": staged_e2e(args, cfg, T, B, model, dev, main_stream, st_sampler, n_gpus, rank, C, "pinned"),
+                  "hbm_store": staged_e2e(args, cfg, T, B, model, dev, main_stream, st_sampler, n_gpus, rank, C, "hbm")}
 
-    # ---- roofline of the dominant kernel (the tcgen05 GEMM): per-launch CUDA events, separate pass ----
-    eng.profile_enable(True)
-    agg = {0: [0.0, 0], 1: [0.0, 0], 2: [0.0, 0], 3: [0.0, 0]}
-    gemm_flops = 0.0
-    by_shape = {}
-    PSTEPS = 3
-    for i in range(PSTEPS):
-        step(i)
-        torch.cuda.synchronize()
-        recs = eng.profile_read()
-        if args.verbose and rank == 0 and i == PSTEPS - 1:
-            names = {0: "gemm", 1: "ln", 2: "attn", 3: "other"}
-            print("[launches] " + " ".join(f"{names[c]}:{ms * 1e3:.0f}" for c, _, _, _, ms in recs), file=sys.stderr)
-        for cat, M, N, K, ms in recs:
-            agg[cat][0] += ms
-            agg[cat][1] += 1
-            if cat == 0:
-                gemm_flops += 2.0 * M * N * K
-                s = by_shape.setdefault((M, N, K), [0.0, 0])
-                s[0] += ms
-                s[1] += 1
-    eng.profile_enable(False)
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM): in-kernel exit timestamps, PDL overlap preserved ----
+    PSTEPS = 5
+    agg, by_shape, gemm_flops, last = run.profile(PSTEPS)
+    if args.verbose and rank == 0:
+        names = {0: "gemm", 1: "ln", 2: "attn", 3: "other"}
+        print("[launches] " + " ".join(f"{names[c]}:{ms * 1e3:.0f}" for c, _, _, _, ms in last), file=sys.stderr)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if os.path.exists(tpath) and args.config == "ek100_sa_tsn" and B == 256 and not args.strict:
-        with open(tpath) as f:  # dram read+write bytes per GEMM launch from the committed ncu capture of this workload
-            traffic = round(json.load(f)["traffic_bytes_per_launch_avg"])
+    for tname in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath) and args.config == "ek100_sa_tsn" and B == 256 and args.precision != "strict":
+            with open(tpath) as f:  # dram read+write bytes per GEMM launch from the committed ncu capture of this workload
+                traffic = round(json.load(f)["traffic_bytes_per_launch_avg"])
+            traffic_src = tname
+            break
     gemm_ms = agg[0][0]
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     kernel_ms_total = sum(v[0] for v in agg.values())
     step_tflops = value / n_gpus * flops_per_clip / 1e12
+    sus_tflops = sustained["value"] / n_gpus * flops_per_clip / 1e12
 
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(args, cfg, T, B, "afft_forward (C ABI), " + ("strict bf16x3" if args.strict else "bf16 operands / fp32 accumulate")),
+        "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "fp16", "strict": "bf16x3"}[args.precision], "data": "synthetic",
+        "config": workload_config(args, cfg, T, B, "afft_forward (C ABI), " + PREC_DESC[args.precision]),
+        "sustained": sustained,
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(e2e_ms / args.steps, 4),
                 "passes_ms_per_step": [round(p / args.steps, 4) for p in e2e_passes], "reported": "median of 3 passes of K steps",
                 "api": "afft_b200.models.BaseModel.__call__ (test.py:72-86 pattern), pinned host inputs, double-buffered H2D, logits of batch i-1 read on the host while batch i computes"},
         "e2e_from_clip_descriptors": staged,
-        "gpu_launches": launches_per_fwd * args.steps,
-        "launches_per_step": launches_per_fwd,
+        "gpu_launches": run.launches_per_fwd * args.steps,
+        "launches_per_step": run.launches_per_fwd,
         "clocks": sampler.summary(),
         "roofline": {
             "bound": "tensor", "kernel": "gemm_bf16_tcgen05_2cta_kernel / gemm_bf16_tcgen05_kernel", "achieved": round(achieved, 1),
             "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": round(achieved / peaks["sustained"], 4),
             "peak_kind": "bf16_tflops_sustained, " + peaks["source"], "frac_of_burst": round(achieved / peaks["burst"], 4),
-            "traffic": traffic, "traffic_note": "dram bytes per GEMM launch, avg over the 52 launches of a forward (profiles/r01_gemm_traffic.json)",
+            "traffic": traffic,
+            "traffic_note": (f"STATIC: dram bytes per GEMM launch, avg over the GEMM launches of a forward, from the committed ncu "
+                             f"capture profiles/{traffic_src} (not measured in this run)") if traffic is not None else None,
+            "how": f"{PSTEPS} profiled forwards; each kernel records its exit %globaltimer, launch i owns (end of i-1, end of i]: "
+                   "the slices sum to the forward's device time and PDL overlap is preserved (afft_profile_enable)",
             "algorithmic_flop_per_launch_avg": round(gemm_flops / max(1, agg[0][1])),
             "launches_per_step": agg[0][1] // PSTEPS, "gemm_ms_per_step": round(gemm_ms / PSTEPS, 4),
+            "kernel_ms_per_step": round(kernel_ms_total / PSTEPS, 4),
             "gemm_share_of_kernel_time": round(gemm_ms / kernel_ms_total, 4) if kernel_ms_total else None,
             "whole_step_tflops": round(step_tflops, 1), "whole_step_frac": round(step_tflops / peaks["sustained"], 4),
             "whole_step_frac_of_burst": round(step_tflops / peaks["burst"], 4),
+            "sustained_whole_step_tflops": round(sus_tflops, 1), "sustained_whole_step_frac": round(sus_tflops / peaks["sustained"], 4),
             "other_kernels_ms_per_step": {"layernorm": round(agg[1][0] / PSTEPS, 4), "attention": round(agg[2][0] / PSTEPS, 4),
                                           "assembly_convert": round(agg[3][0] / PSTEPS, 4)},
         },
@@ -476,23 +615,43 @@ def run_afft(args):
             print(f"[gemm] M={M} N={N} K={K} launches/step={n // PSTEPS} ms/launch={ms / n:.4f} "
                   f"TFLOP/s={2.0 * M * N * K / (ms / n) / 1e9:.0f}", file=sys.stderr)
 
+    # ---- the other precision modes on the same box, same inputs (sub-records) ----
+    runs = {args.precision: run}
+    modes = {args.precision: {"value": round(value, 1), "ms_per_step": round(ms_per_step, 4),
+                              "whole_step_frac": round(step_tflops / peaks["sustained"], 4), "headline": True}}
+    if not args.no_modes:
+        for prec in ("bf16", "fp16", "strict"):
+            if prec in runs:
+                continue
+            r2 = DeviceRun(cfg, T, ncls, B, prec, dev, dev_sets, order)
+            ms2 = r2.timed(args.steps, args.warmup, dev)
+            v2 = n_gpus * B * args.steps / (ms2 / 1e3)
+            sus2_steps = max(args.steps, int(min(args.sustain_s, 1.0) * 1e3 / (ms2 / args.steps)) + 1)
+            sus2 = r2.timed(sus2_steps, 0, dev)
+            a2, _, gf2, _ = r2.profile(3)
+            modes[prec] = {"value": round(v2, 1), "ms_per_step": round(ms2 / args.steps, 4),
+                           "whole_step_frac": round(v2 / n_gpus * flops_per_clip / 1e12 / peaks["sustained"], 4),
+                           "sustained_value": round(n_gpus * B * sus2_steps / (sus2 / 1e3), 1),
+                           "gemm_frac": round(gf2 / (a2[0][0] * 1e-3) / 1e12 / peaks["sustained"], 4) if a2[0][0] > 0 else None,
+                           "path": PREC_DESC[prec]}
+            runs[prec] = r2
+    modes[args.precision].update(sustained_value=sustained["value"], gemm_frac=round(achieved / peaks["sustained"], 4),
+                                 path=PREC_DESC[args.precision])
+    line["modes"] = modes
+
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
-        # parity of exactly this build on a small sample, and the CPU baseline, in the same run
-        from oracle import afft_oracle
-        pb = 4
-        pf = synthetic.synthetic_features(cfg["modal_dims"], pb, T, seed=31)
-        with torch.no_grad():
-            o, _ = model({m: t.reshape(pb, T, -1, 1, 1, 1).to(dev) for m, t in pf.items()}, **KW)
-        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-        ref = afft_oracle.forward(sd, cfg, ncls, pf)
-        got = o["logits/action"]["all-fused"].cpu()
-        line["parity_sample"] = {
-            "clips": pb, "max_abs_dlogit_vs_oracle_fp32": round((got - ref["logits/action"]["all-fused"]).abs().max().item(), 6),
-            "top5_identical_clips": int((got[:, 0].topk(5).indices == afft_oracle.top5(ref["logits/action"]["all-fused"][:, 0])).all(-1).sum()),
-            "mode": "strict" if args.strict else "bf16"}
-        del sd
-        v, cores, desc, _, _ = cpu_forward_timer(cfg, T, ncls, args.cpu_batch or eval_bs, 3, 1, budget_s=60.0)
-        line["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        # parity of exactly this build on >= 1024 clips for every mode, the stock-PyTorch GPU bar and the CPU baseline
+        line["parity"] = parity_block(runs, cfg, T, ncls, dev, n_clips=args.parity_clips)
+        ps = line["parity"]["modes"][args.precision]
+        line["parity_sample"] = {"clips": ps["clips"], "max_abs_dlogit_vs_oracle_fp32": ps["max_abs_dlogit"],
+                                 "top5_identical_clips": ps["ordered_top5_identical"], "mode": args.precision}
+        if args.config == "ek100_sa_tsn":
+            line["gpu_baseline"] = gpu_baseline_block(B, T, dev)
+        best, table = cpu_best_of(cfg, T, ncls, batches=(8, eval_bs, 128))
+        line["cpu_baseline"] = {"value": round(best[0], 3), "unit": UNIT, "cores": best[1], "kind": "port", "sample": best[2],
+                                "clips_per_s_by_batch": table,
+                                "note": "oracle port issuing the reference module's ATen calls (the reference module itself "
+                                        "cannot travel to the GPU box); best of the batch sizes listed"}
     if rank == 0:
         emit(line)
     adist.shutdown()
@@ -652,12 +811,20 @@ def main():
     ap.add_argument("--config", default="ek100_sa_tsn", choices=configs.CONFIG_NAMES)
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=0, help="clips per CPU forward (default: the experiment's eval batch)")
-    ap.add_argument("--strict", action="store_true", help="bf16x3 error-compensated GEMMs")
+    ap.add_argument("--precision", choices=["bf16", "fp16", "strict"], default="bf16",
+                    help="GEMM operand arithmetic: bf16, fp16 (same tensor rate, 8x less rounding) or strict (bf16x3)")
+    ap.add_argument("--strict", action="store_true", help="alias of --precision strict")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="train mode: do not capture the step into a CUDA graph")
     ap.add_argument("--no-staged", action="store_true", help="skip the clip-descriptor (feature store) e2e measurement")
+    ap.add_argument("--no-modes", action="store_true", help="skip the sub-records of the other precision modes")
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="length of the sustained timing loop in seconds")
+    ap.add_argument("--parity-clips", type=int, default=1024, help="clips of the in-run parity block (rank 0, N=1)")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
+    if args.strict:
+        args.precision = "strict"
+    args.strict = args.precision == "strict"
     claim_stdout()
     if args.mode == "train":
         run_train(args)

@@ -63,14 +63,23 @@ AFFT_API const char* afft_last_error(void);
 /* AFFT_ACT_RELU: nn.ReLU (models/feature_mapping.py:81-88 NonLinear, models/fusion.py:41,44 MATT).
  * AFFT_ACT_GATE: out = residual * sigmoid(A . W^T + bias) - ContextGating's cat + glu (models/feature_mapping.py:21-33);
  *                the residual operand is required and multiplies instead of adding. */
+/* Operand arithmetic of the dense contractions (GEMM accumulation, the residual stream, LayerNorm and softmax
+ * statistics are fp32 in every mode; the reference computes everything in fp32):
+ *  AFFT_PREC_BF16   bf16 operands, one tensor-core pass.
+ *  AFFT_PREC_BF16X3 "strict": error-compensated bf16 hi/lo pairs, hi.hi + hi.lo + lo.hi (three passes, fp32-grade products).
+ *  AFFT_PREC_FP16   fp16 operands, one pass at the bf16 rate, 11 significand bits (8x less operand rounding than bf16);
+ *                   conversions saturate to +-65504. */
+enum { AFFT_PREC_BF16 = 0, AFFT_PREC_BF16X3 = 1, AFFT_PREC_FP16 = 2 };
+
 enum { AFFT_ACT_NONE = 0, AFFT_ACT_GELU_ERF = 1, AFFT_ACT_GELU_TANH = 2, AFFT_ACT_RELU = 3, AFFT_ACT_GATE = 4 };
 
 /*
  * C = epilogue(A . W^T): replaces torch.nn.Linear / transformers Conv1D
  * (models/feature_mapping.py:60,74; models/transformerblock.py:21,34,85-87;
  *  models/future_prediction.py:108,149,248,254,267,269; GPT-2 c_attn/c_proj/c_fc).
- * A [M,K] and W [N,K] are bf16, K contiguous, 16-byte aligned with 16-byte multiple pitches.
- * strict != 0: operands are hi/lo bf16 pairs and the product is hi.hi + hi.lo + lo.hi.
+ * A [M,K] and W [N,K] are bf16 (fp16 with AFFT_PREC_FP16), K contiguous, 16-byte aligned with 16-byte multiple pitches.
+ * precision AFFT_PREC_BF16X3: operands are hi/lo bf16 pairs and the product is hi.hi + hi.lo + lo.hi.
+ * The 16-bit output (out_hi) has the operand format of the precision (it feeds the next GEMM).
  * Epilogue, in order: + bias[N] -> activation -> + residual -> stores.
  * Output row of GEMM row r: (r / row_group) * row_stride + r % row_group + row_off
  * (row_group == 0: r).  The residual is read at the same mapped row, or at row r % res_mod when
@@ -84,7 +93,7 @@ typedef struct afft_gemm_desc {
   const void* w_lo; /* strict only */
   int64_t ldw;
   int32_t M, N, K;
-  int32_t strict;
+  int32_t precision; /* AFFT_PREC_* */
   const float* bias;
   const float* res;
   int64_t ld_res;
@@ -92,8 +101,8 @@ typedef struct afft_gemm_desc {
   int32_t act;
   float* out_f32;
   int64_t ld_f32;
-  void* out_hi; /* bf16 */
-  void* out_lo; /* bf16, strict producers */
+  void* out_hi; /* bf16 (fp16 with AFFT_PREC_FP16) */
+  void* out_lo; /* bf16, AFFT_PREC_BF16X3 producers */
   int64_t ld_bf16;
   int32_t row_group, row_stride, row_off;
   int32_t force_block_n; /* 0 = auto, 128 or 256 */
@@ -105,6 +114,9 @@ AFFT_API int afft_gemm(const afft_gemm_desc* d, void* stream);
  * writes dst[c, r].  Weight packing (Conv1D [in,out] -> K-major) and feature inputs. */
 AFFT_API int afft_convert_bf16(const float* src, int64_t lds, int32_t rows, int32_t cols, void* hi, void* lo, int64_t ldd,
                       int32_t transpose, void* stream);
+/* The same for any precision: AFFT_PREC_FP16 writes saturated fp16 to hi (lo must be NULL), AFFT_PREC_BF16X3 needs lo. */
+AFFT_API int afft_convert_operand(const float* src, int64_t lds, int32_t rows, int32_t cols, void* hi, void* lo, int64_t ldd,
+                                  int32_t transpose, int32_t precision, void* stream);
 
 /* LayerNorm over the last dim: replaces nn.LayerNorm (models/fusion.py:281,362;
  * models/transformerblock.py:132,134,157-161; GPT-2 ln_1/ln_2/ln_f).  dim in {512,1024,2048}. */
@@ -126,22 +138,25 @@ typedef struct afft_layernorm_desc {
   void* aux_hi;
   void* aux_lo;
   int64_t ld_aux;
+  int32_t out_fp16; /* y_hi / aux_hi are fp16 (AFFT_PREC_FP16 consumers) instead of bf16 */
 } afft_layernorm_desc;
 
 AFFT_API int afft_layernorm(const afft_layernorm_desc* d, void* stream);
 
 /* Small multi-head attention (L <= 64, head_dim 256 or 512): replaces the two bmm + softmax of
  * models/transformerblock.py:24-33, :64-74 and GPT-2's eager attention.
- * in_f32 != 0: q/k/v are fp32 (strict mode), else bf16.  Element (seq, i, h, d) of q is at
+ * in_dtype: q/k/v element type AFFT_DT_BF16 / AFFT_DT_F32 (strict mode) / AFFT_DT_FP16; the output keeps a 16-bit input
+ * format (fp32 inputs: bf16 hi + optional lo).  Element (seq, i, h, d) of q is at
  * q[(seq*L + i)*ldq + h*head_dim + d].  mask: 0 none, 1 causal, 2 block-causal with period T,
  * 3 diagonal masked.  probs (optional, fp32) element (seq,h,i,j) is at
  * probs[(seq / p_inner)*p_outer + (seq % p_inner)*p_inner_stride + (h*L + i)*L + j]. */
+enum { AFFT_DT_BF16 = 0, AFFT_DT_F32 = 1, AFFT_DT_FP16 = 2 };
 typedef struct afft_attention_desc {
   const void* q;
   const void* k;
   const void* v;
   int64_t ldq, ldk, ldv;
-  int32_t in_f32;
+  int32_t in_dtype;
   int32_t n_seq, L, H, head_dim;
   float scale;
   int32_t mask, T;
@@ -218,7 +233,7 @@ typedef struct afft_config {
   int32_t n_cls;
   char cls_name[AFFT_MAX_CLS][AFFT_NAME_LEN];
   int32_t cls_dim[AFFT_MAX_CLS];
-  int32_t strict;                         /* 0: bf16 operands; 1: bf16x3 error-compensated GEMMs */
+  int32_t precision;                      /* AFFT_PREC_BF16 / AFFT_PREC_BF16X3 (strict) / AFFT_PREC_FP16 */
   int32_t max_batch;                      /* workspace is sized for this many clips per call */
   int32_t device;                         /* CUDA device ordinal */
   int32_t fp_output_len;                  /* model.common.fp_output_len: future steps rolled out (>= 1) */
@@ -262,9 +277,11 @@ AFFT_API int afft_forward(afft_handle* h, int32_t B, const afft_io* io, void* st
 AFFT_API int afft_last_launch_count(const afft_handle* h);
 
 /*
- * Optional per-launch timing (CUDA events recorded on the caller's stream around every kernel of the next
- * forwards).  Used by bench.py for the roofline of the GEMM kernel; off by default (no events recorded).
- * afft_profile_read synchronises on the recorded events and returns the records of the most recent forward.
+ * Optional per-launch timing.  With profiling on, every kernel of the next forwards records the latest %globaltimer value
+ * any of its warps saw on exit into a device slot; afft_profile_read synchronises the forward's stream and attributes to
+ * launch i the interval (end of launch i-1, end of launch i].  The slices add up to the device time of the forward
+ * exactly and the marks do not disturb the programmatic-dependent-launch overlap of consecutive kernels (CUDA events
+ * between the launches would).  Used by bench.py for the roofline of the GEMM kernel; off by default.
  */
 enum { AFFT_CAT_GEMM = 0, AFFT_CAT_LAYERNORM = 1, AFFT_CAT_ATTENTION = 2, AFFT_CAT_OTHER = 3 };
 #define AFFT_MAX_PROFILE_RECS 256

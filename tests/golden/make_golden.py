@@ -49,6 +49,16 @@ CASES_N3 = [
 ]
 
 
+# constructor options without a shipped experiment.  Generic "<outer>|<inner>" layout plus the fuser's
+# attention probabilities.
+CASES_OPT = [
+    ("ek100_sa_3head_b2", "ek100_sa_3head", 2, 123, "randn"),
+    ("ek100_sa_modenc_flt_b2", "ek100_sa_modenc_flt", 2, 123, "randn"),
+    ("ek100_sa_cross_attn_b2", "ek100_sa_cross_attn", 2, 123, "randn"),
+    ("ek100_tsa_mean_b2", "ek100_tsa_mean", 2, 123, "randn"),
+]
+
+
 def flatten_generic(out):
     flat = {}
     for k, inner in out.items():
@@ -129,9 +139,10 @@ def main():
             with open(os.path.join(HERE, f"param_names_{cfg_name}.json"), "w") as f:
                 json.dump({n: list(p.shape) for n, p in model.named_parameters()}, f, indent=0)
 
-    for case, cfg_name, B, seed, family in CASES_N3:
+    for case, cfg_name, B, seed, family in CASES_N3 + CASES_OPT:
         if only and case not in only:
             continue
+        with_attn = (case, cfg_name, B, seed, family) in CASES_OPT
         cfg, T, ncls, _ = configs.named_config(cfg_name)
         model = ref_shim.build_reference_model(cfg, ncls)
         sd = synthetic.synthetic_state_dict(model, seed=0)
@@ -140,14 +151,24 @@ def main():
         assert all(("attn.bias" in m or "masked_bias" in m) for m in missing), missing
         feats6 = synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=seed, family=family, six_d=True)
         feats = {m: t.reshape(B, T, -1) for m, t in feats6.items()}
-        ref32 = flatten_generic(ref_shim.reference_forward(model, feats6))
+        raw32 = ref_shim.reference_forward(model, feats6)
+        ref32 = flatten_generic(raw32)
         model64 = model.double()
-        ref64 = flatten_generic(ref_shim.reference_forward(model64, {m: t.double() for m, t in feats6.items()}))
+        raw64 = ref_shim.reference_forward(model64, {m: t.double() for m, t in feats6.items()})
+        ref64 = flatten_generic(raw64)
         model.float()
         sd_full = {k: v for k, v in model.state_dict().items()}
-        o64 = flatten_generic(afft_oracle.forward(sd_full, cfg, ncls, feats, dtype=torch.float64))
+        rawo64 = afft_oracle.forward(sd_full, cfg, ncls, feats, dtype=torch.float64)
+        o64 = flatten_generic(rawo64)
         o32 = flatten_generic(afft_oracle.forward(sd_full, cfg, ncls, feats, dtype=torch.float32))
         rec, save = {}, {}
+        if with_attn:
+            ma = raw32["attentions"]["all-fused"]["modality_attns"]
+            d = (rawo64["attentions"]["all-fused"]["modality_attns"].double() -
+                 raw64["attentions"]["all-fused"]["modality_attns"].double()).abs().max().item()
+            assert d < 1e-11, (case, "modality_attns", d)
+            rec["modality_attns"] = {"oracle64_vs_ref64": d}
+            save["modality_attns"] = ma.numpy()
         for k in ref64:
             d64 = (o64[k].double() - ref64[k].double()).abs().max().item()
             d32 = (o32[k].double() - ref32[k].double()).abs().max().item()
@@ -166,7 +187,7 @@ def main():
                 save["logits64|" + k] = ref64[k].numpy()
                 save["top5|" + k] = afft_oracle.top5(ref32[k][:, 0]).numpy()
         pin[case] = rec
-        print(case, {k: (round(v["oracle64_vs_ref64"], 18), round(v["oracle32_vs_ref32"], 9)) for k, v in rec.items()},
+        print(case, {k: (round(v["oracle64_vs_ref64"], 18), round(v.get("oracle32_vs_ref32", 0.0), 9)) for k, v in rec.items()},
               flush=True)
         np.savez_compressed(os.path.join(HERE, case + ".npz"), **save)
         with open(os.path.join(HERE, f"param_names_{cfg_name}.json"), "w") as f:
@@ -181,7 +202,7 @@ def main():
     with open(pin_path, "w") as f:
         json.dump({"generated_with": {"torch": torch.__version__, "transformers": __import__("transformers").__version__,
                                       "reference": ref_shim.REFERENCE_ROOT},
-                   "cases": {c: list(x) for c, *x in CASES + CASES_N3}, "pin": pin}, f, indent=1)
+                   "cases": {c: list(x) for c, *x in CASES + CASES_N3 + CASES_OPT}, "pin": pin}, f, indent=1)
     print("wrote fixtures to", HERE)
 
 

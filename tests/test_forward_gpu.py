@@ -3,10 +3,12 @@
   (b) the CPU oracle run here on fresh inputs,
   (c) size-independent properties at the BASELINE batch sizes.
 
-Tolerances (logits have |max| ~ 2.2, std ~ 0.35 with the synthetic weights):
-  fast   mode (bf16 operands, fp32 accumulate/residual/LN/softmax): |dlogit| < 6e-2, features < 8e-2,
-         attention probabilities < 1e-2.  Top-5 identity is NOT required in this mode.
-  strict mode (bf16x3 error-compensated GEMMs): |dlogit| < 4e-4, features < 6e-4, probabilities < 5e-5 and
+Tolerances (logits have |max| ~ 2.2, std ~ 0.35 with the synthetic weights; observed maxima in profiles/r02_parity.txt):
+  bf16   (bf16 operands, fp32 accumulate/residual/LN/softmax): |dlogit| < 3e-2, features < 4e-2, attention
+         probabilities < 1e-2.  Top-5 identity is NOT required in this mode.
+  fp16   (fp16 operands, same kernels and tensor rate): |dlogit| < 5e-3, features < 6e-3, probabilities < 1.5e-3;
+         ordered top-5 identity is measured on a large sample (test_top5_agreement_large_sample, bench.py `parity`).
+  strict (bf16x3 error-compensated GEMMs): |dlogit| < 4e-4, features < 6e-4, probabilities < 5e-5 and
          ordered top-5 indices identical to the fp32 reference on every clip.
 """
 import os
@@ -20,18 +22,21 @@ from afft_b200.models import BaseModel
 
 pytestmark = pytest.mark.gpu
 
-TOL = {False: dict(logits=6e-2, feat=8e-2, attn=1e-2), True: dict(logits=4e-4, feat=6e-4, attn=5e-5)}
+TOL = {"bf16": dict(logits=3e-2, feat=4e-2, attn=1e-2), "fp16": dict(logits=5e-3, feat=6e-3, attn=1.5e-3),
+       "strict": dict(logits=4e-4, feat=6e-4, attn=5e-5)}
+PRECISIONS = ["bf16", "fp16", "strict"]
 KW = dict(mixup_fn=None, target=None, target_subclips=None, target_subclips_ignore_index=None)
 _models = {}
 
 
-def _model(cfg_name, strict, max_batch=64):
-    key = (cfg_name, strict)
+def _model(cfg_name, precision, max_batch=64):
+    precision = {False: "bf16", True: "strict"}.get(precision, precision)
+    key = (cfg_name, precision)
     if key not in _models:
         if len(_models) >= 3:
             _models.pop(next(iter(_models)))
         cfg, T, ncls, _ = configs.named_config(cfg_name)
-        m = BaseModel(cfg, ncls, {}, strict=strict, max_batch=max_batch)
+        m = BaseModel(cfg, ncls, {}, precision=precision, max_batch=max_batch)
         m.load_state_dict(synthetic.synthetic_state_dict(m, seed=0))
         _models[key] = m.to("cuda:0").eval()
     return _models[key]
@@ -50,16 +55,17 @@ CASES = ["egtea_sa_b3", "ek100_sa_tsn_b2", "ek100_sa_tsn_relu_b2", "ek100_sa_tsn
          "ek100_tsa_b2", "ek100_ca_b2", "ek100_sa_wo_token_b2", "egtea_sa_rollout3_b3"]
 
 
-@pytest.mark.parametrize("strict", [False, True])
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("case", CASES)
-def test_golden_parity(case, strict, golden_dir, golden_cases):
+def test_golden_parity(case, precision, golden_dir, golden_cases):
+    strict = precision == "strict"
     cfg_name, B, seed, family = golden_cases[case]
     cfg, T, ncls, _ = configs.named_config(cfg_name)
-    model = _model(cfg_name, strict)
+    model = _model(cfg_name, precision)
     feats = synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=seed, family=family, six_d=True)
     out = _run(model, feats)
     gold = np.load(os.path.join(golden_dir, case + ".npz"))
-    tol = TOL[strict]
+    tol = TOL[precision]
 
     def err(t, ref):
         a = t.float().cpu().numpy()
@@ -86,23 +92,32 @@ def test_golden_parity(case, strict, golden_dir, golden_cases):
 
 CASES_N3 = ["ek100_individual_b2", "ek100_matt_b2", "ek100_sa_gatedlinear_b2", "ek100_sa_nonlinear_b2",
             "ek100_sa_linear_ln_b2"]
+# three classifier heads; SA-Fuser modal_encoding + frame_level_token; cross_attn=True; T-SA without frame-level token
+CASES_OPT = ["ek100_sa_3head_b2", "ek100_sa_modenc_flt_b2", "ek100_sa_cross_attn_b2", "ek100_tsa_mean_b2"]
 
 
-@pytest.mark.parametrize("strict", [False, True])
-@pytest.mark.parametrize("case", CASES_N3)
-def test_golden_parity_head_and_mapping_variants(case, strict, golden_dir, golden_cases):
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("case", CASES_N3 + CASES_OPT)
+def test_golden_parity_head_and_mapping_variants(case, precision, golden_dir, golden_cases):
     """IndividualFuturePrediction, CMFPScoreFusion + MATT, GatedLinear / NonLinear / layer-normed
     Linear mappings against the reference module's outputs (every leaf stored as "<outer>|<inner>")."""
+    strict = precision == "strict"
     cfg_name, B, seed, family = golden_cases[case]
     cfg, T, ncls, _ = configs.named_config(cfg_name)
-    model = _model(cfg_name, strict)
+    model = _model(cfg_name, precision)
     feats = synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=seed, family=family, six_d=True)
     out = _run(model, feats)
     gold = np.load(os.path.join(golden_dir, case + ".npz"))
-    tol = TOL[strict]
+    tol = TOL[precision]
     checked = 0
     for key in gold.files:
         if key.startswith(("logits64|", "top5|")):
+            continue
+        if key == "modality_attns":
+            ma = out["attentions"]["all-fused"]["modality_attns"].float().cpu().numpy()
+            assert ma.shape == gold[key].shape
+            assert np.abs(ma - gold[key]).max() < tol["attn"]
+            checked += 1
             continue
         outer, inner = key.split("|")
         mine = out[outer][inner]
@@ -143,20 +158,21 @@ def test_score_fusion_operator():
     assert torch.equal(only, attn)
 
 
-@pytest.mark.parametrize("strict", [False, True])
-def test_against_oracle_fresh_inputs(strict):
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_against_oracle_fresh_inputs(precision):
     """Same seeded inputs through the CUDA path and the CPU oracle (not a stored fixture)."""
     from oracle import afft_oracle
+    strict = precision == "strict"
     cfg_name = "ek100_sa_tsn"
     cfg, T, ncls, _ = configs.named_config(cfg_name)
-    model = _model(cfg_name, strict)
+    model = _model(cfg_name, precision)
     B = 5  # ragged: 5*18*5 = 450 fuser rows, 90 GPT rows - nothing is a tile multiple
     feats = synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=4242, family="relu")
     out = _run(model, feats)
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     ref = afft_oracle.forward(sd, cfg, ncls, feats, dtype=torch.float32)
-    tol = TOL[strict]
+    tol = TOL[precision]
     for key, t in (("logits/action", tol["logits"]), ("past_logits/action", tol["logits"]), ("orig_past", tol["feat"]),
                    ("future", tol["feat"]), ("past_futures", tol["feat"])):
         d = (out[key]["all-fused"].cpu() - ref[key]["all-fused"]).abs().max().item()
@@ -209,18 +225,19 @@ def test_properties_at_baseline_batch():
     model.future_predictor.max_ksplit = 4
 
 
-@pytest.mark.parametrize("strict", [False, True])
-def test_splitk_small_batches(strict):
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_splitk_small_batches(precision):
     """Small batches run their GEMMs split along K (few output tiles -> the K loop is spread over the SMs).
     The result is bit-reproducible run to run (partials are summed in split order), equals the unsplit result up
     to fp32 summation order, keeps clips independent at a fixed batch size, and matches the oracle."""
     from oracle import afft_oracle
+    strict = precision == "strict"
     cfg_name = "ek100_sa_tsn"
     cfg, T, ncls, _ = configs.named_config(cfg_name)
-    model = _model(cfg_name, strict)
+    model = _model(cfg_name, precision)
     head = model.future_predictor
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-    tol = TOL[strict]
+    tol = TOL[precision]
     keys = ("logits/action", "past_logits/action", "orig_past", "past_futures")
     for B in (1, 3, 8, 32):
         feats = synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=900 + B)
@@ -293,3 +310,63 @@ def test_input_validation_on_device():
         _run(m, bad)
     with pytest.raises(AssertionError):
         _run(m, {"rgb": good["rgb"], "flow": good["flow"][:, :T - 1]})
+
+
+# ------------------------------------------------------------------------------------------------
+# Direct oracle comparison at the BASELINE batch sizes + large-sample top-5 agreement (headline config)
+# ------------------------------------------------------------------------------------------------
+_LARGE = {}
+
+
+def _large_sample(n_clips=512):
+    """Oracle logits of n_clips seeded clips of the headline config, computed once per session (~10 s of CPU)."""
+    if "ref" not in _LARGE:
+        from oracle import afft_oracle
+        cfg, T, ncls, _ = configs.named_config("ek100_sa_tsn")
+        probe = _model("ek100_sa_tsn", "bf16")
+        sd = {k: v.detach().cpu() for k, v in probe.state_dict().items()}
+        feats = synthetic.synthetic_features(cfg["modal_dims"], n_clips, T, seed=123)  # seed 123: SURVEY section 8d
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        afft_oracle.ATEN_OPS = True  # same arithmetic, library calls (tests/test_oracle.py pins both spellings)
+        refs = []
+        with torch.no_grad():
+            for b0 in range(0, n_clips, 64):
+                r = afft_oracle.forward(sd, cfg, ncls, {m: f[b0:b0 + 64] for m, f in feats.items()}, dtype=torch.float32)
+                refs.append((r["logits/action"]["all-fused"][:, 0], r["past_logits/action"]["all-fused"][:, -1]))
+        afft_oracle.ATEN_OPS = False
+        _LARGE["feats"] = feats
+        _LARGE["ref"] = torch.cat([r[0] for r in refs])
+        _LARGE["ref_past_last"] = torch.cat([r[1] for r in refs])
+    return _LARGE
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_top5_agreement_large_sample(precision):
+    """512 clips of the headline config, run at B = 256 (the benchmarked batch) and B = 32 (the shipped eval batch,
+    expts/01_SA-Fuser_ek100_val_TSN.txt:6), compared clip by clip with the fp32 oracle: max |dlogit| within the
+    mode's tolerance and the ordered top-5 identity rate - 100 % in strict mode, >= 97 % with fp16 operands."""
+    from afft_b200 import parity
+    L = _large_sample()
+    model = _model("ek100_sa_tsn", precision, max_batch=256)
+    n = L["ref"].shape[0]
+    got = {}
+    for B in (256, 32):
+        outs = []
+        for b0 in range(0, n if B == 256 else 64, B):
+            o = _run(model, {m: f[b0:b0 + B] for m, f in L["feats"].items()})
+            outs.append(o["logits/action"]["all-fused"][:, 0].cpu())
+        got[B] = torch.cat(outs)
+    st = parity.top5_stats(got[256], L["ref"])
+    print(f"\n[parity {precision}] B=256 x 2: {st}")
+    tol = TOL[precision]["logits"]
+    assert st["max_abs_dlogit"] < tol, st
+    st32 = parity.top5_stats(got[32], L["ref"][:64])
+    assert st32["max_abs_dlogit"] < tol, st32
+    if precision == "strict":
+        assert st["ordered_top5_identical"] == n and st32["ordered_top5_identical"] == 64, (st, st32)
+    elif precision == "fp16":
+        assert st["ordered_top5_identity_rate"] >= 0.97, st
+        assert st["top1_identity_rate"] >= 0.99, st
+    else:
+        assert st["ordered_top5_identity_rate"] >= 0.70, st
+    assert st["top5_set_identity_rate"] >= st["ordered_top5_identity_rate"]

@@ -220,3 +220,84 @@ def test_attention(dev, n_seq, L, H, hd, mask, T, dt):
     assert (probs.sum(-1) - 1).abs().max().item() < 1e-5
     with pytest.raises(capi.AfftError):
         capi.attention(qkv, n_seq, 65, H, hd, out_hi=oh)
+
+
+# ------------------------------------------------------------------------------------------------
+# fp16-operand mode (AFFT_PREC_FP16): same kernels, fp16 A / W / 16-bit outputs, fp32 accumulation
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (1000, 1024, 1024, 0), (90, 3072, 1024, 0), (576, 1024, 352, 0),
+                                      (300, 3806, 1024, 0), (1, 1024, 1024, 0), (2304, 8192, 2048, 256)])
+def test_gemm_fp16_operands(dev, M, N, K, bn):
+    """fp16 operands are exact inputs of the tensor core: the only error is fp32 accumulation order."""
+    g = torch.Generator().manual_seed(M * 7 + N + 1)
+    a = _randn(g, dev, M, K).half()
+    w = _randn(g, dev, N, K, scale=0.05).half()
+    ld = (N + 3) // 4 * 4
+    out = torch.full((M, ld), float("nan"), device=dev)
+    capi.gemm(a, w, out_f32=out, force_block_n=bn)
+    ref = _mm(a, w)
+    assert not torch.isnan(out[:, :N]).any()
+    assert (out[:, :N] - ref).abs().max().item() < 2e-4 * max(1.0, (K / 1024) ** 0.5) * 3
+
+
+def test_gemm_fp16_epilogues_and_saturation(dev):
+    g = torch.Generator().manual_seed(55)
+    M, N, K = 777, 1024, 1024
+    a = _randn(g, dev, M, K).half()
+    w = _randn(g, dev, N, K, scale=0.05).half()
+    bias, res = _randn(g, dev, N), _randn(g, dev, M, N)
+    ref0 = _mm(a, w)
+    F = torch.nn.functional
+    out_h = torch.zeros(M, N, device=dev, dtype=torch.float16)
+    capi.gemm(a, w, bias=bias, act=capi.ACT_GELU_ERF, out_hi=out_h)  # FC1 of the fuser MLP: degree-4 sigmoid form of erf-GELU
+    ref = F.gelu(ref0 + bias)
+    assert (out_h.float() - ref).abs().max().item() < 4e-3  # one fp16 ulp at |x| < 8 (3.9e-3) + 3.2e-6 approximation
+    assert (out_h.float() - ref).abs().mean().item() < 2e-4
+    capi.gemm(a, w, bias=bias, act=capi.ACT_GELU_TANH, out_hi=out_h)
+    assert (out_h.float() - F.gelu(ref0 + bias, approximate="tanh")).abs().max().item() < 4e-3
+    out_f = torch.zeros(M, N, device=dev)
+    capi.gemm(a, w, bias=bias, res=res, out_f32=out_f, out_hi=out_h)
+    assert (out_f - (ref0 + bias + res)).abs().max().item() < 1e-4
+    assert torch.equal(out_h, out_f.half())
+    # saturation instead of inf: a huge bias drives the fp16 output beyond 65504
+    big = torch.full((N,), 1e6, device=dev)
+    capi.gemm(a, w, bias=big, out_hi=out_h)
+    assert torch.isfinite(out_h).all() and (out_h == 65504).all()
+    x = torch.tensor([[1e9, -1e9, 70000.0, 1.0, 0.0, -3.0, 65504.0, 6e-8]], device=dev)
+    h = torch.zeros(1, 8, device=dev, dtype=torch.float16)
+    capi.check(capi.lib().afft_convert_operand(x.data_ptr(), 8, 1, 8, h.data_ptr(), None, 8, 0, capi.PREC_FP16,
+                                               capi.current_stream_ptr(dev)))
+    assert torch.equal(h, x.clamp(-65504, 65504).half())
+
+
+def test_layernorm_fp16_output(dev):
+    g = torch.Generator().manual_seed(77)
+    rows, dim = 1237, 1024
+    x = _randn(g, dev, rows, dim) * 3 + 0.5
+    gm, bt = _randn(g, dev, dim), _randn(g, dev, dim)
+    yf = torch.zeros(rows, dim, device=dev)
+    yh = torch.zeros(rows, dim, device=dev, dtype=torch.float16)
+    capi.layernorm(x, gm, bt, 1e-6, y_f32=yf, y_hi=yh)
+    assert torch.equal(yh, yf.half())
+    yh2 = torch.zeros_like(yh)
+    capi.layernorm(x, gm, bt, 1e-6, y_hi=yh2)  # the hot (16-bit output only) instantiation
+    assert torch.equal(yh2, yh)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n_seq,L,H,hd,mask,T", [(36, 5, 4, 256, 0, 1), (38, 5, 4, 256, 3, 1), (7, 18, 4, 512, 1, 18),
+                                                 (3, 50, 4, 256, 2, 10), (5, 10, 4, 256, 1, 10), (37, 4, 4, 256, 0, 1),
+                                                 (2, 64, 4, 256, 1, 64), (2, 1, 4, 256, 0, 1)])
+def test_attention_tensor_core_paths(dev, n_seq, L, H, hd, mask, T, dt):
+    """The mma.sync attention kernels the forward uses (16-bit inputs, no lo output), bf16 and fp16 operands."""
+    g = torch.Generator().manual_seed(L * 31 + hd + 1)
+    D = H * hd
+    qkv = _randn(g, dev, n_seq * L, 3 * D).to(dt)
+    oh = torch.zeros(n_seq * L, D, device=dev, dtype=dt)
+    probs = torch.zeros(n_seq, H, L, L, device=dev)
+    capi.attention(qkv, n_seq, L, H, hd, mask=mask, T=T, out_hi=oh, probs=probs, p_outer=H * L * L)
+    ro, rp = _ref_attn(qkv, n_seq, L, H, hd, mask, T)
+    # P is re-quantised to the operand format for P.V and the output is rounded to it: 2^-9 (bf16) / 2^-12 (fp16) on |v| ~ 3
+    assert (oh.float() - ro).abs().max().item() < (3e-2 if dt == torch.bfloat16 else 4e-3)
+    assert (probs - rp).abs().max().item() < 2e-5
+    assert (probs.sum(-1) - 1).abs().max().item() < 1e-5

@@ -58,9 +58,12 @@ def test_oracle_matches_golden(case, golden_dir, golden_cases):
 
 CASES_N3 = ["ek100_individual_b2", "ek100_matt_b2", "ek100_sa_gatedlinear_b2", "ek100_sa_nonlinear_b2",
             "ek100_sa_linear_ln_b2"]
+# constructor options no shipped experiment switches on: three heads, SA modal_encoding + frame_level_token,
+# cross_attn=True, T-SA without frame-level token (same fixture layout + the fuser's attention probabilities)
+CASES_OPT = ["ek100_sa_3head_b2", "ek100_sa_modenc_flt_b2", "ek100_sa_cross_attn_b2", "ek100_tsa_mean_b2"]
 
 
-@pytest.mark.parametrize("case", CASES_N3)
+@pytest.mark.parametrize("case", CASES_N3 + CASES_OPT)
 def test_oracle_matches_golden_head_and_mapping_variants(case, golden_dir, golden_cases):
     """SURVEY 8f row N3 (IndividualFuturePrediction, CMFPScoreFusion + MATT, GatedLinear / NonLinear / layer-normed
     mappings): fixtures hold every output leaf of the reference module as "<outer>|<inner>"."""
@@ -74,6 +77,11 @@ def test_oracle_matches_golden_head_and_mapping_variants(case, golden_dir, golde
     checked = 0
     for key in gold.files:
         if key.startswith(("logits64|", "top5|")):
+            continue
+        if key == "modality_attns":
+            ma = out["attentions"]["all-fused"]["modality_attns"].numpy()
+            assert ma.shape == gold[key].shape
+            assert np.abs(ma - gold[key]).max() < 1e-5
             continue
         outer, inner = key.split("|")
         mine = out[outer][inner]
