@@ -357,7 +357,7 @@ extern "C" int afft_marginalize_topk(const float* logits, int64_t ld, int32_t B,
   if (logits == nullptr || verb_of == nullptr || noun_of == nullptr || verb == nullptr || noun == nullptr)
     return fail(AFFT_ERR_INVALID, "marginalize: null pointer");
   if (B <= 0 || A <= 0 || n_verb <= 0 || n_noun <= 0 || ld < A) return fail(AFFT_ERR_INVALID, "marginalize: bad sizes");
-  if (n_verb + n_noun > 8192) return fail(AFFT_ERR_INVALID, "marginalize: too many verb + noun classes (max 8192)");
+  if (n_verb + n_noun > 3072) return fail(AFFT_ERR_INVALID, "marginalize: too many verb + noun classes (max 3072: 12 B of shared memory each)");
   if (topk != nullptr && (K < 1 || K > 16 || K > n_verb || K > n_noun || K > A))
     return fail(AFFT_ERR_INVALID, "marginalize: K must be in [1, 16] and <= every class count");
   MarginalizeArgs a;
@@ -374,7 +374,7 @@ extern "C" int afft_marginalize_topk(const float* logits, int64_t ld, int32_t B,
   a.noun = noun;
   a.topk = topk;
   a.K = K;
-  const size_t smem = static_cast<size_t>(n_verb + n_noun) * 4 + 32 * 8 + 16 * 4;
+  const size_t smem = static_cast<size_t>(n_verb + n_noun) * (8 + 4) + 32 * 8 + 16 * 4;
   marginalize_topk_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail("marginalize launch", e);
@@ -384,7 +384,8 @@ extern "C" int afft_marginalize_topk(const float* logits, int64_t ld, int32_t B,
 extern "C" int afft_score_fusion(const float* attn_logits, int64_t ld_a, int32_t n_mod, const float* const* logits,
                                  int64_t ld_l, int32_t rows, int32_t C, float* attn, float* out, int64_t ld_o, void* stream) {
   if (attn_logits == nullptr) return fail(AFFT_ERR_INVALID, "score_fusion: null attn_logits");
-  if (n_mod < 1 || n_mod > 8 || rows < 1 || rows > 65535 || ld_a < n_mod) return fail(AFFT_ERR_INVALID, "score_fusion: bad sizes");
+  if (n_mod < 1 || n_mod > 8) return fail(AFFT_ERR_INVALID, "score_fusion: n_mod must be in [1, 8]");
+  if (rows < 1 || ld_a < n_mod) return fail(AFFT_ERR_INVALID, "score_fusion: rows must be >= 1 and ld_a >= n_mod");
   const bool softmax_only = (out == nullptr);  // only the modality attention is wanted (MATT.forward)
   if (softmax_only && attn == nullptr) return fail(AFFT_ERR_INVALID, "score_fusion: no output");
   if (softmax_only) C = 0;
@@ -412,7 +413,7 @@ extern "C" int afft_score_fusion(const float* attn_logits, int64_t ld_a, int32_t
   a.out = out;
   a.ld_o = ld_o;
   const int quads = (C + 3) / 4;
-  dim3 grid(std::max(1, (quads + 255) / 256), rows);
+  dim3 grid(rows, std::min(std::max(1, (quads + 255) / 256), 65535));
   score_fusion_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail("score_fusion launch", e);

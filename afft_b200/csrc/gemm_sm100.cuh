@@ -760,7 +760,10 @@ struct Gemm2Traits {
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;       // 128 rows of A
   static constexpr uint32_t kBBytes = 128 * kBlockK * 2;           // this CTA's half of the 256-row B tile
   static constexpr uint32_t kStageBytes = kPairs * (kABytes + kBBytes);
-  static constexpr int kStages = (MODE == MODE_BF16X3) ? 3 : 6;
+#ifndef AFFT_2CTA_STAGES
+#define AFFT_2CTA_STAGES 6  // A/B knob (tools/gemm_time.py with AFFT_B200_LIB): depth of the TMA -> MMA ring
+#endif
+  static constexpr int kStages = (MODE == MODE_BF16X3) ? 3 : AFFT_2CTA_STAGES;
   static constexpr uint32_t kTmemCols = 512;                       // 2 accumulators x 256 columns
   static constexpr uint32_t kBarrierBytes = 256;
   static constexpr uint32_t kStagingBytes = kNumEpilogueWarps * 4096;

@@ -960,6 +960,10 @@ __global__ void __launch_bounds__(256) attention_tokens_mma_kernel(const Attenti
 // noun[n] likewise (the reference multiplies by the 0/1 matrices class_mappings[('verb','action')] /
 // [('noun','action')], which have exactly one 1 per action row);  top-K indices of action / verb / noun scores.
 // One CTA per clip; verb/noun accumulators in shared memory; K rounds of block arg-max (ties -> lower index).
+// The accumulators are 64-bit fixed point (p * 2^40, integer atomics): integer addition is associative, so the verb /
+// noun scores are bit-reproducible run to run whatever order the threads arrive in (float atomics are not); the
+// quantisation is 2^-41 per action, < 2e-9 on a sum of 3806 terms.  NaN logits rank last instead of poisoning the
+// comparisons.
 // ------------------------------------------------------------------------------------------------
 struct MarginalizeArgs {
   const float* logits;  // [B, ld]
@@ -1003,7 +1007,8 @@ __device__ __forceinline__ void block_topk(const float* vals, int n, int K, int*
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       bool taken = false;
       for (int j = 0; j < k; ++j) taken |= (chosen[j] == i);
-      const float v = vals[i];
+      float v = vals[i];
+      if (v != v) v = -INFINITY;  // NaN ranks last
       if (!taken && (v > best || (v == best && i < bi))) { best = v; bi = i; }
     }
     block_argmax(best, bi, red_v, red_i);
@@ -1013,17 +1018,18 @@ __device__ __forceinline__ void block_topk(const float* vals, int n, int K, int*
 }
 
 __global__ void __launch_bounds__(256) marginalize_topk_kernel(const MarginalizeArgs a) {
-  extern __shared__ float smem_mg[];
-  float* sv = smem_mg;            // [n_verb]
+  extern __shared__ unsigned long long smem_mg64[];
+  unsigned long long* acc = smem_mg64;                     // [n_verb + n_noun] fixed-point sums
+  float* sv = reinterpret_cast<float*>(acc + a.n_verb + a.n_noun);  // [n_verb]
   float* sn = sv + a.n_verb;      // [n_noun]
   float* red_v = sn + a.n_noun;   // [32]
   int* red_i = reinterpret_cast<int*>(red_v + 32);
   int* chosen = red_i + 32;       // [K]
   const int b = blockIdx.x;
   const float* lg = a.logits + b * a.ld;
-  for (int i = threadIdx.x; i < a.n_verb + a.n_noun; i += blockDim.x) sv[i] = 0.f;
+  for (int i = threadIdx.x; i < a.n_verb + a.n_noun; i += blockDim.x) acc[i] = 0ull;
   float mx = -INFINITY;
-  for (int i = threadIdx.x; i < a.A; i += blockDim.x) mx = fmaxf(mx, lg[i]);
+  for (int i = threadIdx.x; i < a.A; i += blockDim.x) mx = fmaxf(mx, lg[i]);  // fmaxf drops NaN operands
   int dummy = 0;
   block_argmax(mx, dummy, red_v, red_i);
   float sum = 0.f;
@@ -1039,9 +1045,13 @@ __global__ void __launch_bounds__(256) marginalize_topk_kernel(const Marginalize
   for (int i = threadIdx.x; i < a.A; i += blockDim.x) {
     const float p = expf(lg[i] - mx) * inv;
     if (a.probs != nullptr) a.probs[static_cast<long long>(b) * a.A + i] = p;
-    atomicAdd(&sv[a.verb_of[i]], p);
-    atomicAdd(&sn[a.noun_of[i]], p);
+    const unsigned long long q = (p == p) ? static_cast<unsigned long long>(static_cast<double>(p) * 1099511627776.0) : 0ull;  // 2^40
+    atomicAdd(&acc[a.verb_of[i]], q);
+    atomicAdd(&acc[a.n_verb + a.noun_of[i]], q);
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.n_verb + a.n_noun; i += blockDim.x)
+    sv[i] = static_cast<float>(static_cast<double>(acc[i]) * (1.0 / 1099511627776.0));
   __syncthreads();
   for (int i = threadIdx.x; i < a.n_verb; i += blockDim.x) a.verb[static_cast<long long>(b) * a.n_verb + i] = sv[i];
   for (int i = threadIdx.x; i < a.n_noun; i += blockDim.x) a.noun[static_cast<long long>(b) * a.n_noun + i] = sn[i];
@@ -1140,7 +1150,7 @@ struct ScoreFusionArgs {
 };
 
 __global__ void __launch_bounds__(256) score_fusion_kernel(const ScoreFusionArgs a) {
-  const int r = blockIdx.y;
+  const int r = blockIdx.x;  // rows on gridDim.x (2^31 - 1 limit), column blocks on gridDim.y
   float p[8];
   float mx = -INFINITY;
 #pragma unroll
@@ -1157,7 +1167,7 @@ __global__ void __launch_bounds__(256) score_fusion_kernel(const ScoreFusionArgs
   const float inv = 1.0f / sum;
 #pragma unroll
   for (int i = 0; i < 8; ++i) p[i] *= inv;
-  if (a.attn != nullptr && blockIdx.x == 0 && threadIdx.x < a.M) {
+  if (a.attn != nullptr && blockIdx.y == 0 && threadIdx.x < a.M) {
     float v = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -1165,7 +1175,7 @@ __global__ void __launch_bounds__(256) score_fusion_kernel(const ScoreFusionArgs
     a.attn[static_cast<long long>(r) * a.M + threadIdx.x] = v;
   }
   const int quads = (a.C + 3) / 4;
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
+  for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < quads; q += gridDim.y * blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {

@@ -52,6 +52,7 @@ inline bool orig_video_fps(const std::string& name, double* out) {
 struct afft_feature_store {
   std::vector<Modality> mods;
   std::string err;
+  bool allow_empty_clips = false;  // false: refuse clips without any stored frame in their window (reference behaviour)
 };
 
 static thread_local std::string g_stage_err;
@@ -173,6 +174,12 @@ inline int64_t lookup_row(const VideoIndex& v, long long frame) {
 
 }  // namespace
 
+extern "C" int afft_store_allow_empty_clips(afft_feature_store* s, int32_t allow) {
+  if (s == nullptr) return sfail(nullptr, AFFT_ERR_INVALID, "store_allow_empty_clips: null store");
+  s->allow_empty_clips = allow != 0;
+  return AFFT_OK;
+}
+
 extern "C" int afft_store_plan(afft_feature_store* s, int32_t B, const char* const* video_names, const double* start_sec,
                                const double* end_sec, double fps, int32_t T, double frame_rate, int32_t strategy,
                                int32_t* row_idx, int32_t* frame_ids_out) {
@@ -208,6 +215,22 @@ extern "C" int afft_store_plan(afft_feature_store* s, int32_t B, const char* con
           if (row >= mod.n_rows && mod.rows != nullptr) { errs[tid] = "store_plan: index of " + name + " points past the row table"; return; }
           ri[t] = static_cast<int32_t>(row);
           if (fo) fo[t] = static_cast<int32_t>(f);
+        }
+        // The reference asserts that at least one frame of the window is stored (`assert len(features_not_none) > 0`,
+        // reader_fns.py:97): a clip with no stored frame near any of its T kept frames is a data problem, not zeros.
+        bool any_row = false;
+        for (int t = 0; t < T; ++t) any_row |= (ri[t] >= 0);
+        if (!any_row && !s->allow_empty_clips) {  // rare: look at every frame of the window, as the reference's reader does before it subsamples
+          for (size_t wi = 0; wi < window.size() && !any_row; ++wi) {
+            long long f = window[wi];
+            if (mod.orig_fps) f = round_half_even(static_cast<double>(f) / fps * ofps);
+            any_row = lookup_row(vit->second, f) >= 0;
+          }
+        }
+        if (!any_row && !s->allow_empty_clips) {
+          errs[tid] = "store_plan: clip " + std::to_string(b) + " (" + name + ") has no stored frame in modality " +
+                      std::to_string(m) + " within its window (reader_fns.py:97 asserts)";
+          return;
         }
       }
     }

@@ -35,15 +35,16 @@ class WeightCache:
 
 def to_operand(x: torch.Tensor, precision: str):
     """fp32 [R, K] -> the precision's GEMM operand through afft_convert_operand: bf16 hi (and lo = bf16(x - hi) in strict
-    mode), or saturated fp16."""
+    mode), or saturated fp16.  The result is [R, Kp] with Kp = K rounded up to a multiple of 8 (TMA needs 16-byte row
+    pitches); the pad columns are zero and add nothing to a contraction (MATT with dim=None: 3424 -> 856 -> 428)."""
     if not x.is_cuda:
         raise _capi.AfftError("afft_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
     R, K = x.shape
-    if K % 8 != 0:
-        raise _capi.AfftError(f"feature width {K} must be a multiple of 8 (16-byte bf16 row pitch for TMA)")
-    hi = torch.empty(R, K, device=x.device, dtype=_capi.operand_dtype(precision))
-    lo = torch.empty_like(hi) if precision == "strict" else None
-    _capi.check(_capi.lib().afft_convert_operand(x.data_ptr(), x.stride(0), R, K, hi.data_ptr(), _capi.ptr(lo), K, 0,
+    Kp = (K + 7) // 8 * 8
+    dt = _capi.operand_dtype(precision)
+    hi = torch.empty(R, Kp, device=x.device, dtype=dt) if Kp == K else torch.zeros(R, Kp, device=x.device, dtype=dt)
+    lo = (torch.empty_like(hi) if Kp == K else torch.zeros_like(hi)) if precision == "strict" else None
+    _capi.check(_capi.lib().afft_convert_operand(x.data_ptr(), x.stride(0), R, K, hi.data_ptr(), _capi.ptr(lo), Kp, 0,
                                                  _capi.PRECISIONS[precision], _capi.current_stream_ptr(x.device)))
     return hi, lo
 

@@ -21,7 +21,7 @@ from . import _capi
 
 SAMPLE_STRATEGIES = {"last_clip": 0, "center_clip": 1, "first_clip": 2}  # base_video_dataset.py:28-31
 STAGING_SYMBOLS = ["afft_store_create", "afft_store_destroy", "afft_store_error", "afft_store_add_video",
-                   "afft_store_set_rows", "afft_store_plan", "afft_store_gather"]
+                   "afft_store_set_rows", "afft_store_plan", "afft_store_gather", "afft_store_allow_empty_clips"]
 _KEY_RE = re.compile(r"^(.*)_frame_(\d{10})\.jpg$")  # reader_fns.py:133
 
 
@@ -38,7 +38,9 @@ def _lib():
         l.afft_store_plan.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_double,
                                       C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]
         l.afft_store_gather.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
-        for n in ("afft_store_create", "afft_store_add_video", "afft_store_set_rows", "afft_store_plan", "afft_store_gather"):
+        l.afft_store_allow_empty_clips.argtypes = [C.c_void_p, C.c_int32]
+        for n in ("afft_store_create", "afft_store_add_video", "afft_store_set_rows", "afft_store_plan", "afft_store_gather",
+                  "afft_store_allow_empty_clips"):
             getattr(l, n).restype = C.c_int
         l._staging_bound = True
     return l
@@ -154,9 +156,14 @@ class FeatureStore:
 
     def plan(self, video_names: Sequence[str], start_sec: Sequence[float], end_sec: Sequence[float], fps: float, T: int,
              frame_rate: Optional[float], strategy: str = "last_clip", out: Optional[torch.Tensor] = None,
-             want_frame_ids: bool = False):
-        """Row numbers ``int32 [n_mod, B, T]`` (-1 = zero row) of a batch; host arithmetic only."""
+             want_frame_ids: bool = False, allow_empty: bool = False):
+        """Row numbers ``int32 [n_mod, B, T]`` (-1 = zero row) of a batch; host arithmetic only.  A clip without any
+        stored frame in its window raises, like the reference reader's assertion (reader_fns.py:97), unless
+        ``allow_empty`` (the clip is then T zero rows)."""
         B = len(video_names)
+        if bool(allow_empty) != getattr(self, "_allow_empty", False):
+            self._check(self.lib.afft_store_allow_empty_clips(self.handle, int(bool(allow_empty))))
+            self._allow_empty = bool(allow_empty)
         names = (C.c_char_p * max(B, 1))(*[v.encode() for v in video_names])
         st = np.ascontiguousarray(start_sec, dtype=np.float64)
         en = np.ascontiguousarray(end_sec, dtype=np.float64)

@@ -52,6 +52,11 @@ AFFT_API int afft_store_add_video(afft_feature_store* s, int32_t mod, const char
  * and only from afft_store_gather's kernel. */
 AFFT_API int afft_store_set_rows(afft_feature_store* s, int32_t mod, const void* rows, int64_t n_rows);
 
+/* A clip with no stored frame anywhere in its window makes the reference reader assert
+ * (`assert len(features_not_none) > 0`, datasets/reader_fns.py:97); afft_store_plan refuses such a clip with
+ * AFFT_ERR_INVALID.  allow != 0 turns the check off (the clip is then planned as T zero rows). */
+AFFT_API int afft_store_allow_empty_clips(afft_feature_store* s, int32_t allow);
+
 /* The plan of a batch: for every modality m, clip b and step t the row number (or -1 = zero row) into
  * row_idx[(m * B + b) * T + t], and - when frame_ids_out is not NULL - the frame id the reference would have asked
  * the LMDB for into the same position.  Pure host arithmetic, bit-identical to the reference's float64/int

@@ -301,3 +301,34 @@ def test_attention_tensor_core_paths(dev, n_seq, L, H, hd, mask, T, dt):
     assert (oh.float() - ro).abs().max().item() < (3e-2 if dt == torch.bfloat16 else 4e-3)
     assert (probs - rp).abs().max().item() < 2e-5
     assert (probs.sum(-1) - 1).abs().max().item() < 1e-5
+
+
+def test_hostops_dense_pads_odd_widths(dev):
+    """MATT with dim=None has widths that are not multiples of 8 (3424 -> 856 -> 428): operands are zero-padded."""
+    from afft_b200 import hostops
+    g = torch.Generator().manual_seed(9)
+    x, w, b = _randn(g, dev, 37, 428), _randn(g, dev, 107, 428, scale=0.05), _randn(g, dev, 107)
+    for precision, tol in (("bf16", 1e-4), ("fp16", 1e-4), ("strict", 2e-4)):
+        y = hostops.dense(x, w, b, hostops.WeightCache(), precision=precision)
+        if precision == "strict":
+            ref = _mm(x, w) + b
+        else:
+            dt = torch.bfloat16 if precision == "bf16" else torch.float16
+            ref = _mm(x.to(dt), w.to(dt)) + b
+        assert y.shape == (37, 107)
+        assert (y - ref).abs().max().item() < tol, precision
+
+
+def test_score_fusion_many_rows(dev):
+    """rows beyond the 65535 gridDim.y limit (CMFPScoreFusion at B >= 5958, T = 10)."""
+    g = torch.Generator().manual_seed(4)
+    rows, M, C = 70001, 3, 12
+    scores = _randn(g, dev, rows, 4)
+    logits = [_randn(g, dev, rows, C) for _ in range(M)]
+    attn = torch.empty(rows, M, device=dev)
+    out = torch.empty(rows, C, device=dev)
+    capi.score_fusion(scores, logits, C, attn=attn, out=out)
+    p = torch.softmax(scores[:, :M].double(), dim=-1)
+    ref = sum(p[:, i:i + 1] * logits[i].double() for i in range(M))
+    assert (attn.double() - p).abs().max().item() < 1e-6
+    assert (out.double() - ref).abs().max().item() < 1e-5
