@@ -86,6 +86,7 @@ class AttentionDesc(C.Structure):
         ("scale", C.c_float), ("mask", C.c_int32), ("T", C.c_int32),
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldo", C.c_int64),
         ("probs", C.c_void_p), ("p_outer", C.c_int64), ("p_inner_stride", C.c_int64), ("p_inner", C.c_int32),
+        ("drop_mask", C.c_void_p),
     ]
 
 
@@ -183,7 +184,7 @@ def lib() -> C.CDLL:
     l.afft_gelu_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     l.afft_colsum.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     l.afft_attention_bwd.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
-                                     C.c_int32, C.c_int32, C.c_float, C.c_void_p]
+                                     C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]
     for _n in ("afft_transpose_bf16", "afft_layernorm_bwd", "afft_gelu_fwd", "afft_gelu_bwd", "afft_colsum", "afft_attention_bwd"):
         getattr(l, _n).restype = C.c_int
     l.afft_profile_enable.argtypes = [C.c_void_p, C.c_int32]
@@ -273,7 +274,7 @@ def layernorm(x, gamma, beta, eps, *, rows=None, ldx=None, y_f32=None, y_hi=None
 
 
 def attention(qkv, n_seq, L, H, head_dim, *, mask=0, T=1, out_hi, out_lo=None, probs=None, p_outer=0,
-              p_inner_stride=0, p_inner=1, scale=None):
+              p_inner_stride=0, p_inner=1, scale=None, drop_mask=None):
     """qkv [n_seq*L, 3*H*head_dim] (q | k | v), bf16 or fp32."""
     D = H * head_dim
     es = qkv.element_size()
@@ -287,6 +288,7 @@ def attention(qkv, n_seq, L, H, head_dim, *, mask=0, T=1, out_hi, out_lo=None, p
     d.mask, d.T = mask, T
     d.out_hi, d.out_lo, d.ldo = ptr(out_hi), ptr(out_lo), out_hi.stride(0)
     d.probs, d.p_outer, d.p_inner_stride, d.p_inner = ptr(probs), p_outer, p_inner_stride, p_inner
+    d.drop_mask = ptr(drop_mask)
     check(lib().afft_attention(C.byref(d), current_stream_ptr(qkv.device)))
 
 

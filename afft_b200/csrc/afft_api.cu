@@ -302,13 +302,13 @@ static int run_attention(const AttentionArgs& a, int head_dim, int in_dtype, cud
   // few modality tokens per timestep (SA-Fuser): tensor-core kernel for 16-bit inputs, register-resident
   // warp-per-(timestep, head) kernel for fp32 inputs (strict mode)
   if (head_dim == 256 && a.L >= 2 && a.L <= 6 && (a.mask == 0 || a.mask == 3)) {
-    if (use_mma && !in_f32 && a.out_lo == nullptr && a.H <= 8)
+    if (use_mma && !in_f32 && a.out_lo == nullptr && a.H <= 8 && a.drop == nullptr)
       return fp16 ? run_attention_mma_tokens<true>(a, stream) : run_attention_mma_tokens<false>(a, stream);
     return in_f32 ? launch_attention_tokens<float>(a, stream)
                   : (fp16 ? launch_attention_tokens<__half>(a, stream) : launch_attention_tokens<bf16>(a, stream));
   }
   // short sequences with 16-bit inputs (GPT-2 predictor, CA-Fuser): tensor-core (mma.sync) kernel
-  if (use_mma && !in_f32 && a.out_lo == nullptr && a.L > 6 && a.mask >= 0 && a.mask <= 2) {
+  if (use_mma && !in_f32 && a.out_lo == nullptr && a.L > 6 && a.mask >= 0 && a.mask <= 2 && a.drop == nullptr) {
     if (a.L <= 32) {
       if (head_dim == 256) return fp16 ? launch_attention_mma<256, 32, 4, true>(a, stream) : launch_attention_mma<256, 32, 4, false>(a, stream);
       if (head_dim == 512) return fp16 ? launch_attention_mma<512, 32, 4, true>(a, stream) : launch_attention_mma<512, 32, 4, false>(a, stream);
@@ -348,6 +348,7 @@ extern "C" int afft_attention(const afft_attention_desc* d, void* stream) {
   a.p_inner_stride = d->p_inner_stride;
   a.p_inner = d->p_inner > 0 ? d->p_inner : 1;
   a.t_end = nullptr;
+  a.drop = d->drop_mask;
   return run_attention(a, d->head_dim, d->in_dtype, static_cast<cudaStream_t>(stream));
 }
 
@@ -480,7 +481,7 @@ extern "C" int afft_colsum(const float* x, int64_t ld, int32_t rows, int32_t col
 
 extern "C" int afft_attention_bwd(const float* qkv, int64_t ld, const float* probs, const float* d_out, int64_t ldo,
                                   float* dqkv, int32_t n_seq, int32_t L, int32_t H, int32_t head_dim, float scale,
-                                  void* stream) {
+                                  const float* drop_mask, void* stream) {
   if (qkv == nullptr || probs == nullptr || d_out == nullptr || dqkv == nullptr) return fail(AFFT_ERR_INVALID, "attention_bwd: null pointer");
   if (L < 1 || L > 64 || n_seq <= 0 || H <= 0 || head_dim <= 0) return fail(AFFT_ERR_INVALID, "attention_bwd: bad sizes");
   const size_t smem = (static_cast<size_t>(4) * L * head_dim + 2 * L * L) * sizeof(float);
@@ -489,7 +490,7 @@ extern "C" int afft_attention_bwd(const float* qkv, int64_t ld, const float* pro
     cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return cuda_fail("attention_bwd smem attribute", e);
   }
-  AttentionBwdArgs a{qkv, ld, probs, d_out, ldo, dqkv, n_seq, L, H, head_dim, scale};
+  AttentionBwdArgs a{qkv, ld, probs, d_out, ldo, dqkv, n_seq, L, H, head_dim, scale, drop_mask};
   attention_bwd_kernel<<<n_seq * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
   return launch_check("attention_bwd launch");
 }
@@ -1010,6 +1011,7 @@ struct Fwd {
     a.p_outer = p_outer;
     a.p_inner_stride = p_inner_stride;
     a.p_inner = p_inner > 0 ? p_inner : 1;
+    a.drop = nullptr;
     a.t_end = prof_slot(AFFT_CAT_ATTENTION);
     check(run_attention(a, hd, strict ? AFFT_DT_F32 : (fp16 ? AFFT_DT_FP16 : AFFT_DT_BF16), stream));
   }

@@ -359,6 +359,10 @@ struct AttentionArgs {
   long long p_outer, p_inner_stride;
   int p_inner;
   unsigned long long* t_end;  // profiling slot or nullptr
+  // training (attention-probability dropout, reference models/transformerblock.py:31,71 and GPT-2 attn_pdrop): optional
+  // [n_seq, H, L, L] fp32 factors (0 or 1 / (1 - p)) applied to the softmax before P.V; `probs` keeps the undropped
+  // softmax (the backward needs it).  SIMT kernels only.
+  const float* drop;
 };
 
 template <typename TIn, int HD>
@@ -445,6 +449,11 @@ __global__ void __launch_bounds__(256) attention_small_kernel(const AttentionArg
                   (static_cast<long long>(h) * L + i) * L;
       if (lane < L) pr[lane] = p0;
       if (lane + 32 < L) pr[lane + 32] = p1;
+    }
+    if (a.drop != nullptr) {
+      const float* dm = a.drop + ((static_cast<long long>(seq) * a.H + h) * L + i) * L;
+      if (lane < L) p0 *= dm[lane];
+      if (lane + 32 < L) p1 *= dm[lane + 32];
     }
     float o[A::kPerLane];
 #pragma unroll
@@ -572,10 +581,12 @@ __global__ void __launch_bounds__(128) attention_tokens_kernel(const AttentionAr
 #pragma unroll
     for (int e = 0; e < PL; ++e) o[e] = 0.f;
     float mine = 0.f;
+    const float* dm = a.drop != nullptr ? a.drop + ((static_cast<long long>(seq) * a.H + h) * L + i) * L : nullptr;
 #pragma unroll
     for (int j = 0; j < L; ++j) {
-      const float p = s[j] * inv;
-      if (lane == j) mine = p;
+      float p = s[j] * inv;
+      if (lane == j) mine = p;  // the undropped softmax is what `probs` keeps
+      if (dm != nullptr) p *= dm[j];
 #pragma unroll
       for (int e = 0; e < PL; ++e) o[e] = fmaf(p, v[j][e], o[e]);
     }

@@ -167,6 +167,7 @@ __global__ void colsum_kernel(const float* __restrict__ x, long long ld, int row
 // Backward of the small attentions (SA-Fuser 5x5, GPT-2 18x18 causal, ...): one CTA per (sequence, head).
 //   dV_j = sum_i P_ij dO_i;  dP_ij = dO_i . V_j;  dS_ij = P_ij (dP_ij - sum_j P_ij dP_ij) * scale;
 //   dQ_i = sum_j dS_ij K_j;  dK_j = sum_i dS_ij Q_i.       Masked entries have P = 0, hence dS = 0.
+// With attention-probability dropout (factors M_ij of the forward): dV uses P_ij M_ij and dP_ij = M_ij (dO_i . V_j).
 // q/k/v fp32 at qkv[(seq*L + i)*ld + {0, D, 2D} + h*HD + d]; probs fp32 [n_seq, H, L, L]; dO fp32 [rows, D];
 // dqkv fp32 with the layout of qkv.
 // ------------------------------------------------------------------------------------------------
@@ -179,6 +180,7 @@ struct AttentionBwdArgs {
   float* dqkv;
   int n_seq, L, H, HD;
   float scale;
+  const float* drop;  // attention-probability dropout factors of the forward ([n_seq, H, L, L]; 0 or 1 / (1 - p)) or nullptr
 };
 
 __global__ void __launch_bounds__(256) attention_bwd_kernel(const AttentionBwdArgs a) {
@@ -201,18 +203,20 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const AttentionBwdAr
     sdo[i] = a.d_out[(static_cast<long long>(seq) * L + r) * a.ldo + h * HD + d];
   }
   const float* pg = a.probs + (static_cast<long long>(seq) * a.H + h) * L * L;
+  const float* dm = a.drop != nullptr ? a.drop + (static_cast<long long>(seq) * a.H + h) * L * L : nullptr;
   for (int i = threadIdx.x; i < L * L; i += blockDim.x) sp[i] = pg[i];
   __syncthreads();
   // dP (stored in sds)
   for (int ij = threadIdx.x; ij < L * L; ij += blockDim.x) {
     const int i = ij / L, j = ij % L;
     float acc = 0.f;
-    if (sp[ij] != 0.f) {
+    const float m = dm != nullptr ? dm[ij] : 1.0f;
+    if (sp[ij] != 0.f && m != 0.f) {
       const float* o = sdo + i * HD;
       const float* v = sv + j * HD;
       for (int d = 0; d < HD; ++d) acc = fmaf(o[d], v[d], acc);
     }
-    sds[ij] = acc;
+    sds[ij] = acc * m;
   }
   __syncthreads();
   // dS = P * (dP - rowsum(P * dP)) * scale, one thread per row
@@ -222,6 +226,10 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const AttentionBwdAr
     for (int j = 0; j < L; ++j) sds[i * L + j] = sp[i * L + j] * (sds[i * L + j] - rs) * a.scale;
   }
   __syncthreads();
+  if (dm != nullptr) {  // dV below needs the dropped probabilities P_ij M_ij; dS no longer needs P
+    for (int i = threadIdx.x; i < L * L; i += blockDim.x) sp[i] *= dm[i];
+    __syncthreads();
+  }
   float* dbase = a.dqkv + static_cast<long long>(seq) * L * a.ld + h * HD;
   for (int id = threadIdx.x; id < L * HD; id += blockDim.x) {
     const int r = id / HD, d = id % HD;

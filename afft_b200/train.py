@@ -14,8 +14,10 @@ a hand-written sm_100a kernel behind the C ABI:
 
 PyTorch supplies the autograd graph, residual adds, concatenation, dropout masks and the optimizer (plumbing);
 torch.nn.parallel.DistributedDataParallel supplies the bucketed NCCL all-reduce overlapped with backward.
-Scope of this first version: ModalTokenCMFuser (SA-Fuser) + GPT-2 + heads; activations between kernels are fp32;
-attention-probability dropout is not applied (every other dropout / DropPath site is).
+Scope: CMFPEarly with every fuser (SA / SA without token / T-SA / CA) and every feature mapping + GPT-2 + heads;
+activations between kernels are fp32; every stochastic regulariser of the reference is applied (attention-probability
+dropout inside the attention kernel).  N > 1: afft_b200.dist.GradBuckets all-reduces the gradients per layer group from
+inside the backward pass.
 """
 from __future__ import annotations
 
@@ -164,29 +166,36 @@ class GeluFn(torch.autograd.Function):
 
 
 class AttentionFn(torch.autograd.Function):
-    """Multi-head attention over short sequences on fp32 q|k|v rows [n_seq * L, 3 * H * hd]; mask as afft_attention."""
+    """Multi-head attention over short sequences on fp32 q|k|v rows [n_seq * L, 3 * H * hd]; mask as afft_attention.
+    ``p_drop`` > 0 (training): attention-probability dropout (reference models/transformerblock.py:31,71; GPT-2
+    attn_pdrop) - the keep / (1 - p) factors are drawn here and applied to the softmax inside the kernel before P.V.
+    Returns (merged heads [n_seq * L, H * hd] fp32, probabilities AFTER dropout [n_seq, H, L, L], as the reference)."""
 
     @staticmethod
-    def forward(ctx, qkv, n_seq: int, L: int, H: int, hd: int, mask: int, T: int):
+    def forward(ctx, qkv, n_seq: int, L: int, H: int, hd: int, mask: int, T: int, p_drop: float = 0.0):
         qkv = qkv.contiguous()
         D = H * hd
         hi = torch.empty(n_seq * L, D, device=qkv.device, dtype=torch.bfloat16)
         lo = torch.empty_like(hi)
         probs = torch.empty(n_seq, H, L, L, device=qkv.device, dtype=torch.float32)
-        _capi.attention(qkv, n_seq, L, H, hd, mask=mask, T=T, out_hi=hi, out_lo=lo, probs=probs, p_outer=H * L * L)
-        ctx.save_for_backward(qkv, probs)
+        drop = None
+        if p_drop > 0.0:
+            drop = (torch.rand(n_seq, H, L, L, device=qkv.device) >= p_drop).to(torch.float32).mul_(1.0 / (1.0 - p_drop))
+        _capi.attention(qkv, n_seq, L, H, hd, mask=mask, T=T, out_hi=hi, out_lo=lo, probs=probs, p_outer=H * L * L,
+                        drop_mask=drop)
+        ctx.save_for_backward(qkv, probs, drop)
         ctx.dims = (n_seq, L, H, hd)
-        return hi.float() + lo.float(), probs
+        return hi.float() + lo.float(), (probs if drop is None else probs * drop)
 
     @staticmethod
     def backward(ctx, d_out, _d_probs):
-        qkv, probs = ctx.saved_tensors
+        qkv, probs, drop = ctx.saved_tensors
         n_seq, L, H, hd = ctx.dims
         d_out = d_out.contiguous()
         dqkv = torch.empty_like(qkv)
         _capi.check(_lib().afft_attention_bwd(qkv.data_ptr(), qkv.shape[1], probs.data_ptr(), d_out.data_ptr(), d_out.shape[1],
-                                              dqkv.data_ptr(), n_seq, L, H, hd, hd ** -0.5, _ST(qkv.device)))
-        return dqkv, None, None, None, None, None, None
+                                              dqkv.data_ptr(), n_seq, L, H, hd, hd ** -0.5, _capi.ptr(drop), _ST(qkv.device)))
+        return dqkv, None, None, None, None, None, None, None
 
 
 def _linear(x, lin, conv1d=False):
@@ -207,48 +216,138 @@ def _drop_path(x, rate: float, training: bool, rows_per_sample: int):
     return (x.view(n, rows_per_sample, -1) / keep * mask).view_as(x)
 
 
+def _rate(module, attr="p"):
+    return float(getattr(module, attr, 0.0) or 0.0)
+
+
+def _apply_mapping(mp, x, training: bool):
+    """reference models/feature_mapping.py: Linear (:54-78), GatedLinear (:36-51), NonLinear (:91-107) on [rows, C_m]."""
+    from .models import feature_mapping as fm
+    if isinstance(mp, fm.Linear):
+        lin = mp.mapping[0]
+        y = x if isinstance(lin, torch.nn.Identity) else _linear(x, lin)
+    elif isinstance(mp, fm.GatedLinear):
+        u = _linear(x, mp.mapping[0])
+        y = u * torch.sigmoid(_linear(u, mp.mapping[1].fc))  # ContextGating: cat + glu (:21-33)
+    elif isinstance(mp, fm.NonLinear):
+        u = _linear(x, mp.mapping[0])
+        y = torch.relu(u) if mp.activation == "relu" else (GeluFn.apply(u, _capi.ACT_GELU_ERF) if mp.activation == "gelu" else u)
+    else:
+        raise NotImplementedError(f"training step: unknown mapping {type(mp).__name__}")
+    if mp.use_layernorm:
+        y = _ln(y, mp.mapping[-1])
+    return y
+
+
+def _self_attention(h, attn, n_seq, L, mask, T, training):
+    """reference models/transformerblock.py:19-36 on rows [n_seq * L, D]; returns (proj output after proj_drop, probs)."""
+    H = attn.num_heads
+    D = h.shape[1]
+    a, p = AttentionFn.apply(_linear(h, attn.qkv), n_seq, L, H, D // H, mask, T, _rate(attn.attn_drop) if training else 0.0)
+    return F.dropout(_linear(a, attn.proj), _rate(attn.proj_drop), training), p
+
+
+def _block(h, blk, n_seq, L, mask, T, training):
+    """reference models/transformerblock.py:131-135 (Block); DropPath per sequence of L rows."""
+    dp = getattr(blk.drop_path, "drop_prob", 0.0) or 0.0
+    a, p = _self_attention(_ln(h, blk.norm1), blk.attn, n_seq, L, mask, T, training)
+    h = h + _drop_path(a, dp, training, L)
+    f = GeluFn.apply(_linear(_ln(h, blk.norm2), blk.mlp.mlp[0]), _capi.ACT_GELU_ERF)
+    f = F.dropout(_linear(f, blk.mlp.mlp[2]), _rate(blk.mlp.mlp[3]), training)
+    return h + _drop_path(f, dp, training, L), p
+
+
+def _fuse_sa(fuser, toks, B, T, D, training, with_token: bool):
+    """ModalTokenCMFuser (reference models/fusion.py:319-365) / CMFuser (:86-118): sequences of n tokens per (b, t)."""
+    if with_token:
+        tok = (fuser.modal_token.expand(B * T, -1, -1) if not fuser.frame_level_token
+               else fuser.modal_token.expand(B, -1, -1)).reshape(B * T, D)
+        toks = [tok] + toks
+    n = len(toks)
+    h = torch.stack(toks, dim=1)  # (B*T, n, D)
+    if getattr(fuser, "modality_embedding", None) is not None:
+        h = h + fuser.modality_embedding
+    h = F.dropout(h, _rate(fuser.embd_drop), training).reshape(B * T * n, D)
+    mask = 3 if fuser.cross_attn else 0
+    H = fuser.num_heads
+    attns = []
+    for blk in fuser.blocks:
+        h, p = _block(h, blk, B * T, n, mask, 1, training)
+        attns.append(p.view(B, T, H, n, n))
+    x = _ln(h, fuser.norm).view(B * T, n, D)
+    z = x[:, 0] if with_token else x.mean(dim=1)
+    return z.reshape(B, T, D), torch.stack(attns).transpose(0, 1).detach()
+
+
+def _fuse_tsa(fuser, toks, B, T, D, training):
+    """TemporalCMFuser (reference models/fusion.py:159-215): one sequence of n*T tokens per clip, block-causal mask."""
+    seq = [t.view(B, T, D) for t in toks]
+    if fuser.frame_level_token:
+        seq = [fuser.modal_token.expand(B, -1, -1)] + seq
+    n = len(seq)
+    h = torch.cat(seq, dim=1)  # (B, n*T, D), token index = m*T + t
+    h = h + fuser.position_embeddings.weight[:T].repeat(n, 1)
+    if fuser.modality_embedding is not None:
+        h = h + fuser.modality_embedding.repeat_interleave(T, dim=0)
+    h = F.dropout(h, _rate(fuser.embd_drop), training).reshape(B * n * T, D)
+    attns = []
+    for blk in fuser.blocks:
+        h, p = _block(h, blk, B, n * T, 2, T, training)
+        attns.append(p)
+    x = _ln(h, fuser.norm).view(B, n, T, D)
+    z = x[:, 0] if fuser.frame_level_token else x.mean(dim=1)
+    return z.reshape(B, T, D), torch.stack(attns).transpose(0, 1).detach()
+
+
+def _fuse_ca(fuser, toks, B, T, D, training):
+    """TemporalCrossAttentFuser (reference models/fusion.py:243-270) with DecoderBlock (transformerblock.py:157-162)."""
+    pos = fuser.position_embeddings.weight[:T]
+    seq = [F.dropout(t.view(B, T, D) + pos, _rate(fuser.embd_drop), training).reshape(B * T, D) for t in toks]
+    x, mems = seq[0], seq[1:]
+    for i, blk in enumerate(fuser.blocks):
+        dp = getattr(blk.drop_path, "drop_prob", 0.0) or 0.0
+        a, _ = _self_attention(_ln(x, blk.norm_self), blk.attn, B, T, 1, T, training)
+        x = x + _drop_path(a, dp, training, T)
+        ca = blk.cross_attn
+        H = ca.num_heads
+        mem = _ln(mems[i], blk.norm_kv)
+        qkv = torch.cat([_linear(_ln(x, blk.norm_q), ca.w_q), _linear(mem, ca.w_k), _linear(mem, ca.w_v)], dim=1)
+        c, _ = AttentionFn.apply(qkv, B, T, H, D // H, 1, T, _rate(ca.attn_drop) if training else 0.0)
+        c = F.dropout(_linear(c, ca.proj), _rate(ca.proj_drop), training)
+        x = x + _drop_path(c, dp, training, T)
+        f = GeluFn.apply(_linear(_ln(x, blk.norm_mlp), blk.mlp.mlp[0]), _capi.ACT_GELU_ERF)
+        f = F.dropout(_linear(f, blk.mlp.mlp[2]), _rate(blk.mlp.mlp[3]), training)
+        x = x + _drop_path(f, dp, training, T)
+    return _ln(x, fuser.norm).view(B, T, D), torch.zeros(B)  # the reference's dummy attention (:269)
+
+
 def forward_train(fp, feats: Dict[str, torch.Tensor]) -> Dict[str, Dict[str, torch.Tensor]]:
-    """CMFPEarly.forward (reference models/future_prediction.py:257-291) in training mode, differentiable."""
-    from .models.fusion import ModalTokenCMFuser
+    """CMFPEarly.forward (reference models/future_prediction.py:257-291) in training mode, differentiable, for every
+    fuser (SA / SA without token / T-SA / CA) and every feature mapping.  All stochastic regularisers of the reference
+    are applied: embedding / projection / MLP dropout, attention-probability dropout (in the attention kernel), DropPath,
+    classifier dropout, GPT-2 embd / attn / resid dropout."""
+    from .models import fusion
     fuser = fp.fuser
-    if not isinstance(fuser, ModalTokenCMFuser):
-        raise NotImplementedError("the training-step path is built for the SA-Fuser (ModalTokenCMFuser) only so far")
-    if fuser.cross_attn:
-        raise NotImplementedError("cross_attn=True is not supported in the training-step path")
+    if fp.fp_output_len != 1:
+        raise NotImplementedError("training step: fp_output_len > 1 (autoregressive roll-out) is built for inference only")
     training = fp.training
     order = [m for m in fp.modal_feature_order if m in feats]
     first = feats[order[0]]
     B, T = first.shape[0], first.shape[1]
     D = fp.latent_dim
     toks = []
-    for m in order:  # feature mapping (models/feature_mapping.py:59-63)
-        x = feats[m].reshape(B * T, -1).float()
-        lin = fp.mapping[m].mapping[0]
-        toks.append(x if isinstance(lin, torch.nn.Identity) else _linear(x, lin))
-    n = len(order) + 1
-    if not fuser.frame_level_token:
-        tok = fuser.modal_token.expand(B * T, -1, -1).reshape(B * T, D)
+    for m in order:  # feature mapping (models/future_prediction.py:133-142)
+        toks.append(_apply_mapping(fp.mapping[m], feats[m].reshape(B * T, -1).float(), training))
+    if isinstance(fuser, fusion.ModalTokenCMFuser):
+        z, attn = _fuse_sa(fuser, toks, B, T, D, training, with_token=True)
+    elif isinstance(fuser, fusion.CMFuser):
+        z, attn = _fuse_sa(fuser, toks, B, T, D, training, with_token=False)
+    elif isinstance(fuser, fusion.TemporalCMFuser):
+        z, attn = _fuse_tsa(fuser, toks, B, T, D, training)
+    elif isinstance(fuser, fusion.TemporalCrossAttentFuser):
+        z, attn = _fuse_ca(fuser, toks, B, T, D, training)
     else:
-        tok = fuser.modal_token.expand(B, -1, -1).reshape(B * T, D)
-    h = torch.stack([tok] + toks, dim=1)  # (B*T, n, D): models/fusion.py:338-349
-    if fuser.modality_embedding is not None:
-        h = h + fuser.modality_embedding
-    h = F.dropout(h, fuser.embd_drop.p, training).reshape(B * T * n, D)
-    H1 = fuser.num_heads
-    attns = []
-    for blk in fuser.blocks:  # models/transformerblock.py:131-135
-        dp = getattr(blk.drop_path, "drop_prob", 0.0) or 0.0
-        y = _ln(h, blk.norm1)
-        a, p = AttentionFn.apply(_linear(y, blk.attn.qkv), B * T, n, H1, D // H1, 0, 1)
-        a = F.dropout(_linear(a, blk.attn.proj), blk.attn.proj_drop.p, training)
-        h = h + _drop_path(a, dp, training, n)
-        y = _ln(h, blk.norm2)
-        f = GeluFn.apply(_linear(y, blk.mlp.mlp[0]), _capi.ACT_GELU_ERF)
-        f = F.dropout(_linear(f, blk.mlp.mlp[2]), blk.mlp.mlp[3].p, training)
-        h = h + _drop_path(f, dp, training, n)
-        attns.append(p.view(B, T, H1, n, n))
-    x = _ln(h, fuser.norm)
-    z = x.view(B * T, n, D)[:, 0].reshape(B, T, D)  # models/fusion.py:363-364
+        raise NotImplementedError(f"training step: unknown fuser {type(fuser).__name__}")
 
     gpt = fp.future_predictor.gpt_model
     G, H2 = gpt.n_embd, gpt.n_head
@@ -256,7 +355,8 @@ def forward_train(fp, feats: Dict[str, torch.Tensor]) -> Dict[str, Dict[str, tor
     g = F.dropout(g, gpt.drop.p, training).reshape(B * T, G)
     for blk in gpt.h:  # transformers GPT2Block
         y = _ln(g, blk.ln_1)
-        a, _ = AttentionFn.apply(_linear(y, blk.attn.c_attn, conv1d=True), B, T, H2, G // H2, 1, T)
+        a, _ = AttentionFn.apply(_linear(y, blk.attn.c_attn, conv1d=True), B, T, H2, G // H2, 1, T,
+                                 _rate(blk.attn.attn_dropout) if training else 0.0)
         g = g + F.dropout(_linear(a, blk.attn.c_proj, conv1d=True), blk.attn.resid_dropout.p, training)
         y = _ln(g, blk.ln_2)
         f = GeluFn.apply(_linear(y, blk.mlp.c_fc, conv1d=True), _capi.ACT_GELU_TANH)
@@ -273,8 +373,29 @@ def forward_train(fp, feats: Dict[str, torch.Tensor]) -> Dict[str, Dict[str, tor
         for prefix, src in (("past_", past_futures), ("", future)):
             s = F.dropout(src.reshape(-1, D), head[0].p, training)
             out[f"{prefix}logits/{cls}"] = {"all-fused": _linear(s, head[1]).reshape(B, -1, c)}
-    out["attentions"] = {"all-fused": {"modality_attns": torch.stack(attns).transpose(0, 1).detach(), "temporal_attns": {}}}
+    out["attentions"] = {"all-fused": {"modality_attns": attn, "temporal_attns": {}}}
     return out
+
+
+def grad_groups(fp) -> list:
+    """Parameter groups of a CMFPEarly head in the order the backward pass finishes them (last layers first): the bucket
+    layout of ``afft_b200.dist.GradBuckets`` (reference train.py:366-368 leaves this to DistributedDataParallel)."""
+    groups = [[p for cls in fp.classifiers.values() for p in cls.parameters()] + list(fp.dim_decoder.parameters())]
+    gpt = fp.future_predictor.gpt_model
+    groups[0] += list(gpt.ln_f.parameters())
+    for blk in reversed(gpt.h):
+        groups.append(list(blk.parameters()))
+    tail = list(gpt.wpe.parameters()) + list(fp.dim_encoder.parameters())
+    fuser = fp.fuser
+    tail += list(fuser.norm.parameters())
+    groups.append(tail)
+    for blk in reversed(fuser.blocks):
+        groups.append(list(blk.parameters()))
+    seen = {id(p) for g in groups for p in g}
+    rest = [p for p in fp.parameters() if id(p) not in seen]  # tokens, embeddings, mappings: finished last
+    if rest:
+        groups.append(rest)
+    return groups
 
 
 def reference_losses(outputs, target: torch.Tensor, target_subclips: torch.Tensor, cls: str = "action") -> Dict[str, torch.Tensor]:

@@ -671,27 +671,27 @@ def run_train(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _capi.lib()
-    cfg, T, ncls, _ = configs.named_config(args.config if args.config != "ek100_sa_tsn" else "ek100_sa_swin")
+    train_cfg_name = args.config if args.config != "ek100_sa_tsn" else "ek100_sa_swin"
+    cfg, T, ncls, _ = configs.named_config(train_cfg_name)
     B = args.batch if args.batch != 256 else 16  # expts/01_SA-Fuser_ek100_train.txt:7: 16 clips per GPU
     C = list(ncls.values())[0]
     torch.manual_seed(0)
     model = BaseModel(cfg, ncls, {}).to(dev).train()
-    # N > 1: either DistributedDataParallel (eager, bucketed all-reduce overlapped with backward; --no-graph) or - the
-    # default - the whole step in one CUDA graph with ONE NCCL all-reduce of a flat gradient buffer between backward
-    # and the optimizer (captured with the rest; not overlapped, but the step is no longer launch-bound)
-    flat_graph = world > 1 and not args.no_graph
-    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if (world > 1 and not flat_graph) else model
-    flat = None
-    if flat_graph:
-        import torch.distributed as tdist
-        params = [p for p in model.parameters() if p.requires_grad]
-        for p in params:
-            tdist.broadcast(p.data, src=0)  # what DDP's constructor does
-        flat = torch.zeros(sum(p.numel() for p in params), device=dev)
-        off = 0
-        for p in params:
-            p.grad = flat[off:off + p.numel()].view_as(p)  # autograd accumulates in place into these views
-            off += p.numel()
+    # Gradients live in ONE flat buffer laid out in backward-completion order (afft_b200.dist.GradBuckets); for N > 1 each
+    # layer group's slice is all-reduced over NCCL as soon as backward has finished it, overlapping the remaining dgrad /
+    # wgrad work, eagerly or inside the captured graph.  --grad-comm bf16 halves the bytes on NVLink.  --ddp keeps
+    # torch's DistributedDataParallel (eager only) for comparison.
+    import torch.distributed as tdist
+    use_ddp = world > 1 and args.ddp
+    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if use_ddp else model
+    buckets = None
+    if not use_ddp:
+        if world > 1:
+            for p in model.parameters():
+                tdist.broadcast(p.data, src=0)  # what DDP's constructor does
+        buckets = adist.GradBuckets(atrain.grad_groups(model.future_predictor),
+                                    comm_dtype=torch.bfloat16 if args.grad_comm == "bf16" else torch.float32)
+    flat = buckets.flat if buckets is not None else None
     # expts/01 :48-52; fused=True: one multi-tensor kernel pass over (p, grad, momentum) instead of ~5 foreach passes
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, nesterov=True, weight_decay=1e-6, fused=True)
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
@@ -700,15 +700,15 @@ def run_train(args):
     target_sub = torch.randint(0, C, (B, T), device=dev, generator=g)
 
     def fwd_bwd_opt(feats):
-        if flat is not None:
-            flat.zero_()
+        if buckets is not None:
+            buckets.zero()
         else:
             opt.zero_grad(set_to_none=True)
         out, _ = ddp(feats, **KW)
         loss = atrain.reference_losses(out, target, target_sub)["total"]
-        loss.backward()  # DDP: bucketed NCCL all-reduce overlapped with the remaining backward
-        if flat is not None:
-            tdist.all_reduce(flat, op=tdist.ReduceOp.AVG)  # 1.55 GB over NVLink / NVSwitch
+        loss.backward()  # per-group NCCL all-reduces are issued from inside backward (GradBuckets hooks / DDP)
+        if buckets is not None:
+            buckets.finish()
         opt.step()
         return loss
 
@@ -722,7 +722,7 @@ def run_train(args):
     # One GPU: the whole step (forward, backward, SGD) is captured into ONE CUDA graph - at 16 clips per GPU the step is
     # ~1900 launches of small kernels and Python-launch-bound.  (With DDP the NCCL bucket hooks stay eager.)
     graphed = False
-    if not args.no_graph:
+    if not args.no_graph and not use_ddp:
         try:
             static = {m: torch.empty_like(t) for m, t in sets[0].items()}
             eager_step = step
@@ -736,8 +736,6 @@ def run_train(args):
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            if flat is None:
-                opt.zero_grad(set_to_none=True)
             with torch.cuda.graph(graph):
                 static_loss = fwd_bwd_opt(dict(static))
 
@@ -774,12 +772,14 @@ def run_train(args):
         "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic", "mode": "train",
-        "config": {"workload": "ek100_sa_swin training step (expts/01_SA-Fuser_ek100_train.txt: T=16, 4 modalities, SGD-nesterov)",
+        "config": {"workload": f"{train_cfg_name} training step" + (" (expts/01_SA-Fuser_ek100_train.txt: T=16, 4 modalities, SGD-nesterov)"
+                                                                    if train_cfg_name == "ek100_sa_swin" else " (SGD-nesterov)"),
                    "clips_per_gpu_per_step": B, "T": T, "params": n_params, "grad_allreduce_bytes": 4 * n_params if world > 1 else 0,
-                   "allreduce": ("one NCCL all-reduce (AVG) of the flat fp32 gradient buffer, captured in the step's CUDA graph"
-                                 if (world > 1 and flat is not None and graphed) else
-                                 "one NCCL all-reduce of the flat gradient buffer (eager)" if (world > 1 and flat is not None) else
-                                 "torch DDP bucketed NCCL all-reduce overlapped with backward" if world > 1 else "none (1 GPU)"),
+                   "allreduce": ((f"{len(buckets.groups)} per-layer-group NCCL all-reduces ({args.grad_comm} transport) issued from inside "
+                                  f"backward (GradBuckets), " + ("captured in the step's CUDA graph" if graphed else "eager"))
+                                 if (world > 1 and buckets is not None) else
+                                 "torch DDP bucketed NCCL all-reduce overlapped with backward (eager)" if world > 1 else "none (1 GPU)"),
+                   "grad_allreduce_bytes_on_wire": buckets.bytes_per_step() if buckets is not None else 4 * n_params * (world > 1),
                    "gemm_gflop_per_clip_fwd_bwd": round(flops_per_clip / 1e9, 2), "final_loss": round(float(loss.detach()), 4)},
         "achieved_tflops": round(value * flops_per_clip / 1e12, 1),
         "cuda_graph": graphed,
@@ -816,6 +816,8 @@ def main():
     ap.add_argument("--strict", action="store_true", help="alias of --precision strict")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="train mode: do not capture the step into a CUDA graph")
+    ap.add_argument("--grad-comm", choices=["fp32", "bf16"], default="fp32", help="train mode: gradient all-reduce transport dtype")
+    ap.add_argument("--ddp", action="store_true", help="train mode, N > 1: torch DistributedDataParallel (eager) instead of GradBuckets")
     ap.add_argument("--no-staged", action="store_true", help="skip the clip-descriptor (feature store) e2e measurement")
     ap.add_argument("--no-modes", action="store_true", help="skip the sub-records of the other precision modes")
     ap.add_argument("--sustain-s", type=float, default=2.0, help="length of the sustained timing loop in seconds")

@@ -166,6 +166,10 @@ typedef struct afft_attention_desc {
   float* probs;
   int64_t p_outer, p_inner_stride;
   int32_t p_inner;
+  /* training only - attention-probability dropout (models/transformerblock.py:31,71; GPT-2 attn_pdrop): optional fp32
+   * [n_seq, H, L, L] factors (0 or 1/(1-p)) multiplied into the softmax before P.V.  `probs` receives the UNDROPPED
+   * softmax (afft_attention_bwd needs it).  NULL in inference. */
+  const float* drop_mask;
 } afft_attention_desc;
 
 AFFT_API int afft_attention(const afft_attention_desc* d, void* stream);
@@ -202,9 +206,11 @@ AFFT_API int afft_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n
 /* out[c] += sum over rows of x[r, c] (bias gradient) */
 AFFT_API int afft_colsum(const float* x, int64_t ld, int32_t rows, int32_t cols, float* out, void* stream);
 /* Backward of afft_attention for fp32 q|k|v (layout as afft_attention_desc with ldq = ldk = ldv = ld, q at column 0,
- * k at H*head_dim, v at 2*H*head_dim); probs [n_seq, H, L, L] as written by the forward; d_out [n_seq*L, ldo]. */
+ * k at H*head_dim, v at 2*H*head_dim); probs [n_seq, H, L, L] as written by the forward (undropped); d_out [n_seq*L, ldo];
+ * drop_mask: the forward's dropout factors or NULL. */
 AFFT_API int afft_attention_bwd(const float* qkv, int64_t ld, const float* probs, const float* d_out, int64_t ldo, float* dqkv,
-                                int32_t n_seq, int32_t L, int32_t H, int32_t head_dim, float scale, void* stream);
+                                int32_t n_seq, int32_t L, int32_t H, int32_t head_dim, float scale, const float* drop_mask,
+                                void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Model-level API: everything below BaseModel.future_predictor (models/base_model.py:59)      */

@@ -73,20 +73,50 @@ def test_backward_operators_against_torch():
         dy = torch.randn(n_seq * L, D, generator=g).to(dev)
         ga, gr = torch.autograd.grad(out, qkv, dy)[0], torch.autograd.grad(ref, qkv, dy)[0]
         assert ((ga - gr).norm() / gr.norm()).item() < 1e-4
+    # attention-probability dropout (models/transformerblock.py:31,71; GPT-2 attn_pdrop): the factors are drawn with
+    # torch.rand on the device, so re-seeding reproduces them for the torch reference
+    for n_seq, L, H, hd, mask, T in ((24, 5, 4, 256, 0, 1), (6, 18, 4, 512, 1, 18), (3, 50, 4, 256, 2, 10)):
+        D = H * hd
+        p_drop = 0.3
+        qkv = torch.randn(n_seq * L, 3 * D, generator=g).to(dev).requires_grad_()
+        torch.manual_seed(1234)
+        out, probs = atrain.AttentionFn.apply(qkv, n_seq, L, H, hd, mask, T, p_drop)
+        torch.manual_seed(1234)
+        drop = (torch.rand(n_seq, H, L, L, device=dev) >= p_drop).float() / (1.0 - p_drop)
+        assert 0.55 < (drop > 0).float().mean().item() < 0.85
+        t = qkv.view(n_seq, L, 3, H, hd).permute(2, 0, 3, 1, 4)
+        s = (t[0] @ t[1].transpose(-1, -2)) * hd ** -0.5
+        i, j = torch.arange(L, device=dev)[:, None], torch.arange(L, device=dev)[None, :]
+        if mask == 1:
+            s = s.masked_fill(j > i, float("-inf"))
+        elif mask == 2:
+            s = s.masked_fill((j % T) > (i % T), float("-inf"))
+        pd = s.softmax(-1) * drop
+        ref = (pd @ t[2]).transpose(1, 2).reshape(n_seq * L, D)
+        assert (out - ref).abs().max().item() < 3e-4
+        assert (probs - pd).abs().max().item() < 2e-5  # the returned attention is the dropped one, as the reference's
+        dy = torch.randn(n_seq * L, D, generator=g).to(dev)
+        ga, gr = torch.autograd.grad(out, qkv, dy)[0], torch.autograd.grad(ref, qkv, dy)[0]
+        assert ((ga - gr).norm() / gr.norm()).item() < 1e-4
 
 
-def test_training_step_gradients_match_oracle_autograd():
+# config 5's own model (ek100_sa_swin: K = 352 wgrad, N = 3806 head, 6 + 6 layers), the T-SA / CA training experiments
+# (expts/03, expts/04), the SA-Fuser without token (expts/02) and the ablation mappings
+@pytest.mark.parametrize("cfg_name,B", [("egtea_sa", 8), ("ek100_sa_swin", 2), ("ek100_tsa", 2), ("ek100_ca", 2),
+                                        ("ek100_sa_wo_token", 2), ("ek100_sa_gatedlinear", 2), ("ek100_sa_nonlinear", 2),
+                                        ("ek100_sa_cross_attn", 2), ("ek100_tsa_mean", 2)])
+def test_training_step_gradients_match_oracle_autograd(cfg_name, B):
     from oracle import afft_oracle
-    cfg, T, ncls = _no_dropout_cfg("egtea_sa")
-    B = 8
+    cfg, T, ncls = _no_dropout_cfg(cfg_name)
+    C = ncls["action"]
     model = BaseModel(cfg, ncls, {})
     sd = synthetic.synthetic_state_dict(model, seed=0)
     model.load_state_dict(sd)
     model = model.to("cuda:0").train()
     feats = synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=77)
     gl = torch.Generator().manual_seed(5)
-    target = torch.randint(0, 106, (B, 1), generator=gl)
-    target_sub = torch.randint(0, 106, (B, T), generator=gl)
+    target = torch.randint(0, C, (B, 1), generator=gl)
+    target_sub = torch.randint(0, C, (B, T), generator=gl)
     target_sub[0, :3] = -1  # ignored past frames
 
     out, _ = model({m: t.reshape(B, T, -1, 1, 1, 1).cuda() for m, t in feats.items()}, **KW)
@@ -117,12 +147,44 @@ def test_training_step_gradients_match_oracle_autograd():
         if rel > worst[0]:
             worst = (rel, name)
         assert rel < 5e-2 and cos > 0.995, (name, rel, cos)
-    assert n_checked >= 50, n_checked
-    print("worst relative gradient error", worst)
+    assert n_checked >= 40, n_checked
+    print(f"[{cfg_name}] worst relative gradient error", worst)
+
+
+def test_training_step_with_all_regularisers_on():
+    """The shipped rates (dropout 0.1 / 0.2, DropPath 0.1, attention dropout 0.1): the step runs, the loss is finite,
+    two steps with different RNG states differ, and eval mode is untouched by the training-mode machinery."""
+    cfg, T, ncls, _ = configs.named_config("egtea_sa")
+    B = 8
+    model = BaseModel(cfg, ncls, {})
+    model.load_state_dict(synthetic.synthetic_state_dict(model, seed=0))
+    model = model.to("cuda:0")
+    feats = {m: t.reshape(B, T, -1, 1, 1, 1).cuda() for m, t in synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=7).items()}
+    target = torch.zeros(B, 1, dtype=torch.long, device="cuda:0")
+    target_sub = torch.zeros(B, T, dtype=torch.long, device="cuda:0")
+    model.eval()
+    with torch.no_grad():
+        ev0 = model(dict(feats), **KW)[0]["logits/action"]["all-fused"].clone()
+    model.train()
+    losses = []
+    for seed in (1, 2):
+        torch.manual_seed(seed)
+        model.zero_grad(set_to_none=True)
+        out, _ = model(dict(feats), **KW)
+        loss = atrain.reference_losses(out, target, target_sub)["total"]
+        loss.backward()
+        assert torch.isfinite(loss)
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+        losses.append(loss.item())
+    assert losses[0] != losses[1]
+    model.eval()
+    with torch.no_grad():
+        ev1 = model(dict(feats), **KW)[0]["logits/action"]["all-fused"]
+    assert torch.equal(ev0, ev1)
 
 
 def test_unsupported_training_configs_raise():
-    cfg, T, ncls, _ = configs.named_config("ek100_ca")
+    cfg, T, ncls, _ = configs.named_config("egtea_sa_rollout3")  # fp_output_len = 3: roll-out is inference only
     m = BaseModel(cfg, ncls, {}).to("cuda:0").train()
     x = {k: torch.zeros(8, T, d, 1, 1, 1, device="cuda:0") for k, d in cfg["modal_dims"].items()}
     with pytest.raises(NotImplementedError):
