@@ -1390,6 +1390,11 @@ extern "C" int afft_forward(afft_handle* h, int32_t B, const afft_io* io, void* 
   return F.rc;
 }
 
+extern "C" int afft_set_gemm_epilogue(int32_t v2) {
+  gemm_epilogue_v2_flag().store(v2 != 0 ? 1 : 0, std::memory_order_relaxed);
+  return AFFT_OK;
+}
+
 extern "C" int afft_set_max_ksplit(afft_handle* h, int32_t max_split) {
   if (h == nullptr) return fail(AFFT_ERR_INVALID, "set_max_ksplit: null handle");
   if (max_split < 1 || max_split > 64) return hfail(h, AFFT_ERR_INVALID, "set_max_ksplit: value must be in [1, 64]");

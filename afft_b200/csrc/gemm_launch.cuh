@@ -8,7 +8,9 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <string>
 
@@ -111,6 +113,39 @@ inline bool make_tmap_bf16(CUtensorMap* out, const void* ptr, long long rows, lo
   return true;
 }
 
+// Generic 2-D tiled map (row-major [rows, cols], row pitch ld elements) for the TMA-staged epilogue: fp32 boxes of
+// 32 x 32 elements (128-byte rows, SWIZZLE_128B) and 16-bit boxes of 32 x 32 (64-byte rows, SWIZZLE_64B).
+inline bool make_tmap_epi(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int elem_bytes,
+                          bool fp16, std::string* err) {
+  auto enc = get_tensormap_encoder(err);
+  if (enc == nullptr) return false;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (ld * elem_bytes) % 16 != 0) {
+    if (err) *err = "TMA epilogue tensor must be 16-B aligned with a 16-B multiple row pitch";
+    return false;
+  }
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estride[2] = {1, 1};
+  const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                 : (fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   elem_bytes == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled (epilogue) failed with CUresult " + std::to_string(static_cast<int>(r));
+    return false;
+  }
+  return true;
+}
+
+// Which epilogue the 2-CTA kernel runs: 0 = v1 (smem transposition + coalesced LDG / STG; the default), 1 = v2 (TMA-staged,
+// see gemm_sm100.cuh).  Process-wide; initial value from AFFT_GEMM_EPI_V2.
+inline std::atomic<int>& gemm_epilogue_v2_flag() {
+  static std::atomic<int> flag([] { const char* v = getenv("AFFT_GEMM_EPI_V2"); return v == nullptr ? 0 : atoi(v); }());
+  return flag;
+}
+
 inline bool pdl_enabled() {
   static const bool on = [] { const char* v = getenv("AFFT_PDL"); return v == nullptr || atoi(v) != 0; }();
   return on;
@@ -160,7 +195,8 @@ inline cudaError_t launch_gemm_variant(const CUtensorMap& ta, const CUtensorMap&
 template <int MODE, int EPI>
 inline cudaError_t launch_gemm_2cta_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal,
                                             const CUtensorMap& tbl, const GemmEpilogue& ep, int M, int N, int K,
-                                            int num_sms, GemmSched sched, const SplitKScratch* sk, cudaStream_t stream) {
+                                            int num_sms, GemmSched sched, const SplitKScratch* sk, cudaStream_t stream,
+                                            const GemmTmaEpi& tme) {
   using T = Gemm2Traits<MODE>;
   auto kern = gemm_bf16_tcgen05_2cta_kernel<MODE, EPI>;
   static bool attr_set[64] = {false};
@@ -168,7 +204,7 @@ inline cudaError_t launch_gemm_2cta_variant(const CUtensorMap& ta, const CUtenso
   cudaGetDevice(&dev);
   dev &= 63;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
@@ -178,8 +214,18 @@ inline cudaError_t launch_gemm_2cta_variant(const CUtensorMap& ta, const CUtenso
   sched.partials = sk ? sk->partials : nullptr;
   sched.counters = sk ? sk->counters : nullptr;
   if (num_tiles * sched.ksplit < clusters) clusters = num_tiles * sched.ksplit;
+  // The TMA-staged epilogue needs whole tiles per unit; with split-K the v1 epilogue (partials + in-order sum) runs.
+  // It trades ring depth for slab buffers: 5 stages + 8 KB per warp without a residual operand, 4 stages + 12 KB with.
+  if (sched.ksplit > 1 || EPI < 0 || MODE == MODE_BF16X3) sched.v2_warp_bytes = 0;
+  uint32_t smem = T::kSmemBytes;
+  sched.stages = T::kStages;
+  if (sched.v2_warp_bytes > 0) {
+    sched.stages = (EPI & 4) != 0 ? 4 : 5;
+    sched.v2_warp_bytes = (EPI & 4) != 0 ? 12288 : 8192;
+    smem = T::smem_bytes(sched.stages, kNumEpilogueWarps * sched.v2_warp_bytes);
+  }
   // __cluster_dims__(2) is compiled into the kernel
-  return launch_pdl(kern, dim3(2 * clusters), dim3(kGemmThreads), T::kSmemBytes, stream, ta, tb, tal, tbl, ep, M, N, K, sched);
+  return launch_pdl(kern, dim3(2 * clusters), dim3(kGemmThreads), smem, stream, ta, tb, tal, tbl, ep, M, N, K, sched, tme);
 }
 
 inline int pick_block_n(int M, int N, int num_sms, int forced) {
@@ -212,6 +258,8 @@ inline const GemmSched& default_sched() {
     g.partials = nullptr;
     g.counters = nullptr;
     g.t_end = nullptr;
+    g.stages = 0;
+    g.v2_warp_bytes = 0;
     return g;
   }();
   return s;
@@ -265,8 +313,29 @@ inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, int mode,
   cudaError_t e = cudaErrorInvalidValue;
   GemmSched sched0 = default_sched();
   sched0.t_end = t_end;
+  // TMA-staged epilogue (2-CTA kernel, compiled epilogue variants, plain row mapping): build its tensor maps
+  const int v2_env = gemm_epilogue_v2_flag().load(std::memory_order_relaxed);
+  GemmTmaEpi tme;
+  memset(&tme, 0, sizeof(tme));
+  const bool both_out = ep.out_f32 != nullptr && ep.out_hi != nullptr;
+  bool v2 = v2_env != 0 && use_2cta && !strict && lo_ok && ep.act <= ACT_GELU_TANH && ep.row_group == 0 && ep.res_mod == 0 &&
+            ep.out_lo == nullptr && (!both_out || ep.res != nullptr) && g.N % 32 == 0;
+  if (v2) {
+    switch (code) {  // the variants compiled below
+      case epi_code(ACT_NONE, false, false, true): case epi_code(ACT_NONE, false, true, false):
+      case epi_code(ACT_NONE, true, true, false): case epi_code(ACT_GELU_ERF, false, false, true):
+      case epi_code(ACT_GELU_TANH, false, false, true): case epi_code(ACT_NONE, true, true, true): break;
+      default: v2 = false;
+    }
+  }
+  if (v2) {
+    if (ep.res != nullptr && !make_tmap_epi(&tme.res, ep.res, g.M, g.N, ep.ld_res, 4, false, err)) return false;
+    if (ep.out_f32 != nullptr && !make_tmap_epi(&tme.f32, ep.out_f32, g.M, g.N, ep.ld_f32, 4, false, err)) return false;
+    if (ep.out_hi != nullptr && !make_tmap_epi(&tme.b16, ep.out_hi, g.M, g.N, ep.ld_bf16, 2, fp16, err)) return false;
+    sched0.v2_warp_bytes = 1;  // the variant launcher sizes it
+  }
 #define AFFT_LAUNCH(BN, SP, EP)                                                                                       \
-  e = (BN == 512) ? launch_gemm_2cta_variant<SP, EP>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, sched0, sk, stream) \
+  e = (BN == 512) ? launch_gemm_2cta_variant<SP, EP>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, sched0, sk, stream, tme) \
                   : launch_gemm_variant<(BN == 512 ? 256 : BN), SP, EP>(ta, tb, tal, tbl, ep, g.M, g.N, g.K, num_sms, sched0, sk, stream)
 #define AFFT_DISPATCH_EPI(BN, SP)                                                            \
   do {                                                                                       \
@@ -278,6 +347,7 @@ inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, int mode,
       case epi_code(ACT_GELU_ERF, false, false, true): AFFT_LAUNCH(BN, SP, epi_code(ACT_GELU_ERF, false, false, true)); break;  \
       case epi_code(ACT_GELU_TANH, false, false, true): AFFT_LAUNCH(BN, SP, epi_code(ACT_GELU_TANH, false, false, true)); break; \
       case epi_code(ACT_NONE, false, true, true): AFFT_LAUNCH(BN, SP, epi_code(ACT_NONE, false, true, true)); break;            \
+      case epi_code(ACT_NONE, true, true, true): AFFT_LAUNCH(BN, SP, epi_code(ACT_NONE, true, true, true)); break;              \
       default: AFFT_LAUNCH(BN, SP, EPI_GENERIC); break;                                      \
     }                                                                                        \
   } while (0)

@@ -78,6 +78,18 @@ struct GemmSched {
   float* partials;      // >= grid CTAs * 128 * BLOCK_N floats
   unsigned* counters;   // >= tiles * (CTAs per tile) * kNumEpilogueWarps, zero before the first launch
   unsigned long long* t_end;  // profiling slot (ptx::prof_mark_end) or nullptr
+  // 2-CTA kernel only: depth of the TMA -> MMA ring (runtime: the TMA-staged epilogue trades ring stages for slab buffers)
+  int stages;
+  // TMA-staged epilogue (epilogue_v2 below): 0 = off, else the bytes of shared memory each epilogue warp owns
+  int v2_warp_bytes;
+};
+
+// Tensor maps of the TMA-staged epilogue (fp32 boxes 32 rows x 32 columns = 128-byte rows, SWIZZLE_128B; 16-bit boxes
+// 32 x 32 = 64-byte rows, SWIZZLE_64B).
+struct GemmTmaEpi {
+  CUtensorMap res;  // fp32 residual operand
+  CUtensorMap f32;  // fp32 output
+  CUtensorMap b16;  // bf16 / fp16 output
 };
 
 template <int BLOCK_N, int MODE>
@@ -263,6 +275,13 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 x;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr));
   return x;
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 // Per-tile row pointers of the tensors the epilogue touches (column 0 of each of this lane's 8 rows), so that the
@@ -754,6 +773,169 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 //   - each CTA's epilogue warps drain their own 128 x 256 TMEM accumulator and arrive (remotely for the peer)
 //     on the leader's tmem-empty barrier
 // --------------------------------------------------------------------------------------------
+// --------------------------------------------------------------------------------------------
+// TMA-staged epilogue of the 2-CTA kernel ("v2").  The v1 epilogue above transposes every accumulator slab through
+// shared memory so that the warp's global accesses coalesce, and fetches the fp32 residual with LDGs the adds then wait
+// for (ncu: long_scoreboard on the FADD; 50 % tensor-active on the K = 1024 projection).  Here a thread keeps the TMEM
+// layout - lane = output row, 32 consecutive columns in registers - and the TMA engine moves the data:
+//   * the fp32 residual slab (32 rows x 128 B) is fetched into shared memory by cp.async.bulk.tensor one slab ahead
+//     (the slab after the current one, across tile boundaries) behind a per-warp mbarrier pair, SWIZZLE_128B so that
+//     the row-per-lane 16-byte shared-memory accesses are conflict free;
+//   * results are written back into the same swizzled slab (fp32, in place over the residual) and / or a 64-byte-row
+//     SWIZZLE_64B slab (16-bit operand for the next GEMM) and leave through cp.async.bulk.tensor stores - no STG, no
+//     transposition;
+//   * the two slab buffers of a warp alternate: a buffer is refilled only after the bulk-group of the store that read
+//     it has finished reading (cp.async.bulk.wait_group.read).
+// Per epilogue warp: quadrant = warp % 4 (TMEM lanes = rows), column half = (warp - 4) / 4 (128 of the 256 columns:
+// four 32-column slabs).
+// Conditions (checked by the launcher): ksplit == 1, no output row map, residual at the output row (res_mod == 0),
+// MODE_BF16 / MODE_FP16, N a multiple of 32, one of the compiled epilogue variants.
+//
+// STATUS: opt-in (afft_set_gemm_epilogue(1) / AFFT_GEMM_EPI_V2=1), NOT the default.  A/B on one B200 (isolated launches,
+// profiles/r02_epilogue_v2_ab.txt): the K = 1024 residual projection 57.1 vs 57.8 us (v1), i.e. no gain - that GEMM moves
+// 235 MB per launch (47 MB A + 94 MB residual in + 94 MB out) = 36 us of HBM time next to 37 us of tensor time, it sits on
+// the roofline ridge, not in the epilogue's dependent chain; FC1 + GELU 171 vs 160 us and the GPT-2 projections 4 - 14 %
+// slower (the slab buffers cost ring stages, and a fence.proxy.async + bulk-group wait per 4 KB slab is more overhead than
+// the transposition it replaces).  Kept as the measured answer to "TMA-load the residual, TMA-store the outputs".
+// --------------------------------------------------------------------------------------------
+template <int EPI, int MODE>
+__device__ __forceinline__ void epilogue_v2(const GemmEpilogue& ep, const GemmTmaEpi& tme, const GemmSched& sched,
+                                            const uint32_t wbase, const uint32_t rbar, const uint32_t tmem_base,
+                                            const uint32_t tmem_full_bar0, const uint32_t tmem_empty_leader0, const int quad,
+                                            const int half, const int lane, const uint32_t rank, const int cluster_id,
+                                            const int num_clusters, const int num_tiles, const int num_m, const int num_n,
+                                            const int M, const int N) {
+  constexpr bool kRes = EPI >= 0 && (EPI & 4) != 0, kF32 = EPI >= 0 && (EPI & 8) != 0, kB16 = EPI >= 0 && (EPI & 16) != 0;
+  constexpr uint32_t kB16Off = (kRes || kF32) ? 8192u : 0u;  // 16-bit slabs sit behind the two fp32 slabs when both exist
+  auto tile_rc = [&](int tile, int& row0, int& col0) {
+    const int m_idx = sched.n_fastest ? tile / num_n : tile % num_m;
+    const int n_idx = sched.n_fastest ? tile % num_n : tile / num_m;
+    row0 = m_idx * 256 + static_cast<int>(rank) * 128 + quad * 32;
+    col0 = n_idx * 256 + half * 128;
+  };
+  // advance (tile, s) to the next slab that has rows < M and columns < N; false when this warp has none left
+  auto next_live = [&](int& tile, int& sl, int& row, int& col) -> bool {
+    for (;;) {
+      if (++sl == 4) {
+        sl = 0;
+        tile += num_clusters;
+      }
+      if (tile >= num_tiles) return false;
+      int r0, c0;
+      tile_rc(tile, r0, c0);
+      if (r0 < M && c0 + sl * 32 < N) {
+        row = r0;
+        col = c0 + sl * 32;
+        return true;
+      }
+    }
+  };
+  auto issue_res = [&](uint32_t slab_no, int row, int col) {  // one lane: residual slab -> buffer slab_no & 1
+    const uint32_t bar = rbar + (slab_no & 1u) * 8u;
+    ptx::mbar_arrive_expect_tx(bar, 4096u);
+    ptx::tma_load_2d(wbase + (slab_no & 1u) * 4096u, &tme.res, bar, col, row, ptx::kEvictNormal);
+  };
+
+  uint32_t slab = 0;  // live slabs processed so far by this warp: buffer = slab & 1, mbarrier parity = (slab >> 1) & 1
+  int nt = cluster_id, ns = -1, nrow = 0, ncol = 0;  // the next live slab (prefetch cursor)
+  bool have_next = next_live(nt, ns, nrow, ncol);
+  if (kRes && have_next && lane == 0) issue_res(0, nrow, ncol);
+  uint32_t acc = 0, acc_phase = 0;
+  for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    int row0, col0;
+    tile_rc(tile, row0, col0);
+    ptx::mbar_wait(tmem_full_bar0 + 8u * acc, acc_phase);
+    ptx::tcgen05_fence_after();
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256u + static_cast<uint32_t>(half * 128);
+
+#pragma unroll 1
+    for (int sl = 0; sl < 4; ++sl) {
+      const int col = col0 + sl * 32;
+      if (row0 >= M || col >= N) break;  // warp-uniform; later slabs of this tile are dead as well
+      // this slab is the prefetch cursor's slab: move the cursor to the one after it
+      have_next = next_live(nt, ns, nrow, ncol);
+      const uint32_t fb = wbase + (slab & 1u) * 4096u;
+      const uint32_t hb = wbase + kB16Off + (slab & 1u) * 2048u;
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(t_row + static_cast<uint32_t>(sl * 32), v);
+      if (!kRes) {
+        if (lane == 0) ptx::bulk_wait_group_read<1>();  // the stores of slab - 2 have left this slab's buffers
+        __syncwarp();
+      }
+      ptx::tmem_ld_wait();
+      float x[32];
+      const bool full_cols = (col + 32 <= N);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.bias != nullptr) {
+          if (full_cols) {
+            b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + j);
+          } else {
+            if (col + 4 * j + 0 < N) b4.x = __ldg(ep.bias + col + 4 * j + 0);
+            if (col + 4 * j + 1 < N) b4.y = __ldg(ep.bias + col + 4 * j + 1);
+            if (col + 4 * j + 2 < N) b4.z = __ldg(ep.bias + col + 4 * j + 2);
+            if (col + 4 * j + 3 < N) b4.w = __ldg(ep.bias + col + 4 * j + 3);
+          }
+        }
+        const float4 r4 = epilogue_math<EPI, MODE>(
+            ep, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                            __uint_as_float(v[4 * j + 3])), b4);
+        x[4 * j] = r4.x;
+        x[4 * j + 1] = r4.y;
+        x[4 * j + 2] = r4.z;
+        x[4 * j + 3] = r4.w;
+      }
+      if (kRes) {
+        if (lane == 0) {
+          // Every earlier store has finished reading shared memory: the other buffer (read by the store of slab - 1)
+          // can take the residual of slab + 1, which then has this slab's whole processing time to arrive.
+          ptx::bulk_wait_group_read<0>();
+          if (have_next) issue_res(slab + 1u, nrow, ncol);
+        }
+        ptx::mbar_wait(rbar + (slab & 1u) * 8u, (slab >> 1) & 1u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 r = lds128(fb + static_cast<uint32_t>(lane) * 128u + static_cast<uint32_t>((j ^ (lane & 7)) << 4));
+          x[4 * j] += r.x;
+          x[4 * j + 1] += r.y;
+          x[4 * j + 2] += r.z;
+          x[4 * j + 3] += r.w;
+        }
+      }
+      if (kF32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(fb + static_cast<uint32_t>(lane) * 128u + static_cast<uint32_t>((j ^ (lane & 7)) << 4), x[4 * j], x[4 * j + 1],
+                 x[4 * j + 2], x[4 * j + 3]);
+      }
+      if (kB16) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts128u(hb + static_cast<uint32_t>(lane) * 64u + static_cast<uint32_t>((j ^ ((lane >> 1) & 3)) << 4),
+                  pack2_operand<MODE>(x[8 * j], x[8 * j + 1]), pack2_operand<MODE>(x[8 * j + 2], x[8 * j + 3]),
+                  pack2_operand<MODE>(x[8 * j + 4], x[8 * j + 5]), pack2_operand<MODE>(x[8 * j + 6], x[8 * j + 7]));
+      }
+      ptx::fence_proxy_async_smem();  // this lane's slab rows -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        if (kF32) ptx::tma_store_2d(&tme.f32, fb, col, row0);
+        if (kB16) ptx::tma_store_2d(&tme.b16, hb, col, row0);
+        ptx::bulk_commit_group();
+      }
+      ++slab;
+    }
+    // every tcgen05.ld of this tile has completed: hand the accumulator back to the MMA warp
+    ptx::tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive_cluster(tmem_empty_leader0 + 8u * acc);
+    acc ^= 1u;
+    if (acc == 0) acc_phase ^= 1u;
+  }
+  if (lane == 0) ptx::bulk_wait_group<0>();  // all stores performed before the grid can be considered complete
+  __syncwarp();
+}
+
 template <int MODE>
 struct Gemm2Traits {
   static constexpr int kPairs = (MODE == MODE_BF16X3) ? 2 : 1;
@@ -763,11 +945,16 @@ struct Gemm2Traits {
 #ifndef AFFT_2CTA_STAGES
 #define AFFT_2CTA_STAGES 6  // A/B knob (tools/gemm_time.py with AFFT_B200_LIB): depth of the TMA -> MMA ring
 #endif
-  static constexpr int kStages = (MODE == MODE_BF16X3) ? 3 : AFFT_2CTA_STAGES;
+  static constexpr int kStages = (MODE == MODE_BF16X3) ? 3 : AFFT_2CTA_STAGES;  // default ring depth (v1 epilogue)
+  static constexpr int kMaxStages = 8;
   static constexpr uint32_t kTmemCols = 512;                       // 2 accumulators x 256 columns
-  static constexpr uint32_t kBarrierBytes = 256;
-  static constexpr uint32_t kStagingBytes = kNumEpilogueWarps * 4096;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;
+  static constexpr uint32_t kBarrierBytes = 1024;                  // barriers first: the ring behind them stays 1024-B aligned
+  static constexpr uint32_t kStagingBytes = kNumEpilogueWarps * 4096;  // v1 epilogue: one transposition tile per warp
+  // shared memory of a launch with `stages` ring slots and `epi_bytes` of epilogue staging (+ alignment slack)
+  static constexpr uint32_t smem_bytes(int stages, uint32_t epi_bytes) {
+    return kBarrierBytes + static_cast<uint32_t>(stages) * kStageBytes + epi_bytes + 1024;
+  }
+  static constexpr uint32_t kSmemBytes = smem_bytes(kStages, kStagingBytes);
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
@@ -776,19 +963,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                               const __grid_constant__ CUtensorMap tm_a_lo,
                               const __grid_constant__ CUtensorMap tm_b_lo, const __grid_constant__ GemmEpilogue ep, const int M,
-                              const int N, const int K, const __grid_constant__ GemmSched sched) {
+                              const int N, const int K, const __grid_constant__ GemmSched sched,
+                              const __grid_constant__ GemmTmaEpi tme) {
   using T = Gemm2Traits<MODE>;
   constexpr int BLOCK_N = 256;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_raw_u32 = ptx::smem_u32(smem_raw);
-  const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
-  const uint32_t staging_base = smem_base + T::kStages * T::kStageBytes;
-  const uint32_t bar_base = staging_base + T::kStagingBytes;
+  const uint32_t bar_base = (smem_raw_u32 + 1023u) & ~1023u;   // [barriers 1 KB][ring: stages x kStageBytes][epilogue staging]
+  const uint32_t smem_base = bar_base + T::kBarrierBytes;
+  const uint32_t num_stages = static_cast<uint32_t>(sched.stages);
+  const uint32_t staging_base = smem_base + num_stages * T::kStageBytes;
   auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (T::kStages + s); };
-  auto tmem_full_bar = [&](uint32_t a) { return bar_base + 8u * (2 * T::kStages + a); };
-  auto tmem_empty_bar = [&](uint32_t a) { return bar_base + 8u * (2 * T::kStages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * T::kStages + 4);
+  auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (T::kMaxStages + s); };
+  auto tmem_full_bar = [&](uint32_t a) { return bar_base + 8u * (2 * T::kMaxStages + a); };
+  auto tmem_empty_bar = [&](uint32_t a) { return bar_base + 8u * (2 * T::kMaxStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * T::kMaxStages + 4);
+  auto res_bar = [&](uint32_t w) { return bar_base + 8u * (2 * T::kMaxStages + 6 + 2 * w); };  // v2 epilogue: 2 per warp
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
 
   ptx::griddep_launch();
@@ -814,7 +1004,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
     }
   }
   if (warp == 1 && lane == 0) {
-    for (uint32_t s = 0; s < T::kStages; ++s) {
+    for (uint32_t s = 0; s < num_stages; ++s) {
       ptx::mbar_init(full_bar(s), 2);   // leader's arrive.expect_tx + the peer producer's remote arrive
       ptx::mbar_init(empty_bar(s), 1);  // tcgen05.commit (multicast from the leader)
     }
@@ -822,6 +1012,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
       ptx::mbar_init(tmem_full_bar(a), 1);                        // tcgen05.commit (multicast)
       ptx::mbar_init(tmem_empty_bar(a), 2 * kNumEpilogueWarps);   // epilogue warps of both CTAs
     }
+    for (uint32_t w = 0; w < 2 * kNumEpilogueWarps; ++w) ptx::mbar_init(res_bar(0) + 8u * w, 1);  // residual slabs (v2)
     ptx::fence_mbar_init();
   }
   if (warp == 2) ptx::tmem_alloc_2cta<T::kTmemCols>(tmem_slot);
@@ -857,7 +1048,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
             ptx::tma_load_2d_2cta(a_lo_dst, &tm_a_lo, fb_leader, kb * kBlockK, a_row, sched.policy_a);
             ptx::tma_load_2d_2cta(b_lo_dst, &tm_b_lo, fb_leader, kb * kBlockK, b_row, sched.policy_b);
           }
-          if (++stage == T::kStages) {
+          if (++stage == num_stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -900,7 +1091,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
             }
           }
           ptx::umma_commit_2cta(empty_bar(stage), 0b11);  // frees the slot in both CTAs
-          if (++stage == T::kStages) {
+          if (++stage == num_stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -914,6 +1105,16 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
     // ======================= epilogue (both CTAs, own 128 rows) =======================
     const int quad = warp & 3;
     const int egrp = (warp - 4) >> 2;
+    bool v2 = false;
+    if constexpr (EPI >= 0 && MODE != MODE_BF16X3) {  // TMA-staged epilogue (the launcher guarantees ksplit == 1)
+      v2 = sched.v2_warp_bytes > 0;
+      if (v2)
+        epilogue_v2<EPI, MODE>(ep, tme, sched,
+                               staging_base + static_cast<uint32_t>(warp - 4) * static_cast<uint32_t>(sched.v2_warp_bytes),
+                               res_bar(static_cast<uint32_t>(warp - 4)), tmem_base, tmem_full_bar(0), ptx::mapa(tmem_empty_bar(0), 0),
+                               quad, egrp, lane, rank, cluster_id, num_clusters, num_tiles, num_m, num_n, M, N);
+    }
+    if (!v2) {
     const uint32_t stage = staging_base + static_cast<uint32_t>(warp - 4) * 4096u;
     constexpr size_t kHalfTile = static_cast<size_t>(kBlockM) * BLOCK_N;  // one CTA's 128 x 256 accumulator
     uint32_t acc = 0, acc_phase = 0;
@@ -942,6 +1143,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __
                                          [&] { if (lane == 0) ptx::mbar_arrive_cluster(empty_leader); });
       acc ^= 1u;
       if (acc == 0) acc_phase ^= 1u;
+    }
     }
   }
 

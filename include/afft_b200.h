@@ -110,6 +110,12 @@ typedef struct afft_gemm_desc {
 
 AFFT_API int afft_gemm(const afft_gemm_desc* d, void* stream);
 
+/* Process-wide choice of the large-M GEMM epilogue: 0 (default) = shared-memory transposition + coalesced global
+ * accesses; 1 = TMA-staged (fp32 residual fetched by cp.async.bulk.tensor one slab ahead, outputs written with
+ * cp.async.bulk.tensor stores).  Same results bit for bit; measured slower or equal on every shape of the path
+ * (DESIGN.md section 4.1), kept for A/B runs.  Initial value: environment variable AFFT_GEMM_EPI_V2. */
+AFFT_API int afft_set_gemm_epilogue(int32_t v2);
+
 /* fp32 [rows, cols] (pitch lds) -> bf16 hi (+ lo when lo != NULL), pitch ldd; transpose != 0
  * writes dst[c, r].  Weight packing (Conv1D [in,out] -> K-major) and feature inputs. */
 AFFT_API int afft_convert_bf16(const float* src, int64_t lds, int32_t rows, int32_t cols, void* hi, void* lo, int64_t ldd,

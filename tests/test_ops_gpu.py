@@ -332,3 +332,39 @@ def test_score_fusion_many_rows(dev):
     ref = sum(p[:, i:i + 1] * logits[i].double() for i in range(M))
     assert (attn.double() - p).abs().max().item() < 1e-6
     assert (out.double() - ref).abs().max().item() < 1e-5
+
+
+def test_gemm_tma_staged_epilogue_matches_default(dev):
+    """The opt-in TMA-staged epilogue (afft_set_gemm_epilogue(1): residual fetched by cp.async.bulk.tensor, outputs stored
+    by cp.async.bulk.tensor) computes the same per-element arithmetic as the default one: results are bit-identical."""
+    g = torch.Generator().manual_seed(21)
+    F = torch.nn.functional
+    lib = capi.lib()
+    try:
+        for M, N, K in ((777, 1024, 1024), (1300, 3072, 512), (2304, 2048, 2048)):
+            a = _randn(g, dev, M, K).bfloat16()
+            w = _randn(g, dev, N, K, scale=0.05).bfloat16()
+            bias, res = _randn(g, dev, N), _randn(g, dev, M, N)
+            outs = {}
+            for v2 in (0, 1):
+                capi.check(lib.afft_set_gemm_epilogue(v2))
+                h = res.clone()
+                capi.gemm(a, w, bias=bias, res=h, out_f32=h)                       # in-place residual stream
+                hb = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+                h2 = res.clone()
+                capi.gemm(a, w, bias=bias, res=h2, out_f32=h2, out_hi=hb)          # + 16-bit copy
+                qb = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+                capi.gemm(a, w, out_hi=qb)                                         # qkv-style
+                gb = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+                capi.gemm(a, w, bias=bias, act=capi.ACT_GELU_ERF, out_hi=gb)       # FC1-style
+                f = torch.zeros(M, N, device=dev)
+                capi.gemm(a, w, bias=bias, out_f32=f)                              # classifier-style
+                ah, wh = a.half(), w.half()
+                fh = torch.zeros(M, N, device=dev, dtype=torch.float16)
+                capi.gemm(ah, wh, bias=bias, act=capi.ACT_GELU_TANH, out_hi=fh)    # fp16 operands
+                outs[v2] = (h, h2, hb, qb, gb, f, fh)
+            for t0, t1 in zip(outs[0], outs[1]):
+                assert torch.equal(t0, t1)
+            assert (outs[1][0] - (_mm(a, w) + bias + res)).abs().max().item() < 1e-4
+    finally:
+        capi.check(lib.afft_set_gemm_epilogue(0))
