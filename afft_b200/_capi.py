@@ -20,7 +20,7 @@ AFFT_OK = 0
 AFFT_MAX_MODS = 8
 AFFT_MAX_CLS = 4
 AFFT_NAME_LEN = 32
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH, ACT_RELU, ACT_GATE = 0, 1, 2, 3, 4
 PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2
@@ -44,6 +44,7 @@ def operand_dtype(precision: str):
     """torch dtype of the 16-bit GEMM operands of a precision."""
     return torch.float16 if precision == "fp16" else torch.bfloat16
 FUSER_SA, FUSER_SA_NOTOKEN, FUSER_TSA, FUSER_CA, FUSER_NONE = 0, 1, 2, 3, 4
+STAGE_ALL, STAGE_FUSER, STAGE_GPT = 0, 1, 4
 
 
 class AfftError(RuntimeError):
@@ -103,6 +104,7 @@ class Config(C.Structure):
         ("cls_name", (C.c_char * AFFT_NAME_LEN) * AFFT_MAX_CLS),
         ("cls_dim", C.c_int32 * AFFT_MAX_CLS),
         ("precision", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32), ("fp_output_len", C.c_int32),
+        ("stages", C.c_int32),
     ]
 
 

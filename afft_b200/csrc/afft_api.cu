@@ -35,7 +35,7 @@ static int cuda_fail(const char* what, cudaError_t e) {
   return fail(AFFT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-extern "C" int afft_abi_version(void) { return 5; }
+extern "C" int afft_abi_version(void) { return 6; }
 extern "C" const char* afft_last_error(void) { return g_err.c_str(); }
 
 static int device_sm_count(int* out) {
@@ -577,6 +577,7 @@ static void build_expected(afft_handle* h) {
   const afft_config& c = h->cfg;
   auto& E = h->expected;
   const long long D = c.dim, G = c.gpt_dim;
+  const bool want_fuser = c.stages != AFFT_STAGE_GPT, want_head = c.stages == AFFT_STAGE_ALL, want_gpt = c.stages != AFFT_STAGE_FUSER;
   auto gemm = [&](const std::string& n, long long out, long long in) { E[n] = {Pack::Gemm, out * in, out, in, 0}; };
   auto gemm_t = [&](const std::string& n, long long in, long long out) { E[n] = {Pack::GemmT, out * in, in, out, 0}; };
   auto vec = [&](const std::string& n, long long rows, long long cols) { E[n] = {Pack::F32, rows * cols, rows, cols, 0}; };
@@ -587,13 +588,14 @@ static void build_expected(afft_handle* h) {
       vec(n + ".bias", 1, d);
     }
   };
-  for (int m = 0; m < c.n_mod; ++m)
+  for (int m = 0; want_fuser && m < c.n_mod; ++m)
     if (c.mod_dim[m] != c.dim) gemm(std::string("mapping.") + c.mod_name[m] + ".mapping.0.weight", D, c.mod_dim[m]);
 
   const int n_slots = h->n_slots;
-  const bool has_fuser = c.fuser_kind != AFFT_FUSER_NONE;
+  const bool has_fuser = want_fuser && c.fuser_kind != AFFT_FUSER_NONE;
   const bool affine = (c.fuser_kind == AFFT_FUSER_SA) ? (c.norm_elementwise != 0) : true;
-  if (c.fuser_kind == AFFT_FUSER_SA) {
+  if (!want_fuser) {
+  } else if (c.fuser_kind == AFFT_FUSER_SA) {
     vec("fuser.modal_token", c.frame_level_token ? c.T : 1, D);
     if (c.modal_encoding) vec("fuser.modality_embedding", n_slots, D);
   } else if (c.fuser_kind == AFFT_FUSER_TSA) {
@@ -628,13 +630,13 @@ static void build_expected(afft_handle* h) {
     vec(p + "mlp.mlp.2.bias", 1, D);
   }
   if (has_fuser) ln("fuser.norm", D, affine);
-  if (c.dim != c.gpt_dim) {
+  if (want_head && c.dim != c.gpt_dim) {
     gemm("dim_encoder.weight", G, D);
     gemm("dim_decoder.weight", D, G);
   }
   const std::string gp = "future_predictor.gpt_model.";
-  table(gp + "wpe.weight", G);
-  for (int i = 0; i < c.gpt_layers; ++i) {
+  if (want_gpt) E[gp + "wpe.weight"] = {Pack::F32, 0, 0, G, c.T + c.fp_output_len - 1};
+  for (int i = 0; want_gpt && i < c.gpt_layers; ++i) {
     const std::string p = gp + blk_name("h.", i, ".");
     ln(p + "ln_1", G, true);
     ln(p + "ln_2", G, true);
@@ -647,8 +649,8 @@ static void build_expected(afft_handle* h) {
     gemm_t(p + "mlp.c_proj.weight", 4 * G, G);
     vec(p + "mlp.c_proj.bias", 1, G);
   }
-  ln(gp + "ln_f", G, true);
-  for (int k = 0; k < c.n_cls; ++k) {
+  if (want_gpt) ln(gp + "ln_f", G, true);
+  for (int k = 0; want_head && k < c.n_cls; ++k) {
     const std::string p = std::string("classifiers.") + c.cls_name[k] + ".all-fused.1.";
     gemm(p + "weight", c.cls_dim[k], D);
     vec(p + "bias", 1, c.cls_dim[k]);
@@ -664,8 +666,13 @@ extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
   if (c.fuser_kind < 0 || c.fuser_kind > AFFT_FUSER_NONE) return fail(AFFT_ERR_INVALID, "create: unknown fuser_kind");
   if (c.precision < AFFT_PREC_BF16 || c.precision > AFFT_PREC_FP16) return fail(AFFT_ERR_INVALID, "create: unknown precision");
   const bool no_fuser = c.fuser_kind == AFFT_FUSER_NONE;
+  if (c.stages != AFFT_STAGE_ALL && c.stages != AFFT_STAGE_FUSER && c.stages != AFFT_STAGE_GPT)
+    return fail(AFFT_ERR_INVALID, "create: stages must be AFFT_STAGE_ALL, AFFT_STAGE_FUSER or AFFT_STAGE_GPT");
+  if (c.stages == AFFT_STAGE_FUSER && no_fuser) return fail(AFFT_ERR_INVALID, "create: AFFT_STAGE_FUSER needs a fuser");
+  if (c.stages == AFFT_STAGE_GPT && (!no_fuser || c.n_mod != 1 || c.mod_dim[0] != c.gpt_dim || c.dim != c.gpt_dim))
+    return fail(AFFT_ERR_INVALID, "create: AFFT_STAGE_GPT takes fuser_kind NONE and one modality with mod_dim = dim = gpt_dim");
   if (c.n_mod < 1 || c.n_mod > AFFT_MAX_MODS - 1) return fail(AFFT_ERR_INVALID, "create: n_mod out of range");
-  if (c.n_cls < 1 || c.n_cls > AFFT_MAX_CLS) return fail(AFFT_ERR_INVALID, "create: n_cls out of range");
+  if (c.n_cls < (c.stages == AFFT_STAGE_ALL ? 1 : 0) || c.n_cls > AFFT_MAX_CLS) return fail(AFFT_ERR_INVALID, "create: n_cls out of range");
   if (c.T < 1 || c.T > 64) return fail(AFFT_ERR_INVALID, "create: T must be in [1, 64]");
   if (c.max_batch < 1) return fail(AFFT_ERR_INVALID, "create: max_batch must be >= 1");
   if (no_fuser) {
@@ -679,7 +686,8 @@ extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
   const int hd1 = no_fuser ? 256 : c.dim / c.fuser_heads, hd2 = c.gpt_dim / c.gpt_heads;
   if ((hd1 != 256 && hd1 != 512) || (hd2 != 256 && hd2 != 512))
     return fail(AFFT_ERR_INVALID, "create: head_dim must be 256 or 512");
-  if (c.dim == c.gpt_dim) return fail(AFFT_ERR_INVALID, "create: common_dim == fp_inter_dim (Identity encoder) is not supported");
+  if (c.dim == c.gpt_dim && c.stages == AFFT_STAGE_ALL)
+    return fail(AFFT_ERR_INVALID, "create: common_dim == fp_inter_dim (Identity encoder) is not supported");
   for (int m = 0; m < c.n_mod; ++m)
     if (c.mod_dim[m] < 8 || c.mod_dim[m] % 8 != 0) return fail(AFFT_ERR_INVALID, "create: modality dims must be multiples of 8");
   if (c.fuser_kind == AFFT_FUSER_CA && c.n_mod < 2) return fail(AFFT_ERR_INVALID, "create: CA-Fuser needs >= 2 modalities");
@@ -737,17 +745,20 @@ extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
     for (int m = 1; m < c.n_mod; ++m) want(reinterpret_cast<void**>(&h->mem[m]), R2 * D * 4);
     want_pair(h->ykv, R2 * D);
   }
+  const bool want_gpt = c.stages != AFFT_STAGE_FUSER;
   want(reinterpret_cast<void**>(&h->table), T * D * 4);
   want_pair(h->zb, R2 * D);
-  want(reinterpret_cast<void**>(&h->g), R2 * G * 4);
-  want_pair(h->y2, R2 * G);
-  want_pair(h->att2, R2 * G);
-  want_pair(h->f2, R2 * 4 * G);
-  want(&h->qkv2, R2 * 3 * G * (strict ? 4 : 2));
-  want_pair(h->pfb, RP * D);
+  if (want_gpt) {
+    want(reinterpret_cast<void**>(&h->g), R2 * G * 4);
+    want_pair(h->y2, R2 * G);
+    want_pair(h->att2, R2 * G);
+    want_pair(h->f2, R2 * 4 * G);
+    want(&h->qkv2, R2 * 3 * G * (strict ? 4 : 2));
+  }
+  if (c.stages == AFFT_STAGE_ALL) want_pair(h->pfb, RP * D);
   want(reinterpret_cast<void**>(&h->splitk.partials), kSplitKPartialFloats * 4);
   want(reinterpret_cast<void**>(&h->splitk.counters), kSplitKCounters * 4);
-  if (OL > 1) {
+  if (OL > 1 && want_gpt) {
     h->qkv_layer.assign(c.gpt_layers, nullptr);
     h->qkv_new.assign(c.gpt_layers, nullptr);
     for (int l = 0; l < c.gpt_layers; ++l) {
@@ -1127,10 +1138,13 @@ static void run_fuser(Fwd& F, const afft_io& io, int b0, int nb) {
   const int S = T + c.fp_output_len;                                  // slots per clip in past_futures / logits
   const long long zoff = static_cast<long long>(b0) * T * D;          // into orig_past / zb
   const long long poff = static_cast<long long>(b0) * S * D;          // into past_futures / pfb
+  const bool head = c.stages == AFFT_STAGE_ALL;  // AFFT_STAGE_FUSER: only z = orig_past (+ attention) is produced
   PairBuf zb = {h->zb.hi + zoff, h->zb.lo ? h->zb.lo + zoff : nullptr};
-  PairBuf pfb = {h->pfb.hi + poff, h->pfb.lo ? h->pfb.lo + poff : nullptr};
+  PairBuf pfb_v = {head ? h->pfb.hi + poff : nullptr, (head && h->pfb.lo) ? h->pfb.lo + poff : nullptr};
+  const PairBuf* pfbp = head ? &pfb_v : nullptr;
+  const int aux_T = head ? T : 0;  // LayerNorm aux scatter (slot 0 of past_futures) off without the head
   float* orig_past = io.orig_past + zoff;
-  float* pf = io.past_futures + poff;
+  float* pf = head ? io.past_futures + poff : nullptr;
   const float* feat[AFFT_MAX_MODS];
   for (int m = 0; m < c.n_mod; ++m) feat[m] = io.feat[m] + static_cast<long long>(b0) * T * c.mod_dim[m];
 
@@ -1144,9 +1158,9 @@ static void run_fuser(Fwd& F, const afft_io& io, int b0, int nb) {
       if (e == cudaSuccess)
         e = cudaMemcpy2DAsync(pf, S * row4, feat[0], T * row4, row4, nb, cudaMemcpyDeviceToDevice, F.stream);
       if (e == cudaSuccess)
-        e = cudaMemcpy2DAsync(pfb.hi, S * row2, zb.hi, T * row2, row2, nb, cudaMemcpyDeviceToDevice, F.stream);
+        e = cudaMemcpy2DAsync(pfb_v.hi, S * row2, zb.hi, T * row2, row2, nb, cudaMemcpyDeviceToDevice, F.stream);
       if (e == cudaSuccess && zb.lo != nullptr)
-        e = cudaMemcpy2DAsync(pfb.lo, S * row2, zb.lo, T * row2, row2, nb, cudaMemcpyDeviceToDevice, F.stream);
+        e = cudaMemcpy2DAsync(pfb_v.lo, S * row2, zb.lo, T * row2, row2, nb, cudaMemcpyDeviceToDevice, F.stream);
       if (e != cudaSuccess) F.check(cuda_fail("stage features", e));
     }
     return;
@@ -1192,7 +1206,7 @@ static void run_fuser(Fwd& F, const afft_io& io, int b0, int nb) {
              D, nullptr, 0);
       fuser_mlp(F, p, "norm_mlp", R2);
     }
-    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, 0, 0, 0, 0, T, S, pf, &pfb, D);
+    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, 0, 0, 0, 0, aux_T, S, pf, pfbp, D);
     return;
   }
 
@@ -1271,34 +1285,28 @@ static void run_fuser(Fwd& F, const afft_io& io, int b0, int nb) {
   // 3. final norm + token selection / averaging
   if (c.fuser_kind == AFFT_FUSER_SA) {
     // token 0 of every (b, t): fusion.py:362-364
-    F.layernorm(h->h, static_cast<long long>(n) * D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, 0, 0, 0, 0, T, S,
-                pf, &pfb, D);
+    F.layernorm(h->h, static_cast<long long>(n) * D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, 0, 0, 0, 0, aux_T, S,
+                pf, pfbp, D);
   } else if (c.fuser_kind == AFFT_FUSER_SA_NOTOKEN) {
     // mean over the modality tokens of LN(x): fusion.py:114-116
-    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, 1, n, n, 1, T, S, pf, &pfb, D);
+    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, 1, n, n, 1, aux_T, S, pf, pfbp, D);
   } else if (c.frame_level_token) {
     // first T tokens of every clip: fusion.py:207-209
-    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, T, n * T, 0, 0, T, S, pf, &pfb, D);
+    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, T, n * T, 0, 0, aux_T, S, pf, pfbp, D);
   } else {
     // mean over modalities per timestep: fusion.py:211-214
-    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, T, n * T, n, T, T, S, pf, &pfb, D);
+    F.layernorm(h->h, D, R2, D, "fuser.norm", 1e-6f, &zb, orig_past, D, T, n * T, n, T, aux_T, S, pf, pfbp, D);
   }
 }
 
-// dim_encoder -> GPT-2 -> dim_decoder -> classifiers over all B clips
-// (future_prediction.py:267-269,282-288; transformers GPT2Model; SURVEY.md Appendix A steps 6-9).
-// With fp_output_len = O > 1 the predictor is rolled out O - 1 more positions with its KV cache
-// (future_prediction.py:395-412): z_hat has T + O - 1 rows per clip.
-static void run_predictor(Fwd& F, const afft_io& io, int B) {
+// The GPT-2 blocks over the T prompt positions of B clips: residual stream in h->g [B*T, G] (transformers GPT2Block;
+// SURVEY.md Appendix A step 7).  With a roll-out the per-layer q|k|v buffers are kept as the KV cache.
+static void gpt_prompt_layers(Fwd& F, int B) {
   afft_handle* h = F.h;
   const afft_config& c = h->cfg;
-  const int T = c.T, D = c.dim, G = c.gpt_dim, H = c.gpt_heads, hd = G / H;
-  const int OL = c.fp_output_len, S = T + OL;
+  const int T = c.T, G = c.gpt_dim, H = c.gpt_heads, hd = G / H, OL = c.fp_output_len;
   const int R2 = B * T;
   const std::string gp = "future_predictor.gpt_model.";
-  const float* wpe = F.V(gp + "wpe.weight");
-  // g = z . Wenc^T + wpe[t]
-  F.gemm(h->zb, D, R2, "dim_encoder.weight", nullptr, ACT_NONE, wpe, G, T, h->g, G, nullptr, 0);
   for (int i = 0; i < c.gpt_layers; ++i) {
     const std::string p = gp + blk_name("h.", i, ".");
     void* qkv = (OL > 1) ? h->qkv_layer[i] : h->qkv2;  // kept per layer when it is the KV cache of a roll-out
@@ -1315,6 +1323,50 @@ static void run_predictor(Fwd& F, const afft_io& io, int B) {
     F.gemm(h->f2, 4 * G, R2, p + "mlp.c_proj.weight", F.V(p + "mlp.c_proj.bias"), ACT_NONE, h->g, G, 0, h->g, G, nullptr,
            0);
   }
+}
+
+// One generated position (k-th, k >= 1) of every clip through the GPT-2 blocks with the KV cache: the fed-back hidden
+// state h->hid + wpe[T + k - 1] enters h->gn (future_prediction.py:395-412).
+static void gpt_decode_layers(Fwd& F, int B, int k) {
+  afft_handle* h = F.h;
+  const afft_config& c = h->cfg;
+  const int T = c.T, G = c.gpt_dim, H = c.gpt_heads, hd = G / H, OL = c.fp_output_len;
+  const std::string gp = "future_predictor.gpt_model.";
+  const float* wpe = F.V(gp + "wpe.weight");
+  const int pos = T + k - 1;  // position id of the token being generated (future_prediction.py:398-399)
+  F.add_row_vector(h->gn, h->hid, wpe + static_cast<long long>(pos) * G, B, G);
+  for (int i = 0; i < c.gpt_layers; ++i) {
+    const std::string p = gp + blk_name("h.", i, ".");
+    F.layernorm(h->gn, G, B, G, p + "ln_1", 1e-5f, &h->yn, nullptr, G);
+    QkvOut q = qkv_out(h->qkv_new[i], F.strict, 0);
+    F.gemm(h->yn, G, B, p + "attn.c_attn.weight", F.V(p + "attn.c_attn.bias"), ACT_NONE, nullptr, 0, 0, q.f32, 3 * G,
+           q.bp, 3 * G, 1, OL - 1, k - 1);
+    F.decode_attention(h->qkv_layer[i], h->qkv_new[i], 3 * G, B, T, H, hd, k, OL - 1, h->attn_n);
+    F.gemm(h->attn_n, G, B, p + "attn.c_proj.weight", F.V(p + "attn.c_proj.bias"), ACT_NONE, h->gn, G, 0, h->gn, G,
+           nullptr, 0);
+    F.layernorm(h->gn, G, B, G, p + "ln_2", 1e-5f, &h->yn, nullptr, G);
+    F.gemm(h->yn, G, B, p + "mlp.c_fc.weight", F.V(p + "mlp.c_fc.bias"), ACT_GELU_TANH, nullptr, 0, 0, nullptr, 0, &h->fn,
+           4 * G);
+    F.gemm(h->fn, 4 * G, B, p + "mlp.c_proj.weight", F.V(p + "mlp.c_proj.bias"), ACT_NONE, h->gn, G, 0, h->gn, G, nullptr,
+           0);
+  }
+}
+
+// dim_encoder -> GPT-2 -> dim_decoder -> classifiers over all B clips
+// (future_prediction.py:267-269,282-288; transformers GPT2Model; SURVEY.md Appendix A steps 6-9).
+// With fp_output_len = O > 1 the predictor is rolled out O - 1 more positions with its KV cache
+// (future_prediction.py:395-412): z_hat has T + O - 1 rows per clip.
+static void run_predictor(Fwd& F, const afft_io& io, int B) {
+  afft_handle* h = F.h;
+  const afft_config& c = h->cfg;
+  const int T = c.T, D = c.dim, G = c.gpt_dim;
+  const int OL = c.fp_output_len, S = T + OL;
+  const int R2 = B * T;
+  const std::string gp = "future_predictor.gpt_model.";
+  const float* wpe = F.V(gp + "wpe.weight");
+  // g = z . Wenc^T + wpe[t]
+  F.gemm(h->zb, D, R2, "dim_encoder.weight", nullptr, ACT_NONE, wpe, G, T, h->g, G, nullptr, 0);
+  gpt_prompt_layers(F, B);
   if (OL > 1)  // also keep the last position's hidden state (fp32): it is the next input embedding
     F.layernorm(h->g, G, R2, G, gp + "ln_f", 1e-5f, &h->y2, nullptr, G, 0, 0, 0, 0, T, 1, h->hid, nullptr, G, T - 1);
   else
@@ -1323,23 +1375,7 @@ static void run_predictor(Fwd& F, const afft_io& io, int B) {
   F.gemm(h->y2, G, R2, "dim_decoder.weight", nullptr, ACT_NONE, nullptr, 0, 0, io.past_futures, D, &h->pfb, D, T, S, 1);
 
   for (int k = 1; k < OL; ++k) {
-    const int pos = T + k - 1;  // position id of the token being generated (future_prediction.py:398-399)
-    F.add_row_vector(h->gn, h->hid, wpe + static_cast<long long>(pos) * G, B, G);
-    for (int i = 0; i < c.gpt_layers; ++i) {
-      const std::string p = gp + blk_name("h.", i, ".");
-      F.layernorm(h->gn, G, B, G, p + "ln_1", 1e-5f, &h->yn, nullptr, G);
-      QkvOut q = qkv_out(h->qkv_new[i], F.strict, 0);
-      F.gemm(h->yn, G, B, p + "attn.c_attn.weight", F.V(p + "attn.c_attn.bias"), ACT_NONE, nullptr, 0, 0, q.f32, 3 * G,
-             q.bp, 3 * G, 1, OL - 1, k - 1);
-      F.decode_attention(h->qkv_layer[i], h->qkv_new[i], 3 * G, B, T, H, hd, k, OL - 1, h->attn_n);
-      F.gemm(h->attn_n, G, B, p + "attn.c_proj.weight", F.V(p + "attn.c_proj.bias"), ACT_NONE, h->gn, G, 0, h->gn, G,
-             nullptr, 0);
-      F.layernorm(h->gn, G, B, G, p + "ln_2", 1e-5f, &h->yn, nullptr, G);
-      F.gemm(h->yn, G, B, p + "mlp.c_fc.weight", F.V(p + "mlp.c_fc.bias"), ACT_GELU_TANH, nullptr, 0, 0, nullptr, 0, &h->fn,
-             4 * G);
-      F.gemm(h->fn, 4 * G, B, p + "mlp.c_proj.weight", F.V(p + "mlp.c_proj.bias"), ACT_NONE, h->gn, G, 0, h->gn, G, nullptr,
-             0);
-    }
+    gpt_decode_layers(F, B, k);
     F.layernorm(h->gn, G, B, G, gp + "ln_f", 1e-5f, &h->yn, h->hid, G);
     F.gemm(h->yn, G, B, "dim_decoder.weight", nullptr, ACT_NONE, nullptr, 0, 0, io.past_futures, D, &h->pfb, D, 1, S, T + k);
   }
@@ -1350,6 +1386,40 @@ static void run_predictor(Fwd& F, const afft_io& io, int B) {
   }
 }
 
+// AFFT_STAGE_GPT: BaseFuturePredictor.forward (models/future_prediction.py:387-415 with Identity encoder / decoder):
+// io.feat[0] [B, T, G] -> last hidden states of the T prompt positions (io.orig_past) and of the fp_output_len - 1
+// generated ones (io.past_futures [B, O - 1, G]).
+static void run_gpt_only(Fwd& F, const afft_io& io, int B) {
+  afft_handle* h = F.h;
+  const afft_config& c = h->cfg;
+  const int T = c.T, G = c.gpt_dim, OL = c.fp_output_len;
+  const int R2 = B * T;
+  const std::string gp = "future_predictor.gpt_model.";
+  AssembleArgs a;  // g = inputs_embeds + wpe[t]
+  memset(&a, 0, sizeof(a));
+  a.h = h->g;
+  a.B = B;
+  a.T = T;
+  a.dim = G;
+  a.n_slots = 1;
+  a.layout = 0;
+  a.src[0] = io.feat[0];
+  a.tok_mod = 1;
+  a.pos_emb = F.V(gp + "wpe.weight");
+  F.assemble(a);
+  gpt_prompt_layers(F, B);
+  if (OL > 1)
+    F.layernorm(h->g, G, R2, G, gp + "ln_f", 1e-5f, nullptr, io.orig_past, G, 0, 0, 0, 0, T, 1, h->hid, nullptr, G, T - 1);
+  else
+    F.layernorm(h->g, G, R2, G, gp + "ln_f", 1e-5f, nullptr, io.orig_past, G);
+  for (int k = 1; k < OL; ++k) {
+    gpt_decode_layers(F, B, k);
+    // hidden state of the generated position: fed back (h->hid) and written to io.past_futures[b, k - 1]
+    F.layernorm(h->gn, G, B, G, gp + "ln_f", 1e-5f, nullptr, h->hid, G, 0, 0, 0, 0, 1, OL - 1,
+                io.past_futures + static_cast<long long>(k - 1) * G, nullptr, G);
+  }
+}
+
 extern "C" int afft_forward(afft_handle* h, int32_t B, const afft_io* io, void* stream_) {
   if (h == nullptr) return fail(AFFT_ERR_INVALID, "forward: null handle");
   if (io == nullptr) return hfail(h, AFFT_ERR_INVALID, "forward: null io");
@@ -1357,8 +1427,10 @@ extern "C" int afft_forward(afft_handle* h, int32_t B, const afft_io* io, void* 
   if (B < 1 || B > c.max_batch) return hfail(h, AFFT_ERR_INVALID, "forward: B out of range [1, max_batch]");
   for (int m = 0; m < c.n_mod; ++m)
     if (io->feat[m] == nullptr) return hfail(h, AFFT_ERR_INVALID, "forward: null feature pointer");
-  if (io->orig_past == nullptr || io->past_futures == nullptr) return hfail(h, AFFT_ERR_INVALID, "forward: null output pointer");
-  for (int k = 0; k < c.n_cls; ++k) {
+  if (io->orig_past == nullptr) return hfail(h, AFFT_ERR_INVALID, "forward: null output pointer");
+  if (io->past_futures == nullptr && (c.stages == AFFT_STAGE_ALL || (c.stages == AFFT_STAGE_GPT && c.fp_output_len > 1)))
+    return hfail(h, AFFT_ERR_INVALID, "forward: null past_futures pointer");
+  for (int k = 0; c.stages == AFFT_STAGE_ALL && k < c.n_cls; ++k) {
     if (io->logits[k] == nullptr) return hfail(h, AFFT_ERR_INVALID, "forward: null logits pointer");
     if (io->ld_logits[k] < c.cls_dim[k] || io->ld_logits[k] % 4 != 0)
       return hfail(h, AFFT_ERR_INVALID, "forward: ld_logits must be a multiple of 4 and >= cls_dim");
@@ -1384,9 +1456,13 @@ extern "C" int afft_forward(afft_handle* h, int32_t B, const afft_io* io, void* 
     if (e != cudaSuccess) return hfail(h, AFFT_ERR_CUDA, std::string("profile reset: ") + cudaGetErrorString(e));
     prof_mark_kernel<<<1, 32, 0, F.stream>>>(h->prof_slots);
   }
+  if (c.stages == AFFT_STAGE_GPT) {
+    run_gpt_only(F, *io, B);
+    return F.rc;
+  }
   const int chunk = (h->fuser_chunk > 0) ? h->fuser_chunk : B;
   for (int b0 = 0; b0 < B && F.ok(); b0 += chunk) run_fuser(F, *io, b0, std::min(chunk, B - b0));
-  if (F.ok()) run_predictor(F, *io, B);
+  if (F.ok() && c.stages == AFFT_STAGE_ALL) run_predictor(F, *io, B);
   return F.rc;
 }
 

@@ -21,7 +21,8 @@ class Engine:
     def __init__(self, *, fuser_kind: int, T: int, mod_names: List[str], mod_dims: List[int], dim: int,
                  fuser_depth: int, fuser_heads: int, modal_encoding: bool, frame_level_token: bool, cross_attn: bool,
                  norm_elementwise: bool, gpt_dim: int, gpt_layers: int, gpt_heads: int, cls_names: List[str],
-                 cls_dims: List[int], precision: str, max_batch: int, device: torch.device, fp_output_len: int = 1):
+                 cls_dims: List[int], precision: str, max_batch: int, device: torch.device, fp_output_len: int = 1,
+                 stages: int = _capi.STAGE_ALL):
         if device.type != "cuda":
             raise _capi.AfftError("afft_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
         self.lib = _capi.lib()
@@ -48,6 +49,9 @@ class Engine:
         self.precision = precision
         cfg.precision, cfg.max_batch = _capi.PRECISIONS[precision], max_batch
         cfg.fp_output_len = fp_output_len
+        cfg.stages = stages
+        self.stages = stages
+        self.gpt_dim = gpt_dim
         cfg.device = device.index if device.index is not None else torch.cuda.current_device()
         self.cfg = cfg
         h = C.c_void_p()
@@ -134,6 +138,44 @@ class Engine:
             io.fuser_attn = attn.data_ptr()
         _capi.check(self.lib.afft_forward(self.handle, B, C.byref(io), _capi.current_stream_ptr(dev)), self.handle)
         return orig_past, pf, logits, attn
+
+    def forward_fuser(self, feats: List[torch.Tensor], want_attn: bool = True):
+        """AFFT_STAGE_FUSER handle: (fused (B, T, D), attention or None)."""
+        B = feats[0].shape[0]
+        T, D, dev = self.T, self.dim, self.device
+        io = _capi.IO()
+        for i, f in enumerate(feats):
+            if f.device != dev or f.dtype != torch.float32 or not f.is_contiguous():
+                raise _capi.AfftError("features must be contiguous fp32 tensors on the engine's device")
+            if tuple(f.shape) != (B, T, self.mod_dims[i]):
+                raise _capi.AfftError(f"feature {self.mod_names[i]} has shape {tuple(f.shape)}, expected {(B, T, self.mod_dims[i])}")
+            io.feat[i] = f.data_ptr()
+        fused = torch.empty(B, T, D, device=dev, dtype=torch.float32)
+        io.orig_past = fused.data_ptr()
+        attn = None
+        if want_attn and self.fuser_kind != _capi.FUSER_CA:
+            n, H = self.n_slots, self.fuser_heads
+            shape = (B, self.fuser_depth, H, n * T, n * T) if self.fuser_kind == _capi.FUSER_TSA else (B, self.fuser_depth, T, H, n, n)
+            attn = torch.empty(*shape, device=dev, dtype=torch.float32)
+            io.fuser_attn = attn.data_ptr()
+        _capi.check(self.lib.afft_forward(self.handle, B, C.byref(io), _capi.current_stream_ptr(dev)), self.handle)
+        return fused, attn
+
+    def forward_gpt(self, feats: torch.Tensor):
+        """AFFT_STAGE_GPT handle: feats (B, T, G) fp32 -> hidden states (B, T + O - 1, G)."""
+        B, T, G, dev, O = feats.shape[0], self.T, self.gpt_dim, self.device, self.fp_output_len
+        if feats.device != dev or feats.dtype != torch.float32 or not feats.is_contiguous() or tuple(feats.shape) != (B, T, G):
+            raise _capi.AfftError(f"predictor input must be a contiguous fp32 (B, {T}, {G}) tensor on the engine's device")
+        io = _capi.IO()
+        io.feat[0] = feats.data_ptr()
+        prompt = torch.empty(B, T, G, device=dev, dtype=torch.float32)
+        io.orig_past = prompt.data_ptr()
+        new = None
+        if O > 1:
+            new = torch.empty(B, O - 1, G, device=dev, dtype=torch.float32)
+            io.past_futures = new.data_ptr()
+        _capi.check(self.lib.afft_forward(self.handle, B, C.byref(io), _capi.current_stream_ptr(dev)), self.handle)
+        return prompt if new is None else torch.cat([prompt, new], dim=1)
 
     def forward_into(self, io: "_capi.IO", B: int):
         """Lowest-overhead call for benchmarking: caller pre-fills the io struct with persistent buffers."""

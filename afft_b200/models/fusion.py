@@ -24,11 +24,52 @@ def _init_weights(m):
 
 class _Fuser(nn.Module):
     afft_kind = None
+    precision = "bf16"  # 'bf16' | 'fp16' | 'strict' (set by the owning head; see CMFPEarly)
+    max_batch = 64
 
     def forward(self, modal_feats, ordered_feature_list):
-        raise NotImplementedError(
-            f"{type(self).__name__} is executed inside the fused afft_forward() call of CMFPEarly "
-            "(no standalone PyTorch forward)")
+        """The reference's inner seam ``fuser(modal_feats, ordered_feature_list) -> (fused (B, T, C), attn)``
+        (models/fusion.py:86,159,243,319), evaluated by a native fuser-only handle (AFFT_STAGE_FUSER): the same kernels
+        CMFPEarly's fused call runs, stopping after the fuser's final LayerNorm.  ``modal_feats`` are the mapped
+        features {modality: (B, T, dim)}.  Inference only (the training step goes through afft_b200.train)."""
+        from ..engine import Engine
+        if self.training:
+            raise NotImplementedError("the standalone fuser seam is inference-only; training runs through CMFPEarly.forward")
+        shape = next(iter(modal_feats.values())).shape
+        assert all(v.shape == shape for v in modal_feats.values()), \
+            'The shape of all inputs of the fusion module should be the same!'
+        order = list(modal_feats.keys())
+        feats = ordered_feature_list(modal_feats)
+        assert len(feats) == len(order)
+        # the caller's ordering function decides the token order; recover the modality names in that order
+        names = []
+        for f in feats:
+            names.append(next(m for m in order if modal_feats[m] is f and m not in names))
+        B, T, D = shape
+        first = feats[0]
+        if first.device.type != "cuda":
+            raise _capi.AfftError("afft_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
+        if getattr(self, "frame_level_token", False) and getattr(self, "temporal_sequence_length", None) is not None:
+            assert self.temporal_sequence_length == T, f"Temporal sequence length not valid {self.temporal_sequence_length} vs {T}"
+        engines = self.__dict__.setdefault("_seam_engines", {})
+        key = (tuple(names), T, str(first.device), self.precision)
+        eng = engines.get(key)
+        if eng is not None and B > eng.max_batch:
+            eng.close()
+            eng = None
+        if eng is None:
+            eng = Engine(fuser_kind=self.afft_kind, T=T, mod_names=names, mod_dims=[D] * len(names), dim=D,
+                         fuser_depth=self.depth, fuser_heads=self.num_heads, modal_encoding=bool(self.modal_encoding),
+                         frame_level_token=bool(self.frame_level_token), cross_attn=bool(self.cross_attn),
+                         norm_elementwise=bool(self.norm_elementwise), gpt_dim=2 * D, gpt_layers=1, gpt_heads=max(1, 2 * D // 512),
+                         cls_names=[], cls_dims=[], precision=self.precision, max_batch=max(B, self.max_batch),
+                         device=first.device, stages=_capi.STAGE_FUSER)
+            engines[key] = eng
+        eng.sync_weights({"fuser." + n: p for n, p in self.named_parameters()})
+        fused, attn = eng.forward_fuser([f.to(torch.float32).contiguous() for f in feats])
+        if attn is None:
+            attn = torch.zeros(B)  # CA-Fuser's dummy attention (reference fusion.py:269)
+        return fused, attn
 
     def _check_rates(self, act_layer, mlp_ratio, qkv_bias, qk_scale):
         if act_layer is not nn.GELU or mlp_ratio != 4. or qkv_bias or qk_scale is not None:

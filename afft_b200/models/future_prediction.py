@@ -141,8 +141,37 @@ class BaseFuturePredictor(nn.Module):
         self.decoder = nn.Identity()
         self.gpt_model = _GPT2Model(inter_dim, n_layer, n_head, 1024, embd_pdrop, resid_pdrop, attn_pdrop)
 
+    precision = "bf16"  # 'bf16' | 'fp16' | 'strict' (set by the owning head)
+    max_batch = 64
+
     def forward(self, feats, output_len: int = 1):
-        raise NotImplementedError("the GPT-2 future predictor is executed inside the fused afft_forward() call")
+        """The reference's inner seam ``predictor(feats (B, T, C), output_len) -> ((B, T + output_len - 1, C), {})``
+        (models/future_prediction.py:387-415; encoder / decoder are Identity), evaluated by a native GPT-2-only handle
+        (AFFT_STAGE_GPT): position embedding add, the GPT-2 blocks, ln_f, and the KV-cache roll-out for output_len > 1.
+        Inference only."""
+        if self.training:
+            raise NotImplementedError("the standalone predictor seam is inference-only; training runs through CMFPEarly.forward")
+        if feats.device.type != "cuda":
+            raise _capi.AfftError("afft_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
+        B, T, G = feats.shape
+        gpt = self.gpt_model
+        if G != gpt.n_embd:
+            raise ValueError(f"predictor input width {G} != inter_dim {gpt.n_embd}")
+        engines = self.__dict__.setdefault("_seam_engines", {})
+        key = (T, int(output_len), str(feats.device), self.precision)
+        eng = engines.get(key)
+        if eng is not None and B > eng.max_batch:
+            eng.close()
+            eng = None
+        if eng is None:
+            eng = Engine(fuser_kind=_capi.FUSER_NONE, T=T, mod_names=["feats"], mod_dims=[G], dim=G, fuser_depth=0,
+                         fuser_heads=1, modal_encoding=False, frame_level_token=False, cross_attn=False,
+                         norm_elementwise=True, gpt_dim=G, gpt_layers=gpt.n_layer, gpt_heads=gpt.n_head, cls_names=[],
+                         cls_dims=[], precision=self.precision, max_batch=max(B, self.max_batch), device=feats.device,
+                         fp_output_len=int(output_len), stages=_capi.STAGE_GPT)
+            engines[key] = eng
+        eng.sync_weights({"future_predictor." + n: p for n, p in self.named_parameters()})
+        return eng.forward_gpt(feats.to(torch.float32).contiguous()), {}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -267,6 +296,7 @@ class CMFPEarly(nn.Module):
         f = self.fuser
         if getattr(f, "frame_level_token", False) and f.temporal_sequence_length is not None:
             assert f.temporal_sequence_length == T, f"Temporal sequence length not valid {f.temporal_sequence_length} vs {T}"
+        self.fuser.precision = self.future_predictor.precision = self.precision  # the inner seams follow the head's mode
         eng = self._engine(feats_order, T, B, first.device)
         eng.sync_weights(self._named_weights())
         xs = []

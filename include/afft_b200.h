@@ -232,6 +232,18 @@ enum {
                               315-327); n_mod must be 1, mod_dim[0] == dim, dim a multiple of 8 */
 };
 
+/* Which part of the chain a handle runs (afft_config.stages).  AFFT_STAGE_ALL (0) is the whole of CMFPEarly.forward;
+ * the other two are the reference's inner seams:
+ *  AFFT_STAGE_FUSER  feature mapping + fuser:  fuser(modal_feats, ordered_feature_list) -> (fused, attn)
+ *                    (models/fusion.py:319 and the other fusers' forward); needs the mapping.* / fuser.* weights only,
+ *                    writes io.orig_past [B, T, dim] (+ io.fuser_attn); io.past_futures / io.logits are ignored.
+ *  AFFT_STAGE_GPT    the GPT-2 future predictor alone:  predictor(feats (B, T, fp_inter_dim), output_len) ->
+ *                    (B, T + output_len - 1, fp_inter_dim) (models/future_prediction.py:387-415): fuser_kind =
+ *                    AFFT_FUSER_NONE, n_mod = 1, mod_dim[0] = dim = gpt_dim, n_cls = 0; needs future_predictor.gpt_model.*;
+ *                    io.feat[0] is the input, io.orig_past receives the T prompt positions [B, T, gpt_dim] and
+ *                    io.past_futures the generated ones [B, fp_output_len - 1, gpt_dim] (may be NULL when fp_output_len = 1). */
+enum { AFFT_STAGE_ALL = 0, AFFT_STAGE_FUSER = 1, AFFT_STAGE_GPT = 4 };
+
 typedef struct afft_config {
   int32_t fuser_kind;
   int32_t T;                              /* timesteps per clip */
@@ -249,6 +261,7 @@ typedef struct afft_config {
   int32_t max_batch;                      /* workspace is sized for this many clips per call */
   int32_t device;                         /* CUDA device ordinal */
   int32_t fp_output_len;                  /* model.common.fp_output_len: future steps rolled out (>= 1) */
+  int32_t stages;                         /* AFFT_STAGE_ALL / AFFT_STAGE_FUSER / AFFT_STAGE_GPT */
 } afft_config;
 
 typedef struct afft_handle afft_handle;

@@ -376,3 +376,74 @@ def test_top5_agreement_large_sample(precision):
     else:
         assert st["ordered_top5_identity_rate"] >= 0.70, st
     assert st["top5_set_identity_rate"] >= st["ordered_top5_identity_rate"]
+
+
+# ------------------------------------------------------------------------------------------------
+# The reference's inner seams: fuser(modal_feats, ordered_feature_list) and predictor(feats, output_len)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("fuser", ["SA-Fuser", "SA-Fuser_wo_token", "T-SA-Fuser", "CA-Fuser"])
+def test_fuser_seam_is_callable_and_matches_the_oracle(fuser, precision):
+    """fuser(modal_feats, ordered_feature_list) -> (fused, attn) (models/fusion.py:86,159,243,319) through a native
+    fuser-only handle, against the oracle's fuser function on the same weights, and - same kernels - bit-identical to
+    the `orig_past` of the full fused call."""
+    from oracle import afft_oracle
+    dims = {"rgb": 1024, "flow": 1024, "audio": 1024}
+    kw = dict(frame_level_token=True, temporal_sequence_length=10, modal_encoding=True) if fuser == "T-SA-Fuser" else {}
+    cfg = configs.model_cfg(dims, fuser=fuser, depth=2, fp_layers=2, fuser_kwargs=kw)
+    T, B, ncls = 10, 3, {"action": 106}
+    model = BaseModel(cfg, ncls, {}, precision=precision)
+    sd = synthetic.synthetic_state_dict(model, seed=0)
+    model.load_state_dict(sd)
+    model = model.to("cuda:0").eval()
+    feats = synthetic.synthetic_features(dims, B, T, seed=11)
+    full = _run(model, feats)  # sets the seams' precision and gives the reference point
+    order = [m for m in cfg["modal_feature_order"] if m in dims]
+    head = model.future_predictor
+    with torch.no_grad():
+        fused, attn = head.fuser({m: feats[m].cuda() for m in order}, lambda d: head.ordered_feature_list(d, order))
+    torch.cuda.synchronize()
+    assert torch.equal(fused, full["orig_past"]["all-fused"])
+    w = afft_oracle._W({k: v for k, v in sd.items()}, "future_predictor.fuser.", torch.float32)
+    fl = [feats[m] for m in order]
+    if fuser == "T-SA-Fuser":
+        ref, rattn = afft_oracle._tsa_fuser(fl, w, cfg["fuser"])
+    elif fuser == "CA-Fuser":
+        ref, rattn = afft_oracle._ca_fuser(fl, w, cfg["fuser"])
+    else:
+        ref, rattn = afft_oracle._sa_fuser(fl, w, cfg["fuser"], token=(fuser == "SA-Fuser"))
+    assert (fused.cpu() - ref).abs().max().item() < TOL[precision]["feat"]
+    if fuser == "CA-Fuser":
+        assert attn.shape == (B,)
+    else:
+        assert attn.shape == rattn.shape and (attn.cpu() - rattn).abs().max().item() < TOL[precision]["attn"]
+    head.fuser.train()
+    with pytest.raises(NotImplementedError):
+        head.fuser({m: feats[m].cuda() for m in order}, lambda d: [d[m] for m in order])
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("output_len", [1, 3])
+def test_predictor_seam_is_callable_and_matches_the_oracle(output_len, precision):
+    """predictor(feats (B, T, fp_inter_dim), output_len) -> ((B, T + output_len - 1, fp_inter_dim), {})
+    (models/future_prediction.py:387-415) through a native GPT-2-only handle (position add, blocks, ln_f, KV-cache roll-out)."""
+    from oracle import afft_oracle
+    cfg, T, ncls, _ = configs.named_config("egtea_sa")
+    model = BaseModel(cfg, ncls, {}, precision=precision)
+    sd = synthetic.synthetic_state_dict(model, seed=0)
+    model.load_state_dict(sd)
+    model = model.to("cuda:0").eval()
+    pred = model.future_predictor.future_predictor
+    pred.precision = precision
+    B, G = 5, 2048
+    x = torch.randn(B, T, G, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        out, extra = pred(x.cuda(), output_len)
+    torch.cuda.synchronize()
+    assert out.shape == (B, T + output_len - 1, G) and extra == {}
+    w = afft_oracle._W(sd, "future_predictor.future_predictor.gpt_model.", torch.float32)
+    ref = afft_oracle._gpt2(x, w, cfg["common"]["fp_layers"], cfg["common"]["fp_heads"], output_len)
+    tol = {"bf16": 8e-2, "fp16": 1e-2, "strict": 1e-3}[precision]  # post-ln_f hidden states, |max| ~ 4
+    assert (out.cpu() - ref).abs().max().item() < tol
+    with pytest.raises(ValueError):
+        pred(torch.zeros(B, T, 1024, device="cuda:0"), 1)
