@@ -130,12 +130,12 @@ class Profile(C.Structure):
 
 # every symbol include/afft_b200.h declares
 EXPORTED_SYMBOLS = [
-    "afft_abi_version", "afft_last_error", "afft_gemm", "afft_set_gemm_epilogue", "afft_convert_bf16", "afft_convert_operand",
-    "afft_layernorm", "afft_attention",
-    "afft_create", "afft_destroy", "afft_handle_error", "afft_workspace_bytes", "afft_weight_bytes",
-    "afft_set_weight", "afft_missing_weights", "afft_forward", "afft_last_launch_count",
-    "afft_profile_enable", "afft_profile_read", "afft_set_max_ksplit", "afft_plan_ksplit", "afft_marginalize_topk", "afft_score_fusion",
-    "afft_transpose_bf16", "afft_layernorm_bwd", "afft_gelu_fwd", "afft_gelu_bwd", "afft_colsum", "afft_attention_bwd",
+    "afft_abi_version", "afft_last_error", "afft_gemm", "afft_set_gemm_epilogue", "afft_convert_bf16",
+    "afft_convert_operand", "afft_layernorm", "afft_attention", "afft_create", "afft_destroy", "afft_handle_error",
+    "afft_workspace_bytes", "afft_weight_bytes", "afft_set_weight", "afft_missing_weights", "afft_forward",
+    "afft_last_launch_count", "afft_profile_enable", "afft_profile_read", "afft_set_max_ksplit", "afft_plan_ksplit",
+    "afft_marginalize_topk", "afft_score_fusion", "afft_transpose_bf16", "afft_layernorm_bwd", "afft_gelu_fwd",
+    "afft_gelu_bwd", "afft_colsum", "afft_attention_bwd", "afft_sgd_nesterov",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -188,6 +188,9 @@ def lib() -> C.CDLL:
     l.afft_gelu_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     l.afft_gelu_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     l.afft_colsum.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    l.afft_sgd_nesterov.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
+                                    C.c_int32, C.c_void_p]
+    l.afft_sgd_nesterov.restype = C.c_int
     l.afft_attention_bwd.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]
     for _n in ("afft_transpose_bf16", "afft_layernorm_bwd", "afft_gelu_fwd", "afft_gelu_bwd", "afft_colsum", "afft_attention_bwd"):

@@ -474,9 +474,21 @@ extern "C" int afft_gelu_bwd(const float* x, const float* dy, float* dx, int64_t
 
 extern "C" int afft_colsum(const float* x, int64_t ld, int32_t rows, int32_t cols, float* out, void* stream) {
   if (x == nullptr || out == nullptr || rows <= 0 || cols <= 0) return fail(AFFT_ERR_INVALID, "colsum: bad argument");
-  dim3 grid((cols + 127) / 128, std::min(rows, 64));
-  colsum_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, rows, cols, out);
+  dim3 grid((cols + 31) / 32, std::max(1, std::min((rows + 63) / 64, 64)));
+  colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, rows, cols, out);
   return launch_check("colsum launch");
+}
+
+extern "C" int afft_sgd_nesterov(float* p, const float* g, float* m, void* p16, int64_t n, float lr, float momentum,
+                                 float weight_decay, int32_t nesterov, void* stream) {
+  if (p == nullptr || g == nullptr || m == nullptr || n <= 0) return fail(AFFT_ERR_INVALID, "sgd: bad argument");
+  if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m)) & 15u) != 0 ||
+      (reinterpret_cast<uintptr_t>(p16) & 7u) != 0)
+    return fail(AFFT_ERR_INVALID, "sgd: buffers must be 16-byte aligned (8-byte for the bf16 image)");
+  const int blocks = static_cast<int>(std::min<long long>((n / 4 + 255) / 256 + 1, 148 * 16));
+  sgd_nesterov_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, static_cast<bf16*>(p16), n, lr, momentum,
+                                                                            weight_decay, nesterov);
+  return launch_check("sgd launch");
 }
 
 extern "C" int afft_attention_bwd(const float* qkv, int64_t ld, const float* probs, const float* d_out, int64_t ldo,

@@ -142,25 +142,93 @@ __device__ __forceinline__ float gelu_grad_exact(float x, int kind) {
   const float du = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x * x);
   return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
 }
+// 16-byte accesses when n is a multiple of 4 and the pointers are 16-byte aligned (every activation tensor of the path)
 __global__ void gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int kind) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x)
-    y[i] = gelu_fwd_exact(x[i], kind);
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0) {
+    for (long long i = tid; i < n / 4; i += nth) {
+      const float4 v = reinterpret_cast<const float4*>(x)[i];
+      reinterpret_cast<float4*>(y)[i] = make_float4(gelu_fwd_exact(v.x, kind), gelu_fwd_exact(v.y, kind),
+                                                    gelu_fwd_exact(v.z, kind), gelu_fwd_exact(v.w, kind));
+    }
+    return;
+  }
+  for (long long i = tid; i < n; i += nth) y[i] = gelu_fwd_exact(x[i], kind);
 }
 __global__ void gelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
                                 long long n, int kind) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x)
-    dx[i] = dy[i] * gelu_grad_exact(x[i], kind);
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15u) == 0) {
+    for (long long i = tid; i < n / 4; i += nth) {
+      const float4 v = reinterpret_cast<const float4*>(x)[i];
+      const float4 d = reinterpret_cast<const float4*>(dy)[i];
+      reinterpret_cast<float4*>(dx)[i] = make_float4(d.x * gelu_grad_exact(v.x, kind), d.y * gelu_grad_exact(v.y, kind),
+                                                     d.z * gelu_grad_exact(v.z, kind), d.w * gelu_grad_exact(v.w, kind));
+    }
+    return;
+  }
+  for (long long i = tid; i < n; i += nth) dx[i] = dy[i] * gelu_grad_exact(x[i], kind);
 }
 
-// out[c] += sum_r x[r, c]   (bias gradients)
-__global__ void colsum_kernel(const float* __restrict__ x, long long ld, int rows, int cols, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+// out[c] += sum_r x[r, c]   (bias gradients).  Block = 32 columns x 8 row lanes: every warp reads 128 contiguous bytes
+// of a row, the 8 row lanes (and gridDim.y blocks) stride over the rows, partial sums meet in shared memory and one
+// atomic per column and block reaches global memory.  (The first version gave one thread a whole column stripe: at
+// 2048 x 3806 it took 76 us for 31 MB.)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long ld, int rows, int cols, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float s = 0.f;
-  for (int r = blockIdx.y; r < rows; r += gridDim.y) s += x[r * ld + c];
-  atomicAdd(out + c, s);
+  if (c < cols)
+    for (int r = blockIdx.y * 8 + ry; r < rows; r += gridDim.y * 8) s += x[r * ld + c];
+  red[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][cx];
+    atomicAdd(out + c, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SGD with (Nesterov) momentum and weight decay over a flat parameter buffer - torch.optim.SGD's update
+// (reference expts/01_SA-Fuser_ek100_train.txt:48-52: nesterov, momentum 0.9; train.py builds torch.optim.SGD):
+//   g += wd * p;  buf = momentum * buf + g;  g = nesterov ? g + momentum * buf : buf;  p -= lr * g
+// (a zero-initialised buffer reproduces torch's "buf = g" first step).  The same pass writes the bf16 image of the new
+// parameters: it is the GEMM operand of the next step, so no per-step fp32 -> bf16 conversion of the 388 M weights.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sgd_nesterov_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                           __nv_bfloat16* __restrict__ p16, long long n, float lr, float momentum,
+                                                           float wd, int nesterov) {
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = tid; i < n / 4; i += nth) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float pe[4] = {pv.x, pv.y, pv.z, pv.w};
+    const float ge[4] = {gv.x, gv.y, gv.z, gv.w};
+    float me[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gg = fmaf(wd, pe[e], ge[e]);
+      me[e] = fmaf(momentum, me[e], gg);
+      pe[e] -= lr * (nesterov ? fmaf(momentum, me[e], gg) : me[e]);
+    }
+    reinterpret_cast<float4*>(p)[i] = make_float4(pe[0], pe[1], pe[2], pe[3]);
+    reinterpret_cast<float4*>(m)[i] = make_float4(me[0], me[1], me[2], me[3]);
+    if (p16 != nullptr) reinterpret_cast<uint2*>(p16)[i] = make_uint2(pack_bf16x2(pe[0], pe[1]), pack_bf16x2(pe[2], pe[3]));
+  }
+  for (long long i = (n / 4) * 4 + tid; i < n; i += nth) {
+    const float gg = fmaf(wd, p[i], g[i]);
+    const float mm = fmaf(momentum, m[i], gg);
+    m[i] = mm;
+    p[i] -= lr * (nesterov ? fmaf(momentum, mm, gg) : mm);
+    if (p16 != nullptr) p16[i] = __float2bfloat16_rn(p[i]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

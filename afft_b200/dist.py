@@ -81,7 +81,9 @@ class GradBuckets:
     (the optimizer still sees fp32 gradients).
     """
 
-    def __init__(self, groups, comm_dtype=torch.float32, process_group=None, average=True):
+    def __init__(self, groups, comm_dtype=torch.float32, process_group=None, average=True, align: int = 8):
+        """align: every parameter's slice starts at a multiple of `align` elements (16 bytes for 16-bit images of the
+        buffer: gradient / weight views are TMA operands of the native GEMMs)."""
         self.groups = [[p for p in g if p.requires_grad] for g in groups]
         self.groups = [g for g in self.groups if g]
         self.pg = process_group
@@ -91,8 +93,10 @@ class GradBuckets:
         if not params:
             raise ValueError("GradBuckets: no parameters")
         dev = params[0].device
-        self.flat = torch.zeros(sum(p.numel() for p in params), device=dev, dtype=torch.float32)
+        pad = lambda n: (n + align - 1) // align * align  # noqa: E731
+        self.flat = torch.zeros(sum(pad(p.numel()) for p in params), device=dev, dtype=torch.float32)
         self.slices = []
+        self.offsets = {}  # id(param) -> (start, numel) in the flat buffer
         self._group_of = {}
         off = 0
         for gi, g in enumerate(self.groups):
@@ -100,7 +104,8 @@ class GradBuckets:
             for p in g:
                 p.grad = self.flat[off:off + p.numel()].view_as(p)
                 self._group_of[id(p)] = gi
-                off += p.numel()
+                self.offsets[id(p)] = (off, p.numel())
+                off += pad(p.numel())
             self.slices.append((start, off))
         self.comm = None if comm_dtype == torch.float32 else torch.empty_like(self.flat, dtype=comm_dtype)
         self._pending = [len(g) for g in self.groups]
@@ -135,6 +140,11 @@ class GradBuckets:
         self._pending[gi] -= 1
         if self._pending[gi] == 0:
             self._launch(gi)
+
+    def notify(self, p):
+        """A parameter whose gradient was written into its view by a native kernel (no autograd accumulation, hence no
+        hook): count it as finished."""
+        self._on_grad(p)
 
     def finish(self):
         """After backward(): groups whose hooks never fired completely (unused parameters) are reduced now, then every

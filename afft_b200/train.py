@@ -72,16 +72,149 @@ def bf16_t(xb: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# Flat training state: parameters, gradients, momentum and the bf16 operand image in four flat buffers
+# ------------------------------------------------------------------------------------------------
+_STATE = None  # the active TrainState (consulted by the autograd Functions below) or None
+
+
+class TrainState:
+    """Owns the flat buffers of one model's training step (reference train.py:315-368 builds torch.optim.SGD and wraps
+    the model in DistributedDataParallel; common/runner.py:258-267 runs forward / backward / step).
+
+      flat_p    fp32 parameters; every ``p.data`` is a view (layout = backward-completion order, slices 16-byte aligned)
+      buckets   afft_b200.dist.GradBuckets: fp32 gradients in the same layout, ``p.grad`` are views, one NCCL all-reduce
+                per layer group issued from inside backward
+      flat_m    momentum
+      flat_w16  bf16 image of flat_p, written by the optimizer kernel: the GEMM operands of the next step (nn.Linear
+                weights are used as they lie for the forward GEMM, Conv1D weights as they lie for dgrad; the other
+                orientation is one 2-byte transpose per weight and step instead of an fp32 conversion plus a transpose)
+
+    While a state is active (``with state:``), the native backward kernels write weight, bias and LayerNorm gradients
+    straight into the ``.grad`` views (first write of a step overwrites, later ones accumulate) instead of returning
+    tensors for autograd to add, and ``step()`` is ONE kernel (afft_sgd_nesterov) over the flat buffers."""
+
+    def __init__(self, head, lr: float, momentum: float = 0.9, weight_decay: float = 0.0, nesterov: bool = True,
+                 comm_dtype=torch.float32):
+        from . import dist as adist
+        self.lr, self.momentum, self.weight_decay, self.nesterov = lr, momentum, weight_decay, nesterov
+        groups = grad_groups(head)
+        self.buckets = adist.GradBuckets(groups, comm_dtype=comm_dtype)
+        flat_g = self.buckets.flat
+        self.flat_p = torch.empty_like(flat_g)
+        self.flat_p.zero_()
+        self.flat_m = torch.zeros_like(flat_g)
+        self.flat_w16 = torch.empty(flat_g.numel(), device=flat_g.device, dtype=torch.bfloat16)
+        self.w16 = {}
+        self._params = {}
+        with torch.no_grad():
+            for g in self.buckets.groups:
+                for p in g:
+                    off, n = self.buckets.offsets[id(p)]
+                    view = self.flat_p[off:off + n].view_as(p)
+                    view.copy_(p.data)
+                    p.data = view
+                    self.w16[id(p)] = self.flat_w16[off:off + n].view_as(p)
+                    self._params[id(p)] = p
+        self.refresh_w16()
+        self._uses = {}        # id(param) -> forward uses not yet met by a backward this step
+        self._written = set()  # params whose .grad view has been written by a native kernel this step
+        self._overwritten = set()   # params whose gradient a wgrad GEMM OVERWRITES on its first use (learned in step 1)
+        self._accum_grads = None    # .grad views that are accumulated into (+=) and therefore cleared at step start
+
+    def refresh_w16(self):
+        """bf16 image of the current parameters (after construction / load_state_dict; the optimizer keeps it current)."""
+        n = self.flat_p.numel()
+        _capi.check(_lib().afft_convert_bf16(self.flat_p.data_ptr(), n, 1, n, self.flat_w16.data_ptr(), None, n, 0,
+                                             _ST(self.flat_p.device)))
+
+    def __enter__(self):
+        global _STATE
+        self._prev, _STATE = _STATE, self
+        return self
+
+    def __exit__(self, *exc):
+        global _STATE
+        _STATE = self._prev
+        return False
+
+    # ---- per-step protocol: zero() -> forward -> backward -> finish() -> step() ----
+    def zero(self):
+        """Start of a step.  GEMM weight gradients are overwritten by their first wgrad of the step, so from the second
+        step on only the accumulated-into gradients (biases, LayerNorm, embeddings, tokens) are cleared - 1.5 GB of
+        memset saved per step.  Which parameters are overwritten is learned during the first step."""
+        if self._accum_grads is None:
+            self.buckets.flat.zero_()
+        elif self._accum_grads:
+            torch._foreach_zero_(self._accum_grads)
+        self.buckets._pending = [len(g) for g in self.buckets.groups]
+        self.buckets._works = []
+        self._uses.clear()
+        self._written.clear()
+
+    def note_use(self, p):
+        self._uses[id(p)] = self._uses.get(id(p), 0) + 1
+
+    def grad_target(self, p, overwrites: bool = False):
+        """(.grad view, accumulate?) for a native kernel about to write this parameter's gradient.  overwrites: the
+        kernel replaces the view's contents on the first write of a step (wgrad GEMM) instead of adding to them."""
+        acc = id(p) in self._written
+        self._written.add(id(p))
+        if overwrites and self._accum_grads is None:
+            self._overwritten.add(id(p))
+        return p.grad, acc
+
+    def grad_done(self, p):
+        """One backward use of p finished; when it was the last one of the step, its bucket counts it."""
+        left = self._uses.get(id(p), 1) - 1
+        self._uses[id(p)] = left
+        if left == 0:
+            self.buckets.notify(p)
+
+    def finish(self):
+        """After backward: GEMM weights no kernel wrote this step (unused in the graph) are cleared, outstanding
+        all-reduces are waited for."""
+        if self._accum_grads is None:  # end of the first step: everything not overwritten by a GEMM is cleared per step
+            self._accum_grads = [p.grad for pid, p in self._params.items() if pid not in self._overwritten]
+        for pid in self._overwritten:
+            if pid not in self._written:
+                self._params[pid].grad.zero_()
+        self.buckets.finish()
+
+    def step(self):
+        n = self.flat_p.numel()
+        _capi.check(_lib().afft_sgd_nesterov(self.flat_p.data_ptr(), self.buckets.flat.data_ptr(), self.flat_m.data_ptr(),
+                                             self.flat_w16.data_ptr(), n, self.lr, self.momentum, self.weight_decay,
+                                             int(self.nesterov), _ST(self.flat_p.device)))
+
+
+def _state_for(*params):
+    st = _STATE
+    if st is None:
+        return None
+    return st if all(p is None or id(p) in st.w16 for p in params) else None
+
+
 class LinearFn(torch.autograd.Function):
     """y = x W^T + b for nn.Linear weights [N, K]; y = x W + b for transformers' Conv1D weights [K, N]."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, conv1d: bool):
         xb = to_bf16(x)
-        w_fwd = to_bf16_t(weight) if conv1d else to_bf16(weight)  # [N, K], K contiguous
+        st = _state_for(weight, bias)
+        ctx.st = st
+        if st is not None:  # the optimizer's bf16 image: no conversion
+            w16 = st.w16[id(weight)]
+            w_fwd = bf16_t(w16) if conv1d else w16
+            st.note_use(weight)
+            if bias is not None:
+                st.note_use(bias)
+        else:
+            w_fwd = to_bf16_t(weight) if conv1d else to_bf16(weight)  # [N, K], K contiguous
         N = w_fwd.shape[0]
         Np = (N + 3) // 4 * 4  # fp32 output pitch: 16-byte multiple
         y = torch.empty(x.shape[0], Np, device=x.device, dtype=torch.float32)
+        bias_param = bias
         if bias is not None and Np != N:  # the epilogue reads the bias with 16-byte loads
             bias_p = torch.zeros(Np, device=x.device, dtype=torch.float32)
             bias_p[:N] = bias.detach()
@@ -89,13 +222,14 @@ class LinearFn(torch.autograd.Function):
         _capi.gemm(xb, w_fwd[:, :xb.shape[1]], bias=bias, out_f32=y[:, :N])
         # the bf16 operand is kept for dgrad (its transpose is the dgrad operand): transposing 2-byte elements reads
         # half of what a second conversion of the fp32 weight would
-        ctx.save_for_backward(xb, weight, w_fwd)
-        ctx.conv1d, ctx.has_bias = conv1d, bias is not None
+        ctx.save_for_backward(xb, weight, w_fwd, bias_param)
+        ctx.conv1d, ctx.has_bias = conv1d, bias_param is not None
         return y[:, :N]
 
     @staticmethod
     def backward(ctx, dy):
-        xb, weight, w_fwd = ctx.saved_tensors
+        xb, weight, w_fwd, bias = ctx.saved_tensors
+        st = ctx.st
         dy = dy.contiguous()
         M, N = dy.shape
         K = xb.shape[1]
@@ -103,21 +237,36 @@ class LinearFn(torch.autograd.Function):
         dyb = to_bf16(dy)
         if ctx.needs_input_grad[0]:
             # dgrad: dx [M, K] = dy [M, N] . W;  B operand [K, N] with N contiguous
-            w_dg = bf16_t(w_fwd[:, :K])  # [K, pad8(N)]: W for nn.Linear, W^T^T = W [K, N] for Conv1D
+            if st is not None and ctx.conv1d and N % 8 == 0:
+                w_dg = st.w16[id(weight)]  # Conv1D weights are stored [K, N]: the optimizer's bf16 image is the operand
+            else:
+                w_dg = bf16_t(w_fwd[:, :K])  # [K, pad8(N)]: W for nn.Linear, W^T^T = W [K, N] for Conv1D
             dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
             _capi.gemm(dyb, w_dg[:, :N], out_f32=dx)
         if ctx.needs_input_grad[1]:
             dy_t = to_bf16_t(dy)  # [N, Mp]
             x_t = bf16_t(xb)      # [K, Mp]
+            direct = st is not None and weight.shape[1] % 4 == 0
+            if direct:  # wgrad straight into the .grad view: no temporary, no autograd accumulation pass
+                dw_out, acc = st.grad_target(weight, overwrites=True)
+            else:
+                dw_out, acc = torch.empty(weight.shape, device=dy.device, dtype=torch.float32), False
             if ctx.conv1d:       # dW [K, N] = x^T . dy
-                dw = torch.empty(K, N, device=dy.device, dtype=torch.float32)
-                _capi.gemm(x_t, dy_t, out_f32=dw)
+                _capi.gemm(x_t, dy_t, out_f32=dw_out, res=dw_out if acc else None)
             else:                # dW [N, K] = dy^T . x
-                dw = torch.empty(N, K, device=dy.device, dtype=torch.float32)
-                _capi.gemm(dy_t, x_t, out_f32=dw)
+                _capi.gemm(dy_t, x_t, out_f32=dw_out, res=dw_out if acc else None)
+            if direct:
+                st.grad_done(weight)
+            else:
+                dw = dw_out  # autograd accumulates it and the bucket's hook counts the parameter
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.zeros(N, device=dy.device, dtype=torch.float32)
-            _capi.check(_lib().afft_colsum(dy.data_ptr(), N, M, N, db.data_ptr(), _ST(dy.device)))
+            if st is not None:
+                db_out, _ = st.grad_target(bias)  # zeroed at step start; colsum accumulates
+                _capi.check(_lib().afft_colsum(dy.data_ptr(), N, M, N, db_out.data_ptr(), _ST(dy.device)))
+                st.grad_done(bias)
+            else:
+                db = torch.zeros(N, device=dy.device, dtype=torch.float32)
+                _capi.check(_lib().afft_colsum(dy.data_ptr(), N, M, N, db.data_ptr(), _ST(dy.device)))
         return dx, dw, db, None
 
 
@@ -127,22 +276,34 @@ class LayerNormFn(torch.autograd.Function):
         x = x.contiguous()
         y = torch.empty_like(x)
         _capi.layernorm(x, gamma, beta, eps, y_f32=y)
-        ctx.save_for_backward(x, gamma)
+        ctx.save_for_backward(x, gamma, beta)
         ctx.eps, ctx.affine = eps, gamma is not None
+        ctx.st = _state_for(gamma, beta) if gamma is not None else None
+        if ctx.st is not None:
+            ctx.st.note_use(gamma)
+            ctx.st.note_use(beta)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, gamma = ctx.saved_tensors
+        x, gamma, beta = ctx.saved_tensors
+        st = ctx.st
         dy = dy.contiguous()
         rows, dim = x.shape
         dx = torch.empty_like(x)
         dg = db = None
-        if ctx.affine:
-            dg = torch.zeros(dim, device=x.device, dtype=torch.float32)
-            db = torch.zeros(dim, device=x.device, dtype=torch.float32)
+        if st is not None:  # the kernel accumulates (+=) into the .grad views (cleared at step start)
+            dg_out, db_out = st.grad_target(gamma)[0], st.grad_target(beta)[0]
+        elif ctx.affine:
+            dg_out = dg = torch.zeros(dim, device=x.device, dtype=torch.float32)
+            db_out = db = torch.zeros(dim, device=x.device, dtype=torch.float32)
+        else:
+            dg_out = db_out = None
         _capi.check(_lib().afft_layernorm_bwd(x.data_ptr(), dim, _capi.ptr(gamma), ctx.eps, dy.data_ptr(), dim, rows, dim,
-                                              dx.data_ptr(), dim, _capi.ptr(dg), _capi.ptr(db), _ST(x.device)))
+                                              dx.data_ptr(), dim, _capi.ptr(dg_out), _capi.ptr(db_out), _ST(x.device)))
+        if st is not None:
+            st.grad_done(gamma)
+            st.grad_done(beta)
         return dx, dg, db, None
 
 
@@ -206,6 +367,18 @@ def _ln(x, norm):
     return LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps)
 
 
+def _residual(h, f, p_drop: float, dp_rate: float, training: bool, rows_per_sample: int):
+    """h + drop_path(dropout(f)) (reference models/transformerblock.py:131-135 with :96-104): the dropout is one fused
+    kernel, stochastic depth and the residual add are one addcmul with a per-sample scale."""
+    f = F.dropout(f, p_drop, training)
+    if dp_rate == 0.0 or not training:
+        return h + f
+    keep = 1.0 - dp_rate
+    n = f.shape[0] // rows_per_sample
+    scale = (keep + torch.rand(n, 1, 1, device=f.device, dtype=f.dtype)).floor_().div_(keep)
+    return torch.addcmul(h.view(n, rows_per_sample, -1), f.view(n, rows_per_sample, -1), scale).view_as(h)
+
+
 def _drop_path(x, rate: float, training: bool, rows_per_sample: int):
     """Stochastic depth per sample (reference models/transformerblock.py:96-104); x rows are grouped per sample."""
     if rate == 0.0 or not training:
@@ -239,22 +412,22 @@ def _apply_mapping(mp, x, training: bool):
     return y
 
 
-def _self_attention(h, attn, n_seq, L, mask, T, training):
-    """reference models/transformerblock.py:19-36 on rows [n_seq * L, D]; returns (proj output after proj_drop, probs)."""
+def _self_attention(h, attn, n_seq, L, mask, T, training, proj_drop=True):
+    """reference models/transformerblock.py:19-36 on rows [n_seq * L, D]; returns (proj output [after proj_drop], probs)."""
     H = attn.num_heads
     D = h.shape[1]
     a, p = AttentionFn.apply(_linear(h, attn.qkv), n_seq, L, H, D // H, mask, T, _rate(attn.attn_drop) if training else 0.0)
-    return F.dropout(_linear(a, attn.proj), _rate(attn.proj_drop), training), p
+    a = _linear(a, attn.proj)
+    return (F.dropout(a, _rate(attn.proj_drop), training) if proj_drop else a), p
 
 
 def _block(h, blk, n_seq, L, mask, T, training):
     """reference models/transformerblock.py:131-135 (Block); DropPath per sequence of L rows."""
     dp = getattr(blk.drop_path, "drop_prob", 0.0) or 0.0
-    a, p = _self_attention(_ln(h, blk.norm1), blk.attn, n_seq, L, mask, T, training)
-    h = h + _drop_path(a, dp, training, L)
+    a, p = _self_attention(_ln(h, blk.norm1), blk.attn, n_seq, L, mask, T, training, proj_drop=False)
+    h = _residual(h, a, _rate(blk.attn.proj_drop), dp, training, L)
     f = GeluFn.apply(_linear(_ln(h, blk.norm2), blk.mlp.mlp[0]), _capi.ACT_GELU_ERF)
-    f = F.dropout(_linear(f, blk.mlp.mlp[2]), _rate(blk.mlp.mlp[3]), training)
-    return h + _drop_path(f, dp, training, L), p
+    return _residual(h, _linear(f, blk.mlp.mlp[2]), _rate(blk.mlp.mlp[3]), dp, training, L), p
 
 
 def _fuse_sa(fuser, toks, B, T, D, training, with_token: bool):

@@ -684,32 +684,37 @@ def run_train(args):
     import torch.distributed as tdist
     use_ddp = world > 1 and args.ddp
     ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if use_ddp else model
-    buckets = None
+    buckets = state = None
     if not use_ddp:
         if world > 1:
             for p in model.parameters():
                 tdist.broadcast(p.data, src=0)  # what DDP's constructor does
-        buckets = adist.GradBuckets(atrain.grad_groups(model.future_predictor),
-                                    comm_dtype=torch.bfloat16 if args.grad_comm == "bf16" else torch.float32)
-    flat = buckets.flat if buckets is not None else None
-    # expts/01 :48-52; fused=True: one multi-tensor kernel pass over (p, grad, momentum) instead of ~5 foreach passes
-    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, nesterov=True, weight_decay=1e-6, fused=True)
+        # flat parameter / gradient / momentum / bf16-operand buffers; native wgrad writes into the gradient views, the
+        # optimizer is one kernel that also emits the next step's bf16 weights (afft_b200.train.TrainState)
+        state = atrain.TrainState(model.future_predictor, lr=1e-3, momentum=0.9, weight_decay=1e-6, nesterov=True,
+                                  comm_dtype=torch.bfloat16 if args.grad_comm == "bf16" else torch.float32)
+        buckets = state.buckets
+        state.__enter__()
+    # expts/01 :48-52; DDP arm: torch's fused SGD
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, nesterov=True, weight_decay=1e-6, fused=True) if use_ddp else None
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     sets = [{m: torch.randn(B, T, d, 1, 1, 1, device=dev, generator=g) for m, d in cfg["modal_dims"].items()} for _ in range(2)]
     target = torch.randint(0, C, (B, 1), device=dev, generator=g)
     target_sub = torch.randint(0, C, (B, T), device=dev, generator=g)
 
     def fwd_bwd_opt(feats):
-        if buckets is not None:
-            buckets.zero()
+        if state is not None:
+            state.zero()
         else:
             opt.zero_grad(set_to_none=True)
         out, _ = ddp(feats, **KW)
         loss = atrain.reference_losses(out, target, target_sub)["total"]
-        loss.backward()  # per-group NCCL all-reduces are issued from inside backward (GradBuckets hooks / DDP)
-        if buckets is not None:
-            buckets.finish()
-        opt.step()
+        loss.backward()  # per-group NCCL all-reduces are issued from inside backward (GradBuckets / DDP)
+        if state is not None:
+            state.finish()
+            state.step()
+        else:
+            opt.step()
         return loss
 
     def step(i):

@@ -211,6 +211,11 @@ AFFT_API int afft_gelu_fwd(const float* x, float* y, int64_t n, int32_t kind, vo
 AFFT_API int afft_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n, int32_t kind, void* stream);
 /* out[c] += sum over rows of x[r, c] (bias gradient) */
 AFFT_API int afft_colsum(const float* x, int64_t ld, int32_t rows, int32_t cols, float* out, void* stream);
+/* torch.optim.SGD's update (momentum, weight decay, optional Nesterov; reference train.py / expts/01_SA-Fuser_ek100_train.txt:48-52)
+ * over a flat fp32 parameter buffer: g' = g + wd p; m = momentum m + g'; p -= lr (nesterov ? g' + momentum m : m).  p16 (optional)
+ * receives the bf16 image of the updated parameters - the GEMM operands of the next step. */
+AFFT_API int afft_sgd_nesterov(float* p, const float* g, float* m, void* p16, int64_t n, float lr, float momentum,
+                               float weight_decay, int32_t nesterov, void* stream);
 /* Backward of afft_attention for fp32 q|k|v (layout as afft_attention_desc with ldq = ldk = ldv = ld, q at column 0,
  * k at H*head_dim, v at 2*H*head_dim); probs [n_seq, H, L, L] as written by the forward (undropped); d_out [n_seq*L, ldo];
  * drop_mask: the forward's dropout factors or NULL. */

@@ -192,3 +192,50 @@ def test_unsupported_training_configs_raise():
     x = {k: torch.zeros(8, T, d, 1, 1, 1, device="cuda:0") for k, d in cfg["modal_dims"].items()}
     with pytest.raises(NotImplementedError):
         m(x, **KW)
+
+
+def test_train_state_step_matches_autograd_and_torch_sgd():
+    """TrainState (flat buffers, wgrad / bias / LayerNorm gradients written straight into the .grad views, one native
+    SGD-nesterov kernel that also emits the bf16 weights) against the plain path: autograd-accumulated gradients + torch.optim.SGD
+    on an identical copy of the model, two consecutive steps, all stochastic rates 0."""
+    cfg, T, ncls = _no_dropout_cfg("egtea_sa")
+    B, C = 8, ncls["action"]
+    feats = {m: t.reshape(B, T, -1, 1, 1, 1).cuda() for m, t in synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=3).items()}
+    gl = torch.Generator().manual_seed(5)
+    target, target_sub = torch.randint(0, C, (B, 1), generator=gl).cuda(), torch.randint(0, C, (B, T), generator=gl).cuda()
+    models = []
+    for _ in range(2):
+        m = BaseModel(cfg, ncls, {})
+        m.load_state_dict(synthetic.synthetic_state_dict(m, seed=0))
+        models.append(m.to("cuda:0").train())
+    ref, new = models
+    lr, mom, wd = 0.05, 0.9, 1e-4
+    opt = torch.optim.SGD(ref.parameters(), lr=lr, momentum=mom, nesterov=True, weight_decay=wd)
+    state = atrain.TrainState(new.future_predictor, lr=lr, momentum=mom, weight_decay=wd, nesterov=True)
+    for step in range(2):
+        opt.zero_grad(set_to_none=True)
+        out, _ = ref(dict(feats), **KW)
+        atrain.reference_losses(out, target, target_sub)["total"].backward()
+        with state:
+            state.zero()
+            out2, _ = new(dict(feats), **KW)
+            loss2 = atrain.reference_losses(out2, target, target_sub)["total"]
+            loss2.backward()
+            state.finish()
+        rp, npar = dict(ref.named_parameters()), dict(new.named_parameters())
+        for name in rp:
+            g0, g1 = rp[name].grad, npar[name].grad
+            assert g1 is not None, name
+            if g0 is None:
+                assert g1.abs().max().item() == 0.0, name
+                continue
+            assert ((g1 - g0).norm() / g0.norm().clamp_min(1e-12)).item() < 2e-3, (step, name)  # same kernels, other summation order
+        opt.step()
+        with state:
+            state.step()
+        for name in rp:
+            d = (npar[name].data - rp[name].data).abs().max().item()
+            assert d < 2e-3 * max(1e-3, rp[name].data.abs().max().item()) + lr * 1e-3, (step, name, d)
+        # the optimizer's bf16 image is the parameter rounded to bf16
+        anyp = npar["future_predictor.dim_encoder.weight"]
+        assert torch.equal(state.w16[id(anyp)], anyp.data.bfloat16())
