@@ -135,7 +135,7 @@ EXPORTED_SYMBOLS = [
     "afft_workspace_bytes", "afft_weight_bytes", "afft_set_weight", "afft_missing_weights", "afft_forward",
     "afft_last_launch_count", "afft_profile_enable", "afft_profile_read", "afft_set_max_ksplit", "afft_plan_ksplit",
     "afft_marginalize_topk", "afft_score_fusion", "afft_transpose_bf16", "afft_layernorm_bwd", "afft_gelu_fwd",
-    "afft_gelu_bwd", "afft_colsum", "afft_attention_bwd", "afft_sgd_nesterov",
+    "afft_gelu_bwd", "afft_colsum", "afft_attention_bwd", "afft_sgd_nesterov", "afft_convert_dual",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -188,6 +188,9 @@ def lib() -> C.CDLL:
     l.afft_gelu_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     l.afft_gelu_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     l.afft_colsum.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    l.afft_convert_dual.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                    C.c_void_p, C.c_void_p]
+    l.afft_convert_dual.restype = C.c_int
     l.afft_sgd_nesterov.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
                                     C.c_int32, C.c_void_p]
     l.afft_sgd_nesterov.restype = C.c_int

@@ -439,6 +439,16 @@ extern "C" int afft_transpose_bf16(const void* src, int64_t lds, int32_t rows, i
   return launch_check("transpose launch");
 }
 
+extern "C" int afft_convert_dual(const float* src, int64_t lds, int32_t rows, int32_t cols, void* hi, int64_t ldh, void* tr,
+                                 int64_t ldt, float* colsum, void* stream) {
+  if (src == nullptr || rows <= 0 || cols <= 0 || (hi == nullptr && tr == nullptr && colsum == nullptr))
+    return fail(AFFT_ERR_INVALID, "convert_dual: bad argument");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  convert_dual_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(src, lds, rows, cols, static_cast<bf16*>(hi), ldh,
+                                                                           static_cast<bf16*>(tr), ldt, colsum);
+  return launch_check("convert_dual launch");
+}
+
 extern "C" int afft_layernorm_bwd(const float* x, int64_t ldx, const float* gamma, float eps, const float* dy, int64_t lddy,
                                   int32_t rows, int32_t dim, float* dx, int64_t lddx, float* dgamma, float* dbeta,
                                   void* stream) {
@@ -496,6 +506,9 @@ extern "C" int afft_attention_bwd(const float* qkv, int64_t ld, const float* pro
                                   const float* drop_mask, void* stream) {
   if (qkv == nullptr || probs == nullptr || d_out == nullptr || dqkv == nullptr) return fail(AFFT_ERR_INVALID, "attention_bwd: null pointer");
   if (L < 1 || L > 64 || n_seq <= 0 || H <= 0 || head_dim <= 0) return fail(AFFT_ERR_INVALID, "attention_bwd: bad sizes");
+  if (head_dim % 4 != 0 || ld % 4 != 0 || ldo % 4 != 0 || ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(d_out) |
+                                                             reinterpret_cast<uintptr_t>(dqkv)) & 15u) != 0)
+    return fail(AFFT_ERR_INVALID, "attention_bwd: head_dim and pitches must be multiples of 4 floats, pointers 16-byte aligned");
   const size_t smem = (static_cast<size_t>(4) * L * head_dim + 2 * L * L) * sizeof(float);
   if (smem > 227 * 1024) return fail(AFFT_ERR_INVALID, "attention_bwd: sequence too long for shared memory");
   if (smem > 48 * 1024) {

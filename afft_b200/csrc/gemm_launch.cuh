@@ -13,6 +13,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 
 #include "gemm_sm100.cuh"
 
@@ -89,10 +90,42 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_tensormap_encoder(std::string* err)
   return fn;
 }
 
+// A tensor map is a pure function of (address, extents, pitch, box, type): the same operands come back forward after
+// forward (weights and workspace buffers have stable addresses), so the encoded descriptors are memoised per thread -
+// ~200 driver calls per forward otherwise.
+struct TmapKey {
+  const void* ptr;
+  long long rows, cols, ld;
+  int box_rows, kind;  // kind: 0 bf16 operand, 1 fp16 operand, 2.. epilogue maps
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && kind == o.kind;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h ^= std::hash<long long>()(k.rows * 1000003LL + k.cols) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    h ^= std::hash<long long>()(k.ld * 131 + k.box_rows * 7 + k.kind) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+inline std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash>& tmap_cache() {
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  if (cache.size() > 8192) cache.clear();
+  return cache;
+}
+
 // bf16 matrix [rows, cols] with row pitch ld (elements) -> 2-D tiled map, box = 64 x box_rows,
 // SWIZZLE_128B, out-of-bounds elements read as zero.
 inline bool make_tmap_bf16(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld,
                            int box_rows, std::string* err, bool fp16 = false) {
+  const TmapKey key{ptr, rows, cols, ld, box_rows, fp16 ? 1 : 0};
+  auto& cache = tmap_cache();
+  auto hit = cache.find(key);
+  if (hit != cache.end()) {
+    *out = hit->second;
+    return true;
+  }
   auto enc = get_tensormap_encoder(err);
   if (enc == nullptr) return false;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (ld * 2) % 16 != 0) {
@@ -110,6 +143,7 @@ inline bool make_tmap_bf16(CUtensorMap* out, const void* ptr, long long rows, lo
     if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r));
     return false;
   }
+  cache.emplace(key, *out);
   return true;
 }
 

@@ -60,6 +60,9 @@ class Engine:
         self.max_ksplit = 4  # library default
         self._versions: Optional[tuple] = None
 
+    def __deepcopy__(self, memo):
+        return None  # a native handle belongs to one module instance on one device; copies build their own
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.afft_destroy(self.handle)

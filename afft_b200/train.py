@@ -62,6 +62,21 @@ def to_bf16_t(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def to_bf16_dual(x: torch.Tensor, colsum: torch.Tensor = None):
+    """fp32 [R, C] -> (bf16 [R, C], bf16 [C, pad8(R)]) in one pass (+ colsum[c] += sum_r x[r, c]): both orientations a
+    GEMM needs of an activation / gradient (pad columns are zero)."""
+    x = x.contiguous()
+    R, C = x.shape
+    Cp, Rp = _pad8(C), _pad8(R)
+    hi = torch.zeros(R, Cp, device=x.device, dtype=torch.bfloat16) if Cp != C else \
+        torch.empty(R, Cp, device=x.device, dtype=torch.bfloat16)
+    tr = torch.zeros(C, Rp, device=x.device, dtype=torch.bfloat16) if Rp != R else \
+        torch.empty(C, Rp, device=x.device, dtype=torch.bfloat16)
+    _capi.check(_lib().afft_convert_dual(x.data_ptr(), C, R, C, hi.data_ptr(), Cp, tr.data_ptr(), Rp, _capi.ptr(colsum),
+                                         _ST(x.device)))
+    return hi[:, :C], tr
+
+
 def bf16_t(xb: torch.Tensor) -> torch.Tensor:
     """bf16 [R, C] -> bf16 [C, pad8(R)]."""
     R, C = xb.shape
@@ -200,7 +215,11 @@ class LinearFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, conv1d: bool):
-        xb = to_bf16(x)
+        need_wgrad = weight.requires_grad and torch.is_grad_enabled()
+        if need_wgrad:
+            xb, x_t = to_bf16_dual(x)  # the wgrad operand (x^T) comes out of the same pass over x
+        else:
+            xb, x_t = to_bf16(x), None
         st = _state_for(weight, bias)
         ctx.st = st
         if st is not None:  # the optimizer's bf16 image: no conversion
@@ -222,19 +241,34 @@ class LinearFn(torch.autograd.Function):
         _capi.gemm(xb, w_fwd[:, :xb.shape[1]], bias=bias, out_f32=y[:, :N])
         # the bf16 operand is kept for dgrad (its transpose is the dgrad operand): transposing 2-byte elements reads
         # half of what a second conversion of the fp32 weight would
-        ctx.save_for_backward(xb, weight, w_fwd, bias_param)
+        ctx.save_for_backward(x_t if x_t is not None else xb, weight, w_fwd, bias_param)
+        ctx.x_is_t, ctx.K = x_t is not None, xb.shape[1]
         ctx.conv1d, ctx.has_bias = conv1d, bias_param is not None
         return y[:, :N]
 
     @staticmethod
     def backward(ctx, dy):
-        xb, weight, w_fwd, bias = ctx.saved_tensors
+        xs, weight, w_fwd, bias = ctx.saved_tensors
         st = ctx.st
         dy = dy.contiguous()
         M, N = dy.shape
-        K = xb.shape[1]
+        K = ctx.K
         dx = dw = db = None
-        dyb = to_bf16(dy)
+        # dy in both orientations (dgrad contracts over N, wgrad over the rows) and the bias gradient: one pass over dy
+        db_out = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            if st is not None:
+                db_out, _ = st.grad_target(bias)  # cleared at step start; the kernel accumulates
+            else:
+                db_out = db = torch.zeros(N, device=dy.device, dtype=torch.float32)
+        if ctx.needs_input_grad[1]:
+            dyb, dy_t = to_bf16_dual(dy, db_out)
+        else:
+            dyb, dy_t = to_bf16(dy), None
+            if db_out is not None:
+                _capi.check(_lib().afft_colsum(dy.data_ptr(), N, M, N, db_out.data_ptr(), _ST(dy.device)))
+        if db_out is not None and st is not None:
+            st.grad_done(bias)
         if ctx.needs_input_grad[0]:
             # dgrad: dx [M, K] = dy [M, N] . W;  B operand [K, N] with N contiguous
             if st is not None and ctx.conv1d and N % 8 == 0:
@@ -244,8 +278,7 @@ class LinearFn(torch.autograd.Function):
             dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
             _capi.gemm(dyb, w_dg[:, :N], out_f32=dx)
         if ctx.needs_input_grad[1]:
-            dy_t = to_bf16_t(dy)  # [N, Mp]
-            x_t = bf16_t(xb)      # [K, Mp]
+            x_t = xs if ctx.x_is_t else bf16_t(xs)  # [K, Mp]
             direct = st is not None and weight.shape[1] % 4 == 0
             if direct:  # wgrad straight into the .grad view: no temporary, no autograd accumulation pass
                 dw_out, acc = st.grad_target(weight, overwrites=True)
@@ -259,14 +292,6 @@ class LinearFn(torch.autograd.Function):
                 st.grad_done(weight)
             else:
                 dw = dw_out  # autograd accumulates it and the bucket's hook counts the parameter
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            if st is not None:
-                db_out, _ = st.grad_target(bias)  # zeroed at step start; colsum accumulates
-                _capi.check(_lib().afft_colsum(dy.data_ptr(), N, M, N, db_out.data_ptr(), _ST(dy.device)))
-                st.grad_done(bias)
-            else:
-                db = torch.zeros(N, device=dy.device, dtype=torch.float32)
-                _capi.check(_lib().afft_colsum(dy.data_ptr(), N, M, N, db.data_ptr(), _ST(dy.device)))
         return dx, dw, db, None
 
 

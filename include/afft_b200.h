@@ -202,6 +202,10 @@ AFFT_API int afft_marginalize_topk(const float* logits, int64_t ld, int32_t B, i
 /* through nn.Linear / nn.LayerNorm / nn.GELU / softmax attention).  dgrad and wgrad are afft_gemm calls on       */
 /* transposed bf16 operands; these are the remaining backward kernels.  fp32 in / fp32 out.                       */
 /* ------------------------------------------------------------------------------------------ */
+/* fp32 [rows, cols] -> bf16 copy `hi` (pitch ldh) and bf16 transpose `tr` [cols, rows] (pitch ldt) in one pass, plus
+ * colsum[c] += sum_r src[r, c] (each output optional): the three passes a Linear's backward makes over dy. */
+AFFT_API int afft_convert_dual(const float* src, int64_t lds, int32_t rows, int32_t cols, void* hi, int64_t ldh, void* tr,
+                               int64_t ldt, float* colsum, void* stream);
 AFFT_API int afft_transpose_bf16(const void* src, int64_t lds, int32_t rows, int32_t cols, void* dst, int64_t ldd, void* stream);
 /* dx = LayerNorm backward; dgamma / dbeta are ACCUMULATED (+=) and may be NULL (together with gamma). */
 AFFT_API int afft_layernorm_bwd(const float* x, int64_t ldx, const float* gamma, float eps, const float* dy, int64_t lddy,

@@ -447,3 +447,34 @@ def test_predictor_seam_is_callable_and_matches_the_oracle(output_len, precision
     assert (out.cpu() - ref).abs().max().item() < tol
     with pytest.raises(ValueError):
         pred(torch.zeros(B, T, 1024, device="cuda:0"), 1)
+
+
+def test_dataparallel_dropin_keeps_packed_weights():
+    """afft_b200.parallel.DataParallel (the test.py:130 wrapper): same outputs as the bare model, persistent replicas whose
+    engines do not re-pack weights between forwards, and a changed source parameter reaches the replicas."""
+    from afft_b200.parallel import DataParallel
+    cfg, T, ncls, _ = configs.named_config("egtea_sa")
+    model = BaseModel(cfg, ncls, {})
+    model.load_state_dict(synthetic.synthetic_state_dict(model, seed=0))
+    model = model.to("cuda:0").eval()
+    feats = synthetic.synthetic_features(cfg["modal_dims"], 9, T, seed=12, six_d=True)
+    ref = _run(model, feats)
+    n_dev = torch.cuda.device_count()
+    dp = DataParallel(model, device_ids=[0, 1] if n_dev > 1 else [0, 0]).eval()  # two replicas (same device if only one GPU)
+    with torch.no_grad():
+        out, tgt = dp({m: t.cuda() for m, t in feats.items()}, **KW)
+    assert tgt["target"] is None
+    for k in ("logits/action", "past_logits/action", "orig_past", "past_futures", "future"):
+        assert out[k]["all-fused"].shape == ref[k]["all-fused"].shape
+        assert (out[k]["all-fused"] - ref[k]["all-fused"]).abs().max().item() < 1e-5, k  # other split-K factors per shard
+    assert out["attentions"]["all-fused"]["modality_attns"].shape == ref["attentions"]["all-fused"]["modality_attns"].shape
+    rep = dp._replicas[1]
+    eng = next(iter(rep.future_predictor._engines.values()))
+    v0 = eng._versions
+    with torch.no_grad():
+        dp({m: t.cuda() for m, t in feats.items()}, **KW)
+    assert eng._versions is v0  # nothing re-packed on the second forward
+    with torch.no_grad():
+        model.future_predictor.classifiers["action"]["all-fused"][1].bias.add_(1.0)
+        out2, _ = dp({m: t.cuda() for m, t in feats.items()}, **KW)
+    assert torch.allclose(out2["logits/action"]["all-fused"], out["logits/action"]["all-fused"] + 1.0, atol=1e-5)
