@@ -457,6 +457,7 @@ def test_dataparallel_dropin_keeps_packed_weights():
     model = BaseModel(cfg, ncls, {})
     model.load_state_dict(synthetic.synthetic_state_dict(model, seed=0))
     model = model.to("cuda:0").eval()
+    model.future_predictor.max_ksplit = 1  # shards have other GEMM heights: compare with a fixed summation order
     feats = synthetic.synthetic_features(cfg["modal_dims"], 9, T, seed=12, six_d=True)
     ref = _run(model, feats)
     n_dev = torch.cuda.device_count()
@@ -466,7 +467,7 @@ def test_dataparallel_dropin_keeps_packed_weights():
     assert tgt["target"] is None
     for k in ("logits/action", "past_logits/action", "orig_past", "past_futures", "future"):
         assert out[k]["all-fused"].shape == ref[k]["all-fused"].shape
-        assert (out[k]["all-fused"] - ref[k]["all-fused"]).abs().max().item() < 1e-5, k  # other split-K factors per shard
+        assert torch.equal(out[k]["all-fused"], ref[k]["all-fused"]), k  # clips are independent units: bitwise
     assert out["attentions"]["all-fused"]["modality_attns"].shape == ref["attentions"]["all-fused"]["modality_attns"].shape
     rep = dp._replicas[1]
     eng = next(iter(rep.future_predictor._engines.values()))
