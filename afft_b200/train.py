@@ -110,10 +110,10 @@ class TrainState:
     tensors for autograd to add, and ``step()`` is ONE kernel (afft_sgd_nesterov) over the flat buffers."""
 
     def __init__(self, head, lr: float, momentum: float = 0.9, weight_decay: float = 0.0, nesterov: bool = True,
-                 comm_dtype=torch.float32):
+                 comm_dtype=torch.float32, n_buckets: int = 0):
         from . import dist as adist
         self.lr, self.momentum, self.weight_decay, self.nesterov = lr, momentum, weight_decay, nesterov
-        groups = grad_groups(head)
+        groups = merge_groups(grad_groups(head), n_buckets)
         self.buckets = adist.GradBuckets(groups, comm_dtype=comm_dtype)
         flat_g = self.buckets.flat
         self.flat_p = torch.empty_like(flat_g)
@@ -594,6 +594,25 @@ def grad_groups(fp) -> list:
     if rest:
         groups.append(rest)
     return groups
+
+
+def merge_groups(groups: list, n_buckets: int) -> list:
+    """Merge consecutive layer groups into n_buckets all-reduce buckets of similar size (0: one bucket per group).
+    Fewer, larger collectives cost less launch latency per step; more, smaller ones start earlier in the backward pass."""
+    if n_buckets <= 0 or n_buckets >= len(groups):
+        return groups
+    sizes = [sum(p.numel() for p in g) for g in groups]
+    target = sum(sizes) / n_buckets
+    out, cur, acc = [], [], 0
+    for g, n in zip(groups, sizes):
+        cur += g
+        acc += n
+        if acc >= target and len(out) < n_buckets - 1:
+            out.append(cur)
+            cur, acc = [], 0
+    if cur:
+        out.append(cur)
+    return out
 
 
 def reference_losses(outputs, target: torch.Tensor, target_subclips: torch.Tensor, cls: str = "action") -> Dict[str, torch.Tensor]:

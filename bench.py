@@ -360,12 +360,13 @@ class DeviceRun:
         return adist.max_over_ranks(e0.elapsed_time(e1), dev)
 
     def profile(self, psteps=5):
-        """Per-launch device time slices of `psteps` forwards (in-kernel exit timestamps; see afft_profile_enable)."""
+        """Per-launch device time slices of `psteps` steady-state forwards (in-kernel exit timestamps; afft_profile_enable)."""
         self.eng.profile_enable(True)
         agg = {0: [0.0, 0], 1: [0.0, 0], 2: [0.0, 0], 3: [0.0, 0]}
         by_shape, gemm_flops, last = {}, 0.0, None
         for i in range(psteps):
-            self.step(i)
+            for j in range(3):  # back to back: the profiled (last) forward starts while its predecessor drains - steady state
+                self.step(3 * i + j)
             torch.cuda.synchronize()
             last = self.eng.profile_read()
             for cat, M, N, K, ms in last:
@@ -416,6 +417,49 @@ def parity_block(runs, cfg, T, ncls, dev, n_clips=1024, chunk=128):
                 o, _ = run.model({m: f[b0:b0 + run.B].reshape(-1, T, f.shape[-1], 1, 1, 1).to(dev) for m, f in feats.items()}, **KW)
             got.append(o["logits/action"]["all-fused"][:, 0].float().cpu())
         out["modes"][prec] = parity.top5_stats(torch.cat(got), ref)
+    return out
+
+
+def batch_sweep_block(run, flops_per_clip, peaks, batches=(1, 8, 32, 64, 128)):
+    """BASELINE config 2 ("batch sweep"): the same engine at smaller batches (32 is the reference's shipped eval batch,
+    expts/01_SA-Fuser_ek100_val_TSN.txt:6), plain stream launches and CUDA-graph replay."""
+    out = {}
+    io = run.ios[0]
+
+    def timeit(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    for b in batches:
+        if b > run.B:
+            continue
+        ms_plain = timeit(lambda: run.eng.forward_into(io, b), 50)
+        ms_graph = None
+        try:
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                run.eng.forward_into(io, b)
+            torch.cuda.current_stream().wait_stream(side)
+            with torch.cuda.graph(g):
+                run.eng.forward_into(io, b)
+            ms_graph = timeit(g.replay, 50)
+        except Exception as exc:  # noqa: BLE001 - the plain number stands on its own
+            print(f"[bench] graph capture at B={b} failed: {exc!r}", file=sys.stderr)
+            torch.cuda.synchronize()
+        best = min(ms_plain, ms_graph) if ms_graph is not None else ms_plain
+        out[str(b)] = {"ms_plain": round(ms_plain, 4), "ms_graph_replay": round(ms_graph, 4) if ms_graph is not None else None,
+                       "clips_per_s": round(b / best * 1e3, 1),
+                       "whole_step_frac": round(b * flops_per_clip / best / 1e9 / peaks["sustained"], 4)}
     return out
 
 
@@ -597,8 +641,9 @@ def run_afft(args):
             "traffic": traffic,
             "traffic_note": (f"STATIC: dram bytes per GEMM launch, avg over the GEMM launches of a forward, from the committed ncu "
                              f"capture profiles/{traffic_src} (not measured in this run)") if traffic is not None else None,
-            "how": f"{PSTEPS} profiled forwards; each kernel records its exit %globaltimer, launch i owns (end of i-1, end of i]: "
-                   "the slices sum to the forward's device time and PDL overlap is preserved (afft_profile_enable)",
+            "how": f"{PSTEPS} profiled forwards, each the last of 3 issued back to back; every kernel records its exit %globaltimer, "
+                   "launch i owns (end of i-1, end of i]: the slices sum to the forward's device time and PDL overlap is preserved "
+                   "(afft_profile_enable)",
             "algorithmic_flop_per_launch_avg": round(gemm_flops / max(1, agg[0][1])),
             "launches_per_step": agg[0][1] // PSTEPS, "gemm_ms_per_step": round(gemm_ms / PSTEPS, 4),
             "kernel_ms_per_step": round(kernel_ms_total / PSTEPS, 4),
@@ -645,6 +690,7 @@ def run_afft(args):
         ps = line["parity"]["modes"][args.precision]
         line["parity_sample"] = {"clips": ps["clips"], "max_abs_dlogit_vs_oracle_fp32": ps["max_abs_dlogit"],
                                  "top5_identical_clips": ps["ordered_top5_identical"], "mode": args.precision}
+        line["batch_sweep"] = batch_sweep_block(run, flops_per_clip, peaks)
         if args.config == "ek100_sa_tsn":
             line["gpu_baseline"] = gpu_baseline_block(B, T, dev)
         best, table = cpu_best_of(cfg, T, ncls, batches=(8, eval_bs, 128))
@@ -692,7 +738,8 @@ def run_train(args):
         # flat parameter / gradient / momentum / bf16-operand buffers; native wgrad writes into the gradient views, the
         # optimizer is one kernel that also emits the next step's bf16 weights (afft_b200.train.TrainState)
         state = atrain.TrainState(model.future_predictor, lr=1e-3, momentum=0.9, weight_decay=1e-6, nesterov=True,
-                                  comm_dtype=torch.bfloat16 if args.grad_comm == "bf16" else torch.float32)
+                                  comm_dtype=torch.bfloat16 if args.grad_comm == "bf16" else torch.float32,
+                                  n_buckets=args.grad_buckets)
         buckets = state.buckets
         state.__enter__()
     # expts/01 :48-52; DDP arm: torch's fused SGD
@@ -822,6 +869,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="train mode: do not capture the step into a CUDA graph")
     ap.add_argument("--grad-comm", choices=["fp32", "bf16"], default="fp32", help="train mode: gradient all-reduce transport dtype")
+    ap.add_argument("--grad-buckets", type=int, default=0, help="train mode: merge the layer groups into this many all-reduce buckets (0: one per group)")
     ap.add_argument("--ddp", action="store_true", help="train mode, N > 1: torch DistributedDataParallel (eager) instead of GradBuckets")
     ap.add_argument("--no-staged", action="store_true", help="skip the clip-descriptor (feature store) e2e measurement")
     ap.add_argument("--no-modes", action="store_true", help="skip the sub-records of the other precision modes")
