@@ -81,7 +81,8 @@ for name, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
         net(x).pow(2).sum().backward()
         launched_in_backward = list(order)
         gb.finish()
-        mine = gb.flat.clone()
+        mine = torch.cat([p.grad.flatten() for g in groups for p in g if p is not unused]).clone()  # views into gb.flat
+        mine_unused = unused.grad.clone()
         order.clear()
     # reference: the same gradients computed for both ranks' inputs on one process, averaged
     refs = []
@@ -93,7 +94,8 @@ for name, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
         refs.append(torch.cat([p.grad.flatten() for g in groups for p in g if p is not unused]))
     ref = sum(refs) / world
     n = ref.numel()
-    res[name] = {"err": float((mine[:n] - ref).abs().max()), "scale": float(ref.abs().max()), "unused": float(mine[n:].abs().max()),
+    assert all(p.grad.data_ptr() % 16 == 0 for g in groups for p in g)  # slices are 16-byte aligned (TMA operands)
+    res[name] = {"err": float((mine - ref).abs().max()), "scale": float(ref.abs().max()), "unused": float(mine_unused.abs().max()),
                  "launched_in_backward": launched_in_backward, "bytes": gb.bytes_per_step()}
     gb.remove_hooks()
 print(json.dumps({"rank": rank, **res}), flush=True)
