@@ -20,7 +20,7 @@ AFFT_OK = 0
 AFFT_MAX_MODS = 8
 AFFT_MAX_CLS = 4
 AFFT_NAME_LEN = 32
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH, ACT_RELU, ACT_GATE = 0, 1, 2, 3, 4
 PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2
@@ -113,7 +113,7 @@ class IO(C.Structure):
         ("feat", C.c_void_p * AFFT_MAX_MODS),
         ("orig_past", C.c_void_p), ("past_futures", C.c_void_p),
         ("logits", C.c_void_p * AFFT_MAX_CLS), ("ld_logits", C.c_int64 * AFFT_MAX_CLS),
-        ("fuser_attn", C.c_void_p),
+        ("fuser_attn", C.c_void_p), ("gpt_attn", C.c_void_p),
     ]
 
 

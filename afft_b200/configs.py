@@ -137,6 +137,10 @@ def named_config(name: str):
         # SA-Fuser with cross_attn=True: a token does not attend to itself (fusion.py:330-335)
         "ek100_sa_cross_attn": (lambda: model_cfg(ek3, depth=2, fp_layers=2, fuser_kwargs=dict(cross_attn=True)),
                                 10, {"action": 3806}, 16),
+        # common_dim == fp_inter_dim: dim_encoder / dim_decoder are nn.Identity (future_prediction.py:245-255); GPT-2 width 1024
+        "ek100_sa_identity_enc": (lambda: model_cfg(ek3, depth=2, fp_layers=2, fp_inter_dim=1024), 10, {"action": 3806}, 16),
+        "egtea_sa_identity_rollout3": (lambda: _with_output_len(model_cfg({"rgb": 1024, "flow": 1024}, depth=2, fp_layers=2,
+                                                                         fp_inter_dim=1024), 3), 10, {"action": 106}, 32),
         # T-SA-Fuser without frame-level token: per-timestep mean over the modalities (fusion.py:211-214)
         "ek100_tsa_mean": (lambda: model_cfg(ek4, fuser="T-SA-Fuser", depth=2, fp_layers=2, fuser_kwargs=dict(
             modal_encoding=True, frame_level_token=False, temporal_sequence_length=None)), 10, {"action": 3806}, 16),

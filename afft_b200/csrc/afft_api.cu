@@ -35,7 +35,7 @@ static int cuda_fail(const char* what, cudaError_t e) {
   return fail(AFFT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-extern "C" int afft_abi_version(void) { return 6; }
+extern "C" int afft_abi_version(void) { return 7; }
 extern "C" const char* afft_last_error(void) { return g_err.c_str(); }
 
 static int device_sm_count(int* out) {
@@ -149,7 +149,7 @@ static int run_layernorm(const LayerNormArgs& a, cudaStream_t stream) {
   const int blocks = (a.rows + rows_per_block - 1) / rows_per_block;
   const bool avg = a.n_avg > 1;
   const bool fast = !avg && a.gamma != nullptr && a.beta != nullptr && a.y_hi != nullptr && a.y_f32 == nullptr &&
-                    a.y_lo == nullptr && a.aux_mod == 0;
+                    a.y_lo == nullptr && a.aux_mod == 0;  // (an output row map is honoured by every instantiation)
 #define AFFT_LN(NV)                                                                                          \
   case NV:                                                                                                   \
     if (fast) launch_pdl(layernorm_kernel<NV, false, true>, dim3(blocks), dim3(ln_threads), 0, stream, a);   \
@@ -198,6 +198,7 @@ extern "C" int afft_layernorm(const afft_layernorm_desc* d, void* stream) {
   a.ld_aux = d->ld_aux;
   a.out_fp16 = d->out_fp16 != 0;
   a.t_end = nullptr;
+  a.out_group = a.out_stride = a.out_off = 0;
   if (a.out_fp16 && (a.y_lo != nullptr || a.aux_lo != nullptr)) return fail(AFFT_ERR_INVALID, "layernorm: fp16 outputs have no lo part");
   return run_layernorm(a, static_cast<cudaStream_t>(stream));
 }
@@ -711,8 +712,6 @@ extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
   const int hd1 = no_fuser ? 256 : c.dim / c.fuser_heads, hd2 = c.gpt_dim / c.gpt_heads;
   if ((hd1 != 256 && hd1 != 512) || (hd2 != 256 && hd2 != 512))
     return fail(AFFT_ERR_INVALID, "create: head_dim must be 256 or 512");
-  if (c.dim == c.gpt_dim && c.stages == AFFT_STAGE_ALL)
-    return fail(AFFT_ERR_INVALID, "create: common_dim == fp_inter_dim (Identity encoder) is not supported");
   for (int m = 0; m < c.n_mod; ++m)
     if (c.mod_dim[m] < 8 || c.mod_dim[m] % 8 != 0) return fail(AFFT_ERR_INVALID, "create: modality dims must be multiples of 8");
   if (c.fuser_kind == AFFT_FUSER_CA && c.n_mod < 2) return fail(AFFT_ERR_INVALID, "create: CA-Fuser needs >= 2 modalities");
@@ -993,9 +992,12 @@ struct Fwd {
   void layernorm(const float* x, long long ldx, int rows, int dim, const std::string& name, float eps, const PairBuf* yb,
                  float* y_f32, long long ldy, int in_group = 0, int in_stride = 0, int n_avg = 0, int avg_stride = 0,
                  int aux_mod = 0, int aux_stride = 0, float* aux_f32 = nullptr, const PairBuf* aux_b = nullptr,
-                 long long ld_aux = 0, int aux_rem = 0) {
+                 long long ld_aux = 0, int aux_rem = 0, int out_group = 0, int out_stride = 0, int out_off = 0) {
     if (!ok()) return;
     LayerNormArgs a;
+    a.out_group = out_group;
+    a.out_stride = out_stride;
+    a.out_off = out_off;
     a.x = x;
     a.ldx = ldx;
     a.in_group = in_group;
@@ -1326,7 +1328,7 @@ static void run_fuser(Fwd& F, const afft_io& io, int b0, int nb) {
 
 // The GPT-2 blocks over the T prompt positions of B clips: residual stream in h->g [B*T, G] (transformers GPT2Block;
 // SURVEY.md Appendix A step 7).  With a roll-out the per-layer q|k|v buffers are kept as the KV cache.
-static void gpt_prompt_layers(Fwd& F, int B) {
+static void gpt_prompt_layers(Fwd& F, int B, float* gpt_attn) {
   afft_handle* h = F.h;
   const afft_config& c = h->cfg;
   const int T = c.T, G = c.gpt_dim, H = c.gpt_heads, hd = G / H, OL = c.fp_output_len;
@@ -1339,7 +1341,9 @@ static void gpt_prompt_layers(Fwd& F, int B) {
     QkvOut q = qkv_out(qkv, F.strict, 0);
     F.gemm(h->y2, G, R2, p + "attn.c_attn.weight", F.V(p + "attn.c_attn.bias"), ACT_NONE, nullptr, 0, 0, q.f32, 3 * G,
            q.bp, 3 * G);
-    F.attention(qkv, 3 * G, 0, G, 2 * G, B, T, H, hd, 1, T, h->att2, G, nullptr, 0, 0, 1);
+    const long long per_clip = static_cast<long long>(c.gpt_layers) * H * T * T;  // probabilities [B, layers, H, T, T]
+    F.attention(qkv, 3 * G, 0, G, 2 * G, B, T, H, hd, 1, T, h->att2, G,
+                gpt_attn != nullptr ? gpt_attn + static_cast<long long>(i) * H * T * T : nullptr, per_clip, 0, 1);
     F.gemm(h->att2, G, R2, p + "attn.c_proj.weight", F.V(p + "attn.c_proj.bias"), ACT_NONE, h->g, G, 0, h->g, G, nullptr,
            0);
     F.layernorm(h->g, G, R2, G, p + "ln_2", 1e-5f, &h->y2, nullptr, G);
@@ -1389,20 +1393,50 @@ static void run_predictor(Fwd& F, const afft_io& io, int B) {
   const int R2 = B * T;
   const std::string gp = "future_predictor.gpt_model.";
   const float* wpe = F.V(gp + "wpe.weight");
-  // g = z . Wenc^T + wpe[t]
-  F.gemm(h->zb, D, R2, "dim_encoder.weight", nullptr, ACT_NONE, wpe, G, T, h->g, G, nullptr, 0);
-  gpt_prompt_layers(F, B);
-  if (OL > 1)  // also keep the last position's hidden state (fp32): it is the next input embedding
-    F.layernorm(h->g, G, R2, G, gp + "ln_f", 1e-5f, &h->y2, nullptr, G, 0, 0, 0, 0, T, 1, h->hid, nullptr, G, T - 1);
-  else
-    F.layernorm(h->g, G, R2, G, gp + "ln_f", 1e-5f, &h->y2, nullptr, G);
-  // z_hat[b, t] -> slot t + 1 of the [B, S, D] past_futures buffer (fp32 output + bf16 classifier input)
-  F.gemm(h->y2, G, R2, "dim_decoder.weight", nullptr, ACT_NONE, nullptr, 0, 0, io.past_futures, D, &h->pfb, D, T, S, 1);
+  // common_dim == fp_inter_dim: dim_encoder / dim_decoder are nn.Identity (future_prediction.py:245-255) - z enters
+  // GPT-2 as it is and ln_f's output IS z_hat
+  const bool identity = (D == G);
+  if (identity) {
+    AssembleArgs a;  // g = z + wpe[t]
+    memset(&a, 0, sizeof(a));
+    a.h = h->g;
+    a.B = B;
+    a.T = T;
+    a.dim = G;
+    a.n_slots = 1;
+    a.layout = 0;
+    a.src[0] = io.orig_past;
+    a.tok_mod = 1;
+    a.pos_emb = wpe;
+    F.assemble(a);
+  } else {
+    // g = z . Wenc^T + wpe[t]
+    F.gemm(h->zb, D, R2, "dim_encoder.weight", nullptr, ACT_NONE, wpe, G, T, h->g, G, nullptr, 0);
+  }
+  gpt_prompt_layers(F, B, io.gpt_attn);
+  if (identity) {
+    // z_hat[b, t] = ln_f(g)[b, t] -> slot t + 1 of past_futures (fp32) and of the classifier's 16-bit operand buffer;
+    // roll-out: the last position's hidden state is also kept in h->hid
+    F.layernorm(h->g, G, R2, G, gp + "ln_f", 1e-5f, &h->pfb, io.past_futures, D, 0, 0, 0, 0, OL > 1 ? T : 0, 1,
+                OL > 1 ? h->hid : nullptr, nullptr, G, T - 1, T, S, 1);
+  } else {
+    if (OL > 1)  // also keep the last position's hidden state (fp32): it is the next input embedding
+      F.layernorm(h->g, G, R2, G, gp + "ln_f", 1e-5f, &h->y2, nullptr, G, 0, 0, 0, 0, T, 1, h->hid, nullptr, G, T - 1);
+    else
+      F.layernorm(h->g, G, R2, G, gp + "ln_f", 1e-5f, &h->y2, nullptr, G);
+    // z_hat[b, t] -> slot t + 1 of the [B, S, D] past_futures buffer (fp32 output + bf16 classifier input)
+    F.gemm(h->y2, G, R2, "dim_decoder.weight", nullptr, ACT_NONE, nullptr, 0, 0, io.past_futures, D, &h->pfb, D, T, S, 1);
+  }
 
   for (int k = 1; k < OL; ++k) {
     gpt_decode_layers(F, B, k);
-    F.layernorm(h->gn, G, B, G, gp + "ln_f", 1e-5f, &h->yn, h->hid, G);
-    F.gemm(h->yn, G, B, "dim_decoder.weight", nullptr, ACT_NONE, nullptr, 0, 0, io.past_futures, D, &h->pfb, D, 1, S, T + k);
+    if (identity) {
+      F.layernorm(h->gn, G, B, G, gp + "ln_f", 1e-5f, &h->pfb, io.past_futures, D, 0, 0, 0, 0, 1, 1, h->hid, nullptr, G, 0,
+                  1, S, T + k);
+    } else {
+      F.layernorm(h->gn, G, B, G, gp + "ln_f", 1e-5f, &h->yn, h->hid, G);
+      F.gemm(h->yn, G, B, "dim_decoder.weight", nullptr, ACT_NONE, nullptr, 0, 0, io.past_futures, D, &h->pfb, D, 1, S, T + k);
+    }
   }
   for (int k = 0; k < c.n_cls; ++k) {
     const std::string p = std::string("classifiers.") + c.cls_name[k] + ".all-fused.1.";
@@ -1432,7 +1466,7 @@ static void run_gpt_only(Fwd& F, const afft_io& io, int B) {
   a.tok_mod = 1;
   a.pos_emb = F.V(gp + "wpe.weight");
   F.assemble(a);
-  gpt_prompt_layers(F, B);
+  gpt_prompt_layers(F, B, io.gpt_attn);
   if (OL > 1)
     F.layernorm(h->g, G, R2, G, gp + "ln_f", 1e-5f, nullptr, io.orig_past, G, 0, 0, 0, 0, T, 1, h->hid, nullptr, G, T - 1);
   else

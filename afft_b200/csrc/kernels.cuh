@@ -165,9 +165,10 @@ struct LayerNormArgs {
   long long ld_aux;
   int out_fp16;  // y_hi / aux_hi are fp16 (MODE_FP16) instead of bf16
   unsigned long long* t_end;  // profiling slot or nullptr
+  int out_group, out_stride, out_off;  // output row of row r: (r / out_group) * out_stride + r % out_group + out_off (0: r)
 };
 
-__device__ __forceinline__ void ln_store(const LayerNormArgs& a, int row, bool aux, long long arow, int c4, const float4& y) {
+__device__ __forceinline__ void ln_store(const LayerNormArgs& a, long long row, bool aux, long long arow, int c4, const float4& y) {
   const uint2 hi = make_uint2(pack_op16x2(y.x, y.y, a.out_fp16), pack_op16x2(y.z, y.w, a.out_fp16));
   if (a.y_f32 != nullptr) reinterpret_cast<float4*>(a.y_f32 + row * a.ldy)[c4] = y;
   if (a.y_hi != nullptr) reinterpret_cast<uint2*>(a.y_hi + row * a.ldy)[c4] = hi;
@@ -201,6 +202,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs a) {
   const float4* b4 = reinterpret_cast<const float4*>(a.beta);
   const bool aux = a.aux_mod > 0 && (warp % a.aux_mod) == a.aux_rem;
   const long long arow = aux ? static_cast<long long>(warp / a.aux_mod) * a.aux_stride : 0;
+  long long orow = warp;  // output row (row map: the Identity dim_decoder writes z_hat[b, t] to slot t + 1 of past_futures)
+  if (a.out_group > 0) orow = static_cast<long long>(warp / a.out_group) * a.out_stride + (warp % a.out_group) + a.out_off;
   const int n_avg = (AVG && a.n_avg > 1) ? a.n_avg : 1;
   float4 acc[AVG ? NV : 1];
   if (AVG) {
@@ -235,13 +238,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs a) {
       y.z = fmaf((v[i].z - mean) * rstd, g.z, b.z);
       y.w = fmaf((v[i].w - mean) * rstd, g.w, b.w);
       if (FAST) {
-        reinterpret_cast<uint2*>(a.y_hi + warp * a.ldy)[c4] =
+        reinterpret_cast<uint2*>(a.y_hi + orow * a.ldy)[c4] =
             make_uint2(pack_op16x2(y.x, y.y, a.out_fp16), pack_op16x2(y.z, y.w, a.out_fp16));
       } else if (AVG) {
         float4& t = acc[AVG ? i : 0];
         t.x += y.x; t.y += y.y; t.z += y.z; t.w += y.w;
       } else {
-        ln_store(a, warp, aux, arow, c4, y);
+        ln_store(a, orow, aux, arow, c4, y);
       }
     }
   }
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs a) {
     for (int i = 0; i < NV; ++i) {
       float4 y = acc[AVG ? i : 0];
       y.x *= inv_avg; y.y *= inv_avg; y.z *= inv_avg; y.w *= inv_avg;
-      ln_store(a, warp, aux, arow, lane + 32 * i, y);
+      ln_store(a, orow, aux, arow, lane + 32 * i, y);
     }
   }
   ptx::prof_mark_end(a.t_end);

@@ -26,7 +26,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 __device__ __forceinline__ void prof_mark_end(unsigned long long* slot) {  // call as the last statement of a warp
-  if (slot != nullptr && (threadIdx.x & 31) == 0) atomicMax(slot, globaltimer_ns());
+  // one mark per CTA (its warp 0; linear thread index so that 2-D blocks work): a CTA's warps finish within a fraction of a
+  // microsecond of each other, and one atomic per CTA instead of one per warp keeps the profiled run close to the plain one
+  if (slot != nullptr && (threadIdx.x + threadIdx.y * blockDim.x) == 0) atomicMax(slot, globaltimer_ns());
 }
 
 __device__ __forceinline__ uint32_t lane_id() {

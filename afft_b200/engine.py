@@ -51,7 +51,7 @@ class Engine:
         cfg.fp_output_len = fp_output_len
         cfg.stages = stages
         self.stages = stages
-        self.gpt_dim = gpt_dim
+        self.gpt_dim, self.gpt_layers, self.gpt_heads = gpt_dim, gpt_layers, gpt_heads
         cfg.device = device.index if device.index is not None else torch.cuda.current_device()
         self.cfg = cfg
         h = C.c_void_p()
@@ -108,9 +108,10 @@ class Engine:
             return n + (1 if self.frame_level_token else 0)
         return n
 
-    def forward(self, feats: List[torch.Tensor], want_attn: bool = True):
+    def forward(self, feats: List[torch.Tensor], want_attn: bool = True, want_gpt_attn: bool = False):
         """feats: per modality (fusion order) (B, T, C_m) fp32 contiguous CUDA tensors.
-        Returns (orig_past (B,T,D), past_futures_buf (B,T+O,D), [logits_buf (B,T+O,ld)], attn or None), O = fp_output_len."""
+        Returns (orig_past (B,T,D), past_futures_buf (B,T+O,D), [logits_buf (B,T+O,ld)], attn or None), O = fp_output_len;
+        with want_gpt_attn a fifth element: the GPT-2 attention probabilities (B, layers, heads, T, T)."""
         B = feats[0].shape[0]
         T, D, dev = self.T, self.dim, self.device
         io = _capi.IO()
@@ -139,8 +140,12 @@ class Engine:
             else:
                 attn = torch.empty(B, self.fuser_depth, T, H, n, n, device=dev, dtype=torch.float32)
             io.fuser_attn = attn.data_ptr()
+        gpt_attn = None
+        if want_gpt_attn:
+            gpt_attn = torch.empty(B, self.gpt_layers, self.gpt_heads, T, T, device=dev, dtype=torch.float32)
+            io.gpt_attn = gpt_attn.data_ptr()
         _capi.check(self.lib.afft_forward(self.handle, B, C.byref(io), _capi.current_stream_ptr(dev)), self.handle)
-        return orig_past, pf, logits, attn
+        return (orig_past, pf, logits, attn, gpt_attn) if want_gpt_attn else (orig_past, pf, logits, attn)
 
     def forward_fuser(self, feats: List[torch.Tensor], want_attn: bool = True):
         """AFFT_STAGE_FUSER handle: (fused (B, T, D), attention or None)."""
@@ -164,8 +169,8 @@ class Engine:
         _capi.check(self.lib.afft_forward(self.handle, B, C.byref(io), _capi.current_stream_ptr(dev)), self.handle)
         return fused, attn
 
-    def forward_gpt(self, feats: torch.Tensor):
-        """AFFT_STAGE_GPT handle: feats (B, T, G) fp32 -> hidden states (B, T + O - 1, G)."""
+    def forward_gpt(self, feats: torch.Tensor, want_attn: bool = False):
+        """AFFT_STAGE_GPT handle: feats (B, T, G) fp32 -> (hidden states (B, T + O - 1, G), attention (B, layers, H, T, T) or None)."""
         B, T, G, dev, O = feats.shape[0], self.T, self.gpt_dim, self.device, self.fp_output_len
         if feats.device != dev or feats.dtype != torch.float32 or not feats.is_contiguous() or tuple(feats.shape) != (B, T, G):
             raise _capi.AfftError(f"predictor input must be a contiguous fp32 (B, {T}, {G}) tensor on the engine's device")
@@ -173,12 +178,16 @@ class Engine:
         io.feat[0] = feats.data_ptr()
         prompt = torch.empty(B, T, G, device=dev, dtype=torch.float32)
         io.orig_past = prompt.data_ptr()
+        gpt_attn = None
+        if want_attn:
+            gpt_attn = torch.empty(B, self.gpt_layers, self.gpt_heads, T, T, device=dev, dtype=torch.float32)
+            io.gpt_attn = gpt_attn.data_ptr()
         new = None
         if O > 1:
             new = torch.empty(B, O - 1, G, device=dev, dtype=torch.float32)
             io.past_futures = new.data_ptr()
         _capi.check(self.lib.afft_forward(self.handle, B, C.byref(io), _capi.current_stream_ptr(dev)), self.handle)
-        return prompt if new is None else torch.cat([prompt, new], dim=1)
+        return (prompt if new is None else torch.cat([prompt, new], dim=1)), gpt_attn
 
     def forward_into(self, io: "_capi.IO", B: int):
         """Lowest-overhead call for benchmarking: caller pre-fills the io struct with persistent buffers."""

@@ -133,8 +133,6 @@ class BaseFuturePredictor(nn.Module):
         super().__init__()
         if dimension_mapping:
             raise NotImplementedError("dimension_mapping inside GPT-2 is deprecated in the reference and not supported")
-        if output_attentions:
-            raise NotImplementedError("fp_output_attentions=true (visualisation only) is not supported")
         self.in_features = in_features
         self.output_attentions = output_attentions
         self.encoder = nn.Identity()
@@ -171,7 +169,11 @@ class BaseFuturePredictor(nn.Module):
                          fp_output_len=int(output_len), stages=_capi.STAGE_GPT)
             engines[key] = eng
         eng.sync_weights({"future_predictor." + n: p for n, p in self.named_parameters()})
-        return eng.forward_gpt(feats.to(torch.float32).contiguous()), {}
+        if self.output_attentions and output_len != 1:
+            raise NotImplementedError("output_attentions with output_len > 1: the single-query roll-out kernel does not keep its probabilities")
+        hidden, att = eng.forward_gpt(feats.to(torch.float32).contiguous(), want_attn=bool(self.output_attentions))
+        # reference :403-409: {'gpt2_att_<output_id>': (B, n_layer, n_head, T, T)} when output_attentions is set
+        return hidden, ({"gpt2_att_0": att} if att is not None else {})
 
 
 # ------------------------------------------------------------------------------------------------
@@ -212,10 +214,11 @@ class CMFPEarly(nn.Module):
         for mod, dim in self.modality_dims.items():  # reference :47-54
             self.mapping[mod] = instantiate(cfg_get(model_cfg, "mapping"), in_features=dim, out_features=self.latent_dim)
         self.fuser = instantiate(cfg_get(model_cfg, "fuser"))  # reference :74-76
-        if self.latent_dim == self.fp_inter_dim:
-            raise NotImplementedError("common_dim == fp_inter_dim (Identity dim_encoder) is not supported")
-        self.dim_encoder = nn.Linear(self.latent_dim, self.fp_inter_dim, bias=False)  # reference :245-255
-        self.dim_decoder = nn.Linear(self.fp_inter_dim, self.latent_dim, bias=False)
+        if self.latent_dim != self.fp_inter_dim:  # reference :245-255 (Identity when the widths match)
+            self.dim_encoder = nn.Linear(self.latent_dim, self.fp_inter_dim, bias=False)
+            self.dim_decoder = nn.Linear(self.fp_inter_dim, self.latent_dim, bias=False)
+        else:
+            self.dim_encoder, self.dim_decoder = nn.Identity(), nn.Identity()
         self.future_predictor = instantiate(cfg_get(model_cfg, "future_predictor"), in_features=self.fp_inter_dim,
                                             dimension_mapping=False)  # reference :84-87
         self.classifiers = nn.ModuleDict()  # reference :97-122 (shared classifier, fusion_cls only)
@@ -306,7 +309,12 @@ class CMFPEarly(nn.Module):
                 self.mapping[m].precision = self.precision
                 x = self.mapping[m](x).contiguous()
             xs.append(x)
-        z, pf, logits, attn = eng.forward(xs, want_attn=self.return_attentions)
+        want_t = bool(getattr(self.future_predictor, "output_attentions", False))
+        if want_t and self.fp_output_len != 1:
+            raise NotImplementedError("fp_output_attentions with fp_output_len > 1: the single-query roll-out kernel does not keep its probabilities")
+        res = eng.forward(xs, want_attn=self.return_attentions, want_gpt_attn=want_t)
+        z, pf, logits, attn = res[:4]
+        temporal = {"gpt2_att_0": res[4]} if want_t else {}  # reference future_prediction.py:403-409
 
         out = {  # reference prepare_output :155-182 (views into the native output buffers)
             'orig_past': {'all-fused': z},
@@ -319,7 +327,7 @@ class CMFPEarly(nn.Module):
             out[f'logits/{cls}'] = {'all-fused': logits[k][:, T:, :c]}
         if attn is None:
             attn = torch.zeros(B)  # CA-Fuser's dummy attention (reference fusion.py:269)
-        out['attentions'] = {'all-fused': {'modality_attns': attn, 'temporal_attns': {}}}
+        out['attentions'] = {'all-fused': {'modality_attns': attn, 'temporal_attns': temporal}}
         return out
 
     def last_launch_count(self) -> int:

@@ -549,7 +549,8 @@ def forward_train(fp, feats: Dict[str, torch.Tensor]) -> Dict[str, Dict[str, tor
 
     gpt = fp.future_predictor.gpt_model
     G, H2 = gpt.n_embd, gpt.n_head
-    g = _linear(z.reshape(B * T, D), fp.dim_encoder).view(B, T, G) + gpt.wpe.weight[:T]
+    identity = isinstance(fp.dim_encoder, torch.nn.Identity)  # common_dim == fp_inter_dim (future_prediction.py:245-255)
+    g = (z if identity else _linear(z.reshape(B * T, D), fp.dim_encoder).view(B, T, G)) + gpt.wpe.weight[:T]
     g = F.dropout(g, gpt.drop.p, training).reshape(B * T, G)
     for blk in gpt.h:  # transformers GPT2Block
         y = _ln(g, blk.ln_1)
@@ -560,7 +561,7 @@ def forward_train(fp, feats: Dict[str, torch.Tensor]) -> Dict[str, Dict[str, tor
         f = GeluFn.apply(_linear(y, blk.mlp.c_fc, conv1d=True), _capi.ACT_GELU_TANH)
         g = g + F.dropout(_linear(f, blk.mlp.c_proj, conv1d=True), blk.mlp.dropout.p, training)
     g = _ln(g, gpt.ln_f)
-    z_hat = _linear(g, fp.dim_decoder).view(B, T, D)
+    z_hat = (g if identity else _linear(g, fp.dim_decoder)).view(B, T, D)
 
     past_futures = torch.cat([z[:, :1], z_hat[:, :T - 1]], dim=1)  # models/future_prediction.py:172-176
     future = z_hat[:, T - 1:]
@@ -578,7 +579,7 @@ def forward_train(fp, feats: Dict[str, torch.Tensor]) -> Dict[str, Dict[str, tor
 def grad_groups(fp) -> list:
     """Parameter groups of a CMFPEarly head in the order the backward pass finishes them (last layers first): the bucket
     layout of ``afft_b200.dist.GradBuckets`` (reference train.py:366-368 leaves this to DistributedDataParallel)."""
-    groups = [[p for cls in fp.classifiers.values() for p in cls.parameters()] + list(fp.dim_decoder.parameters())]
+    groups = [[p for cls in fp.classifiers.values() for p in cls.parameters()] + list(fp.dim_decoder.parameters())]  # Identity: none
     gpt = fp.future_predictor.gpt_model
     groups[0] += list(gpt.ln_f.parameters())
     for blk in reversed(gpt.h):

@@ -302,6 +302,9 @@ typedef struct afft_io {
   float* logits[AFFT_MAX_CLS];      /* [B, T+O, ld_logits] slots 0..T-1 = past_logits, T.. = logits */
   int64_t ld_logits[AFFT_MAX_CLS];  /* row pitch in floats, multiple of 4, >= cls_dim            */
   float* fuser_attn;                /* SA: [B, depth, T, H, n, n]; T-SA: [B, depth, H, nT, nT]; NULL = skip */
+  float* gpt_attn;                  /* fp_output_attentions (models/future_prediction.py:403-409, 'gpt2_att_0'): the GPT-2
+                                       attention probabilities of the T prompt positions [B, gpt_layers, gpt_heads, T, T];
+                                       NULL = skip */
 } afft_io;
 
 /* One forward of CMFPEarly.forward (models/future_prediction.py:257-291) for B <= max_batch clips. */

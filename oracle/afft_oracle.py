@@ -263,8 +263,11 @@ def _ca_fuser(feats: List[torch.Tensor], w: _W, fcfg):
 # ------------------------------------------------------------------------------------------------
 # GPT-2 (transformers GPT2Model, restated)
 # ------------------------------------------------------------------------------------------------
-def _gpt2_once(emb, w: _W, n_layer, n_head):
-    """GPT2Model on input embeddings that already include the position embeddings."""
+def _gpt2_once(emb, w: _W, n_layer, n_head, probs_out=None):
+    """GPT2Model on input embeddings that already include the position embeddings.  probs_out (a list) receives the
+    attention probabilities of every layer, (B, H, T, T) each - what `output_attentions=True` returns from
+    transformers' eager GPT-2 attention (modeling_gpt2.py: softmax of the masked, scaled scores, before attn_dropout,
+    which is the identity in eval mode)."""
     B, T, G = emb.shape
     h = emb
     mask = _causal_mask(T, emb.dtype)
@@ -275,7 +278,10 @@ def _gpt2_once(emb, w: _W, n_layer, n_head):
         q, k, v = qkv.split(G, dim=2)
         q, k, v = _heads(q, n_head), _heads(k, n_head), _heads(v, n_head)
         s = (q @ k.transpose(-1, -2)) / math.sqrt(G // n_head) + mask
-        a = _merge(_softmax(s) @ v)
+        p = _softmax(s)
+        if probs_out is not None:
+            probs_out.append(p)
+        a = _merge(p @ v)
         h = h + _conv1d(a, wl("attn.c_proj.weight"), wl("attn.c_proj.bias"))
         y = _ln(h, wl("ln_2.weight"), wl("ln_2.bias"), 1e-5)
         h = h + _conv1d(_gelu_new(_conv1d(y, wl("mlp.c_fc.weight"), wl("mlp.c_fc.bias"))), wl("mlp.c_proj.weight"),
@@ -283,7 +289,7 @@ def _gpt2_once(emb, w: _W, n_layer, n_head):
     return _ln(h, w("ln_f.weight"), w("ln_f.bias"), 1e-5)
 
 
-def _gpt2(x, w: _W, n_layer, n_head, output_len=1):
+def _gpt2(x, w: _W, n_layer, n_head, output_len=1, probs_out=None):
     """BaseFuturePredictor.forward (future_prediction.py:387-415).  output_len > 1: the last hidden state is fed
     back as the next input embedding at position T + k - 1 (:398-412).  The reference runs that single position
     against its KV cache; because attention is causal that equals re-running the extended sequence, which is
@@ -291,7 +297,7 @@ def _gpt2(x, w: _W, n_layer, n_head, output_len=1):
     B, T, G = x.shape
     wpe = w("wpe.weight")
     emb = x + wpe[:T]
-    hidden = _gpt2_once(emb, w, n_layer, n_head)
+    hidden = _gpt2_once(emb, w, n_layer, n_head, probs_out)
     outs = [hidden]
     for k in range(1, output_len):
         emb = torch.cat([emb, hidden[:, -1:] + wpe[T + k - 1]], dim=1)
@@ -434,8 +440,13 @@ def forward(state_dict: Dict[str, torch.Tensor], cfg: Dict, num_classes: Dict[st
     enc = w("dim_encoder.weight", optional=True)
     dec = w("dim_decoder.weight", optional=True)
     z_enc = z if enc is None else _linear(z, enc)  # future_prediction.py:267
+    # fp_output_attentions (future_prediction.py:403-409): {'gpt2_att_0': (B, n_layer, n_head, T, T)}.  PARITY UNPINNED for
+    # this one output: transformers 5.5 (installed) runs GPT-2 attention through SDPA and returns no probabilities - the
+    # reference module itself fails at :409 here - so this restates the eager attention of the pinned 4.18.
+    want_t = bool(cfg.get("future_predictor", {}).get("output_attentions", False))
+    t_probs = [] if want_t else None
     g = _gpt2(z_enc, w.sub("future_predictor.gpt_model."), cfg["common"]["fp_layers"], cfg["common"]["fp_heads"],
-              cfg["common"].get("fp_output_len", 1))
+              cfg["common"].get("fp_output_len", 1), t_probs)
     z_hat = g if dec is None else _linear(g, dec)  # future_prediction.py:269
 
     out = {  # prepare_output, future_prediction.py:155-182
@@ -448,7 +459,8 @@ def forward(state_dict: Dict[str, torch.Tensor], cfg: Dict, num_classes: Dict[st
         for c in num_classes:  # apply_classifier, future_prediction.py:144-153 (Dropout is identity in eval)
             out[f"{prefix}logits/{c}"] = {"all-fused": _linear(src, w(f"classifiers.{c}.all-fused.1.weight"),
                                                                w(f"classifiers.{c}.all-fused.1.bias"))}
-    out["attentions"] = {"all-fused": {"modality_attns": mattn, "temporal_attns": {}}}
+    temporal = {"gpt2_att_0": torch.stack(t_probs).transpose(0, 1)} if want_t else {}
+    out["attentions"] = {"all-fused": {"modality_attns": mattn, "temporal_attns": temporal}}
     return out
 
 

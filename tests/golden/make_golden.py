@@ -56,6 +56,8 @@ CASES_OPT = [
     ("ek100_sa_modenc_flt_b2", "ek100_sa_modenc_flt", 2, 123, "randn"),
     ("ek100_sa_cross_attn_b2", "ek100_sa_cross_attn", 2, 123, "randn"),
     ("ek100_tsa_mean_b2", "ek100_tsa_mean", 2, 123, "randn"),
+    ("ek100_sa_identity_enc_b2", "ek100_sa_identity_enc", 2, 123, "randn"),
+    ("egtea_sa_identity_rollout3_b3", "egtea_sa_identity_rollout3", 3, 123, "randn"),
 ]
 
 

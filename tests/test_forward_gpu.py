@@ -93,7 +93,8 @@ def test_golden_parity(case, precision, golden_dir, golden_cases):
 CASES_N3 = ["ek100_individual_b2", "ek100_matt_b2", "ek100_sa_gatedlinear_b2", "ek100_sa_nonlinear_b2",
             "ek100_sa_linear_ln_b2"]
 # three classifier heads; SA-Fuser modal_encoding + frame_level_token; cross_attn=True; T-SA without frame-level token
-CASES_OPT = ["ek100_sa_3head_b2", "ek100_sa_modenc_flt_b2", "ek100_sa_cross_attn_b2", "ek100_tsa_mean_b2"]
+CASES_OPT = ["ek100_sa_3head_b2", "ek100_sa_modenc_flt_b2", "ek100_sa_cross_attn_b2", "ek100_tsa_mean_b2",
+             "ek100_sa_identity_enc_b2", "egtea_sa_identity_rollout3_b3"]  # + common_dim == fp_inter_dim (Identity dim_encoder)
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -479,3 +480,36 @@ def test_dataparallel_dropin_keeps_packed_weights():
         model.future_predictor.classifiers["action"]["all-fused"][1].bias.add_(1.0)
         out2, _ = dp({m: t.cuda() for m, t in feats.items()}, **KW)
     assert torch.allclose(out2["logits/action"]["all-fused"], out["logits/action"]["all-fused"] + 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_fp_output_attentions(precision):
+    """model.common.fp_output_attentions / future_predictor.output_attentions (models/future_prediction.py:403-409): the
+    GPT-2 attention probabilities come back as attentions['all-fused']['temporal_attns']['gpt2_att_0'] (B, layers, heads,
+    T, T), against the oracle's restatement of transformers' eager attention; roll-out + attentions raises."""
+    from oracle import afft_oracle
+    cfg, T, ncls, _ = configs.named_config("egtea_sa")
+    cfg["common"]["fp_output_attentions"] = True
+    cfg["future_predictor"]["output_attentions"] = True
+    model = BaseModel(cfg, ncls, {}, precision=precision)
+    sd = synthetic.synthetic_state_dict(model, seed=0)
+    model.load_state_dict(sd)
+    model = model.to("cuda:0").eval()
+    B = 3
+    feats = synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=8)
+    out = _run(model, feats)
+    att = out["attentions"]["all-fused"]["temporal_attns"]["gpt2_att_0"]
+    ref = afft_oracle.forward({k: v for k, v in sd.items()}, cfg, ncls, feats, dtype=torch.float32)
+    rat = ref["attentions"]["all-fused"]["temporal_attns"]["gpt2_att_0"]
+    assert att.shape == rat.shape == (B, 2, 4, T, T)
+    assert (att.cpu() - rat).abs().max().item() < TOL[precision]["attn"]
+    assert (att.sum(-1) - 1).abs().max().item() < 1e-5
+    assert torch.equal(att.triu(1), torch.zeros_like(att))  # causal
+    assert (out["logits/action"]["all-fused"].cpu() - ref["logits/action"]["all-fused"]).abs().max().item() < TOL[precision]["logits"]
+    # the standalone predictor seam returns them the same way
+    pred = model.future_predictor.future_predictor
+    with torch.no_grad():
+        _, extra = pred(torch.randn(B, T, 2048, device="cuda:0"), 1)
+    assert extra["gpt2_att_0"].shape == (B, 2, 4, T, T)
+    with pytest.raises(NotImplementedError):
+        pred(torch.randn(B, T, 2048, device="cuda:0"), 2)

@@ -12,7 +12,8 @@ from afft_b200.models import future_prediction as fp
 
 
 N3_CONFIGS = ["ek100_individual", "ek100_matt", "ek100_sa_gatedlinear", "ek100_sa_nonlinear", "ek100_sa_linear_ln",
-              "ek100_sa_3head", "ek100_sa_modenc_flt", "ek100_sa_cross_attn", "ek100_tsa_mean"]
+              "ek100_sa_3head", "ek100_sa_modenc_flt", "ek100_sa_cross_attn", "ek100_tsa_mean", "ek100_sa_identity_enc",
+              "egtea_sa_identity_rollout3"]
 
 
 @pytest.mark.parametrize("name", configs.CONFIG_NAMES + N3_CONFIGS)

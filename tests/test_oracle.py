@@ -60,7 +60,8 @@ CASES_N3 = ["ek100_individual_b2", "ek100_matt_b2", "ek100_sa_gatedlinear_b2", "
             "ek100_sa_linear_ln_b2"]
 # constructor options no shipped experiment switches on: three heads, SA modal_encoding + frame_level_token,
 # cross_attn=True, T-SA without frame-level token (same fixture layout + the fuser's attention probabilities)
-CASES_OPT = ["ek100_sa_3head_b2", "ek100_sa_modenc_flt_b2", "ek100_sa_cross_attn_b2", "ek100_tsa_mean_b2"]
+CASES_OPT = ["ek100_sa_3head_b2", "ek100_sa_modenc_flt_b2", "ek100_sa_cross_attn_b2", "ek100_tsa_mean_b2",
+             "ek100_sa_identity_enc_b2", "egtea_sa_identity_rollout3_b3"]  # + Identity dim_encoder / dim_decoder (+ roll-out)
 
 
 @pytest.mark.parametrize("case", CASES_N3 + CASES_OPT)
