@@ -113,8 +113,10 @@ namespace {
 
 // The T frame ids (30-fps numbering) the model sees for one clip, in model order; false = reader_fns.py:122 assertion.
 // Every operation mirrors the reference's float64 / Python-int arithmetic in the same order.
+// AFFT_SAMPLE_RANDOM: rand_start_frame / rand_offset are the two numbers the reference draws per (clip, modality) call
+// (base_video_dataset.py:246-248 rng.integers, :283-286 random.random()); the caller supplies them.
 bool clip_frames(double start, double end, double fps, int T, double frame_rate, int strategy, std::vector<long long>* out,
-                 std::vector<long long>* window_scratch) {
+                 std::vector<long long>* window_scratch, long long rand_start_frame = 0, long long rand_offset = 0) {
   start = std::max(start, 0.0);                                         // base_video_dataset.py:236-237
   end = std::max(end, 0.0);
   const double req_fps = frame_rate > 0 ? frame_rate : fps;            // :238-240
@@ -126,6 +128,8 @@ bool clip_frames(double start, double end, double fps, int T, double frame_rate,
     start_frame = d > 0 ? d / 2 : 0;
   } else if (strategy == AFFT_SAMPLE_LAST) {
     start_frame = std::max(nframes - frames_to_ext, 0LL);
+  } else if (strategy == AFFT_SAMPLE_RANDOM) {
+    start_frame = rand_start_frame;                                     // :246-248 (drawn in [0, max(nframes - frames_to_ext, 0)))
   } else {
     start_frame = 0;
   }
@@ -145,15 +149,19 @@ bool clip_frames(double start, double end, double fps, int T, double frame_rate,
   const long long n = static_cast<long long>(w.size());
   const long long step = std::max(round_half_even(fps / req_fps), 1LL);
   std::vector<long long> keep;
-  if (strategy == AFFT_SAMPLE_LAST) {
+  const bool from_back = (strategy == AFFT_SAMPLE_LAST || strategy == AFFT_SAMPLE_RANDOM);
+  if (from_back) {
     for (long long i = n - 1; i >= 0; i -= step) keep.push_back(i);
     std::reverse(keep.begin(), keep.end());
+    if (strategy == AFFT_SAMPLE_RANDOM)                                  // :283-287
+      for (auto& i : keep)
+        if (i - rand_offset > 0) i -= rand_offset;
   } else {
     for (long long i = 0; i < n; i += step) keep.push_back(i);
   }
   out->clear();
   const long long have = static_cast<long long>(keep.size());
-  if (strategy == AFFT_SAMPLE_LAST) {
+  if (from_back) {
     for (long long i = 0; i < T - have; ++i) out->push_back(w[keep.front()]);
     for (long long i = std::max(have - T, 0LL); i < have; ++i) out->push_back(w[keep[i]]);
   } else {
@@ -180,14 +188,17 @@ extern "C" int afft_store_allow_empty_clips(afft_feature_store* s, int32_t allow
   return AFFT_OK;
 }
 
-extern "C" int afft_store_plan(afft_feature_store* s, int32_t B, const char* const* video_names, const double* start_sec,
-                               const double* end_sec, double fps, int32_t T, double frame_rate, int32_t strategy,
-                               int32_t* row_idx, int32_t* frame_ids_out) {
+static int store_plan_impl(afft_feature_store* s, int32_t B, const char* const* video_names, const double* start_sec,
+                           const double* end_sec, double fps, int32_t T, double frame_rate, int32_t strategy,
+                           const int64_t* rand_start_frame, const int32_t* rand_offset, int32_t* row_idx, int32_t* frame_ids_out) {
   if (s == nullptr) return sfail(nullptr, AFFT_ERR_INVALID, "store_plan: null store");
   if (B < 0 || T < 1 || video_names == nullptr || start_sec == nullptr || end_sec == nullptr || row_idx == nullptr || !(fps > 0))
     return sfail(s, AFFT_ERR_INVALID, "store_plan: bad arguments");
-  if (strategy != AFFT_SAMPLE_LAST && strategy != AFFT_SAMPLE_CENTER && strategy != AFFT_SAMPLE_FIRST)
+  const bool random = (strategy == AFFT_SAMPLE_RANDOM);
+  if (strategy != AFFT_SAMPLE_LAST && strategy != AFFT_SAMPLE_CENTER && strategy != AFFT_SAMPLE_FIRST && !random)
     return sfail(s, AFFT_ERR_INVALID, "store_plan: unknown sampling strategy");
+  if (random && (rand_start_frame == nullptr || rand_offset == nullptr))
+    return sfail(s, AFFT_ERR_INVALID, "store_plan: AFFT_SAMPLE_RANDOM needs the drawn start frames and offsets (afft_store_plan_random)");
   const int n_mod = static_cast<int>(s->mods.size());
   const int n_threads = B >= 64 ? static_cast<int>(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()))) : 1;
   std::vector<std::string> errs(n_threads);
@@ -196,11 +207,21 @@ extern "C" int afft_store_plan(afft_feature_store* s, int32_t B, const char* con
     for (int b = tid; b < B; b += n_threads) {
       if (video_names[b] == nullptr) { errs[tid] = "store_plan: null video name"; return; }
       const std::string name(video_names[b]);
-      if (!clip_frames(start_sec[b], end_sec[b], fps, T, frame_rate, strategy, &frames, &window)) {
+      if (!random && !clip_frames(start_sec[b], end_sec[b], fps, T, frame_rate, strategy, &frames, &window)) {
         errs[tid] = "store_plan: clip " + std::to_string(b) + " (" + name + ") has no frame id >= 1 in its window (reader_fns.py:122)";
         return;
       }
       for (int m = 0; m < n_mod; ++m) {
+        // random_clip: the reference calls _sample once per modality, each call with its own two draws
+        if (random) {
+          const size_t di = static_cast<size_t>(m) * B + b;
+          if (rand_start_frame[di] < 0 || rand_offset[di] < 0) { errs[tid] = "store_plan: negative random draw"; return; }
+          if (!clip_frames(start_sec[b], end_sec[b], fps, T, frame_rate, strategy, &frames, &window, rand_start_frame[di],
+                           rand_offset[di])) {
+            errs[tid] = "store_plan: clip " + std::to_string(b) + " (" + name + ") has no frame id >= 1 in its window (reader_fns.py:122)";
+            return;
+          }
+        }
         const Modality& mod = s->mods[m];
         auto vit = mod.videos.find(name);
         if (vit == mod.videos.end()) { errs[tid] = "store_plan: video " + name + " is not in modality " + std::to_string(m); return; }
@@ -245,6 +266,22 @@ extern "C" int afft_store_plan(afft_feature_store* s, int32_t B, const char* con
   for (auto& e : errs)
     if (!e.empty()) return sfail(s, AFFT_ERR_INVALID, e);
   return AFFT_OK;
+}
+
+extern "C" int afft_store_plan(afft_feature_store* s, int32_t B, const char* const* video_names, const double* start_sec,
+                               const double* end_sec, double fps, int32_t T, double frame_rate, int32_t strategy,
+                               int32_t* row_idx, int32_t* frame_ids_out) {
+  if (strategy == AFFT_SAMPLE_RANDOM)
+    return sfail(s, AFFT_ERR_INVALID, "store_plan: AFFT_SAMPLE_RANDOM needs the drawn numbers: use afft_store_plan_random");
+  return store_plan_impl(s, B, video_names, start_sec, end_sec, fps, T, frame_rate, strategy, nullptr, nullptr, row_idx, frame_ids_out);
+}
+
+extern "C" int afft_store_plan_random(afft_feature_store* s, int32_t B, const char* const* video_names, const double* start_sec,
+                                      const double* end_sec, double fps, int32_t T, double frame_rate,
+                                      const int64_t* rand_start_frame, const int32_t* rand_offset, int32_t* row_idx,
+                                      int32_t* frame_ids_out) {
+  return store_plan_impl(s, B, video_names, start_sec, end_sec, fps, T, frame_rate, AFFT_SAMPLE_RANDOM, rand_start_frame,
+                         rand_offset, row_idx, frame_ids_out);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -19,9 +19,33 @@ import torch
 
 from . import _capi
 
-SAMPLE_STRATEGIES = {"last_clip": 0, "center_clip": 1, "first_clip": 2}  # base_video_dataset.py:28-31
+SAMPLE_STRATEGIES = {"last_clip": 0, "center_clip": 1, "first_clip": 2, "random_clip": 3}  # base_video_dataset.py:28-31
 STAGING_SYMBOLS = ["afft_store_create", "afft_store_destroy", "afft_store_error", "afft_store_add_video",
-                   "afft_store_set_rows", "afft_store_plan", "afft_store_gather", "afft_store_allow_empty_clips"]
+                   "afft_store_set_rows", "afft_store_plan", "afft_store_plan_random", "afft_store_gather",
+                   "afft_store_allow_empty_clips"]
+
+
+def random_clip_draws(start_sec, end_sec, fps: float, T: int, frame_rate: Optional[float], n_mod: int, rng, pyrandom=None):
+    """The random numbers of sample_strategy='random_clip' for a batch, drawn exactly as the reference draws them
+    (datasets/base_video_dataset.py:236-248,283-286): clip by clip, and within a clip once per modality (``_get_video``
+    calls ``_sample`` per modality, :369-373) - first ``rng.integers(bound)`` from the dataset's numpy Generator when the
+    window is longer than the clip, then ``random.random()`` from Python's global generator.  Returns
+    (start_frame int64 [n_mod, B], offset int32 [n_mod, B])."""
+    import random as _random
+    pyrandom = pyrandom if pyrandom is not None else _random
+    B = len(start_sec)
+    sf = np.zeros((n_mod, B), dtype=np.int64)
+    off = np.zeros((n_mod, B), dtype=np.int32)
+    req_fps = fps if not frame_rate else frame_rate
+    frames_to_ext = int(round(T * (fps / req_fps)))
+    shift = max(int(round(fps / req_fps / 3)), 1)
+    for b in range(B):
+        start, end = max(float(start_sec[b]), 0), max(float(end_sec[b]), 0)
+        bound = max(int(fps * (end - start)) - frames_to_ext, 0)
+        for m in range(n_mod):
+            sf[m, b] = int(rng.integers(bound)) if bound > 0 else 0
+            off[m, b] = int(round(pyrandom.random() * shift))
+    return sf, off
 _KEY_RE = re.compile(r"^(.*)_frame_(\d{10})\.jpg$")  # reader_fns.py:133
 
 
@@ -39,6 +63,9 @@ def _lib():
                                       C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]
         l.afft_store_gather.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
         l.afft_store_allow_empty_clips.argtypes = [C.c_void_p, C.c_int32]
+        l.afft_store_plan_random.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_double,
+                                             C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.afft_store_plan_random.restype = C.c_int
         for n in ("afft_store_create", "afft_store_add_video", "afft_store_set_rows", "afft_store_plan", "afft_store_gather",
                   "afft_store_allow_empty_clips"):
             getattr(l, n).restype = C.c_int
@@ -156,10 +183,13 @@ class FeatureStore:
 
     def plan(self, video_names: Sequence[str], start_sec: Sequence[float], end_sec: Sequence[float], fps: float, T: int,
              frame_rate: Optional[float], strategy: str = "last_clip", out: Optional[torch.Tensor] = None,
-             want_frame_ids: bool = False, allow_empty: bool = False):
+             want_frame_ids: bool = False, allow_empty: bool = False, rng=None, pyrandom=None):
         """Row numbers ``int32 [n_mod, B, T]`` (-1 = zero row) of a batch; host arithmetic only.  A clip without any
         stored frame in its window raises, like the reference reader's assertion (reader_fns.py:97), unless
-        ``allow_empty`` (the clip is then T zero rows)."""
+        ``allow_empty`` (the clip is then T zero rows).  strategy='random_clip' (training-time jitter,
+        base_video_dataset.py:245-248,282-287) needs ``rng`` - the numpy Generator the reference dataset owns
+        (``np.random.default_rng(seed)``, :155) - and draws from Python's global ``random`` (or ``pyrandom``) as the
+        reference does: same seeds, same clips, same rows."""
         B = len(video_names)
         if bool(allow_empty) != getattr(self, "_allow_empty", False):
             self._check(self.lib.afft_store_allow_empty_clips(self.handle, int(bool(allow_empty))))
@@ -170,6 +200,14 @@ class FeatureStore:
         idx = out if out is not None else torch.empty(len(self.mods), B, T, dtype=torch.int32)
         assert idx.dtype == torch.int32 and idx.is_contiguous() and idx.numel() >= len(self.mods) * B * T and not idx.is_cuda
         fids = torch.empty(len(self.mods), B, T, dtype=torch.int32) if want_frame_ids else None
+        if strategy == "random_clip":
+            if rng is None:
+                raise ValueError("strategy='random_clip' needs the numpy Generator to draw from (rng=np.random.default_rng(seed))")
+            sf, off = random_clip_draws(st, en, float(fps), int(T), frame_rate, len(self.mods), rng, pyrandom)
+            self._check(self.lib.afft_store_plan_random(self.handle, B, names, st.ctypes.data, en.ctypes.data, float(fps), int(T),
+                                                        float(frame_rate) if frame_rate else 0.0, sf.ctypes.data, off.ctypes.data,
+                                                        idx.data_ptr(), fids.data_ptr() if fids is not None else None))
+            return (idx, fids) if want_frame_ids else idx
         self._check(self.lib.afft_store_plan(self.handle, B, names, st.ctypes.data, en.ctypes.data, float(fps), int(T),
                                              float(frame_rate) if frame_rate else 0.0, SAMPLE_STRATEGIES[strategy],
                                              idx.data_ptr(), fids.data_ptr() if fids is not None else None))
@@ -186,8 +224,11 @@ class FeatureStager:
     be in flight."""
 
     def __init__(self, store: FeatureStore, T: int, max_batch: int, device="cuda:0", depth: int = 2, fps: float = 30.0,
-                 frame_rate: Optional[float] = 4.0, strategy: str = "last_clip"):
+                 frame_rate: Optional[float] = 4.0, strategy: str = "last_clip", rng=None, pyrandom=None):
+        """rng / pyrandom: the generators 'random_clip' draws from (the dataset's ``np.random.default_rng(seed)`` and Python's
+        ``random`` module by default), see FeatureStore.plan."""
         self.store, self.T, self.max_batch = store, T, max_batch
+        self.rng, self.pyrandom = rng, pyrandom
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _capi.AfftError("FeatureStager gathers on the GPU; there is no CPU path")
@@ -214,7 +255,8 @@ class FeatureStager:
         self.events[k].synchronize()  # the slot's previous gather has finished reading plan_dev / the consumer was ordered after it
         n_mod, T = len(self.store.mods), self.T
         ph = self.plan_host[k].view(-1)[:n_mod * B * T].view(n_mod, B, T)
-        self.store.plan(video_names, start_sec, end_sec, self.fps, T, self.frame_rate, self.strategy, out=ph)
+        self.store.plan(video_names, start_sec, end_sec, self.fps, T, self.frame_rate, self.strategy, out=ph, rng=self.rng,
+                        pyrandom=self.pyrandom)
         stream = stream or self.stream
         if self.consumed[k] is not None:
             stream.wait_event(self.consumed[k])  # the forward that read this slot's tensors

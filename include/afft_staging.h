@@ -32,7 +32,7 @@ extern "C" {
 typedef struct afft_feature_store afft_feature_store;
 
 /* base_video_dataset.py:28-31 (SAMPLE_STRAT_*).  'random_clip' draws from process-global RNGs and is not offered. */
-enum { AFFT_SAMPLE_LAST = 0, AFFT_SAMPLE_CENTER = 1, AFFT_SAMPLE_FIRST = 2 };
+enum { AFFT_SAMPLE_LAST = 0, AFFT_SAMPLE_CENTER = 1, AFFT_SAMPLE_FIRST = 2, AFFT_SAMPLE_RANDOM = 3 };
 
 /* n_mod modalities of row width widths[m]; orig_fps_index[m] != 0: the modality's frames are numbered in the ORIGINAL
  * video's frame rate (audio / poses LMDBs, reader_fns.py:131-133), 50 fps for EK100 names (3-digit suffix) and
@@ -65,6 +65,16 @@ AFFT_API int afft_store_allow_empty_clips(afft_feature_store* s, int32_t allow);
 AFFT_API int afft_store_plan(afft_feature_store* s, int32_t B, const char* const* video_names, const double* start_sec,
                              const double* end_sec, double fps, int32_t T, double frame_rate /* <= 0: the video's fps */,
                              int32_t strategy, int32_t* row_idx, int32_t* frame_ids_out);
+
+/* sample_strategy = random_clip (datasets/base_video_dataset.py:245-248,282-287): the reference calls _sample once per
+ * (clip, modality) and draws two numbers per call - rng.integers(max(nframes - frames_to_ext, 0)) from its numpy Generator
+ * (only when that bound is positive) and random.random() from Python's global generator, turned into
+ * offset = round(random * max(round(fps / frame_rate / 3), 1)).  The caller makes those draws (afft_b200.staging does it in
+ * the reference's order) and passes them as rand_start_frame / rand_offset [n_mod, B]; everything else is afft_store_plan. */
+AFFT_API int afft_store_plan_random(afft_feature_store* s, int32_t B, const char* const* video_names, const double* start_sec,
+                                    const double* end_sec, double fps, int32_t T, double frame_rate,
+                                    const int64_t* rand_start_frame, const int32_t* rand_offset, int32_t* row_idx,
+                                    int32_t* frame_ids_out);
 
 /* Device gather: out[m] (B, T, widths[m]) fp32 device tensors, row_idx_dev the plan on the device (same layout).
  * One kernel launch per call (all modalities), enqueued on `stream`. */

@@ -26,7 +26,7 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-STRATEGIES = ("last_clip", "center_clip", "first_clip")  # base_video_dataset.py:28-31; 'random_clip' draws from global RNGs, not restated
+STRATEGIES = ("last_clip", "center_clip", "first_clip", "random_clip")  # base_video_dataset.py:28-31
 SEARCH_RADIUS = 10                          # reader_fns.py:76  range(10)
 
 
@@ -34,8 +34,27 @@ def _py_round(x: float) -> int:
     return int(round(x))  # Python 3 round(): half to even, like np.rint
 
 
-def window(start: float, end: float, fps: float, frames_per_clip: int, frame_rate: Optional[float], strategy: str):
-    """base_video_dataset.py:236-263 -> (new_start, new_end) in seconds."""
+def random_draws(start: float, end: float, fps: float, frames_per_clip: int, frame_rate: Optional[float], rng, pyrandom):
+    """The two random numbers ``_sample`` consumes for ONE (clip, modality) call with sample_strategy == 'random_clip', in
+    the reference's order: ``rng.integers(start_frame)`` (numpy Generator, only when the window is longer than the clip;
+    base_video_dataset.py:246-248) and, after the read, ``random.random()`` (Python's global generator, :283-286).
+    Returns (start_frame, offset)."""
+    start = max(start, 0)
+    end = max(end, 0)
+    req_fps = fps if frame_rate is None else frame_rate
+    nframes = int(fps * (end - start))
+    frames_to_ext = _py_round(frames_per_clip * (fps / req_fps))
+    start_frame = max(nframes - frames_to_ext, 0)
+    if start_frame > 0:
+        start_frame = int(rng.integers(start_frame))
+    shift = max(_py_round(fps / req_fps / 3), 1)  # "we select frame randomly from the 1/3 of the desired time zone"
+    offset = _py_round(pyrandom.random() * shift)
+    return start_frame, offset
+
+
+def window(start: float, end: float, fps: float, frames_per_clip: int, frame_rate: Optional[float], strategy: str,
+           rand_start_frame: Optional[int] = None):
+    """base_video_dataset.py:236-263 -> (new_start, new_end) in seconds.  'random_clip': rand_start_frame is the draw."""
     start = max(start, 0)
     end = max(end, 0)
     req_fps = fps if frame_rate is None else frame_rate
@@ -47,6 +66,9 @@ def window(start: float, end: float, fps: float, frames_per_clip: int, frame_rat
         start_frame = max(nframes - frames_to_ext, 0)
     elif strategy == "first_clip":
         start_frame = 0
+    elif strategy == "random_clip":
+        assert rand_start_frame is not None, "random_clip needs the drawn start frame (random_draws)"
+        start_frame = int(rand_start_frame)
     else:
         raise NotImplementedError(strategy)
     new_start = start + max(start_frame / fps, 0)
@@ -67,18 +89,24 @@ def window_frame_ids(new_start: float, new_end: float, fps: float) -> np.ndarray
     return frames
 
 
-def kept_positions(n: int, fps: float, frame_rate: Optional[float], frames_per_clip: int, strategy: str) -> List[int]:
-    """base_video_dataset.py:279-335: positions (into the window's frame list) the model finally sees, padded."""
+def kept_positions(n: int, fps: float, frame_rate: Optional[float], frames_per_clip: int, strategy: str,
+                   rand_offset: int = 0) -> List[int]:
+    """base_video_dataset.py:279-335: positions (into the window's frame list) the model finally sees, padded.
+    'random_clip' subsamples from the back like 'last_clip', shifts every kept position by the drawn offset where that
+    stays positive (:283-287), and pads / crops like 'last_clip' (:313-316,326-329)."""
     req_fps = fps if frame_rate is None else frame_rate
     step = max(_py_round(fps / req_fps), 1)
-    if strategy == "last_clip":
+    from_back = strategy in ("last_clip", "random_clip")
+    if from_back:
         keep = list(range(n))[::-step][::-1]
+        if strategy == "random_clip":
+            keep = [i - rand_offset if i - rand_offset > 0 else i for i in keep]
     else:
         keep = list(range(n))[::step]
     if len(keep) < frames_per_clip:
         npad = frames_per_clip - len(keep)
-        keep = [keep[0]] * npad + keep if strategy == "last_clip" else keep + [keep[-1]] * npad
-    return keep[-frames_per_clip:] if strategy == "last_clip" else keep[:frames_per_clip]
+        keep = [keep[0]] * npad + keep if from_back else keep + [keep[-1]] * npad
+    return keep[-frames_per_clip:] if from_back else keep[:frames_per_clip]
 
 
 def orig_video_fps(video_name: str) -> float:
@@ -92,14 +120,15 @@ def orig_video_fps(video_name: str) -> float:
 
 
 def clip_frame_ids(video_name: str, start: float, end: float, fps: float, frames_per_clip: int,
-                   frame_rate: Optional[float], strategy: str = "last_clip", orig_fps_index: bool = False) -> np.ndarray:
+                   frame_rate: Optional[float], strategy: str = "last_clip", orig_fps_index: bool = False,
+                   rand: Optional[Sequence[int]] = None) -> np.ndarray:
     """The T frame ids whose features form the clip, in model order.  ``orig_fps_index``: the store is keyed in the
-    original video's frame rate (audio, poses)."""
-    ns, ne = window(start, end, fps, frames_per_clip, frame_rate, strategy)
+    original video's frame rate (audio, poses).  ``rand``: (start_frame, offset) of ``random_draws`` for 'random_clip'."""
+    ns, ne = window(start, end, fps, frames_per_clip, frame_rate, strategy, rand[0] if rand is not None else None)
     frames = window_frame_ids(ns, ne, fps)
     if orig_fps_index:
         frames = np.rint(frames / fps * orig_video_fps(video_name)).astype(int)  # reader_fns.py:143-145
-    keep = kept_positions(len(frames), fps, frame_rate, frames_per_clip, strategy)
+    keep = kept_positions(len(frames), fps, frame_rate, frames_per_clip, strategy, rand[1] if rand is not None else 0)
     return frames[keep]
 
 

@@ -146,6 +146,47 @@ def main():
         keys = sorted(stores[mod])
         out[f"keys_{mod}"] = np.array(keys)
         out[f"rows_{mod}"] = np.stack([stores[mod][k] for k in keys])
+    # ---- sample_strategy = random_clip: the reference draws from a numpy Generator and from Python's global `random`, once
+    # per (clip, modality) call, clips in order and modalities within a clip (BaseVideoDataset._get_video :369-373).
+    # Both are seeded here; the oracle / native plan re-draw with the same seeds and must select the same rows.
+    import random as pyrandom
+    rcases = [c for c in cases if c[4] == "last_clip"][:40]
+    rcases = [(v, s - extra, e, T) for (v, s, e, T, _), extra in zip(rcases, np.random.default_rng(5).choice([0.0, 1.5, 4.0], 40))]
+    rng_ref = np.random.default_rng(77)
+    pyrandom.seed(77)
+    rfeat = {m: [] for m in MODS}
+    rvalid = np.ones(len(rcases), dtype=bool)
+    for ci, (v, s, e, T) in enumerate(rcases):
+        for mod in MODS:
+            try:
+                video, _, _, _, _, _ = sample(None, f"/videos/{v}.MP4", FPS, s, e, None, T, REQ_FPS, "random_clip", readers[mod], rng_ref)
+                ref = video.reshape(T, -1).numpy()
+            except AssertionError:
+                rvalid[ci] = False
+                ref = np.zeros((T, MODS[mod]), np.float32)
+            rfeat[mod].append(np.concatenate([ref, np.zeros((18 - T, ref.shape[1]), np.float32)]))
+    rng_or = np.random.default_rng(77)
+    pyrandom.seed(77)
+    n_rand = 0
+    for ci, (v, s, e, T) in enumerate(rcases):
+        for mod in MODS:
+            draws = feats_oracle.random_draws(s, e, FPS, T, REQ_FPS, rng_or, pyrandom)
+            if not rvalid[ci]:
+                continue
+            ids = feats_oracle.clip_frame_ids(v, s, e, FPS, T, REQ_FPS, "random_clip", orig_fps_index=mod in ORIG_FPS_MODS, rand=draws)
+            mine = feats_oracle.gather_clip(stores[mod], v, ids, MODS[mod])
+            if not np.array_equal(mine, rfeat[mod][ci][:T]):
+                raise SystemExit(f"oracle != reference (random_clip) for {mod} {v} [{s}, {e}] T={T}")
+            n_rand += 1
+    out["r_videos"] = np.array([c[0] for c in rcases])
+    out["r_start"] = np.array([c[1] for c in rcases])
+    out["r_end"] = np.array([c[2] for c in rcases])
+    out["r_T"] = np.array([c[3] for c in rcases])
+    out["r_valid"] = rvalid
+    out["r_seed"] = np.array(77)
+    for mod in MODS:
+        out[f"r_feat_{mod}"] = np.stack(rfeat[mod])
+    print(f"random_clip: oracle == reference on {n_rand} (modality, clip) pairs ({int((~rvalid).sum())} clips refused)")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "feats_reader.npz")
     np.savez_compressed(path, **out)
     print(f"oracle == reference on {n_checked} (modality, clip) pairs; wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")

@@ -287,3 +287,53 @@ def test_from_lmdb_uses_the_reference_open_mode_and_path_rule(golden, monkeypatc
     assert torch.equal(store.plan(*args), ref_store.plan(*args))
     for m in MODS:
         assert torch.equal(store.rows[m], ref_store.rows[m])
+
+
+def test_random_clip_matches_reference_fixture(golden):
+    """sample_strategy='random_clip' (base_video_dataset.py:245-248,282-287): with the numpy Generator and Python's `random`
+    seeded as in the fixture run of the reference classes, the native plan selects exactly the rows the reference read -
+    clip by clip, one pair of draws per (clip, modality) in the reference's order."""
+    import random as pyrandom
+    z, stores = golden
+    store, dims = _native_store(stores, "host")
+    assert store.mods == MODS  # the draws are consumed in modality order
+    vids, st, en, Ts = z["r_videos"].tolist(), z["r_start"], z["r_end"], z["r_T"]
+    assert bool(z["r_valid"].all())
+    seed = int(z["r_seed"])
+    # (a) the oracle, clip by clip
+    rng = np.random.default_rng(seed)
+    pyrandom.seed(seed)
+    for ci, v in enumerate(vids):
+        for m in MODS:
+            d = feats_oracle.random_draws(float(st[ci]), float(en[ci]), FPS, int(Ts[ci]), REQ_FPS, rng, pyrandom)
+            ids = feats_oracle.clip_frame_ids(v, float(st[ci]), float(en[ci]), FPS, int(Ts[ci]), REQ_FPS, "random_clip",
+                                              orig_fps_index=(m == "audio"), rand=d)
+            mine = feats_oracle.gather_clip(stores[m], v, ids, dims[m])
+            assert np.array_equal(mine, z[f"r_feat_{m}"][ci][:int(Ts[ci])]), (m, ci)
+    # (b) the native plan: batches of one clip in order, so that the draws interleave as in the reference's loop
+    rng = np.random.default_rng(seed)
+    pyrandom.seed(seed)
+    moved = 0
+    for ci, v in enumerate(vids):
+        T = int(Ts[ci])
+        idx, fids = store.plan([v], st[[ci]], en[[ci]], FPS, T, REQ_FPS, "random_clip", want_frame_ids=True, rng=rng)
+        feats = _rows_from_plan(store, idx, dims)
+        last = store.plan([v], st[[ci]], en[[ci]], FPS, T, REQ_FPS, "last_clip", want_frame_ids=True)[1]
+        moved += int(not np.array_equal(fids.numpy(), last.numpy()))
+        for m in MODS:
+            assert np.array_equal(feats[m][0], z[f"r_feat_{m}"][ci][:T]), (m, ci)
+    assert moved > 20  # the jitter really moves the windows
+    # (c) a whole batch at once consumes the generators in the same order (clip-major, modality-minor)
+    rng = np.random.default_rng(seed)
+    pyrandom.seed(seed)
+    same_T = [i for i in range(len(vids)) if Ts[i] == 18][:12]
+    rng_b = np.random.default_rng(3)
+    pyrandom.seed(3)
+    idx_b = store.plan([vids[i] for i in same_T], st[same_T], en[same_T], FPS, 18, REQ_FPS, "random_clip", rng=rng_b)
+    rng_c = np.random.default_rng(3)
+    pyrandom.seed(3)
+    for bi, i in enumerate(same_T):
+        idx_1 = store.plan([vids[i]], st[[i]], en[[i]], FPS, 18, REQ_FPS, "random_clip", rng=rng_c)
+        assert np.array_equal(idx_b[:, bi].numpy(), idx_1[:, 0].numpy())
+    with pytest.raises(ValueError):
+        store.plan([vids[0]], st[[0]], en[[0]], FPS, 18, REQ_FPS, "random_clip")  # no generator given
