@@ -866,8 +866,11 @@ def main():
     ap.add_argument("--config", default="ek100_sa_tsn", choices=configs.CONFIG_NAMES)
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=0, help="clips per CPU forward (default: the experiment's eval batch)")
-    ap.add_argument("--precision", choices=["bf16", "fp16", "strict"], default="bf16",
-                    help="GEMM operand arithmetic: bf16, fp16 (same tensor rate, 8x less rounding) or strict (bf16x3)")
+    ap.add_argument("--precision", choices=["bf16", "fp16", "strict"], default="fp16",
+                    help="GEMM operand arithmetic of the headline numbers: fp16 (default: the mode that meets the north star's "
+                         "roofline AND top-5 clauses together - same kernels and tensor rate as bf16, 8x less operand rounding, "
+                         "1-2 %% slower), bf16 (the library's default: widest range) or strict (bf16x3); the other two modes "
+                         "are reported in `modes`")
     ap.add_argument("--strict", action="store_true", help="alias of --precision strict")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="train mode: do not capture the step into a CUDA graph")

@@ -249,9 +249,9 @@ def test_gemm_fp16_epilogues_and_saturation(dev):
     ref0 = _mm(a, w)
     F = torch.nn.functional
     out_h = torch.zeros(M, N, device=dev, dtype=torch.float16)
-    capi.gemm(a, w, bias=bias, act=capi.ACT_GELU_ERF, out_hi=out_h)  # FC1 of the fuser MLP: degree-4 sigmoid form of erf-GELU
+    capi.gemm(a, w, bias=bias, act=capi.ACT_GELU_ERF, out_hi=out_h)  # FC1 of the fuser MLP: sigmoid form of erf-GELU
     ref = F.gelu(ref0 + bias)
-    assert (out_h.float() - ref).abs().max().item() < 4e-3  # one fp16 ulp at |x| < 8 (3.9e-3) + 3.2e-6 approximation
+    assert (out_h.float() - ref).abs().max().item() < 4e-3  # one fp16 ulp at |x| < 8 (3.9e-3) + 2.5e-5 approximation
     assert (out_h.float() - ref).abs().mean().item() < 2e-4
     capi.gemm(a, w, bias=bias, act=capi.ACT_GELU_TANH, out_hi=out_h)
     assert (out_h.float() - F.gelu(ref0 + bias, approximate="tanh")).abs().max().item() < 4e-3

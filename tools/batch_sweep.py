@@ -1,6 +1,6 @@
 """Batch sweep of the forward path (BASELINE config 2: 'inference on 1 B200, batch sweep'):
 ms per forward and clips/s for plain stream launches and for CUDA-graph replay.
-usage: python tools/batch_sweep.py [config] [strict]"""
+usage: python tools/batch_sweep.py [config] [bf16|fp16|strict] [b1,b2,...]"""
 import json
 import os
 import sys
@@ -12,13 +12,14 @@ from afft_b200 import _capi, configs  # noqa: E402
 from afft_b200.models import BaseModel  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "ek100_sa_tsn_wo_audio"
-strict = len(sys.argv) > 2 and sys.argv[2] == "strict"
+precision = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+BATCHES = tuple(int(b) for b in sys.argv[3].split(",")) if len(sys.argv) > 3 else (1, 8, 32, 64, 128, 256, 512, 1024)
 cfg, T, ncls, _ = configs.named_config(name)
 flops = configs.gemm_flops_per_clip(cfg, T, ncls)
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 BMAX = 1024
-model = BaseModel(cfg, ncls, {}, strict=strict, max_batch=BMAX).to(dev).eval()
+model = BaseModel(cfg, ncls, {}, precision=precision, max_batch=BMAX).to(dev).eval()
 order = [m for m in cfg["modal_feature_order"] if m in cfg["modal_dims"]]
 kw = dict(mixup_fn=None, target=None, target_subclips=None, target_subclips_ignore_index=None)
 feats = {m: torch.randn(BMAX, T, cfg["modal_dims"][m], 1, 1, 1, device=dev) for m in order}
@@ -54,7 +55,7 @@ def timeit(fn, iters):
 
 
 rows = []
-for B, ks in [(b, k) for b in (1, 8, 32, 64, 128, 256, 512, 1024) for k in ((1, 4) if b <= 128 else (4,))]:
+for B, ks in [(b, k) for b in BATCHES for k in ((1, 4) if b <= 128 else (4,))]:
     eng.set_max_ksplit(ks)  # 1 = split-K off (for comparison); 4 = library default
     iters = 50 if B <= 128 else 20
     ms_plain = timeit(lambda: eng.forward_into(io, B), iters)
