@@ -135,7 +135,7 @@ EXPORTED_SYMBOLS = [
     "afft_workspace_bytes", "afft_weight_bytes", "afft_set_weight", "afft_missing_weights", "afft_forward",
     "afft_last_launch_count", "afft_profile_enable", "afft_profile_read", "afft_set_max_ksplit", "afft_plan_ksplit",
     "afft_marginalize_topk", "afft_score_fusion", "afft_transpose_bf16", "afft_layernorm_bwd", "afft_gelu_fwd",
-    "afft_gelu_bwd", "afft_colsum", "afft_attention_bwd", "afft_sgd_nesterov", "afft_convert_dual",
+    "afft_gelu_bwd", "afft_colsum", "afft_attention_bwd", "afft_sgd_nesterov", "afft_convert_dual", "afft_workspace_bytes_for", "afft_create_in",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -164,6 +164,10 @@ def lib() -> C.CDLL:
     l.afft_layernorm.argtypes = [C.POINTER(LayerNormDesc), C.c_void_p]
     l.afft_attention.argtypes = [C.POINTER(AttentionDesc), C.c_void_p]
     l.afft_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    l.afft_workspace_bytes_for.argtypes = [C.POINTER(Config), C.POINTER(C.c_size_t)]
+    l.afft_workspace_bytes_for.restype = C.c_int
+    l.afft_create_in.argtypes = [C.POINTER(Config), C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]
+    l.afft_create_in.restype = C.c_int
     l.afft_destroy.argtypes = [C.c_void_p]
     l.afft_destroy.restype = None
     l.afft_handle_error.argtypes = [C.c_void_p]

@@ -561,6 +561,7 @@ struct afft_handle {
   // workspace
   char* ws = nullptr;
   size_t ws_bytes = 0;
+  bool ws_owned = true;  // false: caller-owned workspace (afft_create_in)
   SplitKScratch splitk{nullptr, 0, nullptr, 0, 4};  // partial tiles + band counters of the split-K GEMM path
   int n_slots = 0;  // tokens per (b, t) in the fuser stream (CA: 1)
   float* h = nullptr;
@@ -685,9 +686,12 @@ static void build_expected(afft_handle* h) {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
-  if (cfg == nullptr || out == nullptr) return fail(AFFT_ERR_INVALID, "create: null argument");
-  *out = nullptr;
+// One body for afft_create (library-owned workspace), afft_create_in (caller-owned workspace) and
+// afft_workspace_bytes_for (size query: `need` set, nothing allocated).
+static int create_impl(const afft_config* cfg, void* ws_dev, size_t ws_dev_bytes, bool caller_ws, cudaStream_t stream,
+                       size_t* need, afft_handle** out) {
+  if (cfg == nullptr || (out == nullptr && need == nullptr)) return fail(AFFT_ERR_INVALID, "create: null argument");
+  if (out != nullptr) *out = nullptr;
   const afft_config& c = *cfg;
   if (c.fuser_kind < 0 || c.fuser_kind > AFFT_FUSER_NONE) return fail(AFFT_ERR_INVALID, "create: unknown fuser_kind");
   if (c.precision < AFFT_PREC_BF16 || c.precision > AFFT_PREC_FP16) return fail(AFFT_ERR_INVALID, "create: unknown precision");
@@ -718,11 +722,14 @@ extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
   if (c.fp_output_len < 1 || c.T + c.fp_output_len - 1 > 1024)
     return fail(AFFT_ERR_INVALID, "create: fp_output_len must be >= 1 and T + fp_output_len - 1 <= 1024 (GPT-2 positions)");
 
-  cudaError_t e = cudaSetDevice(c.device);
-  if (e != cudaSuccess) return cuda_fail("cudaSetDevice", e);
-  int sms = 0;
-  int rc = device_sm_count(&sms);
-  if (rc != AFFT_OK) return rc;
+  cudaError_t e = cudaSuccess;
+  int sms = 148;
+  if (need == nullptr) {  // the size query is host arithmetic only
+    e = cudaSetDevice(c.device);
+    if (e != cudaSuccess) return cuda_fail("cudaSetDevice", e);
+    int rc = device_sm_count(&sms);
+    if (rc != AFFT_OK) return rc;
+  }
 
   afft_handle* h = new afft_handle();
   h->cfg = c;
@@ -797,10 +804,24 @@ extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
   }
   size_t total = 0;
   for (auto& r : reqs) total += r.bytes;
-  e = cudaMalloc(reinterpret_cast<void**>(&h->ws), total);
-  if (e != cudaSuccess) {
+  if (need != nullptr) {  // size query only
+    *need = total;
     delete h;
-    return cuda_fail("cudaMalloc(workspace)", e);
+    return AFFT_OK;
+  }
+  if (caller_ws) {
+    if (ws_dev == nullptr || ws_dev_bytes < total || (reinterpret_cast<uintptr_t>(ws_dev) & 255u) != 0) {
+      delete h;
+      return fail(AFFT_ERR_INVALID, "create_in: workspace must be 256-byte aligned device memory of at least afft_workspace_bytes_for() bytes");
+    }
+    h->ws = static_cast<char*>(ws_dev);
+    h->ws_owned = false;
+  } else {
+    e = cudaMalloc(reinterpret_cast<void**>(&h->ws), total);
+    if (e != cudaSuccess) {
+      delete h;
+      return cuda_fail("cudaMalloc(workspace)", e);
+    }
   }
   h->ws_bytes = total;
   size_t off = 0;
@@ -810,15 +831,31 @@ extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
   }
   h->splitk.partial_floats = kSplitKPartialFloats;
   h->splitk.n_counters = kSplitKCounters;
-  e = cudaMemset(h->splitk.counters, 0, kSplitKCounters * 4);  // once: the kernels leave the counters at zero
-  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  // once: the kernels leave the counters at zero.  Caller-owned workspace: enqueued on the caller's stream, no synchronisation
+  e = caller_ws ? cudaMemsetAsync(h->splitk.counters, 0, kSplitKCounters * 4, stream) : cudaMemset(h->splitk.counters, 0, kSplitKCounters * 4);
+  if (e == cudaSuccess && !caller_ws) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
-    cudaFree(h->ws);
+    if (h->ws_owned) cudaFree(h->ws);
     delete h;
     return cuda_fail("cudaMemset(split-K counters)", e);
   }
   *out = h;
   return AFFT_OK;
+}
+
+extern "C" int afft_create(const afft_config* cfg, afft_handle** out) {
+  if (out == nullptr) return fail(AFFT_ERR_INVALID, "create: null argument");
+  return create_impl(cfg, nullptr, 0, false, nullptr, nullptr, out);
+}
+
+extern "C" int afft_workspace_bytes_for(const afft_config* cfg, size_t* bytes) {
+  if (bytes == nullptr) return fail(AFFT_ERR_INVALID, "workspace_bytes_for: null argument");
+  return create_impl(cfg, nullptr, 0, false, nullptr, bytes, nullptr);
+}
+
+extern "C" int afft_create_in(const afft_config* cfg, void* workspace_dev, size_t workspace_bytes, void* stream, afft_handle** out) {
+  if (out == nullptr) return fail(AFFT_ERR_INVALID, "create_in: null argument");
+  return create_impl(cfg, workspace_dev, workspace_bytes, true, static_cast<cudaStream_t>(stream), nullptr, out);
 }
 
 extern "C" void afft_destroy(afft_handle* h) {
@@ -829,7 +866,7 @@ extern "C" void afft_destroy(afft_handle* h) {
     if (kv.second.lo) cudaFree(kv.second.lo);
     if (kv.second.f32) cudaFree(kv.second.f32);
   }
-  if (h->ws) cudaFree(h->ws);
+  if (h->ws && h->ws_owned) cudaFree(h->ws);
   if (h->prof_slots) cudaFree(h->prof_slots);
   delete h;
 }

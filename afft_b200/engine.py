@@ -54,8 +54,14 @@ class Engine:
         self.gpt_dim, self.gpt_layers, self.gpt_heads = gpt_dim, gpt_layers, gpt_heads
         cfg.device = device.index if device.index is not None else torch.cuda.current_device()
         self.cfg = cfg
+        # The workspace is a PyTorch-allocator tensor owned by this object (caller-owned device memory); the
+        # library carves its activation buffers out of it and never allocates or synchronises for them.
+        need = C.c_size_t()
+        _capi.check(self.lib.afft_workspace_bytes_for(C.byref(cfg), C.byref(need)))
+        self.workspace = torch.empty(int(need.value) + 256, dtype=torch.uint8, device=device)
+        base = (self.workspace.data_ptr() + 255) // 256 * 256
         h = C.c_void_p()
-        _capi.check(self.lib.afft_create(C.byref(cfg), C.byref(h)))
+        _capi.check(self.lib.afft_create_in(C.byref(cfg), base, need.value, _capi.current_stream_ptr(device), C.byref(h)))
         self.handle = h
         self.max_ksplit = 4  # library default
         self._versions: Optional[tuple] = None
@@ -67,6 +73,7 @@ class Engine:
         if getattr(self, "handle", None):
             self.lib.afft_destroy(self.handle)
             self.handle = None
+            self.workspace = None  # returned to PyTorch's allocator (stream-ordered: queued kernels keep it valid)
 
     def __del__(self):
         try:

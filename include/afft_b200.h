@@ -276,6 +276,13 @@ typedef struct afft_config {
 typedef struct afft_handle afft_handle;
 
 AFFT_API int afft_create(const afft_config* cfg, afft_handle** out);
+/* The same with a CALLER-OWNED workspace ("all tensors are caller-owned device memory (PyTorch
+ * allocator) ... no hidden synchronisation"): afft_workspace_bytes_for() is host arithmetic; afft_create_in() carves the
+ * handle's activation buffers out of `workspace_dev` (256-byte aligned, at least that many bytes, alive until
+ * afft_destroy), clears its split-K counters with a memset enqueued on `stream` and does not synchronise.  Packed
+ * weights remain the library's (afft_set_weight allocates them). */
+AFFT_API int afft_workspace_bytes_for(const afft_config* cfg, size_t* bytes);
+AFFT_API int afft_create_in(const afft_config* cfg, void* workspace_dev, size_t workspace_bytes, void* stream, afft_handle** out);
 AFFT_API void afft_destroy(afft_handle* h);
 AFFT_API const char* afft_handle_error(const afft_handle* h);
 

@@ -184,3 +184,36 @@ def test_splitk_plan_cost_model():
             assert 1 <= s <= max(1, kb // 2)
             per = -(-kb // s)
             assert (s - 1) * per < kb
+
+
+def test_workspace_size_query_is_host_arithmetic():
+    """afft_workspace_bytes_for: the caller-owned-workspace contract of SURVEY 8b starts with a size query that needs no
+    device; it grows with max_batch and with the strict mode's hi/lo pairs, and afft_create_in refuses a short buffer."""
+    import ctypes as C
+    from afft_b200 import _capi
+    lib = _capi.lib()
+
+    def need(max_batch, precision=0, stages=0):
+        cfg = _capi.Config()
+        cfg.fuser_kind, cfg.T, cfg.n_mod = 0, 18, 4
+        for i, (n, d) in enumerate([("rgb", 1024), ("objects", 352), ("audio", 1024), ("flow", 1024)]):
+            cfg.mod_name[i].value = n.encode()
+            cfg.mod_dim[i] = d
+        cfg.dim, cfg.fuser_depth, cfg.fuser_heads, cfg.norm_elementwise = 1024, 6, 4, 1
+        cfg.gpt_dim, cfg.gpt_layers, cfg.gpt_heads = 2048, 6, 4
+        cfg.n_cls = 1
+        cfg.cls_name[0].value = b"action"
+        cfg.cls_dim[0] = 3806
+        cfg.precision, cfg.max_batch, cfg.device, cfg.fp_output_len, cfg.stages = precision, max_batch, 0, 1, stages
+        n = C.c_size_t()
+        assert lib.afft_workspace_bytes_for(C.byref(cfg), C.byref(n)) == 0
+        return n.value, cfg
+
+    b32, _ = need(32)
+    b256, cfg = need(256)
+    assert 0 < b32 < b256 < 2 * 1024 ** 3
+    assert need(256, precision=1)[0] > b256            # strict: hi/lo pairs and fp32 q|k|v
+    assert need(256, precision=2)[0] == b256           # fp16 operands take the room of bf16 operands
+    assert need(256, stages=1)[0] < b256               # fuser-only handle: no GPT-2 buffers
+    h = C.c_void_p()
+    assert lib.afft_create_in(C.byref(cfg), None, 0, None, C.byref(h)) != 0  # no buffer: refused before any device work...
