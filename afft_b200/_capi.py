@@ -20,7 +20,7 @@ AFFT_OK = 0
 AFFT_MAX_MODS = 8
 AFFT_MAX_CLS = 4
 AFFT_NAME_LEN = 32
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH, ACT_RELU, ACT_GATE = 0, 1, 2, 3, 4
 PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2
@@ -135,7 +135,8 @@ EXPORTED_SYMBOLS = [
     "afft_workspace_bytes", "afft_weight_bytes", "afft_set_weight", "afft_missing_weights", "afft_forward",
     "afft_last_launch_count", "afft_profile_enable", "afft_profile_read", "afft_set_max_ksplit", "afft_plan_ksplit",
     "afft_marginalize_topk", "afft_score_fusion", "afft_transpose_bf16", "afft_layernorm_bwd", "afft_gelu_fwd",
-    "afft_gelu_bwd", "afft_colsum", "afft_attention_bwd", "afft_sgd_nesterov", "afft_convert_dual", "afft_workspace_bytes_for", "afft_create_in",
+    "afft_gelu_bwd", "afft_colsum", "afft_attention_bwd", "afft_sgd_nesterov", "afft_convert_dual",
+    "afft_convert_dual_gelu", "afft_workspace_bytes_for", "afft_create_in",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -195,6 +196,9 @@ def lib() -> C.CDLL:
     l.afft_convert_dual.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_void_p]
     l.afft_convert_dual.restype = C.c_int
+    l.afft_convert_dual_gelu.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
+                                         C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    l.afft_convert_dual_gelu.restype = C.c_int
     l.afft_sgd_nesterov.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
                                     C.c_int32, C.c_void_p]
     l.afft_sgd_nesterov.restype = C.c_int

@@ -35,7 +35,7 @@ static int cuda_fail(const char* what, cudaError_t e) {
   return fail(AFFT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-extern "C" int afft_abi_version(void) { return 7; }
+extern "C" int afft_abi_version(void) { return 8; }
 extern "C" const char* afft_last_error(void) { return g_err.c_str(); }
 
 static int device_sm_count(int* out) {
@@ -445,9 +445,26 @@ extern "C" int afft_convert_dual(const float* src, int64_t lds, int32_t rows, in
   if (src == nullptr || rows <= 0 || cols <= 0 || (hi == nullptr && tr == nullptr && colsum == nullptr))
     return fail(AFFT_ERR_INVALID, "convert_dual: bad argument");
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-  convert_dual_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(src, lds, rows, cols, static_cast<bf16*>(hi), ldh,
-                                                                           static_cast<bf16*>(tr), ldt, colsum);
+  convert_dual_kernel<0><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, lds, rows, cols, static_cast<bf16*>(hi), ldh, static_cast<bf16*>(tr), ldt, colsum, nullptr, 0, 0);
   return launch_check("convert_dual launch");
+}
+
+extern "C" int afft_convert_dual_gelu(const float* src, int64_t lds, int32_t rows, int32_t cols, void* hi, int64_t ldh,
+                                      void* tr, int64_t ldt, float* colsum, const float* d_act, int64_t ldd, int32_t kind,
+                                      void* stream) {
+  if (src == nullptr || rows <= 0 || cols <= 0 || (hi == nullptr && tr == nullptr && colsum == nullptr) ||
+      (kind != 1 && kind != 2))
+    return fail(AFFT_ERR_INVALID, "convert_dual_gelu: bad argument");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d_act == nullptr)
+    convert_dual_kernel<1><<<grid, block, 0, st>>>(src, lds, rows, cols, static_cast<bf16*>(hi), ldh, static_cast<bf16*>(tr),
+                                                  ldt, colsum, nullptr, 0, kind);
+  else
+    convert_dual_kernel<2><<<grid, block, 0, st>>>(src, lds, rows, cols, static_cast<bf16*>(hi), ldh, static_cast<bf16*>(tr),
+                                                  ldt, colsum, d_act, ldd, kind);
+  return launch_check("convert_dual_gelu launch");
 }
 
 extern "C" int afft_layernorm_bwd(const float* x, int64_t ldx, const float* gamma, float eps, const float* dy, int64_t lddy,

@@ -33,16 +33,25 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, lon
 // source, optionally with the column sums (bias gradient: colsum[c] += sum_r src[r, c]).  A Linear's backward needs its
 // dy in both orientations (dgrad contracts over N, wgrad over the rows) and the bias gradient: three passes over the
 // fp32 tensor become one.  32 x 32 tiles through shared memory; grid (cols / 32, rows / 32), block (32, 8).
+// OP 0: v = src.  OP 1: v = gelu(src) (the MLP's activation feeding the second Linear, both operand orientations from one
+// pass over the pre-activation).  OP 2: v = aux * gelu'(src) (the activation's backward feeding the first Linear's
+// dgrad/wgrad operands and its bias gradient; aux = the gradient w.r.t. the activation's output, pitch lda).
+__device__ __forceinline__ float gelu_fwd_exact(float x, int kind);
+__device__ __forceinline__ float gelu_grad_exact(float x, int kind);
+template <int OP>
 __global__ void __launch_bounds__(256) convert_dual_kernel(const float* __restrict__ src, long long lds, int rows, int cols,
                                                            __nv_bfloat16* __restrict__ hi, long long ldh,
                                                            __nv_bfloat16* __restrict__ tr, long long ldt,
-                                                           float* __restrict__ colsum) {
+                                                           float* __restrict__ colsum, const float* __restrict__ aux,
+                                                           long long lda, int kind) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   float csum = 0.f;
   for (int j = threadIdx.y; j < 32; j += 8) {
     const int r = r0 + j, c = c0 + threadIdx.x;
-    const float v = (r < rows && c < cols) ? src[r * lds + c] : 0.f;
+    float v = (r < rows && c < cols) ? src[r * lds + c] : 0.f;
+    if (OP == 1) v = gelu_fwd_exact(v, kind);
+    if (OP == 2) v = (r < rows && c < cols) ? aux[r * lda + c] * gelu_grad_exact(v, kind) : 0.f;
     tile[j][threadIdx.x] = v;
     csum += v;
     if (hi != nullptr && r < rows && c < cols) hi[r * ldh + c] = __float2bfloat16_rn(v);

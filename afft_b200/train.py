@@ -11,6 +11,9 @@ a hand-written sm_100a kernel behind the C ABI:
   LayerNormFn  afft_layernorm / afft_layernorm_bwd
   GeluFn       afft_gelu_fwd / afft_gelu_bwd   (erf for the fuser MLP, tanh for GPT-2)
   AttentionFn  afft_attention (fp32 q|k|v, probabilities saved) / afft_attention_bwd
+  MlpFn        Linear -> GELU -> Linear as one node: the activation (and its backward) is produced directly as the next
+               GEMM's bf16 operands by afft_convert_dual_gelu, never in fp32
+  AttnProjFn   attention -> output projection as one node: the kernel's bf16 heads feed the projection GEMM directly
 
 PyTorch supplies the autograd graph, residual adds, concatenation, dropout masks and the optimizer (plumbing);
 torch.nn.parallel.DistributedDataParallel supplies the bucketed NCCL all-reduce overlapped with backward.
@@ -210,6 +213,88 @@ def _state_for(*params):
     return st if all(p is None or id(p) in st.w16 for p in params) else None
 
 
+def gelu_bf16_dual(u: torch.Tensor, kind: int, d_act: torch.Tensor = None, colsum: torch.Tensor = None, want_t: bool = True):
+    """fp32 pre-activation u [R, C] -> bf16 gelu(u) (d_act None) or bf16 d_act * gelu'(u), as [R, C] and [C, pad8(R)], plus
+    the column sums of the same values: afft_convert_dual_gelu - the activation never exists in fp32."""
+    R, C = u.shape
+    Cp, Rp = _pad8(C), _pad8(R)
+    hi = torch.zeros(R, Cp, device=u.device, dtype=torch.bfloat16) if Cp != C else \
+        torch.empty(R, Cp, device=u.device, dtype=torch.bfloat16)
+    tr = None
+    if want_t:
+        tr = torch.zeros(C, Rp, device=u.device, dtype=torch.bfloat16) if Rp != R else \
+            torch.empty(C, Rp, device=u.device, dtype=torch.bfloat16)
+    _capi.check(_lib().afft_convert_dual_gelu(u.data_ptr(), u.stride(0), R, C, hi.data_ptr(), Cp, _capi.ptr(tr), Rp,
+                                              _capi.ptr(colsum), _capi.ptr(d_act), d_act.stride(0) if d_act is not None else 0,
+                                              kind, _ST(u.device)))
+    return hi[:, :C], tr
+
+
+# ---- the pieces of a Linear's forward / backward, shared by LinearFn and the fused nodes below ----
+def _weight_operand(weight, bias, conv1d: bool, st):
+    """bf16 [N, K] (K contiguous) forward operand of an nn.Linear [N, K] / Conv1D [K, N] weight."""
+    if st is not None:  # the optimizer's bf16 image: no conversion
+        w16 = st.w16[id(weight)]
+        st.note_use(weight)
+        if bias is not None:
+            st.note_use(bias)
+        return bf16_t(w16) if conv1d else w16
+    return to_bf16_t(weight) if conv1d else to_bf16(weight)
+
+
+def _gemm_bias(xb, w_fwd, bias):
+    """fp32 y [M, N] = xb . w_fwd^T + bias (output pitch padded to 16 bytes)."""
+    N = w_fwd.shape[0]
+    Np = (N + 3) // 4 * 4
+    y = torch.empty(xb.shape[0], Np, device=xb.device, dtype=torch.float32)
+    if bias is not None and Np != N:  # the epilogue reads the bias with 16-byte loads
+        bias_p = torch.zeros(Np, device=xb.device, dtype=torch.float32)
+        bias_p[:N] = bias.detach()
+        bias = bias_p[:N]
+    _capi.gemm(xb, w_fwd[:, :xb.shape[1]], bias=bias, out_f32=y[:, :N])
+    return y[:, :N]
+
+
+def _bias_grad_target(bias, st, N: int, device, needed: bool):
+    """(buffer the colsum kernel accumulates into, tensor to hand back to autograd or None)."""
+    if bias is None or not needed:
+        return None, None
+    if st is not None:
+        return st.grad_target(bias)[0], None  # cleared at step start; the kernel accumulates
+    t = torch.zeros(N, device=device, dtype=torch.float32)
+    return t, t
+
+
+def _dgrad(dyb, weight, w_fwd, K: int, conv1d: bool, st):
+    """dx [M, K] = dy [M, N] . W;  B operand [K, N] with N contiguous."""
+    M, N = dyb.shape
+    if st is not None and conv1d and N % 8 == 0:
+        w_dg = st.w16[id(weight)]  # Conv1D weights are stored [K, N]: the optimizer's bf16 image is the operand
+    else:
+        w_dg = bf16_t(w_fwd[:, :K])  # [K, pad8(N)]: W for nn.Linear, W^T^T = W [K, N] for Conv1D
+    dx = torch.empty(M, K, device=dyb.device, dtype=torch.float32)
+    _capi.gemm(dyb, w_dg[:, :N], out_f32=dx)
+    return dx
+
+
+def _wgrad(dy_t, x_t, weight, conv1d: bool, st):
+    """dW from the transposed bf16 operands dy^T [N, Mp] and x^T [K, Mp].  With a TrainState the GEMM writes the .grad view
+    (no temporary, no autograd accumulation pass) and None is returned; otherwise the fp32 gradient is returned."""
+    direct = st is not None and weight.shape[1] % 4 == 0
+    if direct:
+        dw_out, acc = st.grad_target(weight, overwrites=True)
+    else:
+        dw_out, acc = torch.empty(weight.shape, device=dy_t.device, dtype=torch.float32), False
+    if conv1d:       # dW [K, N] = x^T . dy
+        _capi.gemm(x_t, dy_t, out_f32=dw_out, res=dw_out if acc else None)
+    else:            # dW [N, K] = dy^T . x
+        _capi.gemm(dy_t, x_t, out_f32=dw_out, res=dw_out if acc else None)
+    if direct:
+        st.grad_done(weight)
+        return None
+    return dw_out  # autograd accumulates it and the bucket's hook counts the parameter
+
+
 class LinearFn(torch.autograd.Function):
     """y = x W^T + b for nn.Linear weights [N, K]; y = x W + b for transformers' Conv1D weights [K, N]."""
 
@@ -222,29 +307,14 @@ class LinearFn(torch.autograd.Function):
             xb, x_t = to_bf16(x), None
         st = _state_for(weight, bias)
         ctx.st = st
-        if st is not None:  # the optimizer's bf16 image: no conversion
-            w16 = st.w16[id(weight)]
-            w_fwd = bf16_t(w16) if conv1d else w16
-            st.note_use(weight)
-            if bias is not None:
-                st.note_use(bias)
-        else:
-            w_fwd = to_bf16_t(weight) if conv1d else to_bf16(weight)  # [N, K], K contiguous
-        N = w_fwd.shape[0]
-        Np = (N + 3) // 4 * 4  # fp32 output pitch: 16-byte multiple
-        y = torch.empty(x.shape[0], Np, device=x.device, dtype=torch.float32)
-        bias_param = bias
-        if bias is not None and Np != N:  # the epilogue reads the bias with 16-byte loads
-            bias_p = torch.zeros(Np, device=x.device, dtype=torch.float32)
-            bias_p[:N] = bias.detach()
-            bias = bias_p[:N]
-        _capi.gemm(xb, w_fwd[:, :xb.shape[1]], bias=bias, out_f32=y[:, :N])
+        w_fwd = _weight_operand(weight, bias, conv1d, st)
+        y = _gemm_bias(xb, w_fwd, bias)
         # the bf16 operand is kept for dgrad (its transpose is the dgrad operand): transposing 2-byte elements reads
         # half of what a second conversion of the fp32 weight would
-        ctx.save_for_backward(x_t if x_t is not None else xb, weight, w_fwd, bias_param)
+        ctx.save_for_backward(x_t if x_t is not None else xb, weight, w_fwd, bias)
         ctx.x_is_t, ctx.K = x_t is not None, xb.shape[1]
-        ctx.conv1d, ctx.has_bias = conv1d, bias_param is not None
-        return y[:, :N]
+        ctx.conv1d, ctx.has_bias = conv1d, bias is not None
+        return y
 
     @staticmethod
     def backward(ctx, dy):
@@ -252,15 +322,9 @@ class LinearFn(torch.autograd.Function):
         st = ctx.st
         dy = dy.contiguous()
         M, N = dy.shape
-        K = ctx.K
-        dx = dw = db = None
+        dx = dw = None
         # dy in both orientations (dgrad contracts over N, wgrad over the rows) and the bias gradient: one pass over dy
-        db_out = None
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            if st is not None:
-                db_out, _ = st.grad_target(bias)  # cleared at step start; the kernel accumulates
-            else:
-                db_out = db = torch.zeros(N, device=dy.device, dtype=torch.float32)
+        db_out, db = _bias_grad_target(bias, st, N, dy.device, ctx.has_bias and ctx.needs_input_grad[2])
         if ctx.needs_input_grad[1]:
             dyb, dy_t = to_bf16_dual(dy, db_out)
         else:
@@ -270,29 +334,52 @@ class LinearFn(torch.autograd.Function):
         if db_out is not None and st is not None:
             st.grad_done(bias)
         if ctx.needs_input_grad[0]:
-            # dgrad: dx [M, K] = dy [M, N] . W;  B operand [K, N] with N contiguous
-            if st is not None and ctx.conv1d and N % 8 == 0:
-                w_dg = st.w16[id(weight)]  # Conv1D weights are stored [K, N]: the optimizer's bf16 image is the operand
-            else:
-                w_dg = bf16_t(w_fwd[:, :K])  # [K, pad8(N)]: W for nn.Linear, W^T^T = W [K, N] for Conv1D
-            dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
-            _capi.gemm(dyb, w_dg[:, :N], out_f32=dx)
+            dx = _dgrad(dyb, weight, w_fwd, ctx.K, ctx.conv1d, st)
         if ctx.needs_input_grad[1]:
             x_t = xs if ctx.x_is_t else bf16_t(xs)  # [K, Mp]
-            direct = st is not None and weight.shape[1] % 4 == 0
-            if direct:  # wgrad straight into the .grad view: no temporary, no autograd accumulation pass
-                dw_out, acc = st.grad_target(weight, overwrites=True)
-            else:
-                dw_out, acc = torch.empty(weight.shape, device=dy.device, dtype=torch.float32), False
-            if ctx.conv1d:       # dW [K, N] = x^T . dy
-                _capi.gemm(x_t, dy_t, out_f32=dw_out, res=dw_out if acc else None)
-            else:                # dW [N, K] = dy^T . x
-                _capi.gemm(dy_t, x_t, out_f32=dw_out, res=dw_out if acc else None)
-            if direct:
-                st.grad_done(weight)
-            else:
-                dw = dw_out  # autograd accumulates it and the bucket's hook counts the parameter
+            dw = _wgrad(dy_t, x_t, weight, ctx.conv1d, st)
         return dx, dw, db, None
+
+
+class MlpFn(torch.autograd.Function):
+    """Linear -> GELU -> Linear (reference models/transformerblock.py:39-56 Mlp; GPT-2's c_fc / act / c_proj) as one
+    node: the activation is produced directly as the second GEMM's bf16 operands (afft_convert_dual_gelu) and its backward
+    directly as the first Linear's backward operands + bias gradient, so neither gelu(u) nor d/du exists in fp32 - two
+    fp32 [rows, 4D] round trips less per block and direction than LinearFn / GeluFn / LinearFn."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, kind: int, conv1d: bool):
+        st = _state_for(w1, b1, w2, b2)
+        ctx.st = st
+        xb, x_t = to_bf16_dual(x)
+        w1f = _weight_operand(w1, b1, conv1d, st)
+        w2f = _weight_operand(w2, b2, conv1d, st)
+        u = _gemm_bias(xb, w1f, b1)
+        ab, a_t = gelu_bf16_dual(u, kind)
+        y = _gemm_bias(ab, w2f, b2)
+        ctx.save_for_backward(x_t, u, a_t, w1, w1f, b1, w2, w2f, b2)
+        ctx.kind, ctx.conv1d, ctx.K = kind, conv1d, xb.shape[1]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_t, u, a_t, w1, w1f, b1, w2, w2f, b2 = ctx.saved_tensors
+        st, conv1d = ctx.st, ctx.conv1d
+        dy = dy.contiguous()
+        Fdim = u.shape[1]
+        db2_out, db2 = _bias_grad_target(b2, st, dy.shape[1], dy.device, b2 is not None)
+        dyb, dy_t = to_bf16_dual(dy, db2_out)
+        if db2_out is not None and st is not None:
+            st.grad_done(b2)
+        dw2 = _wgrad(dy_t, a_t, w2, conv1d, st)
+        da = _dgrad(dyb, w2, w2f, Fdim, conv1d, st)  # gradient w.r.t. gelu(u), fp32 [rows, F]
+        db1_out, db1 = _bias_grad_target(b1, st, Fdim, dy.device, b1 is not None)
+        dub, du_t = gelu_bf16_dual(u, ctx.kind, d_act=da, colsum=db1_out)
+        if db1_out is not None and st is not None:
+            st.grad_done(b1)
+        dw1 = _wgrad(du_t, x_t, w1, conv1d, st)
+        dx = _dgrad(dub, w1, w1f, ctx.K, conv1d, st) if ctx.needs_input_grad[0] else None
+        return dx, dw1, db1, dw2, db2, None, None
 
 
 class LayerNormFn(torch.autograd.Function):
@@ -384,6 +471,68 @@ class AttentionFn(torch.autograd.Function):
         return dqkv, None, None, None, None, None, None, None
 
 
+class AttnProjFn(torch.autograd.Function):
+    """AttentionFn followed by the output projection (reference models/transformerblock.py:30-35; GPT-2 c_proj) as one
+    node: the kernel's bf16 merged heads are the projection GEMM's operand as they are (no fp32 copy of the attention output,
+    no conversion back), and the projection's dgrad output is the attention backward's input."""
+
+    @staticmethod
+    def forward(ctx, qkv, weight, bias, conv1d: bool, n_seq: int, L: int, H: int, hd: int, mask: int, T: int, p_drop: float):
+        qkv = qkv.contiguous()
+        D = H * hd
+        st = _state_for(weight, bias)
+        ctx.st = st
+        hi = torch.empty(n_seq * L, D, device=qkv.device, dtype=torch.bfloat16)
+        probs = torch.empty(n_seq, H, L, L, device=qkv.device, dtype=torch.float32)
+        drop = None
+        if p_drop > 0.0:
+            drop = (torch.rand(n_seq, H, L, L, device=qkv.device) >= p_drop).to(torch.float32).mul_(1.0 / (1.0 - p_drop))
+        _capi.attention(qkv, n_seq, L, H, hd, mask=mask, T=T, out_hi=hi, probs=probs, p_outer=H * L * L, drop_mask=drop)
+        w_fwd = _weight_operand(weight, bias, conv1d, st)
+        y = _gemm_bias(hi, w_fwd, bias)
+        ctx.save_for_backward(qkv, probs, drop, bf16_t(hi), weight, w_fwd, bias)
+        ctx.dims, ctx.conv1d = (n_seq, L, H, hd), conv1d
+        return y, (probs if drop is None else probs * drop)
+
+    @staticmethod
+    def backward(ctx, dy, _d_probs):
+        qkv, probs, drop, x_t, weight, w_fwd, bias = ctx.saved_tensors
+        st = ctx.st
+        n_seq, L, H, hd = ctx.dims
+        dy = dy.contiguous()
+        db_out, db = _bias_grad_target(bias, st, dy.shape[1], dy.device, bias is not None)
+        dyb, dy_t = to_bf16_dual(dy, db_out)
+        if db_out is not None and st is not None:
+            st.grad_done(bias)
+        dw = _wgrad(dy_t, x_t, weight, ctx.conv1d, st)
+        d_attn = _dgrad(dyb, weight, w_fwd, H * hd, ctx.conv1d, st)
+        dqkv = torch.empty_like(qkv)
+        _capi.check(_lib().afft_attention_bwd(qkv.data_ptr(), qkv.shape[1], probs.data_ptr(), d_attn.data_ptr(), d_attn.shape[1],
+                                              dqkv.data_ptr(), n_seq, L, H, hd, hd ** -0.5, _capi.ptr(drop), _ST(qkv.device)))
+        return dqkv, dw, db, None, None, None, None, None, None, None, None
+
+
+def _fusable(*params) -> bool:
+    return torch.is_grad_enabled() and all(p is None or p.requires_grad for p in params)
+
+
+def _mlp(x, fc1, fc2, kind: int, conv1d: bool = False):
+    """fc2(gelu(fc1(x))): one fused node when every parameter trains, the three separate ones otherwise."""
+    b1, b2 = getattr(fc1, "bias", None), getattr(fc2, "bias", None)
+    if _fusable(fc1.weight, b1, fc2.weight, b2):
+        return MlpFn.apply(x, fc1.weight, b1, fc2.weight, b2, kind, conv1d)
+    return _linear(GeluFn.apply(_linear(x, fc1, conv1d), kind), fc2, conv1d)
+
+
+def _attn_proj(qkv, proj, n_seq, L, H, hd, mask, T, p_drop, conv1d: bool = False):
+    """proj(attention(qkv)) -> (projection output, probabilities after dropout)."""
+    bias = getattr(proj, "bias", None)
+    if _fusable(proj.weight, bias):
+        return AttnProjFn.apply(qkv, proj.weight, bias, conv1d, n_seq, L, H, hd, mask, T, p_drop)
+    a, p = AttentionFn.apply(qkv, n_seq, L, H, hd, mask, T, p_drop)
+    return _linear(a, proj, conv1d), p
+
+
 def _linear(x, lin, conv1d=False):
     return LinearFn.apply(x, lin.weight, getattr(lin, "bias", None), conv1d)
 
@@ -441,8 +590,8 @@ def _self_attention(h, attn, n_seq, L, mask, T, training, proj_drop=True):
     """reference models/transformerblock.py:19-36 on rows [n_seq * L, D]; returns (proj output [after proj_drop], probs)."""
     H = attn.num_heads
     D = h.shape[1]
-    a, p = AttentionFn.apply(_linear(h, attn.qkv), n_seq, L, H, D // H, mask, T, _rate(attn.attn_drop) if training else 0.0)
-    a = _linear(a, attn.proj)
+    a, p = _attn_proj(_linear(h, attn.qkv), attn.proj, n_seq, L, H, D // H, mask, T,
+                      _rate(attn.attn_drop) if training else 0.0)
     return (F.dropout(a, _rate(attn.proj_drop), training) if proj_drop else a), p
 
 
@@ -451,8 +600,8 @@ def _block(h, blk, n_seq, L, mask, T, training):
     dp = getattr(blk.drop_path, "drop_prob", 0.0) or 0.0
     a, p = _self_attention(_ln(h, blk.norm1), blk.attn, n_seq, L, mask, T, training, proj_drop=False)
     h = _residual(h, a, _rate(blk.attn.proj_drop), dp, training, L)
-    f = GeluFn.apply(_linear(_ln(h, blk.norm2), blk.mlp.mlp[0]), _capi.ACT_GELU_ERF)
-    return _residual(h, _linear(f, blk.mlp.mlp[2]), _rate(blk.mlp.mlp[3]), dp, training, L), p
+    f = _mlp(_ln(h, blk.norm2), blk.mlp.mlp[0], blk.mlp.mlp[2], _capi.ACT_GELU_ERF)
+    return _residual(h, f, _rate(blk.mlp.mlp[3]), dp, training, L), p
 
 
 def _fuse_sa(fuser, toks, B, T, D, training, with_token: bool):
@@ -510,11 +659,11 @@ def _fuse_ca(fuser, toks, B, T, D, training):
         H = ca.num_heads
         mem = _ln(mems[i], blk.norm_kv)
         qkv = torch.cat([_linear(_ln(x, blk.norm_q), ca.w_q), _linear(mem, ca.w_k), _linear(mem, ca.w_v)], dim=1)
-        c, _ = AttentionFn.apply(qkv, B, T, H, D // H, 1, T, _rate(ca.attn_drop) if training else 0.0)
-        c = F.dropout(_linear(c, ca.proj), _rate(ca.proj_drop), training)
+        c, _ = _attn_proj(qkv, ca.proj, B, T, H, D // H, 1, T, _rate(ca.attn_drop) if training else 0.0)
+        c = F.dropout(c, _rate(ca.proj_drop), training)
         x = x + _drop_path(c, dp, training, T)
-        f = GeluFn.apply(_linear(_ln(x, blk.norm_mlp), blk.mlp.mlp[0]), _capi.ACT_GELU_ERF)
-        f = F.dropout(_linear(f, blk.mlp.mlp[2]), _rate(blk.mlp.mlp[3]), training)
+        f = _mlp(_ln(x, blk.norm_mlp), blk.mlp.mlp[0], blk.mlp.mlp[2], _capi.ACT_GELU_ERF)
+        f = F.dropout(f, _rate(blk.mlp.mlp[3]), training)
         x = x + _drop_path(f, dp, training, T)
     return _ln(x, fuser.norm).view(B, T, D), torch.zeros(B)  # the reference's dummy attention (:269)
 
@@ -554,12 +703,12 @@ def forward_train(fp, feats: Dict[str, torch.Tensor]) -> Dict[str, Dict[str, tor
     g = F.dropout(g, gpt.drop.p, training).reshape(B * T, G)
     for blk in gpt.h:  # transformers GPT2Block
         y = _ln(g, blk.ln_1)
-        a, _ = AttentionFn.apply(_linear(y, blk.attn.c_attn, conv1d=True), B, T, H2, G // H2, 1, T,
-                                 _rate(blk.attn.attn_dropout) if training else 0.0)
-        g = g + F.dropout(_linear(a, blk.attn.c_proj, conv1d=True), blk.attn.resid_dropout.p, training)
+        a, _ = _attn_proj(_linear(y, blk.attn.c_attn, conv1d=True), blk.attn.c_proj, B, T, H2, G // H2, 1, T,
+                          _rate(blk.attn.attn_dropout) if training else 0.0, conv1d=True)
+        g = g + F.dropout(a, blk.attn.resid_dropout.p, training)
         y = _ln(g, blk.ln_2)
-        f = GeluFn.apply(_linear(y, blk.mlp.c_fc, conv1d=True), _capi.ACT_GELU_TANH)
-        g = g + F.dropout(_linear(f, blk.mlp.c_proj, conv1d=True), blk.mlp.dropout.p, training)
+        f = _mlp(y, blk.mlp.c_fc, blk.mlp.c_proj, _capi.ACT_GELU_TANH, conv1d=True)
+        g = g + F.dropout(f, blk.mlp.dropout.p, training)
     g = _ln(g, gpt.ln_f)
     z_hat = (g if identity else _linear(g, fp.dim_decoder)).view(B, T, D)
 

@@ -206,6 +206,12 @@ AFFT_API int afft_marginalize_topk(const float* logits, int64_t ld, int32_t B, i
  * colsum[c] += sum_r src[r, c] (each output optional): the three passes a Linear's backward makes over dy. */
 AFFT_API int afft_convert_dual(const float* src, int64_t lds, int32_t rows, int32_t cols, void* hi, int64_t ldh, void* tr,
                                int64_t ldt, float* colsum, void* stream);
+/* The same pass with the MLP's activation folded in (kind: AFFT_ACT_GELU_ERF / AFFT_ACT_GELU_TANH).  d_act == NULL:
+ * v = gelu(src), the second Linear's operands straight from the first Linear's fp32 output.  d_act != NULL (pitch ldd):
+ * v = d_act * gelu'(src), the first Linear's backward operands and bias gradient from the gradient w.r.t. the activation. */
+AFFT_API int afft_convert_dual_gelu(const float* src, int64_t lds, int32_t rows, int32_t cols, void* hi, int64_t ldh,
+                                    void* tr, int64_t ldt, float* colsum, const float* d_act, int64_t ldd, int32_t kind,
+                                    void* stream);
 AFFT_API int afft_transpose_bf16(const void* src, int64_t lds, int32_t rows, int32_t cols, void* dst, int64_t ldd, void* stream);
 /* dx = LayerNorm backward; dgamma / dbeta are ACCUMULATED (+=) and may be NULL (together with gamma). */
 AFFT_API int afft_layernorm_bwd(const float* x, int64_t ldx, const float* gamma, float eps, const float* dy, int64_t lddy,
