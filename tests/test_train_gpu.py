@@ -100,6 +100,53 @@ def test_backward_operators_against_torch():
         assert ((ga - gr).norm() / gr.norm()).item() < 1e-4
 
 
+def test_fused_mlp_and_attention_projection_nodes_against_torch():
+    """MlpFn (Linear -> GELU -> Linear, activation produced as bf16 GEMM operands by afft_convert_dual_gelu) and AttnProjFn
+    (attention -> projection) against torch autograd of the same expressions, and against the unfused native nodes."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    for conv1d, kind, approx, (M, K, Fd) in ((False, _capi.ACT_GELU_ERF, "none", (264, 1024, 4096)),
+                                             (True, _capi.ACT_GELU_TANH, "tanh", (90, 2048, 8192)),
+                                             (False, _capi.ACT_GELU_ERF, "none", (37, 512, 520))):
+        x = torch.randn(M, K, generator=g).to(dev).requires_grad_()
+        w1 = (torch.randn(*((K, Fd) if conv1d else (Fd, K)), generator=g) * 0.03).to(dev).requires_grad_()
+        b1 = (torch.randn(Fd, generator=g) * 0.1).to(dev).requires_grad_()
+        w2 = (torch.randn(*((Fd, K) if conv1d else (K, Fd)), generator=g) * 0.03).to(dev).requires_grad_()
+        b2 = (torch.randn(K, generator=g) * 0.1).to(dev).requires_grad_()
+        y = atrain.MlpFn.apply(x, w1, b1, w2, b2, kind, conv1d)
+        lin = (lambda a, w, b: a @ w + b) if conv1d else torch.nn.functional.linear
+        ref = lin(torch.nn.functional.gelu(lin(x, w1, b1), approximate=approx), w2, b2)
+        unf = atrain.LinearFn.apply(atrain.GeluFn.apply(atrain.LinearFn.apply(x, w1, b1, conv1d), kind), w2, b2, conv1d)
+        assert (y - ref).abs().max().item() < 5e-2
+        assert (y - unf).abs().max().item() < 1e-5  # the same bf16 operands reach the same GEMMs
+        dy = torch.randn(M, K, generator=g).to(dev)
+        got = torch.autograd.grad(y, (x, w1, b1, w2, b2), dy)
+        want = torch.autograd.grad(ref, (x, w1, b1, w2, b2), dy)
+        for a_, r_ in zip(got, want):
+            assert ((a_ - r_).norm() / r_.norm()).item() < 1e-2
+    for conv1d, (n_seq, L, H, hd, mask, T) in ((False, (24, 5, 4, 256, 0, 1)), (True, (6, 18, 4, 512, 1, 18))):
+        D = H * hd
+        qkv = torch.randn(n_seq * L, 3 * D, generator=g).to(dev).requires_grad_()
+        w = (torch.randn(D, D, generator=g) * 0.03).to(dev).requires_grad_()
+        b = (torch.randn(D, generator=g) * 0.1).to(dev).requires_grad_()
+        torch.manual_seed(77)
+        y, probs = atrain.AttnProjFn.apply(qkv, w, b, conv1d, n_seq, L, H, hd, mask, T, 0.25)
+        torch.manual_seed(77)
+        drop = (torch.rand(n_seq, H, L, L, device=dev) >= 0.25).float() / 0.75
+        t = qkv.view(n_seq, L, 3, H, hd).permute(2, 0, 3, 1, 4)
+        s = (t[0] @ t[1].transpose(-1, -2)) * hd ** -0.5
+        if mask == 1:
+            s = s + torch.triu(torch.full((L, L), float("-inf"), device=dev), 1)
+        pd = s.softmax(-1) * drop
+        a = (pd @ t[2]).transpose(1, 2).reshape(n_seq * L, D)
+        ref = (a @ w + b) if conv1d else torch.nn.functional.linear(a, w, b)
+        assert (y - ref).abs().max().item() < 5e-2
+        assert (probs - pd).abs().max().item() < 2e-5
+        dy = torch.randn(n_seq * L, D, generator=g).to(dev)
+        for a_, r_ in zip(torch.autograd.grad(y, (qkv, w, b), dy), torch.autograd.grad(ref, (qkv, w, b), dy)):
+            assert ((a_ - r_).norm() / r_.norm()).item() < 1e-2
+
+
 # config 5's own model (ek100_sa_swin: K = 352 wgrad, N = 3806 head, 6 + 6 layers), the T-SA / CA training experiments
 # (expts/03, expts/04), the SA-Fuser without token (expts/02) and the ablation mappings
 @pytest.mark.parametrize("cfg_name,B", [("egtea_sa", 8), ("ek100_sa_swin", 2), ("ek100_tsa", 2), ("ek100_ca", 2),
