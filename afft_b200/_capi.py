@@ -130,7 +130,7 @@ class Profile(C.Structure):
 
 # every symbol include/afft_b200.h declares
 EXPORTED_SYMBOLS = [
-    "afft_abi_version", "afft_last_error", "afft_gemm", "afft_set_gemm_epilogue", "afft_convert_bf16",
+    "afft_abi_version", "afft_last_error", "afft_gemm", "afft_set_gemm_epilogue", "afft_set_gemm_skinny", "afft_convert_bf16",
     "afft_convert_operand", "afft_layernorm", "afft_attention", "afft_create", "afft_destroy", "afft_handle_error",
     "afft_workspace_bytes", "afft_weight_bytes", "afft_set_weight", "afft_missing_weights", "afft_forward",
     "afft_last_launch_count", "afft_profile_enable", "afft_profile_read", "afft_set_max_ksplit", "afft_plan_ksplit",
@@ -162,6 +162,8 @@ def lib() -> C.CDLL:
     l.afft_convert_operand.restype = C.c_int
     l.afft_set_gemm_epilogue.argtypes = [C.c_int32]
     l.afft_set_gemm_epilogue.restype = C.c_int
+    l.afft_set_gemm_skinny.argtypes = [C.c_int32]
+    l.afft_set_gemm_skinny.restype = C.c_int
     l.afft_layernorm.argtypes = [C.POINTER(LayerNormDesc), C.c_void_p]
     l.afft_attention.argtypes = [C.POINTER(AttentionDesc), C.c_void_p]
     l.afft_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]

@@ -61,8 +61,9 @@ static int device_sm_count(int* out) {
 // ================================================================================================
 // stateless operators
 // ================================================================================================
+// w_static: the W operand is a packed weight of a handle (never written by a kernel of the stream)
 static int run_gemm(const afft_gemm_desc& d, int num_sms, cudaStream_t stream, const SplitKScratch* sk = nullptr,
-                    unsigned long long* t_end = nullptr) {
+                    unsigned long long* t_end = nullptr, bool w_static = false) {
   GemmOperands g;
   g.a = static_cast<const bf16*>(d.a_hi);
   g.a_lo = static_cast<const bf16*>(d.a_lo);
@@ -96,7 +97,7 @@ static int run_gemm(const afft_gemm_desc& d, int num_sms, cudaStream_t stream, c
   if (d.precision == AFFT_PREC_FP16 && (ep.out_lo != nullptr || g.a_lo != nullptr || g.w_lo != nullptr))
     return fail(AFFT_ERR_INVALID, "gemm: AFFT_PREC_FP16 takes no lo operands / outputs");
   const int mode = d.precision == AFFT_PREC_BF16X3 ? MODE_BF16X3 : (d.precision == AFFT_PREC_FP16 ? MODE_FP16 : MODE_BF16);
-  if (!launch_gemm(g, ep, mode, d.force_block_n, num_sms, stream, &err, sk, t_end)) return fail(AFFT_ERR_CUDA, err);
+  if (!launch_gemm(g, ep, mode, d.force_block_n, num_sms, stream, &err, sk, t_end, w_static)) return fail(AFFT_ERR_CUDA, err);
   return AFFT_OK;
 }
 
@@ -579,6 +580,10 @@ struct afft_handle {
   char* ws = nullptr;
   size_t ws_bytes = 0;
   bool ws_owned = true;  // false: caller-owned workspace (afft_create_in)
+  // true from afft_set_weight until one whole forward has been enqueued behind the packing kernels: only then may a GEMM
+  // request its weight bytes ahead of griddepcontrol.wait (gemm_skinny.cuh: w_static) - with a forward's ~90 kernels in
+  // between, no chain of early-launched kernels reaches back to the packing kernel
+  bool weights_fresh = true;
   SplitKScratch splitk{nullptr, 0, nullptr, 0, 4};  // partial tiles + band counters of the split-K GEMM path
   int n_slots = 0;  // tokens per (b, t) in the fuser stream (CA: 1)
   float* h = nullptr;
@@ -899,6 +904,7 @@ extern "C" int afft_set_weight(afft_handle* h, const char* name, const float* sr
   if (name == nullptr || src == nullptr || shape == nullptr || ndim < 1 || ndim > 3)
     return hfail(h, AFFT_ERR_INVALID, "set_weight: bad argument");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  h->weights_fresh = true;
   auto it = h->expected.find(name);
   if (it == h->expected.end()) return hfail(h, AFFT_ERR_INVALID, std::string("set_weight: unexpected tensor name '") + name + "'");
   const Expect& ex = it->second;
@@ -1040,7 +1046,7 @@ struct Fwd {
     d.row_group = row_group;
     d.row_stride = row_stride;
     d.row_off = row_off;
-    check(run_gemm(d, h->num_sms, stream, &h->splitk, prof_slot(AFFT_CAT_GEMM, d.M, d.N, d.K)));
+    check(run_gemm(d, h->num_sms, stream, &h->splitk, prof_slot(AFFT_CAT_GEMM, d.M, d.N, d.K), !h->weights_fresh));
   }
 
   void layernorm(const float* x, long long ldx, int rows, int dim, const std::string& name, float eps, const PairBuf* yb,
@@ -1571,16 +1577,23 @@ extern "C" int afft_forward(afft_handle* h, int32_t B, const afft_io* io, void* 
   }
   if (c.stages == AFFT_STAGE_GPT) {
     run_gpt_only(F, *io, B);
+    if (F.ok()) h->weights_fresh = false;
     return F.rc;
   }
   const int chunk = (h->fuser_chunk > 0) ? h->fuser_chunk : B;
   for (int b0 = 0; b0 < B && F.ok(); b0 += chunk) run_fuser(F, *io, b0, std::min(chunk, B - b0));
   if (F.ok() && c.stages == AFFT_STAGE_ALL) run_predictor(F, *io, B);
+  if (F.ok()) h->weights_fresh = false;
   return F.rc;
 }
 
 extern "C" int afft_set_gemm_epilogue(int32_t v2) {
   gemm_epilogue_v2_flag().store(v2 != 0 ? 1 : 0, std::memory_order_relaxed);
+  return AFFT_OK;
+}
+
+extern "C" int afft_set_gemm_skinny(int32_t on) {
+  gemm_skinny_flag().store(on != 0 ? 1 : 0, std::memory_order_relaxed);
   return AFFT_OK;
 }
 

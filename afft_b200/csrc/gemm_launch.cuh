@@ -16,6 +16,7 @@
 #include <unordered_map>
 
 #include "gemm_sm100.cuh"
+#include "gemm_skinny.cuh"
 
 namespace afft {
 
@@ -180,6 +181,13 @@ inline std::atomic<int>& gemm_epilogue_v2_flag() {
   return flag;
 }
 
+// Skinny problems (M <= kSkinnyMaxM rows, bf16 / fp16 operands) run gemm_skinny_kernel (gemm_skinny.cuh) instead of the
+// tcgen05 kernels: 1 (default) = on, 0 = off.  Process-wide; initial value from AFFT_GEMM_SKINNY.
+inline std::atomic<int>& gemm_skinny_flag() {
+  static std::atomic<int> flag([] { const char* v = getenv("AFFT_GEMM_SKINNY"); return v == nullptr ? 1 : atoi(v); }());
+  return flag;
+}
+
 inline bool pdl_enabled() {
   static const bool on = [] { const char* v = getenv("AFFT_PDL"); return v == nullptr || atoi(v) != 0; }();
   return on;
@@ -262,6 +270,44 @@ inline cudaError_t launch_gemm_2cta_variant(const CUtensorMap& ta, const CUtenso
   return launch_pdl(kern, dim3(2 * clusters), dim3(kGemmThreads), smem, stream, ta, tb, tal, tbl, ep, M, N, K, sched, tme);
 }
 
+template <int MT, int NT, bool FP16>
+inline cudaError_t launch_skinny_variant(const SkinnyArgs& p, cudaStream_t stream) {
+  using T = SkinnyTraits<MT, NT>;
+  auto kern = gemm_skinny_kernel<MT, NT, FP16>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  const int grid = (p.N + 8 * NT - 1) / (8 * NT);
+  return launch_pdl(kern, dim3(grid), dim3(kSkinnyThreads), T::kSmemBytes, stream, p);
+}
+
+// M <= 16 / 32 / 64 / 96 rows -> 1 / 2 / 4 / 6 m16 tiles; two n8 tiles per CTA once that still gives every SM two CTAs.
+inline cudaError_t launch_skinny(const SkinnyArgs& p, bool fp16, int num_sms, cudaStream_t stream) {
+  const int mt = p.M <= 16 ? 1 : (p.M <= 32 ? 2 : (p.M <= 64 ? 4 : 6));
+  const int nt = ((p.N + 15) / 16 >= 2 * num_sms) ? 2 : 1;
+#define AFFT_SKINNY(MT_, NT_)                                                      \
+  if (mt == MT_ && nt == NT_)                                                      \
+    return fp16 ? launch_skinny_variant<MT_, NT_, true>(p, stream) : launch_skinny_variant<MT_, NT_, false>(p, stream)
+  AFFT_SKINNY(1, 1); AFFT_SKINNY(1, 2); AFFT_SKINNY(2, 1); AFFT_SKINNY(2, 2);
+  AFFT_SKINNY(4, 1); AFFT_SKINNY(4, 2); AFFT_SKINNY(6, 1); AFFT_SKINNY(6, 2);
+#undef AFFT_SKINNY
+  return cudaErrorInvalidValue;
+}
+
+// Which problems take the skinny kernel (cost model in gemm_skinny.cuh): up to 32 rows always; up to 96 rows when the
+// weight is small (<= 4 M elements: the fuser's at batch 1), where the launch floor of the tcgen05 kernel dominates.
+inline bool skinny_eligible(int M, int N, int K) {
+  static const int max_m = [] { const char* v = getenv("AFFT_GEMM_SKINNY_M"); return v == nullptr ? 32 : atoi(v); }();
+  if (M > kSkinnyMaxM || K % 8 != 0) return false;
+  return M <= max_m || static_cast<long long>(N) * K <= (4ll << 20);
+}
+
 inline int pick_block_n(int M, int N, int num_sms, int forced) {
   if (forced == 128 || forced == 256) return forced;
   // Fewest waves wins; ties go to the 256-wide tile (less A re-streaming through shared memory).
@@ -302,7 +348,7 @@ inline const GemmSched& default_sched() {
 // Returns false and fills *err on failure.  mode: MODE_BF16 / MODE_FP16 / MODE_BF16X3.  force_block_n: 0 = auto.
 inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, int mode, int force_block_n,
                         int num_sms, cudaStream_t stream, std::string* err, const SplitKScratch* sk = nullptr,
-                        unsigned long long* t_end = nullptr) {
+                        unsigned long long* t_end = nullptr, bool w_static = false) {
   if (mode != MODE_BF16 && mode != MODE_FP16 && mode != MODE_BF16X3) {
     if (err) *err = "gemm: unknown precision mode";
     return false;
@@ -324,6 +370,17 @@ inline bool launch_gemm(const GemmOperands& g, const GemmEpilogue& ep, int mode,
       (ep.bias != nullptr && (reinterpret_cast<uintptr_t>(ep.bias) & 15u) != 0)) {
     if (err) *err = "gemm: epilogue pointers must be 16-B aligned with 16-B multiple pitches";
     return false;
+  }
+  // skinny problems: the weight-streaming kernel (no TMEM / TMA / split-K machinery)
+  if (!strict && force_block_n == 0 && skinny_eligible(g.M, g.N, g.K) && !misaligned(g.a, g.lda, 2) &&
+      !misaligned(g.w, g.ldw, 2) && gemm_skinny_flag().load(std::memory_order_relaxed) != 0) {
+    SkinnyArgs p{g.a, g.lda, g.w, g.ldw, g.M, g.N, g.K, ep, t_end, w_static ? 1 : 0};
+    const cudaError_t se = launch_skinny(p, fp16, num_sms, stream);
+    if (se != cudaSuccess) {
+      if (err) *err = std::string("skinny gemm launch failed: ") + cudaGetErrorString(se);
+      return false;
+    }
+    return true;
   }
   int bn = pick_block_n(g.M, g.N, num_sms, force_block_n);
   // CTA pairs (cta_group::2, 256 x 256 tiles) whenever the 256-wide tile is chosen and there is enough work

@@ -116,6 +116,11 @@ AFFT_API int afft_gemm(const afft_gemm_desc* d, void* stream);
  * (DESIGN.md section 4.1), kept for A/B runs.  Initial value: environment variable AFFT_GEMM_EPI_V2. */
 AFFT_API int afft_set_gemm_epilogue(int32_t v2);
 
+/* Process-wide: GEMMs with at most 96 rows (bf16 / fp16 operands) run the weight-streaming mma.sync kernel
+ * (csrc/gemm_skinny.cuh) instead of the tcgen05 kernels: 1 (default) = on, 0 = off (A/B runs, tests of the tcgen05 tail
+ * handling).  Initial value: environment variable AFFT_GEMM_SKINNY. */
+AFFT_API int afft_set_gemm_skinny(int32_t on);
+
 /* fp32 [rows, cols] (pitch lds) -> bf16 hi (+ lo when lo != NULL), pitch ldd; transpose != 0
  * writes dst[c, r].  Weight packing (Conv1D [in,out] -> K-major) and feature inputs. */
 AFFT_API int afft_convert_bf16(const float* src, int64_t lds, int32_t rows, int32_t cols, void* hi, void* lo, int64_t ldd,

@@ -368,3 +368,88 @@ def test_gemm_tma_staged_epilogue_matches_default(dev):
             assert (outs[1][0] - (_mm(a, w) + bias + res)).abs().max().item() < 1e-4
     finally:
         capi.check(lib.afft_set_gemm_epilogue(0))
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", [(1, 1024, 1024), (16, 8, 64), (18, 2048, 8192), (18, 8192, 2048), (18, 3806, 1024),
+                                   (33, 1024, 352), (36, 6144, 2048), (64, 1001, 1000), (90, 3072, 1024), (90, 1024, 4096),
+                                   (96, 4096, 1024), (5, 4, 2048)])
+def test_gemm_skinny_kernel(dev, M, N, K, dt):
+    """M <= 96 rows run the weight-streaming mma.sync kernel (csrc/gemm_skinny.cuh): against float64 on the same 16-bit
+    operands, and against the tcgen05 kernels on the same problem (afft_set_gemm_skinny(0))."""
+    g = torch.Generator().manual_seed(M * 13 + N + K)
+    a = _randn(g, dev, M, K).to(dt)
+    w = _randn(g, dev, N, K, scale=0.05).to(dt)
+    ld = (N + 3) // 4 * 4
+    ref = _mm(a, w)
+    tol = 2e-4 * max(1.0, (K / 1024) ** 0.5) * 3
+    outs = []
+    try:
+        for skinny in (1, 0):
+            capi.check(capi.lib().afft_set_gemm_skinny(skinny))
+            out = torch.full((M, ld), float("nan"), device=dev)
+            capi.gemm(a, w, out_f32=out)
+            assert not torch.isnan(out[:, :N]).any()
+            assert (out[:, :N] - ref).abs().max().item() < tol
+            if ld > N:
+                assert torch.isnan(out[:, N:]).all()  # padding columns are never written
+            outs.append(out[:, :N].clone())
+    finally:
+        capi.check(capi.lib().afft_set_gemm_skinny(1))
+    assert (outs[0] - outs[1]).abs().max().item() < tol
+
+
+def test_gemm_skinny_epilogues(dev):
+    """Every epilogue feature on the skinny kernel: bias, GELU (erf / tanh), ReLU, gate, residual in place, residual by
+    row modulus + output row map, strided output slots, 16-bit outputs in both formats, an odd N with padded pitch."""
+    g = torch.Generator().manual_seed(21)
+    F = torch.nn.functional
+    M, N, K = 90, 1024, 1024
+    a = _randn(g, dev, M, K).bfloat16()
+    w = _randn(g, dev, N, K, scale=0.05).bfloat16()
+    bias, res = _randn(g, dev, N), _randn(g, dev, M, N)
+    ref0 = _mm(a, w)
+    out = torch.zeros(M, N, device=dev)
+    capi.gemm(a, w, bias=bias, act=capi.ACT_GELU_ERF, out_f32=out)
+    assert (out - F.gelu(ref0 + bias)).abs().max().item() < 1e-4
+    capi.gemm(a, w, bias=bias, act=capi.ACT_GELU_TANH, out_f32=out)
+    assert (out - F.gelu(ref0 + bias, approximate="tanh")).abs().max().item() < 1e-4
+    capi.gemm(a, w, bias=bias, act=capi.ACT_RELU, out_f32=out)
+    assert (out - torch.relu(ref0 + bias)).abs().max().item() < 1e-4
+    capi.gemm(a, w, bias=bias, act=capi.ACT_GATE, res=res, out_f32=out)
+    assert (out - res * torch.sigmoid(ref0 + bias)).abs().max().item() < 1e-4
+    h = res.clone()
+    capi.gemm(a, w, bias=bias, res=h, out_f32=h)  # in-place residual stream update
+    assert (h - (ref0 + bias + res)).abs().max().item() < 1e-4
+    ob = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    of = torch.zeros(M, N, device=dev)
+    capi.gemm(a, w, bias=bias, res=res, out_f32=of, out_hi=ob)
+    assert torch.equal(ob, of.bfloat16())
+    T = 18
+    pos = _randn(g, dev, T, N)
+    outm = torch.zeros(M // T * (T + 1) + T + 1, N, device=dev)
+    capi.gemm(a, w, res=pos, res_mod=T, out_f32=outm, row_map=(T, T + 1, 1))
+    r = torch.arange(M, device=dev)
+    assert (outm[(r // T) * (T + 1) + r % T + 1] - (ref0 + pos[r % T])).abs().max().item() < 1e-4
+    slots = 5
+    hbuf = torch.zeros(M * slots, N, device=dev)
+    capi.gemm(a, w, out_f32=hbuf.view(M, slots * N)[:, 2 * N:3 * N])
+    assert (hbuf.view(M, slots, N)[:, 2] - ref0).abs().max().item() < 1e-4
+    assert hbuf.view(M, slots, N)[:, [0, 1, 3, 4]].abs().max().item() == 0.0
+    # fp16 operands and output, saturation to the finite range
+    a16, w16 = a.half(), w.half()
+    big = torch.full((N,), 1e6, device=dev)
+    o16 = torch.zeros(M, N, device=dev, dtype=torch.float16)
+    capi.gemm(a16, w16, bias=big, out_hi=o16)
+    assert torch.isfinite(o16).all() and (o16 == 65504).all()
+    capi.gemm(a16, w16, bias=bias, act=capi.ACT_GELU_ERF, out_hi=o16)
+    assert (o16.float() - F.gelu(_mm(a16, w16) + bias)).abs().max().item() < 4e-3
+    # classifier width (N = 3806, pitch 3808), 18 rows
+    Nc = 3806
+    wc = _randn(g, dev, Nc, K, scale=0.05).bfloat16()
+    bc = torch.zeros(Nc + 16, device=dev)[:Nc]
+    bc.copy_(_randn(g, dev, Nc))
+    oc = torch.full((18, 3808), 7.0, device=dev)
+    capi.gemm(a[:18], wc, bias=bc, out_f32=oc)
+    assert (oc[:, :Nc] - (_mm(a[:18], wc) + bc)).abs().max().item() < 1e-4
+    assert (oc[:, Nc:] == 7.0).all()
