@@ -21,3 +21,6 @@ for c in egtea_sa ek100_tsa ek100_ca; do
   timeout 600 compute-sanitizer --tool memcheck python tools/sanitize_train.py $c > gpurun_out/r02z_sanitize_$c.log 2>&1; echo "sanitizer $c rc=$?"; grep -E "ERROR SUMMARY|done" gpurun_out/r02z_sanitize_$c.log | tail -2
 done
 timeout 600 compute-sanitizer --tool memcheck python tools/ncu_forward.py 5 ek100_sa_tsn fp16 > gpurun_out/r02z_sanitize_fp16.log 2>&1; grep -E "ERROR SUMMARY" gpurun_out/r02z_sanitize_fp16.log | tail -1
+for b in 16 128; do
+  timeout 600 python bench.py --mode train --batch $b --steps 10 > gpurun_out/r02z_train_b$b.json 2> gpurun_out/r02z_train_b$b.err; echo "train b$b rc=$?"; tail -c 500 gpurun_out/r02z_train_b$b.json | cut -c1-500
+done
