@@ -749,16 +749,23 @@ def run_train(args):
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, nesterov=True, weight_decay=1e-6, fused=True) if use_ddp else None
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     sets = [{m: torch.randn(B, T, d, 1, 1, 1, device=dev, generator=g) for m, d in cfg["modal_dims"].items()} for _ in range(2)]
-    target = torch.randint(0, C, (B, 1), device=dev, generator=g)
-    target_sub = torch.randint(0, C, (B, T), device=dev, generator=g)
+    cls_name = list(ncls.keys())[0]
+    target = {cls_name: torch.randint(0, C, (B, 1), device=dev, generator=g)}
+    target_sub = {cls_name: torch.randint(0, C, (B, T), device=dev, generator=g)}
+    # the experiment trains with MixUp on the backbone outputs and smoothed soft labels (expts/01_SA-Fuser_ek100_train.txt:10-12,
+    # conf/config.yaml:16-22); afft_b200.runner restates common/mixup.py + common/runner.py with static shapes (capturable)
+    from afft_b200 import runner as arunner
+    mixup_fn = None
+    if not args.no_mixup:
+        mixup_fn = arunner.MixUp(alpha=0.1, label_smoothing={"action": 0.4, "verb": 0.01, "noun": 0.03}, num_classes=dict(ncls),
+                                 device_lambda=True)
 
     def fwd_bwd_opt(feats):
         if state is not None:
             state.zero()
         else:
             opt.zero_grad(set_to_none=True)
-        out, _ = ddp(feats, **KW)
-        loss = atrain.reference_losses(out, target, target_sub)["total"]
+        loss, _, _ = arunner.training_losses(ddp, feats, target, target_sub, mixup_fn=mixup_fn, mixup_backbone=True)
         loss.backward()  # per-group NCCL all-reduces are issued from inside backward (GradBuckets / DDP)
         if state is not None:
             state.finish()
@@ -829,7 +836,9 @@ def run_train(args):
         "dtype": "bf16", "data": "synthetic", "mode": "train",
         "config": {"workload": f"{train_cfg_name} training step" + (" (expts/01_SA-Fuser_ek100_train.txt: T=16, 4 modalities, SGD-nesterov)"
                                                                     if train_cfg_name == "ek100_sa_swin" else " (SGD-nesterov)"),
-                   "clips_per_gpu_per_step": B, "T": T, "params": n_params, "grad_allreduce_bytes": 4 * n_params if world > 1 else 0,
+                   "clips_per_gpu_per_step": B, "T": T, "params": n_params,
+                   "mixup": ("MixUp(alpha 0.1) on the backbone outputs + label smoothing 0.4, soft-label losses, acc1 / acc5 per step "
+                             "(afft_b200.runner = common/mixup.py + common/runner.py)") if mixup_fn is not None else "off (--no-mixup)", "grad_allreduce_bytes": 4 * n_params if world > 1 else 0,
                    "allreduce": ((f"{len(buckets.groups)} per-layer-group NCCL all-reduces ({args.grad_comm} transport) issued from inside "
                                   f"backward (GradBuckets), " + ("captured in the step's CUDA graph" if graphed else "eager"))
                                  if (world > 1 and buckets is not None) else
@@ -874,6 +883,7 @@ def main():
     ap.add_argument("--strict", action="store_true", help="alias of --precision strict")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="train mode: do not capture the step into a CUDA graph")
+    ap.add_argument("--no-mixup", action="store_true", help="train mode: hard labels, no MixUp (the experiment uses MixUp)")
     ap.add_argument("--grad-comm", choices=["fp32", "bf16"], default="fp32", help="train mode: gradient all-reduce transport dtype")
     ap.add_argument("--grad-buckets", type=int, default=4,
                     help="train mode: merge the layer groups into this many all-reduce buckets (0: one per group); 4 measured best at N = 8")

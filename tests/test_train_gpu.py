@@ -286,3 +286,93 @@ def test_train_state_step_matches_autograd_and_torch_sgd():
         # the optimizer's bf16 image is the parameter rounded to bf16
         anyp = npar["future_predictor.dim_encoder.weight"]
         assert torch.equal(state.w16[id(anyp)], anyp.data.bfloat16())
+
+
+def test_training_iteration_with_mixup_matches_oracle_and_captures():
+    """The experiment's iteration (MixUp on the backbone outputs, smoothed soft labels, runner losses: afft_b200/runner.py,
+    pinned to the reference's common/mixup.py + common/runner.py on the CPU) through the native training path: the losses
+    equal the CPU oracle's on the same mixed inputs, the gradients of the soft-label losses match, and the whole iteration
+    captures into one CUDA graph that draws a new lambda on every replay."""
+    from afft_b200 import runner
+    from oracle import afft_oracle
+    cfg, T, ncls = _no_dropout_cfg("egtea_sa")
+    C = ncls["action"]
+    B = 6
+    model = BaseModel(cfg, ncls, {})
+    sd = synthetic.synthetic_state_dict(model, seed=0)
+    model.load_state_dict(sd)
+    model = model.to("cuda:0").train()
+    feats = synthetic.synthetic_features(cfg["modal_dims"], B, T, seed=31)
+    gl = torch.Generator().manual_seed(9)
+    target = {"action": torch.randint(0, C, (B, 1), generator=gl)}
+    target_sub = {"action": torch.randint(0, C, (B, T), generator=gl)}
+    target_sub["action"][1, 2] = -1  # clip 1 is not mixable and its frame 2 is dropped from the past loss
+    smooth = {"action": 0.4}
+
+    mix = runner.MixUp(alpha=0.8, label_smoothing=smooth, num_classes=ncls)
+    torch.manual_seed(4321)  # lambda comes from the CPU generator (device_lambda=False), as in the reference
+    dev_feats = {m: t.reshape(B, T, -1, 1, 1, 1).cuda() for m, t in feats.items()}
+    total, means, metrics = runner.training_losses(model, dev_feats, {k: v.cuda() for k, v in target.items()},
+                                                   {k: v.cuda() for k, v in target_sub.items()}, mixup_fn=mix)
+    total.backward()
+    torch.cuda.synchronize()
+
+    torch.manual_seed(4321)
+    x_mix, l_mix, s_mix, s_ign = runner.MixUp(alpha=0.8, label_smoothing=smooth, num_classes=ncls)(
+        {m: t.clone() for m, t in feats.items()}, target, target_sub)
+    assert not torch.equal(x_mix["rgb"], feats["rgb"]) and torch.equal(x_mix["rgb"][1], feats["rgb"][1])
+    sd_ref = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref_out = afft_oracle.forward(sd_ref, cfg, ncls, x_mix)
+    rl, rk, rmet = runner.loss_and_accuracy(ref_out, l_mix, s_mix, mixup_enable=True, target_subclips_ignore_index=s_ign)
+    ref_total, ref_means = runner.reduce_loss(rl, rk)
+    ref_total.backward()
+    assert set(means) == set(ref_means)
+    for k, v in ref_means.items():
+        assert abs(means[k].item() - v.item()) < 2e-2 * max(1.0, abs(v.item())), k
+    assert abs(total.item() - ref_total.item()) < 2e-2 * max(1.0, abs(ref_total.item()))
+    n_checked = 0
+    for name, p in model.named_parameters():
+        gref = sd_ref[name].grad
+        if gref is None or gref.norm().item() == 0.0:
+            continue
+        g = p.grad.detach().cpu()
+        rel = ((g - gref).norm() / gref.norm()).item()
+        assert rel < 5e-2, (name, rel)
+        n_checked += 1
+    assert n_checked >= 40
+
+    # one CUDA graph for MixUp -> forward -> losses -> backward, lambda drawn on the device.  A fresh model that has only ever
+    # run on the capture's side stream (PyTorch's whole-network capture recipe: autograd's accumulation nodes remember the
+    # stream of a parameter's first use, and the legacy default stream may not depend on a capturing stream)
+    model = BaseModel(cfg, ncls, {})
+    model.load_state_dict(sd)
+    model = model.to("cuda:0").train()
+    mix_dev = runner.MixUp(alpha=0.8, label_smoothing=smooth, num_classes=ncls, device_lambda=True)
+    tgt_dev = {k: v.cuda() for k, v in target.items()}
+    sub_dev = {k: v.cuda() for k, v in target_sub.items()}
+    static = {m: t.clone() for m, t in dev_feats.items()}
+
+    def iteration():
+        for p in model.parameters():
+            p.grad = None
+        loss, _, _ = runner.training_losses(model, dict(static), tgt_dev, sub_dev, mixup_fn=mix_dev)
+        loss.backward()
+        return loss
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            iteration()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_loss = iteration()
+    seen = []
+    for _ in range(4):
+        graph.replay()
+        torch.cuda.synchronize()
+        seen.append(static_loss.item())
+    assert all(torch.isfinite(torch.tensor(seen))) and len({round(v, 5) for v in seen}) > 1, seen
