@@ -287,10 +287,12 @@ inline cudaError_t launch_skinny_variant(const SkinnyArgs& p, cudaStream_t strea
   return launch_pdl(kern, dim3(grid), dim3(kSkinnyThreads), T::kSmemBytes, stream, p);
 }
 
-// M <= 16 / 32 / 64 / 96 rows -> 1 / 2 / 4 / 6 m16 tiles; two n8 tiles per CTA once that still gives every SM two CTAs.
+// M <= 16 / 32 / 64 / 96 rows -> 1 / 2 / 4 / 6 m16 tiles; two n8 tiles per CTA once that still fills the SMs' CTA slots
+// (two per SM up to 32 rows, one above: ncu showed the 6-tile variant at one CTA per SM running N = 4096 in 3.5 waves).
 inline cudaError_t launch_skinny(const SkinnyArgs& p, bool fp16, int num_sms, cudaStream_t stream) {
   const int mt = p.M <= 16 ? 1 : (p.M <= 32 ? 2 : (p.M <= 64 ? 4 : 6));
-  const int nt = ((p.N + 15) / 16 >= 2 * num_sms) ? 2 : 1;
+  const int slots = (mt <= 2 ? 2 : 1) * num_sms;
+  const int nt = ((p.N + 15) / 16 >= slots) ? 2 : 1;
 #define AFFT_SKINNY(MT_, NT_)                                                      \
   if (mt == MT_ && nt == NT_)                                                      \
     return fp16 ? launch_skinny_variant<MT_, NT_, true>(p, stream) : launch_skinny_variant<MT_, NT_, false>(p, stream)
